@@ -1,0 +1,69 @@
+"""Build the UNMODIFIED reference MuZero ctree (Cython + C++) into oracle/_ref/.
+
+TEST INFRASTRUCTURE ONLY.  Nothing under oracle/ is imported by the product
+package `lightzero_b200`; only tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs may use it.
+
+Sources are compiled from where they lie under /root/reference (read-only); no
+reference source is copied into this repository.  Only the Cython-generated
+.cpp (written to a temp dir) and the final extension module (oracle/_ref/, which
+is git-ignored but travels to the GPU box) are produced.
+
+Reference files compiled:
+  lzero/mcts/ctree/ctree_muzero/mz_tree.pyx (+ mz_tree.pxd)
+  lzero/mcts/ctree/ctree_muzero/lib/cnode.cpp, cnode.h   (textually included by the .pxd)
+  lzero/mcts/ctree/common_lib/cminimax.cpp, cminimax.h, utils.cpp
+Flags mirror the reference setup.py:58,89-91 (-std=c++11, distutils -O2 -DNDEBUG).
+Quirk: cnode.h:6 includes "./../common_lib/cminimax.h", which only
+resolves with -I <ctree_muzero> on the include path.
+"""
+import os
+import shutil
+import subprocess
+import sys
+import sysconfig
+import tempfile
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+OUT = os.path.join(HERE, "_ref")
+REF = os.environ.get("LZ_REFERENCE", "/root/reference")
+CTREE = os.path.join(REF, "lzero", "mcts", "ctree")
+
+
+def ref_module_path():
+    suffix = sysconfig.get_config_var("EXT_SUFFIX")
+    return os.path.join(OUT, "mz_tree" + suffix)
+
+
+def build(force: bool = False) -> str:
+    """Returns the path of the built module, or '' if the reference tree is absent."""
+    target = ref_module_path()
+    if os.path.exists(target) and not force:
+        return target
+    src_dir = os.path.join(CTREE, "ctree_muzero")
+    if not os.path.isdir(src_dir):
+        return ""
+    import numpy
+    os.makedirs(OUT, exist_ok=True)
+    with tempfile.TemporaryDirectory() as tmp:
+        gen_cpp = os.path.join(tmp, "mz_tree.cpp")
+        # cython reads the .pyx/.pxd in place; only the generated C++ goes to tmp
+        subprocess.check_call(
+            [sys.executable, "-m", "cython", "--cplus", "-3", "-I", src_dir,
+             os.path.join(src_dir, "mz_tree.pyx"), "-o", gen_cpp])
+        inc = sysconfig.get_paths()["include"]
+        cmd = ["g++", "-std=c++11", "-O2", "-DNDEBUG", "-fPIC", "-shared", "-w",
+               "-I", inc, "-I", numpy.get_include(),
+               "-I", src_dir,                      # resolves "lib/cnode.cpp" from the pxd
+               "-I", os.path.join(src_dir, "lib"),
+               "-I", CTREE,                        # cnode.h:6 quirk: ./../common_lib
+               gen_cpp, "-o", target]
+        # cnode.h includes "./../common_lib/cminimax.h" relative to ctree_muzero/lib -> ctree_muzero/common_lib
+        # (does not exist). g++ then searches -I dirs: <ctree_muzero>/./../common_lib == ctree/common_lib.
+        subprocess.check_call(cmd)
+    return target
+
+
+if __name__ == "__main__":
+    p = build(force="--force" in sys.argv)
+    print(p if p else "reference tree not present; nothing built")

@@ -1,0 +1,118 @@
+"""Generate the committed golden fixtures for the MuZero ctree path by RUNNING THE COMPILED,
+UNMODIFIED REFERENCE (oracle/_ref/mz_tree, built from /root/reference by oracle/build_ref.py).
+
+Run in the build container (the GPU box has no /root/reference; it uses the committed .npz files):
+    python tests/golden/make_golden.py
+
+Each fixture is a replay-mode trace: all inputs the tree consumes (legal lists, root logits,
+Dirichlet noise, per-simulation reward / value / policy-logit batches) and everything it produces
+(per-simulation (ix, iy, last_action, search_len, virtual_to_play), final visit distributions,
+root values as raw fp32 bits, best-action trajectories).  deterministic=True.
+"""
+import copy
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle", "_ref"))
+
+CASES = [
+    # name,            B,  A,  S,  masks, noise, two_player, scale, seed
+    ("survey_b4a6",     4,  6, 10, 0, 0, 0, 1.0, 0),   # SURVEY.md 8c session vector (same draws)
+    ("atari_a6",       32,  6, 50, 0, 1, 0, 1.0, 1),
+    ("atari_a18",      32, 18, 50, 0, 1, 0, 1.0, 2),
+    ("atari_a18_mask", 32, 18, 50, 1, 1, 0, 2.0, 3),
+    ("deep_s200",       8, 18, 200, 0, 1, 0, 0.5, 4),
+    ("board_2p_a9",    16,  9, 40, 1, 1, 1, 1.0, 5),
+    ("wide_a40",        6, 40, 60, 1, 0, 0, 3.0, 6),
+    ("cartpole_a2",     8,  2, 25, 0, 1, 0, 1.0, 7),
+]
+PB_C_BASE, PB_C_INIT, DISCOUNT, DELTA, NOISE_W = 19652, 1.25, 0.997, 0.01, 0.25
+
+
+def make_case(mz, B, A, S, masks, noise, two_player, scale, seed):
+    rng = np.random.default_rng(seed)
+    if masks:
+        legal = []
+        for _ in range(B):
+            m = rng.random(A) < 0.6
+            if not m.any():
+                m[rng.integers(A)] = True
+            legal.append(np.nonzero(m)[0].tolist())
+    else:
+        legal = [list(range(A)) for _ in range(B)]
+    pol = (rng.standard_normal((B, A)) * scale).astype(np.float32)
+    to_play = rng.integers(1, 3, size=B).astype(np.int32) if two_player else np.full(B, -1, np.int32)
+    roots = mz.Roots(B, legal)
+    noises = np.zeros((B, A), np.float32)
+    if noise:
+        nz = []
+        for b, l in enumerate(legal):
+            d = rng.dirichlet([0.3] * len(l)).astype(np.float32)
+            noises[b, :len(l)] = d
+            nz.append(d.tolist())
+        roots.prepare(NOISE_W, nz, [0.] * B, pol.tolist(), to_play.tolist())
+    else:
+        roots.prepare_no_noise([0.] * B, pol.tolist(), to_play.tolist())
+    mm = mz.MinMaxStatsList(B)
+    mm.set_delta(DELTA)
+    rew = np.zeros((S, B), np.float32); val = np.zeros((S, B), np.float32)
+    pols = np.zeros((S, B, A), np.float32)
+    ix = np.zeros((S, B), np.int32); iy = np.zeros((S, B), np.int32)
+    la = np.zeros((S, B), np.int32); sl = np.zeros((S, B), np.int32); vtp = np.zeros((S, B), np.int32)
+    for s in range(S):
+        res = mz.ResultsWrapper(B)
+        a, b_, c, d = mz.batch_traverse(roots, PB_C_BASE, PB_C_INIT, DISCOUNT, mm, res,
+                                        copy.deepcopy(to_play.tolist()), True)
+        ix[s], iy[s], la[s], vtp[s] = a, b_, c, d
+        sl[s] = res.get_search_len()
+        # draw order matches SURVEY.md 8c: r, v, p
+        rew[s] = (rng.standard_normal(B) * scale).astype(np.float32)
+        val[s] = (rng.standard_normal(B) * scale).astype(np.float32)
+        pols[s] = (rng.standard_normal((B, A)) * scale).astype(np.float32)
+        mz.batch_backpropagate(s + 1, DISCOUNT, rew[s].tolist(), val[s].tolist(), pols[s].tolist(), mm, res, d)
+    dist = np.full((B, A), -1, np.int32)
+    for b, dd in enumerate(roots.get_distributions()):
+        dist[b, :len(dd)] = dd
+    values = np.asarray(roots.get_values(), np.float32)
+    traj = np.full((B, S + 1), -1, np.int32)
+    for b, t in enumerate(roots.get_trajectories()):
+        traj[b, :len(t)] = t
+    legal_arr = np.full((B, A), -1, np.int32)
+    nlegal = np.zeros(B, np.int32)
+    for b, l in enumerate(legal):
+        legal_arr[b, :len(l)] = l
+        nlegal[b] = len(l)
+    return dict(B=B, A=A, S=S, use_noise=noise, legal=legal_arr, nlegal=nlegal, root_logits=pol,
+                noises=noises, to_play=to_play, rewards=rew, values_in=val, policies=pols,
+                ix=ix, iy=iy, last_action=la, search_len=sl, virtual_to_play=vtp,
+                distributions=dist, root_values_bits=values.view(np.uint32), trajectories=traj,
+                pb_c_base=PB_C_BASE, pb_c_init=np.float32(PB_C_INIT), discount=np.float32(DISCOUNT),
+                delta=np.float32(DELTA), noise_w=np.float32(NOISE_W))
+
+
+def main():
+    import mz_tree
+    for name, *args in CASES:
+        case = make_case(mz_tree, *args)
+        np.savez_compressed(os.path.join(HERE, f"tree_{name}.npz"), **case)
+        print(name, "sum visits ok:", bool((np.where(case["distributions"] < 0, 0, case["distributions"]).sum(1) == case["S"]).all()))
+    # the reference's own known-answer test (lzero/mcts/tests/test_muzero_ctree_deterministic.py:4-25)
+    roots = mz_tree.Roots(1, [[0, 1, 2]])
+    roots.prepare_no_noise([0.], [[0., 0., 0.]], [-1])
+    mm = mz_tree.MinMaxStatsList(1); mm.set_delta(0.01)
+    acts = []
+    for _ in range(5):
+        res = mz_tree.ResultsWrapper(1)
+        _, _, la, _ = mz_tree.batch_traverse(roots, 19652, 1.25, 0.997, mm, res, [-1], True)
+        acts.append(la[0])
+    assert acts == [0] * 5, acts
+    print("reference KAT ok", acts)
+
+
+if __name__ == "__main__":
+    main()
