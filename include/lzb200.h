@@ -1,0 +1,156 @@
+/*
+ * lzb200.h -- C ABI of the B200-native batched MuZero MCTS + inference engine.
+ *
+ * This is the drop-in boundary for ONE hot path of opendilab/LightZero (file:line relative to the
+ * reference repository root):
+ *
+ *   lzero/mcts/ctree/ctree_muzero/mz_tree.pyx:5-107   (the Cython surface: Roots, MinMaxStatsList,
+ *        ResultsWrapper, batch_traverse, batch_backpropagate)  -> lz_tree_*
+ *   lzero/mcts/ctree/ctree_muzero/lib/cnode.cpp:83-147,169-203,301-358,387-500,551-595,654-698,754-825
+ *        (expand / compute_mean_q / prepare / results / backpropagate / select / ucb / traverse)
+ *   lzero/mcts/ctree/common_lib/cminimax.cpp:7-66      (MinMaxStats)          -> folded into lz_tree
+ *   lzero/model/muzero_model.py:210-272                (initial/recurrent_inference) -> lz_model_*
+ *   lzero/policy/scaling_transform.py:64-92            (InverseScalarTransform) -> fused in lz_model_*
+ *   lzero/mcts/tree_search/mcts_ctree.py:267-368       (MuZeroMCTSCtree.search loop) -> lz_search_*
+ *   lzero/policy/muzero.py:749-779                     (_forward_collect inner part) -> lz_search_collect
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative LZ_E* code; lz_last_error() gives the
+ *     message of the last failure on the calling thread.  No C++ exception crosses this boundary.
+ *   - pointers named d_* are DEVICE pointers, h_* are HOST pointers.  Plain pointers and sizes only.
+ *   - every compute call takes the cudaStream_t (passed as void*) it is enqueued on and performs
+ *     NO host<->device synchronisation; results are valid once the stream reaches that point.
+ *   - a handle must be used from one stream at a time (thread-compatible, no global state).
+ *   - there is no CPU fallback: without a CUDA device every create call fails with LZ_ECUDA.
+ *   - tie-breaking: `deterministic != 0` picks the first legal action attaining the exact maximum
+ *     (cnode.cpp:592 front()); 0 draws uniformly among the reference's epsilon-tie list with a
+ *     counter-based device RNG (the reference reseeds rand() from the wall clock, cnode.cpp:770).
+ */
+#ifndef LZB200_H
+#define LZB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LZ_OK 0
+#define LZ_EINVAL (-1)   /* bad argument */
+#define LZ_ECUDA (-2)    /* CUDA runtime error (message has the cudaError string) */
+#define LZ_ESTATE (-3)   /* call order violated (e.g. search before prepare) */
+#define LZ_ENOMEM (-4)
+
+typedef struct lz_tree lz_tree;
+typedef struct lz_model lz_model;
+typedef struct lz_search lz_search;
+typedef void *lz_stream;   /* cudaStream_t */
+
+int lz_version(void);
+const char *lz_last_error(void);
+
+/* ------------------------------------------------------------------ tree (mz_tree / cnode.cpp) */
+
+/* B trees, A actions, room for max_sims expansions per tree (node slot k == latent index k). */
+int lz_tree_create(int B, int A, int max_sims, lz_tree **out);
+int lz_tree_destroy(lz_tree *t);
+
+/* Search constants (mcts_ctree.py:286,292): PUCT constants, discount, MinMax value_delta_max.
+ * Precomputes the per-visit-count exploration table on the host with libm logf (cnode.cpp:672). */
+int lz_tree_set_params(lz_tree *t, int pb_c_base, float pb_c_init, float discount, float value_delta_max);
+
+/* CRoots::CRoots (cnode.cpp:301-317).  d_legal: int32 [B,A] legal action ids in the caller's order,
+ * -1 padded; d_nlegal: int32 [B] (0 == all actions, cnode.cpp:101-107).  Both NULL == all legal.
+ * Also resets MinMax stats (a fresh MinMaxStatsList per search, mcts_ctree.py:291-292). */
+int lz_tree_reset(lz_tree *t, const int32_t *d_legal, const int32_t *d_nlegal, lz_stream s);
+/* Same from a mask uint8 [B,A] (legal ids ascending == np.nonzero order, policy/muzero.py:760). */
+int lz_tree_reset_mask(lz_tree *t, const uint8_t *d_mask, lz_stream s);
+
+/* CRoots::prepare / prepare_no_noise (cnode.cpp:321-358).  d_logits f32 [B,A] by action id;
+ * d_noise f32 [B,A] rows in LEGAL ORDER (first nlegal[b] used) or NULL for prepare_no_noise;
+ * d_rewards f32 [B] or NULL (zeros); d_to_play int32 [B] (-1 == single player). */
+int lz_tree_prepare(lz_tree *t, const float *d_logits, const float *d_noise, float noise_weight,
+                    const float *d_rewards, const int32_t *d_to_play, lz_stream s);
+
+/* cbatch_traverse (cnode.cpp:754-825): one PUCT descent per tree.  Outputs (each int32 [B], may be
+ * NULL): latent-pool slot of the leaf's parent (== its current_latent_state_index), batch index
+ * (== tree index), last action, search length, virtual to_play after the descent. */
+int lz_tree_traverse(lz_tree *t, int deterministic, int32_t *d_ix, int32_t *d_iy,
+                     int32_t *d_last_action, int32_t *d_search_len, int32_t *d_virtual_to_play,
+                     lz_stream s);
+
+/* cbatch_backpropagate (cnode.cpp:480-500): expand the leaves found by the last traverse into slot
+ * `latent_index` (simulation_index + 1) and back up.  d_reward/d_value f32 [B] (scalars, after the
+ * inverse transform), d_logits f32 [B,A]; d_to_play int32 [B] or NULL (use the virtual to_play the
+ * last traverse produced, which is what mcts_ctree.py:365-368 passes). */
+int lz_tree_backpropagate(lz_tree *t, int latent_index, const float *d_reward, const float *d_value,
+                          const float *d_logits, const int32_t *d_to_play, lz_stream s);
+
+/* get_distributions / get_values / get_trajectories (cnode.cpp:237-277,369-417).
+ * d_visits int32 [B,A] in legal order, -1 padded; d_values f32 [B]; d_nlegal int32 [B];
+ * d_traj int32 [B, max_sims+1] -1 padded.  Any pointer may be NULL. */
+int lz_tree_results(lz_tree *t, int32_t *d_visits, float *d_values, int32_t *d_nlegal,
+                    int32_t *d_traj, lz_stream s);
+
+/* ------------------------------------------------------------------ model (muzero_model.py) */
+
+typedef struct lz_model_config {
+    int obs_c, obs_h, obs_w;       /* observation planes and size: (4|12, 64|84|96, same) */
+    int action_space_size;
+    int num_res_blocks;            /* per network (reference default 1) */
+    int num_channels;              /* 64 */
+    int reward_head_channels, value_head_channels, policy_head_channels;   /* 16 */
+    int reward_hidden, value_hidden, policy_hidden;                         /* one hidden layer: 32 */
+    float support_min, support_max, support_step;                           /* -300, 301, 1 (value == reward) */
+} lz_model_config;
+
+int lz_model_create(const lz_model_config *cfg, lz_model **out);
+int lz_model_destroy(lz_model *m);
+/* Feed one tensor of the reference state_dict (names as produced by MuZeroModel.state_dict(),
+ * SURVEY.md App. B.4; fp32, contiguous, HOST memory).  Unknown names are ignored (returns 1). */
+int lz_model_set_tensor(lz_model *m, const char *name, const float *h_data, int64_t numel);
+/* Folds eval-mode BatchNorm into per-channel scale/shift, packs weights for the kernels, uploads. */
+int lz_model_finalize(lz_model *m);
+int lz_model_latent_hw(const lz_model *m);   /* 6 for 84/96, 8 for 64 */
+int lz_model_support_size(const lz_model *m);
+
+/* initial_inference (muzero_model.py:210-240).  d_obs f32 [B,obs_c,H,W].  Outputs (NULL to skip):
+ * d_latent f32 [B,C,h,w] (NCHW, as the reference returns), d_policy_logits f32 [B,A],
+ * d_value_logits f32 [B,support], d_value f32 [B] (inverse-transformed scalar). */
+int lz_model_initial_inference(lz_model *m, int B, const float *d_obs, float *d_latent,
+                               float *d_policy_logits, float *d_value_logits, float *d_value,
+                               lz_stream s);
+/* recurrent_inference (muzero_model.py:242-272).  d_latent f32 [B,C,h,w], d_action int32 [B].
+ * Outputs (NULL to skip): d_next_latent [B,C,h,w], d_reward_logits/d_value_logits [B,support],
+ * d_policy_logits [B,A], d_reward/d_value f32 [B] scalars after the inverse transform. */
+int lz_model_recurrent_inference(lz_model *m, int B, const float *d_latent, const int32_t *d_action,
+                                 float *d_next_latent, float *d_reward_logits, float *d_value_logits,
+                                 float *d_policy_logits, float *d_reward, float *d_value, lz_stream s);
+/* InverseScalarTransform (scaling_transform.py:82-92) on its own: logits f32 [B,support] -> f32 [B]. */
+int lz_inverse_scalar_transform(lz_model *m, int B, const float *d_logits, float *d_out, lz_stream s);
+
+/* ------------------------------------------------------------------ fused search (mcts_ctree.py) */
+
+/* Binds a tree and a model; owns the latent pool [(num_simulations+1), B, C, h, w] and the CUDA
+ * graph holding [traverse -> recurrent_inference -> backpropagate] x num_simulations. */
+int lz_search_create(lz_tree *t, lz_model *m, int num_simulations, lz_search **out);
+int lz_search_destroy(lz_search *q);
+/* MuZeroMCTSCtree.search (mcts_ctree.py:267-368) on roots already prepared with lz_tree_prepare.
+ * d_latent_roots f32 [B,C,h,w].  One graph launch, zero host syncs. */
+int lz_search_run(lz_search *q, const float *d_latent_roots, int deterministic, lz_stream s);
+/* The search-feeding part of _forward_collect (policy/muzero.py:749-779): initial_inference ->
+ * reset(mask) -> prepare(noise) -> search.  d_obs f32 [B,obs_c,H,W]; d_mask uint8 [B,A] or NULL;
+ * d_noise f32 [B,A] legal-order rows or NULL; d_to_play int32 [B] or NULL (-1).
+ * Optional outputs: d_pred_value f32 [B] (root value prediction), d_policy_logits f32 [B,A]. */
+int lz_search_collect(lz_search *q, const float *d_obs, const uint8_t *d_mask, const float *d_noise,
+                      float noise_weight, const int32_t *d_to_play, int deterministic,
+                      float *d_pred_value, float *d_policy_logits, lz_stream s);
+/* Number of kernel nodes one lz_search_run enqueues (for launch accounting). */
+int lz_search_num_kernels(const lz_search *q);
+/* Device pointer of the latent pool (NCHW per slot) for inspection in tests. */
+const float *lz_search_latent_pool(const lz_search *q);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LZB200_H */

@@ -1,0 +1,158 @@
+"""Mirror of the search-driving part of ``MuZeroPolicy._forward_collect`` / ``_forward_eval``
+(lzero/policy/muzero.py:705-829, 872-956) and of ``select_action`` (lzero/policy/utils.py:637-661).
+
+``MuZeroCollectPolicy.forward_collect(obs, action_mask, temperature, to_play)`` takes what the
+reference's collector passes (a stacked observation batch, a 0/1 action mask, to_play) and returns
+the same per-environment output dict.  Observations may live in (pinned) HOST memory: the copy to the
+device, the representation+prediction networks, root preparation with Dirichlet noise, the whole
+num_simulations search (one CUDA graph) and the result read-back are issued back to back on one
+stream; the only host synchronisation is the final read of the results.
+"""
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+from . import cabi, mz_tree
+from .mcts_ctree import MuZeroMCTSCtree
+from .muzero_model import MuZeroModel
+
+
+def select_action(visit_counts: np.ndarray, temperature: float = 1, deterministic: bool = True):
+    """lzero/policy/utils.py:637-661 (same arithmetic, fp64 numpy)."""
+    action_probs = [visit_count_i ** (1 / temperature) for visit_count_i in visit_counts]
+    action_probs = [x / sum(action_probs) for x in action_probs]
+    if deterministic:
+        action_pos = int(np.argmax([v for v in visit_counts]))
+    else:
+        action_pos = int(np.random.choice(len(visit_counts), p=action_probs))
+    p = np.asarray(action_probs, np.float64)
+    nz = p[p > 0]
+    entropy = float(-(nz * np.log(nz)).sum())   # scipy.stats.entropy(action_probs, base=None)
+    return action_pos, entropy
+
+
+class MuZeroCollectPolicy:
+    def __init__(self, model: MuZeroModel, cfg: Optional[dict] = None):
+        self.model = model
+        self.mcts = MuZeroMCTSCtree(cfg or {})
+        self.cfg = self.mcts._cfg
+        self.device = model.device
+        self._buf = {}
+
+    # ---- device-resident fast path ---------------------------------------------------------------
+    def _bufs(self, B, A):
+        key = (B, A)
+        if key not in self._buf:
+            d = self.device
+            self._buf[key] = dict(
+                pred_value=torch.empty(B, device=d), logits=torch.empty(B, A, device=d),
+                obs=None, mask=torch.empty(B, A, dtype=torch.uint8, device=d), noise=torch.empty(B, A, device=d),
+                to_play=torch.empty(B, dtype=torch.int32, device=d),
+                h_visits=torch.empty(B, A, dtype=torch.int32).pin_memory(),
+                h_values=torch.empty(B).pin_memory(), h_pred=torch.empty(B).pin_memory(),
+                h_logits=torch.empty(B, A).pin_memory(), h_nlegal=torch.empty(B, dtype=torch.int32).pin_memory())
+        return self._buf[key]
+
+    def search_batch(self, obs: torch.Tensor, action_mask, noises, to_play=None, deterministic=None,
+                     read_back: bool = True):
+        """obs [B,C,H,W] (host or device), action_mask [B,A] 0/1, noises [B,A] rows in legal order or None
+        (eval).  Returns dict of tensors; with read_back=True they are pinned host tensors and the call
+        ends with the single stream synchronisation of the step."""
+        B = obs.shape[0]
+        A = self.model.action_space_size
+        S = int(self.cfg.num_simulations)
+        bufs = self._bufs(B, A)
+        dev = self.device
+        det = self.mcts.deterministic if deterministic is None else bool(deterministic)
+        with torch.cuda.device(dev):
+            if obs.is_cuda:
+                d_obs = obs.to(torch.float32).contiguous()
+            else:
+                if bufs["obs"] is None or bufs["obs"].shape != obs.shape:
+                    bufs["obs"] = torch.empty(obs.shape, device=dev, dtype=torch.float32)
+                bufs["obs"].copy_(obs, non_blocking=True)
+                d_obs = bufs["obs"]
+            mask_t = action_mask if isinstance(action_mask, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(action_mask))
+            bufs["mask"].copy_(mask_t.to(torch.uint8), non_blocking=True)
+            d_noise = None
+            if noises is not None:
+                nz = noises if isinstance(noises, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(noises, dtype=np.float32))
+                bufs["noise"].copy_(nz, non_blocking=True)
+                d_noise = bufs["noise"]
+            d_tp = None
+            if to_play is not None:
+                tp = to_play if isinstance(to_play, torch.Tensor) else torch.from_numpy(np.asarray(to_play, np.int32).reshape(-1))
+                bufs["to_play"].copy_(tp.to(torch.int32), non_blocking=True)
+                d_tp = bufs["to_play"]
+            tree = mz_tree.acquire_tree(dev, B, A, S)
+            try:
+                tree.set_params(*self.mcts._params())
+                q = tree.search_for(self.model, S)
+                s = cabi.stream_ptr()
+                cabi.check(tree.lib.lz_search_collect(q, d_obs.data_ptr(), bufs["mask"].data_ptr(), cabi.ptr(d_noise),
+                                                      float(self.cfg.root_noise_weight), cabi.ptr(d_tp), int(det),
+                                                      bufs["pred_value"].data_ptr(), bufs["logits"].data_ptr(), s),
+                           "lz_search_collect")
+                cabi.check(tree.lib.lz_tree_results(tree.h, tree.visits.data_ptr(), tree.values.data_ptr(),
+                                                    tree.nlegal.data_ptr(), None, s), "lz_tree_results")
+                self.last_num_kernels = tree.lib.lz_search_num_kernels(q)
+                if not read_back:
+                    return dict(visits=tree.visits.clone(), values=tree.values.clone(), nlegal=tree.nlegal.clone(),
+                                pred_value=bufs["pred_value"], policy_logits=bufs["logits"])
+                bufs["h_visits"].copy_(tree.visits, non_blocking=True)
+                bufs["h_values"].copy_(tree.values, non_blocking=True)
+                bufs["h_nlegal"].copy_(tree.nlegal, non_blocking=True)
+                bufs["h_pred"].copy_(bufs["pred_value"], non_blocking=True)
+                bufs["h_logits"].copy_(bufs["logits"], non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+            finally:
+                tree.busy = False
+        return dict(visits=bufs["h_visits"], values=bufs["h_values"], nlegal=bufs["h_nlegal"],
+                    pred_value=bufs["h_pred"], policy_logits=bufs["h_logits"])
+
+    # ---- reference-shaped API --------------------------------------------------------------------
+    def forward_collect(self, data: torch.Tensor, action_mask, temperature: float = 1, to_play=(-1,),
+                        epsilon: float = 0.25, ready_env_id=None, **kwargs) -> Dict[int, dict]:
+        """policy/muzero.py:705-829 (collect_with_pure_policy=False, no eps-greedy)."""
+        B = data.shape[0]
+        if ready_env_id is None:
+            ready_env_id = np.arange(B)
+        action_mask = np.asarray(action_mask)
+        A = action_mask.shape[1]
+        alpha = float(self.cfg.root_dirichlet_alpha)
+        noises = np.zeros((B, A), np.float32)
+        for j in range(B):                                   # policy/muzero.py:763-766
+            n = int(action_mask[j].sum())
+            noises[j, :n] = np.random.dirichlet([alpha] * n).astype(np.float32)
+        tp = np.broadcast_to(np.asarray(to_play, np.int32).reshape(-1), (B,)) if np.size(to_play) in (1, B) else to_play
+        r = self.search_batch(data, action_mask, noises, tp, deterministic=self.mcts.deterministic)
+        return self._format(r, action_mask, ready_env_id, temperature, deterministic_action=False)
+
+    def forward_eval(self, data: torch.Tensor, action_mask, to_play=(-1,), ready_env_id=None, **kwargs):
+        """policy/muzero.py:872-956: no noise, arg-max action."""
+        B = data.shape[0]
+        if ready_env_id is None:
+            ready_env_id = np.arange(B)
+        action_mask = np.asarray(action_mask)
+        tp = np.broadcast_to(np.asarray(to_play, np.int32).reshape(-1), (B,)) if np.size(to_play) in (1, B) else to_play
+        r = self.search_batch(data, action_mask, None, tp, deterministic=self.mcts.deterministic)
+        return self._format(r, action_mask, ready_env_id, 1, deterministic_action=True)
+
+    def _format(self, r, action_mask, ready_env_id, temperature, deterministic_action) -> Dict[int, dict]:
+        visits, nl = r["visits"].numpy(), r["nlegal"].numpy()
+        values, pred, logits = r["values"].numpy(), r["pred_value"].numpy(), r["policy_logits"].numpy()
+        output = {}
+        for i, env_id in enumerate(ready_env_id):
+            distributions = visits[i, :nl[i]].tolist()
+            pos, ent = select_action(distributions, temperature=temperature, deterministic=deterministic_action)
+            action = np.where(action_mask[i] == 1.0)[0][pos]            # policy/muzero.py:800
+            output[env_id] = {
+                'action': action,
+                'visit_count_distributions': distributions,
+                'visit_count_distribution_entropy': ent,
+                'searched_value': float(values[i]),
+                'predicted_value': float(pred[i]),
+                'predicted_policy_logits': logits[i].tolist(),
+            }
+        return output

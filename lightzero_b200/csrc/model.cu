@@ -1,0 +1,676 @@
+// model.cu -- MuZero conv model forward paths (initial_inference / recurrent_inference) as fused fp32
+// CUDA kernels, plus the host-side weight registry that ingests the reference state_dict.
+//
+// Replaces the forward paths of lzero/model/muzero_model.py:210-272 (MuZeroModel), :309-374 (_dynamics
+// one-hot encoding), :505-538 (DynamicsNetwork.forward), lzero/model/common.py:334-366 (DownSample),
+// :764-787 (RepresentationNetwork), :1189-1215 (PredictionNetwork) and
+// lzero/policy/scaling_transform.py:82-92 (InverseScalarTransform), eval mode only.
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "model.cuh"
+
+namespace lz {
+
+// ------------------------------------------------------------------------------------------------
+// Fused recurrent inference: gather latent -> dynamics -> reward head -> prediction -> heads.
+// One warp per root, W roots per CTA (see net6.cuh).  Shared memory (floats):
+//   actA[W][2304] | actB[W][2304] | hrew[W][576] | wstage[2][4608]
+// ------------------------------------------------------------------------------------------------
+constexpr int kActFloats = kC * kP;          // 2304
+constexpr int kHFlatMax = 16 * kP;           // head channels <= 16
+constexpr int kKpad = 608;                   // support size 601 padded
+
+template <int W>
+__device__ __forceinline__ void heads_and_outputs(const NetDev &net, float *actA, float *actB, float *hrew,
+                                                  float *wstage, bool with_reward, int B, float *o_reward,
+                                                  float *o_value, float *o_policy, float *o_reward_logits,
+                                                  float *o_value_logits)
+{
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int A = net.A, Apad = (A + 31) & ~31;
+    // On entry: hrew[r][..] = reward-head features, actA[r][0..576) = value features,
+    // actA[r][576..1152) = policy features; actB and wstage are free.  CTA-wide sync done by caller.
+    float *lg_rew = actB;                          // [W][kKpad]
+    float *lg_val = actB + W * kKpad;              // [W][kKpad]
+    float *lg_pol = actB + 2 * W * kKpad;          // [W][Apad]
+    float *hidden = wstage;                        // [3][W][32]
+    for (int h = w; h < 3; h += W) {
+        if (h == 0) {
+            if (with_reward) head_fc<W>(net.reward, hrew, kHFlatMax, hidden, lg_rew, kKpad, lane);
+        } else if (h == 1) {
+            head_fc<W>(net.value, actA, kActFloats, hidden + W * 32, lg_val, kKpad, lane);
+        } else {
+            head_fc<W>(net.policy, actA + kHFlatMax, kActFloats, hidden + 2 * W * 32, lg_pol, Apad, lane);
+        }
+    }
+    __syncthreads();
+    const int b = blockIdx.x * W + w;
+    if (b < B) {
+        const int K = net.value.K;
+        if (with_reward) {
+            float r = categorical_to_scalar(lg_rew + w * kKpad, net.reward.K, net.support_min, net.support_step, lane);
+            if (lane == 0 && o_reward) o_reward[b] = r;
+            if (o_reward_logits)
+                for (int k = lane; k < net.reward.K; k += 32) o_reward_logits[(size_t)b * net.reward.K + k] = lg_rew[w * kKpad + k];
+        }
+        float v = categorical_to_scalar(lg_val + w * kKpad, K, net.support_min, net.support_step, lane);
+        if (lane == 0 && o_value) o_value[b] = v;
+        if (o_value_logits)
+            for (int k = lane; k < K; k += 32) o_value_logits[(size_t)b * K + k] = lg_val[w * kKpad + k];
+        if (o_policy)
+            for (int a = lane; a < A; a += 32) o_policy[(size_t)b * A + a] = lg_pol[w * Apad + a];
+    }
+}
+
+template <int W>
+__global__ void __launch_bounds__(W * 32) k_recurrent(NetDev net, RecIO io)
+{
+    extern __shared__ __align__(16) float smem[];
+    float *actA_all = smem, *actB_all = smem + W * kActFloats;
+    float *hrew_all = actB_all + W * kActFloats;
+    float *wstage = hrew_all + W * kHFlatMax;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x * W + w;
+    const bool valid = b < io.B;
+    float *actA = actA_all + w * kActFloats, *actB = actB_all + w * kActFloats, *hrew = hrew_all + w * kHFlatMax;
+
+    // gather the parent latent (NCHW [64][36], contiguous 9216 B) selected by the tree
+    if (valid) {
+        const size_t slot = io.ix ? (size_t)io.ix[b] : 0;
+        const float *src = io.latent_base + slot * io.slot_stride + (size_t)b * kActFloats;
+        for (int i = lane * 4; i < kActFloats; i += 128) cp_async16(actA + i, src + i);
+    } else {
+        for (int i = lane; i < kActFloats; i += 32) actA[i] = 0.0f;
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncwarp();
+    int act = valid ? io.action[b] : 0;
+    act = min(max(act, 0), net.A - 1);
+
+    // dynamics: x = relu(bn(conv(cat(latent, onehot))) + latent)      muzero_model.py:518-524
+    conv3x3_layer(net.dyn_conv, actA, actB, actA, act, wstage, lane);
+    float *x = actB, *t = actA;
+    for (int i = 0; i < net.nres; ++i) {                            // muzero_model.py:526-527
+        conv3x3_layer(net.dyn_res[2 * i], x, t, nullptr, -1, wstage, lane);
+        conv3x3_layer(net.dyn_res[2 * i + 1], t, x, x, -1, wstage, lane);
+    }
+    // x == next_latent_state
+    if (valid && io.next_latent) {
+        float4 *dst = reinterpret_cast<float4 *>(io.next_latent + (size_t)b * kActFloats);
+        const float4 *srcv = reinterpret_cast<const float4 *>(x);
+        for (int i = lane; i < kActFloats / 4; i += 32) dst[i] = srcv[i];
+    }
+    head_conv1x1(net.reward, x, hrew, lane);                        // muzero_model.py:530-533
+    for (int i = 0; i < net.nres; ++i) {                            // common.py:1199-1200
+        conv3x3_layer(net.pred_res[2 * i], x, t, nullptr, -1, wstage, lane);
+        conv3x3_layer(net.pred_res[2 * i + 1], t, x, x, -1, wstage, lane);
+    }
+    head_conv1x1(net.value, x, t, lane);                            // common.py:1202-1208
+    head_conv1x1(net.policy, x, t + kHFlatMax, lane);
+    __syncthreads();
+    heads_and_outputs<W>(net, actA_all, actB_all, hrew_all, wstage, true, io.B, io.reward, io.value,
+                         io.policy_logits, io.reward_logits, io.value_logits);
+}
+
+// Tail of initial inference on the latent grid: representation resblocks -> latent -> prediction.
+template <int W>
+__global__ void __launch_bounds__(W * 32) k_initial_tail(NetDev net, TailIO io)
+{
+    extern __shared__ __align__(16) float smem[];
+    float *actA_all = smem, *actB_all = smem + W * kActFloats;
+    float *hrew_all = actB_all + W * kActFloats;
+    float *wstage = hrew_all + W * kHFlatMax;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x * W + w;
+    const bool valid = b < io.B;
+    float *actA = actA_all + w * kActFloats, *actB = actB_all + w * kActFloats;
+    if (valid) {
+        const float *src = io.pre_latent + (size_t)b * kActFloats;
+        for (int i = lane * 4; i < kActFloats; i += 128) cp_async16(actA + i, src + i);
+    } else {
+        for (int i = lane; i < kActFloats; i += 32) actA[i] = 0.0f;
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncwarp();
+    float *x = actA, *t = actB;
+    for (int i = 0; i < net.nres; ++i) {                            // common.py:774-775
+        conv3x3_layer(net.rep_res[2 * i], x, t, nullptr, -1, wstage, lane);
+        conv3x3_layer(net.rep_res[2 * i + 1], t, x, x, -1, wstage, lane);
+    }
+    if (valid) {
+        const float4 *srcv = reinterpret_cast<const float4 *>(x);
+        if (io.latent) {
+            float4 *dst = reinterpret_cast<float4 *>(io.latent + (size_t)b * kActFloats);
+            for (int i = lane; i < kActFloats / 4; i += 32) dst[i] = srcv[i];
+        }
+        if (io.latent2) {
+            float4 *dst = reinterpret_cast<float4 *>(io.latent2 + (size_t)b * kActFloats);
+            for (int i = lane; i < kActFloats / 4; i += 32) dst[i] = srcv[i];
+        }
+    }
+    for (int i = 0; i < net.nres; ++i) {
+        conv3x3_layer(net.pred_res[2 * i], x, t, nullptr, -1, wstage, lane);
+        conv3x3_layer(net.pred_res[2 * i + 1], t, x, x, -1, wstage, lane);
+    }
+    // x == actA here; the head features must land in actA for heads_and_outputs, so stage via t
+    head_conv1x1(net.value, x, t, lane);
+    head_conv1x1(net.policy, x, t + kHFlatMax, lane);
+    __syncwarp();
+    for (int i = lane; i < 2 * kHFlatMax; i += 32) x[i] = t[i];
+    __syncthreads();
+    heads_and_outputs<W>(net, actA_all, actB_all, hrew_all, wstage, false, io.B, nullptr, io.value,
+                         io.policy_logits, nullptr, io.value_logits);
+}
+
+static inline size_t fused_smem_bytes(int W)
+{
+    return (size_t)(2 * W * kActFloats + W * kHFlatMax + 2 * kStageFloats) * sizeof(float);
+}
+
+// ------------------------------------------------------------------------------------------------
+// DownSample tower (common.py:334-366): generic direct 3x3 convolution, NCHW, stride 1 or 2, folded
+// BN + optional residual + optional ReLU.  One thread per output pixel (128 consecutive linear
+// pixels per CTA), 32 output channels per CTA.
+// ------------------------------------------------------------------------------------------------
+template <int S>
+__global__ void __launch_bounds__(128)
+k_conv3x3_generic(ConvG L, const float *__restrict__ in, float *__restrict__ out, const float *__restrict__ res,
+                  int relu, int cic, int nrows_max)
+{
+    extern __shared__ __align__(16) float sm[];
+    const int pitch = L.win + 2;
+    float *in_t = sm;
+    float *w_t = sm + (((size_t)cic * nrows_max * pitch + 3) & ~(size_t)3);
+    const int b = blockIdx.z, co0 = blockIdx.y * 32, tid = threadIdx.x;
+    const int npx = L.hout * L.wout;
+    const int p0 = blockIdx.x * 128, p = p0 + tid;
+    const bool valid = p < npx;
+    const int y = valid ? p / L.wout : 0, x = valid ? p - y * L.wout : 0;
+    const int y_first = p0 / L.wout, y_last = min(p0 + 127, npx - 1) / L.wout;
+    const int r0 = y_first * S - 1, nrows = (y_last - y_first) * S + 3;
+    float acc[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[j] = 0.0f;
+
+    for (int c0 = 0; c0 < L.cin; c0 += cic) {
+        const int per_c = nrows * pitch, nin = cic * per_c;
+        for (int i = tid; i < nin; i += 128) {
+            int cl = i / per_c, rem = i - cl * per_c, rr = rem / pitch, cc = rem - rr * pitch;
+            int gy = r0 + rr, gx = cc - 1, c = c0 + cl;
+            float v = 0.0f;
+            if (c < L.cin && gy >= 0 && gy < L.hin && gx >= 0 && gx < L.win)
+                v = in[(((size_t)b * L.cin + c) * L.hin + gy) * L.win + gx];
+            in_t[((size_t)cl * nrows_max + rr) * pitch + cc] = v;
+        }
+        for (int i = tid; i < cic * 288; i += 128) {
+            int cl = i / 288, rem = i - cl * 288, tap = rem >> 5, j = rem & 31, c = c0 + cl;
+            w_t[i] = c < L.cin ? L.w[((size_t)c * 9 + tap) * L.cout + co0 + j] : 0.0f;
+        }
+        __syncthreads();
+        if (valid) {
+            for (int cl = 0; cl < cic; ++cl) {
+#pragma unroll
+                for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx) {
+                        const float v = in_t[((size_t)cl * nrows_max + (y - y_first) * S + ky) * pitch + x * S + kx];
+                        const float4 *wv = reinterpret_cast<const float4 *>(w_t + (cl * 9 + ky * 3 + kx) * 32);
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const float4 w4 = wv[q];
+                            acc[4 * q + 0] = fmaf(v, w4.x, acc[4 * q + 0]);
+                            acc[4 * q + 1] = fmaf(v, w4.y, acc[4 * q + 1]);
+                            acc[4 * q + 2] = fmaf(v, w4.z, acc[4 * q + 2]);
+                            acc[4 * q + 3] = fmaf(v, w4.w, acc[4 * q + 3]);
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (valid) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const size_t o = (((size_t)b * L.cout + co0 + j) * L.hout + y) * L.wout + x;
+            float v = fmaf(acc[j], __ldg(L.scale + co0 + j), __ldg(L.shift + co0 + j));
+            if (res) v += res[o];
+            if (relu) v = fmaxf(v, 0.0f);
+            out[o] = v;
+        }
+    }
+}
+
+// nn.AvgPool2d(kernel_size=3, stride=2, padding=1), count_include_pad=True (divisor 9)
+__global__ void k_avgpool3s2(const float *__restrict__ in, float *__restrict__ out, int planes, int hin, int win,
+                             int hout, int wout)
+{
+    const size_t n = (size_t)planes * hout * wout;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        int xo = (int)(i % wout), yo = (int)((i / wout) % hout);
+        size_t pl = i / ((size_t)wout * hout);
+        const float *src = in + pl * hin * win;
+        float s = 0.0f;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            int yy = yo * 2 + ky - 1;
+            if (yy < 0 || yy >= hin) continue;
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                int xx = xo * 2 + kx - 1;
+                if (xx < 0 || xx >= win) continue;
+                s += src[yy * win + xx];
+            }
+        }
+        out[i] = s / 9.0f;
+    }
+}
+
+__global__ void k_inverse_scalar(const float *logits, float *out, int B, int K, float smin, float sstep)
+{
+    const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (b >= B) return;
+    float v = categorical_to_scalar(logits + (size_t)b * K, K, smin, sstep, lane);
+    if (lane == 0) out[b] = v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static int pick_W(int B)
+{
+    // largest roots-per-CTA that still yields ~one CTA per SM (148 SMs); small batches use small CTAs
+    if (B >= 8 * 120) return 8;
+    if (B >= 4 * 120) return 4;
+    if (B >= 2 * 120) return 2;
+    return 1;
+}
+
+template <int W>
+static int launch_recurrent(const NetDev &net, const RecIO &io, cudaStream_t s)
+{
+    const size_t smem = fused_smem_bytes(W);
+    k_recurrent<W><<<ceil_div(io.B, W), W * 32, smem, s>>>(net, io);
+    LZ_KERNEL_CHECK();
+    return LZ_OK;
+}
+
+template <int W>
+static int launch_tail(const NetDev &net, const TailIO &io, cudaStream_t s)
+{
+    const size_t smem = fused_smem_bytes(W);
+    k_initial_tail<W><<<ceil_div(io.B, W), W * 32, smem, s>>>(net, io);
+    LZ_KERNEL_CHECK();
+    return LZ_OK;
+}
+
+template <int W>
+static int set_fused_attrs()
+{
+    const int smem = (int)fused_smem_bytes(W);
+    LZ_CUDA_CHECK(cudaFuncSetAttribute(k_recurrent<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    LZ_CUDA_CHECK(cudaFuncSetAttribute(k_initial_tail<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    return LZ_OK;
+}
+
+// opt-in shared memory sizes are set once, outside any stream capture
+static int model_prepare_launch()
+{
+    int rc;
+    if ((rc = set_fused_attrs<8>()) || (rc = set_fused_attrs<4>()) || (rc = set_fused_attrs<2>()) || (rc = set_fused_attrs<1>())) return rc;
+    const int big = 200 * 1024;
+    LZ_CUDA_CHECK(cudaFuncSetAttribute(k_conv3x3_generic<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    LZ_CUDA_CHECK(cudaFuncSetAttribute(k_conv3x3_generic<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    return LZ_OK;
+}
+
+int model_recurrent(lz_model *m, const RecIO &io, cudaStream_t s)
+{
+    switch (pick_W(io.B)) {
+        case 8: return launch_recurrent<8>(m->net, io, s);
+        case 4: return launch_recurrent<4>(m->net, io, s);
+        case 2: return launch_recurrent<2>(m->net, io, s);
+        default: return launch_recurrent<1>(m->net, io, s);
+    }
+}
+
+static int launch_convg(const ConvG &L, const float *in, float *out, const float *res, int relu, int B, cudaStream_t s)
+{
+    const int cic = std::min(8, L.cin);
+    const int rows_out_max = std::min(L.hout, 127 / L.wout + 2);
+    const int nrows_max = (rows_out_max - 1) * L.stride + 3;
+    const int pitch = L.win + 2;
+    const size_t smem = ((((size_t)cic * nrows_max * pitch + 3) & ~(size_t)3) + (size_t)cic * 288) * sizeof(float);
+    dim3 grid(ceil_div(L.hout * L.wout, 128), L.cout / 32, B);
+    LZ_REQUIRE(smem <= 200 * 1024, LZ_EINVAL, "conv tower stage needs %zu B shared memory", smem);
+    if (L.stride == 1) k_conv3x3_generic<1><<<grid, 128, smem, s>>>(L, in, out, res, relu, cic, nrows_max);
+    else k_conv3x3_generic<2><<<grid, 128, smem, s>>>(L, in, out, res, relu, cic, nrows_max);
+    LZ_KERNEL_CHECK();
+    return LZ_OK;
+}
+
+static int launch_pool(const float *in, float *out, int planes, int hin, int hout, cudaStream_t s)
+{
+    const size_t n = (size_t)planes * hout * hout;
+    int blocks = (int)std::min<size_t>((n + 255) / 256, 148 * 16);
+    k_avgpool3s2<<<blocks, 256, 0, s>>>(in, out, planes, hin, hin, hout, hout);
+    LZ_KERNEL_CHECK();
+    return LZ_OK;
+}
+
+int model_reserve(lz_model *m, int B)
+{
+    if (B <= m->ws_B) return LZ_OK;
+    size_t per_root = 0;
+    for (const ConvG &L : m->tower) per_root = std::max(per_root, (size_t)L.cout * L.hout * L.wout);
+    per_root = std::max(per_root, (size_t)kActFloats);
+    for (int i = 0; i < 3; ++i) {
+        if (m->ws[i]) cudaFree(m->ws[i]);
+        m->ws[i] = nullptr;
+        int rc = dev_alloc(&m->ws[i], per_root * B);
+        if (rc != LZ_OK) return rc;
+    }
+    m->ws_floats = per_root * B;
+    m->ws_B = B;
+    return LZ_OK;
+}
+
+int model_initial(lz_model *m, int B, const float *d_obs, const TailIO &io_in, cudaStream_t s)
+{
+    LZ_REQUIRE(B <= m->ws_B, LZ_ESTATE, "model_initial: workspace sized for %d roots, got %d (call model_reserve outside capture)", m->ws_B, B);
+    float *a = m->ws[0], *b = m->ws[1], *c = m->ws[2];
+    const std::vector<ConvG> &T = m->tower;
+    int rc;
+    // DownSample.forward, common.py:340-366
+    if ((rc = launch_convg(T[0], d_obs, a, nullptr, 1, B, s))) return rc;          // conv1 + norm1 + relu
+    if ((rc = launch_convg(T[1], a, b, nullptr, 1, B, s))) return rc;              // resblocks1.0
+    if ((rc = launch_convg(T[2], b, c, a, 1, B, s))) return rc;
+    if ((rc = launch_convg(T[3], c, a, nullptr, 0, B, s))) return rc;              // downsample_block.conv3 (identity path)
+    if ((rc = launch_convg(T[4], c, b, nullptr, 1, B, s))) return rc;              // downsample_block.conv1
+    if ((rc = launch_convg(T[5], b, c, a, 1, B, s))) return rc;                    // downsample_block.conv2 + identity
+    if ((rc = launch_convg(T[6], c, a, nullptr, 1, B, s))) return rc;              // resblocks2.0
+    if ((rc = launch_convg(T[7], a, b, c, 1, B, s))) return rc;
+    const int h2 = T[7].hout, h3 = (h2 - 1) / 2 + 1;
+    if ((rc = launch_pool(b, a, B * kC, h2, h3, s))) return rc;                    // pooling1
+    if ((rc = launch_convg(T[8], a, b, nullptr, 1, B, s))) return rc;              // resblocks3.0
+    if ((rc = launch_convg(T[9], b, c, a, 1, B, s))) return rc;
+    const float *pre = c;
+    if (m->cfg.obs_h != 64) {                                                      // pooling2 for 84 / 96
+        const int h4 = (h3 - 1) / 2 + 1;
+        if ((rc = launch_pool(c, a, B * kC, h3, h4, s))) return rc;
+        pre = a;
+    }
+    TailIO io = io_in;
+    io.B = B;
+    io.pre_latent = pre;
+    switch (pick_W(B)) {
+        case 8: return launch_tail<8>(m->net, io, s);
+        case 4: return launch_tail<4>(m->net, io, s);
+        case 2: return launch_tail<2>(m->net, io, s);
+        default: return launch_tail<1>(m->net, io, s);
+    }
+}
+
+// ---- weight ingestion -------------------------------------------------------------------------
+struct Packer {
+    std::vector<float> host;
+    size_t add(const std::vector<float> &v)
+    {
+        while (host.size() % 4) host.push_back(0.0f);
+        size_t off = host.size();
+        host.insert(host.end(), v.begin(), v.end());
+        return off;
+    }
+};
+
+static const std::vector<float> *find(lz_model *m, const std::string &name, size_t expect)
+{
+    auto it = m->tensors.find(name);
+    if (it == m->tensors.end()) { set_error("lz_model_finalize: missing tensor '%s'", name.c_str()); return nullptr; }
+    if (expect && it->second.size() != expect) {
+        set_error("lz_model_finalize: tensor '%s' has %zu elements, expected %zu", name.c_str(), it->second.size(), expect);
+        return nullptr;
+    }
+    return &it->second;
+}
+
+// eval-mode BatchNorm -> y = x * scale + shift  (eps = 1e-5, nn.BatchNorm default)
+static bool fold_bn(lz_model *m, const std::string &prefix, int n, std::vector<float> &scale, std::vector<float> &shift)
+{
+    auto g = find(m, prefix + ".weight", n), bta = find(m, prefix + ".bias", n);
+    auto mu = find(m, prefix + ".running_mean", n), var = find(m, prefix + ".running_var", n);
+    if (!g || !bta || !mu || !var) return false;
+    scale.resize(n); shift.resize(n);
+    for (int i = 0; i < n; ++i) {
+        float invstd = 1.0f / sqrtf((*var)[i] + 1e-5f);
+        scale[i] = (*g)[i] * invstd;
+        shift[i] = (*bta)[i] - (*mu)[i] * scale[i];
+    }
+    return true;
+}
+
+struct ConvOff { size_t w, scale, shift; int cin, cout; };
+
+// torch conv weight [cout][cin][3][3] -> [cin][9][cout]
+static bool pack_conv3(lz_model *m, Packer &P, const std::string &wname, const std::string &bnprefix, int cin,
+                       int cout, ConvOff &o)
+{
+    auto w = find(m, wname, (size_t)cout * cin * 9);
+    if (!w) return false;
+    std::vector<float> wp((size_t)cin * 9 * cout), scale(cout, 1.0f), shift(cout, 0.0f);
+    for (int co = 0; co < cout; ++co)
+        for (int ci = 0; ci < cin; ++ci)
+            for (int t = 0; t < 9; ++t) wp[((size_t)ci * 9 + t) * cout + co] = (*w)[((size_t)co * cin + ci) * 9 + t];
+    if (!bnprefix.empty() && !fold_bn(m, bnprefix, cout, scale, shift)) return false;
+    o.w = P.add(wp); o.scale = P.add(scale); o.shift = P.add(shift);
+    o.cin = cin; o.cout = cout;
+    return true;
+}
+
+struct HeadOff { size_t w1, s1, t1, fc1, s2, t2, fc2, b2; int hc, hid, K; };
+
+static bool pack_head(lz_model *m, Packer &P, const std::string &conv, const std::string &norm, const std::string &fc,
+                      int hc, int hid, int K, int Pix, HeadOff &o)
+{
+    auto w1 = find(m, conv + ".weight", (size_t)hc * kC), b1 = find(m, conv + ".bias", hc);
+    if (!w1 || !b1) return false;
+    std::vector<float> s1, t1, s2, t2;
+    if (!fold_bn(m, norm, hc, s1, t1)) return false;
+    for (int i = 0; i < hc; ++i) t1[i] += s1[i] * (*b1)[i];
+    auto W0 = find(m, fc + ".0.weight", (size_t)hid * hc * Pix), B0 = find(m, fc + ".0.bias", hid);
+    auto W3 = find(m, fc + ".3.weight", (size_t)K * hid), B3 = find(m, fc + ".3.bias", K);
+    if (!W0 || !B0 || !W3 || !B3) return false;
+    if (!fold_bn(m, fc + ".1", hid, s2, t2)) return false;
+    for (int j = 0; j < hid; ++j) t2[j] += s2[j] * (*B0)[j];
+    const int nin = hc * Pix;
+    std::vector<float> fc1((size_t)nin * hid), fc2((size_t)hid * K);
+    for (int j = 0; j < hid; ++j)
+        for (int i = 0; i < nin; ++i) fc1[(size_t)i * hid + j] = (*W0)[(size_t)j * nin + i];
+    for (int k = 0; k < K; ++k)
+        for (int j = 0; j < hid; ++j) fc2[(size_t)j * K + k] = (*W3)[(size_t)k * hid + j];
+    o.w1 = P.add(*w1); o.s1 = P.add(s1); o.t1 = P.add(t1); o.fc1 = P.add(fc1);
+    o.s2 = P.add(s2); o.t2 = P.add(t2); o.fc2 = P.add(fc2); o.b2 = P.add(*B3);
+    o.hc = hc; o.hid = hid; o.K = K;
+    return true;
+}
+
+}  // namespace lz
+
+using namespace lz;
+
+extern "C" {
+
+int lz_model_create(const lz_model_config *cfg, lz_model **out)
+{
+    LZ_REQUIRE(cfg && out, LZ_EINVAL, "lz_model_create: null argument");
+    LZ_REQUIRE(cfg->num_channels == kC, LZ_EINVAL, "lz_model_create: num_channels must be %d (got %d)", kC, cfg->num_channels);
+    LZ_REQUIRE(cfg->obs_h == cfg->obs_w && (cfg->obs_h == 84 || cfg->obs_h == 96), LZ_EINVAL,
+               "lz_model_create: observation %dx%d not supported (84x84 and 96x96 -> 6x6 latent)", cfg->obs_h, cfg->obs_w);
+    LZ_REQUIRE(cfg->num_res_blocks >= 1 && cfg->num_res_blocks <= kMaxResBlocks, LZ_EINVAL, "lz_model_create: num_res_blocks must be in [1,%d]", kMaxResBlocks);
+    LZ_REQUIRE(cfg->reward_head_channels <= 16 && cfg->value_head_channels <= 16 && cfg->policy_head_channels <= 16, LZ_EINVAL, "lz_model_create: head channels must be <= 16");
+    LZ_REQUIRE(cfg->reward_hidden <= 32 && cfg->value_hidden <= 32 && cfg->policy_hidden <= 32, LZ_EINVAL, "lz_model_create: head hidden sizes must be <= 32");
+    LZ_REQUIRE(cfg->action_space_size >= 1 && cfg->action_space_size <= 1024, LZ_EINVAL, "lz_model_create: action_space_size out of range");
+    const int K = (int)ceil((cfg->support_max - cfg->support_min) / cfg->support_step);   // len(torch.arange(min, max, step))
+    LZ_REQUIRE(K >= 2 && K <= kKpad, LZ_EINVAL, "lz_model_create: support size %d not in [2, %d]", K, kKpad);
+    int ndev = 0;
+    LZ_CUDA_CHECK(cudaGetDeviceCount(&ndev));
+    LZ_REQUIRE(ndev > 0, LZ_ECUDA, "lz_model_create: no CUDA device (this library has no CPU fallback)");
+    lz_model *m = new lz_model();
+    m->cfg = *cfg;
+    m->finalized = false;
+    m->d_weights = nullptr;
+    m->hw = kHW; m->P = kP; m->K = K;
+    m->ws[0] = m->ws[1] = m->ws[2] = nullptr;
+    m->ws_floats = 0; m->ws_B = 0;
+    *out = m;
+    return LZ_OK;
+}
+
+int lz_model_destroy(lz_model *m)
+{
+    if (!m) return LZ_OK;
+    cudaFree(m->d_weights);
+    for (int i = 0; i < 3; ++i) cudaFree(m->ws[i]);
+    delete m;
+    return LZ_OK;
+}
+
+int lz_model_set_tensor(lz_model *m, const char *name, const float *h_data, int64_t numel)
+{
+    LZ_REQUIRE(m && name && h_data && numel >= 0, LZ_EINVAL, "lz_model_set_tensor: bad argument");
+    std::string n(name);
+    if (n.find("num_batches_tracked") != std::string::npos) return 1;
+    if (n.rfind("representation_network.", 0) != 0 && n.rfind("dynamics_network.", 0) != 0 &&
+        n.rfind("prediction_network.", 0) != 0)
+        return 1;   // e.g. the optional SSL projection heads (muzero_model.py:198-208), unused at inference
+    m->tensors[n].assign(h_data, h_data + numel);
+    m->finalized = false;
+    return LZ_OK;
+}
+
+int lz_model_finalize(lz_model *m)
+{
+    LZ_REQUIRE(m, LZ_EINVAL, "lz_model_finalize: null model");
+    const lz_model_config &c = m->cfg;
+    const int A = c.action_space_size, n = c.num_res_blocks;
+    Packer P;
+    std::vector<ConvOff> tower(10);
+    ConvOff dyn_conv, dyn_res[2 * kMaxResBlocks], pred_res[2 * kMaxResBlocks], rep_res[2 * kMaxResBlocks];
+    HeadOff hr, hv, hp;
+    const std::string R = "representation_network.downsample_net.", D = "dynamics_network.", Q = "prediction_network.";
+    const int c2 = kC / 2;
+    bool ok = pack_conv3(m, P, R + "conv1.weight", R + "norm1", c.obs_c, c2, tower[0]) &&
+              pack_conv3(m, P, R + "resblocks1.0.conv1.0.weight", R + "resblocks1.0.conv1.1", c2, c2, tower[1]) &&
+              pack_conv3(m, P, R + "resblocks1.0.conv2.0.weight", R + "resblocks1.0.conv2.1", c2, c2, tower[2]) &&
+              pack_conv3(m, P, R + "downsample_block.conv3.0.weight", "", c2, kC, tower[3]) &&
+              pack_conv3(m, P, R + "downsample_block.conv1.0.weight", R + "downsample_block.conv1.1", c2, kC, tower[4]) &&
+              pack_conv3(m, P, R + "downsample_block.conv2.0.weight", R + "downsample_block.conv2.1", kC, kC, tower[5]) &&
+              pack_conv3(m, P, R + "resblocks2.0.conv1.0.weight", R + "resblocks2.0.conv1.1", kC, kC, tower[6]) &&
+              pack_conv3(m, P, R + "resblocks2.0.conv2.0.weight", R + "resblocks2.0.conv2.1", kC, kC, tower[7]) &&
+              pack_conv3(m, P, R + "resblocks3.0.conv1.0.weight", R + "resblocks3.0.conv1.1", kC, kC, tower[8]) &&
+              pack_conv3(m, P, R + "resblocks3.0.conv2.0.weight", R + "resblocks3.0.conv2.1", kC, kC, tower[9]);
+    if (!ok) return LZ_EINVAL;
+    ok = pack_conv3(m, P, D + "conv.weight", D + "norm_common", kC + A, kC, dyn_conv);
+    for (int i = 0; ok && i < n; ++i) {
+        const std::string si = std::to_string(i);
+        ok = pack_conv3(m, P, D + "resblocks." + si + ".conv1.0.weight", D + "resblocks." + si + ".conv1.1", kC, kC, dyn_res[2 * i]) &&
+             pack_conv3(m, P, D + "resblocks." + si + ".conv2.0.weight", D + "resblocks." + si + ".conv2.1", kC, kC, dyn_res[2 * i + 1]) &&
+             pack_conv3(m, P, Q + "resblocks." + si + ".conv1.0.weight", Q + "resblocks." + si + ".conv1.1", kC, kC, pred_res[2 * i]) &&
+             pack_conv3(m, P, Q + "resblocks." + si + ".conv2.0.weight", Q + "resblocks." + si + ".conv2.1", kC, kC, pred_res[2 * i + 1]) &&
+             pack_conv3(m, P, "representation_network.resblocks." + si + ".conv1.0.weight", "representation_network.resblocks." + si + ".conv1.1", kC, kC, rep_res[2 * i]) &&
+             pack_conv3(m, P, "representation_network.resblocks." + si + ".conv2.0.weight", "representation_network.resblocks." + si + ".conv2.1", kC, kC, rep_res[2 * i + 1]);
+    }
+    if (!ok) return LZ_EINVAL;
+    ok = pack_head(m, P, D + "conv1x1_reward", D + "norm_reward", D + "fc_reward_head", c.reward_head_channels, c.reward_hidden, m->K, kP, hr) &&
+         pack_head(m, P, Q + "conv1x1_value", Q + "norm_value", Q + "fc_value", c.value_head_channels, c.value_hidden, m->K, kP, hv) &&
+         pack_head(m, P, Q + "conv1x1_policy", Q + "norm_policy", Q + "fc_policy", c.policy_head_channels, c.policy_hidden, A, kP, hp);
+    if (!ok) return LZ_EINVAL;
+
+    if (m->d_weights) cudaFree(m->d_weights);
+    m->d_weights = nullptr;
+    int rc = dev_alloc(&m->d_weights, P.host.size());
+    if (rc != LZ_OK) return rc;
+    LZ_CUDA_CHECK(cudaMemcpy(m->d_weights, P.host.data(), P.host.size() * sizeof(float), cudaMemcpyHostToDevice));
+    m->n_weight_floats = P.host.size();
+    const float *base = m->d_weights;
+    auto mk3 = [&](const ConvOff &o) { Conv3 L; L.w = base + o.w; L.scale = base + o.scale; L.shift = base + o.shift; L.cin = o.cin; return L; };
+    auto mkh = [&](const HeadOff &o) {
+        Head H; H.w1 = base + o.w1; H.s1 = base + o.s1; H.t1 = base + o.t1; H.fc1 = base + o.fc1; H.s2 = base + o.s2;
+        H.t2 = base + o.t2; H.fc2 = base + o.fc2; H.b2 = base + o.b2; H.hc = o.hc; H.hid = o.hid; H.K = o.K; return H;
+    };
+    NetDev &net = m->net;
+    memset(&net, 0, sizeof(net));
+    net.dyn_conv = mk3(dyn_conv);
+    for (int i = 0; i < 2 * n; ++i) { net.dyn_res[i] = mk3(dyn_res[i]); net.pred_res[i] = mk3(pred_res[i]); net.rep_res[i] = mk3(rep_res[i]); }
+    net.reward = mkh(hr); net.value = mkh(hv); net.policy = mkh(hp);
+    net.nres = n; net.A = A;
+    net.support_min = c.support_min; net.support_step = c.support_step;
+
+    // DownSample geometry: conv s2 p1: h -> (h-1)/2+1
+    const int h0 = c.obs_h, h1 = (h0 - 1) / 2 + 1, h2 = (h1 - 1) / 2 + 1, h3 = (h2 - 1) / 2 + 1;
+    struct G { int stride, hin, hout; };
+    const G geo[10] = {{2, h0, h1}, {1, h1, h1}, {1, h1, h1}, {2, h1, h2}, {2, h1, h2}, {1, h2, h2},
+                       {1, h2, h2}, {1, h2, h2}, {1, h3, h3}, {1, h3, h3}};
+    m->tower.clear();
+    for (int i = 0; i < 10; ++i) {
+        ConvG L;
+        L.w = base + tower[i].w; L.scale = base + tower[i].scale; L.shift = base + tower[i].shift;
+        L.cin = tower[i].cin; L.cout = tower[i].cout; L.stride = geo[i].stride;
+        L.hin = L.win = geo[i].hin; L.hout = L.wout = geo[i].hout;
+        m->tower.push_back(L);
+    }
+    const int h4 = (h3 - 1) / 2 + 1;
+    LZ_REQUIRE(h4 == kHW, LZ_EINVAL, "lz_model_finalize: latent grid %d != %d", h4, kHW);
+    rc = model_prepare_launch();
+    if (rc != LZ_OK) return rc;
+    m->finalized = true;
+    m->tensors.clear();
+    return LZ_OK;
+}
+
+int lz_model_latent_hw(const lz_model *m) { return m ? m->hw : 0; }
+int lz_model_support_size(const lz_model *m) { return m ? m->K : 0; }
+
+int lz_model_initial_inference(lz_model *m, int B, const float *d_obs, float *d_latent, float *d_policy_logits,
+                               float *d_value_logits, float *d_value, lz_stream s)
+{
+    LZ_REQUIRE(m && d_obs && B > 0, LZ_EINVAL, "lz_model_initial_inference: bad argument");
+    LZ_REQUIRE(m->finalized, LZ_ESTATE, "lz_model_initial_inference: model not finalized");
+    if (B > m->ws_B) {
+        int rc = model_reserve(m, B);
+        if (rc != LZ_OK) return rc;
+    }
+    TailIO io;
+    memset(&io, 0, sizeof(io));
+    io.latent = d_latent; io.policy_logits = d_policy_logits; io.value_logits = d_value_logits; io.value = d_value;
+    return model_initial(m, B, d_obs, io, (cudaStream_t)s);
+}
+
+int lz_model_recurrent_inference(lz_model *m, int B, const float *d_latent, const int32_t *d_action,
+                                 float *d_next_latent, float *d_reward_logits, float *d_value_logits,
+                                 float *d_policy_logits, float *d_reward, float *d_value, lz_stream s)
+{
+    LZ_REQUIRE(m && d_latent && d_action && B > 0, LZ_EINVAL, "lz_model_recurrent_inference: bad argument");
+    LZ_REQUIRE(m->finalized, LZ_ESTATE, "lz_model_recurrent_inference: model not finalized");
+    RecIO io;
+    memset(&io, 0, sizeof(io));
+    io.B = B; io.latent_base = d_latent; io.ix = nullptr; io.slot_stride = 0; io.action = d_action;
+    io.next_latent = d_next_latent; io.reward = d_reward; io.value = d_value; io.policy_logits = d_policy_logits;
+    io.reward_logits = d_reward_logits; io.value_logits = d_value_logits;
+    return model_recurrent(m, io, (cudaStream_t)s);
+}
+
+int lz_inverse_scalar_transform(lz_model *m, int B, const float *d_logits, float *d_out, lz_stream s)
+{
+    LZ_REQUIRE(m && d_logits && d_out && B > 0, LZ_EINVAL, "lz_inverse_scalar_transform: bad argument");
+    k_inverse_scalar<<<ceil_div(B, 4), 128, 0, (cudaStream_t)s>>>(d_logits, d_out, B, m->K, m->cfg.support_min, m->cfg.support_step);
+    LZ_KERNEL_CHECK();
+    return LZ_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,74 @@
+// model.cuh -- device-side weight tables of the MuZero conv model and the internal launch API.
+#pragma once
+#include <map>
+#include <string>
+#include <vector>
+
+#include "lz_common.cuh"
+#include "net6.cuh"
+
+namespace lz {
+
+constexpr int kMaxResBlocks = 4;
+
+struct NetDev {                       // passed by value to kernels
+    Conv3 dyn_conv;                   // dynamics_network.conv (+ norm_common)
+    Conv3 dyn_res[2 * kMaxResBlocks]; // dynamics_network.resblocks
+    Conv3 pred_res[2 * kMaxResBlocks];
+    Conv3 rep_res[2 * kMaxResBlocks]; // representation_network.resblocks (on the latent grid)
+    Head reward, value, policy;
+    int nres;
+    int A;
+    float support_min, support_step;
+};
+
+struct ConvG {                        // generic 3x3 conv of the DownSample tower
+    const float *w;                   // [cin][9][cout]
+    const float *scale, *shift;       // [cout]
+    int cin, cout, stride, hin, win, hout, wout;
+};
+
+struct RecIO {
+    int B;
+    const float *latent_base;         // latent source: base + ix[b]*slot_stride + b*C*P  (ix == nullptr: slot 0)
+    const int *ix;
+    size_t slot_stride;
+    const int *action;                // [B]
+    float *next_latent;               // [B][C][P] destination (pool slot or API buffer) or nullptr
+    float *reward, *value;            // [B] scalars or nullptr
+    float *policy_logits;             // [B][A] or nullptr
+    float *reward_logits, *value_logits;   // [B][K] or nullptr
+};
+
+struct TailIO {
+    int B;
+    const float *pre_latent;          // [B][C][P] output of the DownSample tower
+    float *latent;                    // [B][C][P] (NCHW) or nullptr
+    float *latent2;                   // second copy (latent pool slot 0) or nullptr
+    float *value;                     // [B] scalar or nullptr
+    float *policy_logits;             // [B][A] or nullptr
+    float *value_logits;              // [B][K] or nullptr
+};
+
+}  // namespace lz
+
+struct lz_model {
+    lz_model_config cfg;
+    std::map<std::string, std::vector<float>> tensors;   // raw reference state_dict (host)
+    bool finalized;
+    float *d_weights;                 // one packed device allocation
+    size_t n_weight_floats;
+    lz::NetDev net;
+    std::vector<lz::ConvG> tower;     // DownSample convs in execution order
+    int hw, P, K;
+    // workspace for initial inference (grown on demand, outside graph capture)
+    float *ws[3];
+    size_t ws_floats;
+    int ws_B;
+};
+
+namespace lz {
+int model_recurrent(lz_model *m, const RecIO &io, cudaStream_t s);
+int model_initial(lz_model *m, int B, const float *d_obs, const TailIO &io, cudaStream_t s);
+int model_reserve(lz_model *m, int B);   // sizes the initial-inference workspace (synchronous)
+}  // namespace lz

@@ -1,0 +1,143 @@
+// search.cu -- the whole MuZeroMCTSCtree.search loop (lzero/mcts/tree_search/mcts_ctree.py:267-368) as ONE
+// CUDA graph: [traverse] + num_simulations x [recurrent_inference -> backpropagate(+next traverse)].
+// The reference's per-simulation host work (Python list gather of latents :323-324, two H2D copies
+// :326-329, a duplicated recurrent_inference :338/:345, four blocking D2H copies :347-350 and three
+// .tolist() conversions :355-357) has no counterpart here: the tree hands (slot, action) to the
+// network through device memory and the network hands (reward, value, logits) back the same way.
+#include <string.h>
+
+#include "model.cuh"
+#include "tree.cuh"
+
+struct lz_search {
+    lz_tree *tree;
+    lz_model *model;
+    int S, B, A;
+    float *pool;                 // [(S+1)][B][C*P] latent pool, slot-major, NCHW per root
+    size_t slot_stride;          // B*C*P floats
+    int32_t *d_ix, *d_action;    // [B]
+    float *d_reward, *d_value;   // [B]
+    float *d_policy;             // [B][A]
+    float *d_root_logits;        // [B][A]
+    float *d_root_value;         // [B]
+    cudaGraphExec_t exec[2];     // [deterministic]
+    int num_kernels;
+};
+
+using namespace lz;
+
+static int enqueue_search(lz_search *q, int deterministic, cudaStream_t s)
+{
+    int rc;
+    lz_tree *t = q->tree;
+    t->step_counter = 0;
+    if ((rc = tree_launch_traverse(t, deterministic, q->d_ix, nullptr, q->d_action, nullptr, nullptr, s))) return rc;
+    for (int sim = 0; sim < q->S; ++sim) {
+        RecIO io;
+        memset(&io, 0, sizeof(io));
+        io.B = q->B;
+        io.latent_base = q->pool;
+        io.ix = q->d_ix;
+        io.slot_stride = q->slot_stride;
+        io.action = q->d_action;
+        io.next_latent = q->pool + (size_t)(sim + 1) * q->slot_stride;   // mcts_ctree.py:352,364
+        io.reward = q->d_reward;
+        io.value = q->d_value;
+        io.policy_logits = q->d_policy;
+        if ((rc = model_recurrent(q->model, io, s))) return rc;
+        if (sim + 1 < q->S)
+            rc = tree_launch_backprop_traverse(t, sim + 1, q->d_reward, q->d_value, q->d_policy, deterministic, q->d_ix, q->d_action, s);
+        else
+            rc = tree_launch_backprop(t, sim + 1, q->d_reward, q->d_value, q->d_policy, nullptr, s);
+        if (rc) return rc;
+    }
+    return LZ_OK;
+}
+
+static int run_graph(lz_search *q, int deterministic, cudaStream_t s)
+{
+    const int d = deterministic ? 1 : 0;
+    if (!q->exec[d]) {
+        cudaGraph_t graph = nullptr;
+        LZ_CUDA_CHECK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+        int rc = enqueue_search(q, deterministic, s);
+        cudaError_t e = cudaStreamEndCapture(s, &graph);
+        if (rc != LZ_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+        if (e != cudaSuccess) { set_error("cudaStreamEndCapture failed: %s", cudaGetErrorString(e)); return LZ_ECUDA; }
+        size_t n = 0;
+        LZ_CUDA_CHECK(cudaGraphGetNodes(graph, nullptr, &n));
+        q->num_kernels = (int)n;
+        e = cudaGraphInstantiate(&q->exec[d], graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) { set_error("cudaGraphInstantiate failed: %s", cudaGetErrorString(e)); return LZ_ECUDA; }
+    }
+    LZ_CUDA_CHECK(cudaGraphLaunch(q->exec[d], s));
+    return LZ_OK;
+}
+
+extern "C" {
+
+int lz_search_create(lz_tree *t, lz_model *m, int num_simulations, lz_search **out)
+{
+    LZ_REQUIRE(t && m && out && num_simulations > 0, LZ_EINVAL, "lz_search_create: bad argument");
+    LZ_REQUIRE(m->finalized, LZ_ESTATE, "lz_search_create: model not finalized");
+    LZ_REQUIRE(num_simulations <= t->max_sims, LZ_EINVAL, "lz_search_create: num_simulations %d > tree capacity %d", num_simulations, t->max_sims);
+    LZ_REQUIRE(t->p.A == m->cfg.action_space_size, LZ_EINVAL, "lz_search_create: tree has %d actions, model %d", t->p.A, m->cfg.action_space_size);
+    lz_search *q = new lz_search();
+    memset(q, 0, sizeof(*q));
+    q->tree = t; q->model = m; q->S = num_simulations; q->B = t->p.B; q->A = t->p.A;
+    q->slot_stride = (size_t)q->B * kC * kP;
+    int rc = dev_alloc(&q->pool, q->slot_stride * (size_t)(q->S + 1));
+    if (rc == LZ_OK) rc = dev_alloc(&q->d_ix, (size_t)q->B);
+    if (rc == LZ_OK) rc = dev_alloc(&q->d_action, (size_t)q->B);
+    if (rc == LZ_OK) rc = dev_alloc(&q->d_reward, (size_t)q->B);
+    if (rc == LZ_OK) rc = dev_alloc(&q->d_value, (size_t)q->B);
+    if (rc == LZ_OK) rc = dev_alloc(&q->d_policy, (size_t)q->B * q->A);
+    if (rc == LZ_OK) rc = dev_alloc(&q->d_root_logits, (size_t)q->B * q->A);
+    if (rc == LZ_OK) rc = dev_alloc(&q->d_root_value, (size_t)q->B);
+    if (rc == LZ_OK) rc = model_reserve(m, q->B);
+    if (rc != LZ_OK) { lz_search_destroy(q); return rc; }
+    *out = q;
+    return LZ_OK;
+}
+
+int lz_search_destroy(lz_search *q)
+{
+    if (!q) return LZ_OK;
+    for (int d = 0; d < 2; ++d) if (q->exec[d]) cudaGraphExecDestroy(q->exec[d]);
+    cudaFree(q->pool); cudaFree(q->d_ix); cudaFree(q->d_action); cudaFree(q->d_reward); cudaFree(q->d_value);
+    cudaFree(q->d_policy); cudaFree(q->d_root_logits); cudaFree(q->d_root_value);
+    delete q;
+    return LZ_OK;
+}
+
+int lz_search_run(lz_search *q, const float *d_latent_roots, int deterministic, lz_stream s)
+{
+    LZ_REQUIRE(q, LZ_EINVAL, "lz_search_run: null search");
+    LZ_REQUIRE(q->tree->prepared, LZ_ESTATE, "lz_search_run: roots not prepared (call lz_tree_prepare first)");
+    if (d_latent_roots && d_latent_roots != q->pool)
+        LZ_CUDA_CHECK(cudaMemcpyAsync(q->pool, d_latent_roots, q->slot_stride * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)s));
+    return run_graph(q, deterministic, (cudaStream_t)s);
+}
+
+int lz_search_collect(lz_search *q, const float *d_obs, const uint8_t *d_mask, const float *d_noise, float noise_weight,
+                      const int32_t *d_to_play, int deterministic, float *d_pred_value, float *d_policy_logits,
+                      lz_stream s)
+{
+    LZ_REQUIRE(q && d_obs, LZ_EINVAL, "lz_search_collect: bad argument");
+    TailIO io;
+    memset(&io, 0, sizeof(io));
+    io.latent2 = q->pool;                                   // latent roots go straight into pool slot 0
+    io.policy_logits = d_policy_logits ? d_policy_logits : q->d_root_logits;
+    io.value = d_pred_value ? d_pred_value : q->d_root_value;
+    int rc = model_initial(q->model, q->B, d_obs, io, (cudaStream_t)s);          // policy/muzero.py:749
+    if (rc) return rc;
+    if ((rc = lz_tree_reset_mask(q->tree, d_mask, s))) return rc;                // :760,769
+    if ((rc = lz_tree_prepare(q->tree, io.policy_logits, d_noise, noise_weight, nullptr, d_to_play, s))) return rc;   // :774
+    return run_graph(q, deterministic, (cudaStream_t)s);                         // :775
+}
+
+int lz_search_num_kernels(const lz_search *q) { return q ? q->num_kernels : 0; }
+const float *lz_search_latent_pool(const lz_search *q) { return q ? q->pool : nullptr; }
+
+}  // extern "C"

@@ -1,0 +1,333 @@
+// tree.cu -- kernels + C ABI for the device-resident batched MuZero trees (see tree.cuh for the design).
+// Compiled with -fmad=false: no fp32 contraction anywhere in this translation unit.
+#include <math.h>
+#include <stdarg.h>
+#include <limits.h>
+#include <vector>
+
+#include "lz_common.cuh"
+#include "tree.cuh"
+
+namespace lz {
+
+static thread_local char g_err[512] = "";
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+constexpr int kTreeBlock = 64;   // 2 warps = 2 trees per CTA: latency-bound work, spread over all SMs
+
+__global__ void __launch_bounds__(kTreeBlock)
+k_tree_reset(TreeParams p, const int32_t *legal, const int32_t *nlegal, const uint8_t *mask)
+{
+    const int b = blockIdx.x * (kTreeBlock / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        *p.players_max = INT_MIN;
+        *p.rng_epoch += 1ull;
+    }
+    if (b >= p.B) return;
+    const int A = p.A;
+    int *lg = p.legal + (size_t)b * A;
+    int n = 0;
+    if (mask) {                              // ascending ids == np.nonzero order (policy/muzero.py:760)
+        for (int c0 = 0; c0 < A; c0 += 32) {
+            int a = c0 + lane;
+            bool on = a < A && mask[(size_t)b * A + a] != 0;
+            unsigned m = __ballot_sync(0xffffffffu, on);
+            if (on) lg[n + __popc(m & ((1u << lane) - 1u))] = a;
+            n += __popc(m);
+        }
+    } else if (legal && nlegal) {
+        n = nlegal[b];
+        for (int k = lane; k < n; k += 32) lg[k] = legal[(size_t)b * A + k];
+    }
+    if (n == 0) {                            // cnode.cpp:101-107: empty list == every action
+        n = A;
+        for (int k = lane; k < A; k += 32) lg[k] = k;
+    }
+    for (int k = n + lane; k < A; k += 32) lg[k] = -1;
+    if (lane == 0) {
+        p.nlegal[b] = n;
+        p.root_visit[b] = 0;
+        p.root_vsum[b] = 0.0f;
+        p.root_reward[b] = 0.0f;
+        p.mm_max[b] = kFloatMin;             // cminimax.cpp:7-11
+        p.mm_min[b] = kFloatMax;
+        p.path_len[b] = 0;
+        p.search_len[b] = 0;
+    }
+}
+
+// CRoots::prepare / prepare_no_noise (cnode.cpp:321-358)
+__global__ void __launch_bounds__(kTreeBlock)
+k_tree_prepare(TreeParams p, const float *logits, const float *noise, float noise_w, const float *rewards,
+               const int32_t *to_play)
+{
+    const int b = blockIdx.x * (kTreeBlock / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (b >= p.B) return;
+    const int A = p.A, N = p.N;
+    uint32_t *nb = p.edges + (size_t)b * N * kEdgeFields * A;   // slot 0
+    const int *lg = p.legal + (size_t)b * A;
+    const int n = p.nlegal[b];
+    expand_block(nb, A, logits + (size_t)b * A, lg, n, lane);
+    __syncwarp();
+    if (noise) {                             // add_exploration_noise (cnode.cpp:149-167)
+        const float keep = __fsub_rn(1.0f, noise_w);
+        for (int k = lane; k < n; k += 32) {
+            int a = lg[k];
+            float prior = u2f(nb[F_PRIOR * A + a]);
+            float nz = noise[(size_t)b * A + k];
+            nb[F_PRIOR * A + a] = f2u(__fadd_rn(__fmul_rn(prior, keep), __fmul_rn(nz, noise_w)));
+        }
+    }
+    if (lane == 0) {
+        const int tp = to_play ? to_play[b] : -1;
+        p.to_play[b] = tp;
+        p.n_to_play[(size_t)b * N] = tp;
+        p.n_best[(size_t)b * N] = -1;
+        p.root_reward[b] = rewards ? rewards[b] : 0.0f;
+        p.root_visit[b] += 1;                // cnode.cpp:338,356
+        p.vtp[b] = tp;
+        atomicMax(p.players_max, tp);
+    }
+}
+
+__global__ void __launch_bounds__(kTreeBlock)
+k_tree_traverse(TreeParams p, int deterministic, unsigned step, int32_t *ix, int32_t *iy, int32_t *act,
+                int32_t *len, int32_t *vtp)
+{
+    const int b = blockIdx.x * (kTreeBlock / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (b >= p.B) return;
+    tree_traverse(p, b, lane, deterministic, step, ix, iy, act, len, vtp);
+}
+
+__global__ void __launch_bounds__(kTreeBlock)
+k_tree_backprop(TreeParams p, int latent_index, const float *reward, const float *value, const float *logits,
+                const int32_t *to_play)
+{
+    const int b = blockIdx.x * (kTreeBlock / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (b >= p.B) return;
+    tree_backprop(p, b, lane, latent_index, reward[b], value[b], logits + (size_t)b * p.A, to_play);
+}
+
+__global__ void __launch_bounds__(kTreeBlock)
+k_tree_backprop_traverse(TreeParams p, int latent_index, const float *reward, const float *value,
+                         const float *logits, int deterministic, unsigned step, int32_t *ix, int32_t *act)
+{
+    const int b = blockIdx.x * (kTreeBlock / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (b >= p.B) return;
+    tree_backprop(p, b, lane, latent_index, reward[b], value[b], logits + (size_t)b * p.A, nullptr);
+    tree_traverse(p, b, lane, deterministic, step, ix, nullptr, act, nullptr, nullptr);
+}
+
+// get_distributions / get_values / get_trajectories (cnode.cpp:237-277,369-417)
+__global__ void __launch_bounds__(kTreeBlock)
+k_tree_results(TreeParams p, int32_t *visits, float *values, int32_t *nlegal, int32_t *traj)
+{
+    const int b = blockIdx.x * (kTreeBlock / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (b >= p.B) return;
+    const int A = p.A, N = p.N;
+    const uint32_t *tree_edges = p.edges + (size_t)b * N * kEdgeFields * A;
+    const int n = p.nlegal[b];
+    if (visits) {
+        for (int k = lane; k < A; k += 32)
+            visits[(size_t)b * A + k] = k < n ? (int)tree_edges[F_VISIT * A + p.legal[(size_t)b * A + k]] : -1;
+    }
+    if (lane == 0) {
+        if (values) {
+            int vc = p.root_visit[b];
+            values[b] = vc == 0 ? 0.0f : __fdiv_rn(p.root_vsum[b], (float)vc);
+        }
+        if (nlegal) nlegal[b] = n;
+    }
+    if (traj) {
+        for (int k = lane; k < N; k += 32) traj[(size_t)b * N + k] = -1;
+        __syncwarp();
+        if (lane == 0) {
+            int slot = 0, len = 0;
+            while (slot >= 0 && len < N) {
+                int a = p.n_best[(size_t)b * N + slot];
+                if (a < 0) break;
+                traj[(size_t)b * N + len++] = a;
+                slot = (int)tree_edges[(size_t)slot * kEdgeFields * A + F_CSLOT * A + a];
+            }
+        }
+    }
+}
+
+static inline dim3 tree_grid(int B) { return dim3(ceil_div(B, kTreeBlock / 32)); }
+
+int tree_launch_traverse(lz_tree *t, int deterministic, int32_t *d_ix, int32_t *d_iy, int32_t *d_action,
+                         int32_t *d_len, int32_t *d_vtp, cudaStream_t s)
+{
+    k_tree_traverse<<<tree_grid(t->p.B), kTreeBlock, 0, s>>>(t->p, deterministic, t->step_counter++, d_ix, d_iy,
+                                                            d_action, d_len, d_vtp);
+    LZ_KERNEL_CHECK();
+    return LZ_OK;
+}
+
+int tree_launch_backprop(lz_tree *t, int latent_index, const float *d_reward, const float *d_value,
+                         const float *d_logits, const int32_t *d_to_play, cudaStream_t s)
+{
+    k_tree_backprop<<<tree_grid(t->p.B), kTreeBlock, 0, s>>>(t->p, latent_index, d_reward, d_value, d_logits,
+                                                            d_to_play);
+    LZ_KERNEL_CHECK();
+    return LZ_OK;
+}
+
+int tree_launch_backprop_traverse(lz_tree *t, int latent_index, const float *d_reward, const float *d_value,
+                                  const float *d_logits, int deterministic, int32_t *d_ix, int32_t *d_action,
+                                  cudaStream_t s)
+{
+    k_tree_backprop_traverse<<<tree_grid(t->p.B), kTreeBlock, 0, s>>>(t->p, latent_index, d_reward, d_value,
+                                                                     d_logits, deterministic, t->step_counter++,
+                                                                     d_ix, d_action);
+    LZ_KERNEL_CHECK();
+    return LZ_OK;
+}
+
+}  // namespace lz
+
+using namespace lz;
+
+extern "C" {
+
+int lz_version(void) { return 100; }
+const char *lz_last_error(void) { return lz::g_err; }
+
+int lz_tree_create(int B, int A, int max_sims, lz_tree **out)
+{
+    LZ_REQUIRE(out && B > 0 && A > 0 && max_sims > 0, LZ_EINVAL, "lz_tree_create: bad arguments B=%d A=%d max_sims=%d", B, A, max_sims);
+    int ndev = 0;
+    LZ_CUDA_CHECK(cudaGetDeviceCount(&ndev));
+    LZ_REQUIRE(ndev > 0, LZ_ECUDA, "lz_tree_create: no CUDA device (this library has no CPU fallback)");
+    lz_tree *t = new lz_tree();
+    memset(t, 0, sizeof(*t));
+    const int N = max_sims + 1;
+    TreeParams &p = t->p;
+    p.B = B; p.A = A; p.N = N;
+    t->max_sims = max_sims;
+    // one allocation, carved
+    size_t words = 0;
+    auto take = [&](size_t n) { size_t o = words; words += (n + 31) & ~(size_t)31; return o; };
+    size_t o_edges = take((size_t)B * N * kEdgeFields * A);
+    size_t o_ntp = take((size_t)B * N), o_nbest = take((size_t)B * N);
+    size_t o_legal = take((size_t)B * A), o_nlegal = take(B);
+    size_t o_rvis = take(B), o_rvsum = take(B), o_rrew = take(B), o_mmax = take(B), o_mmin = take(B);
+    size_t o_tp = take(B), o_players = take(1), o_pslot = take((size_t)B * N), o_pact = take((size_t)B * N);
+    size_t o_plen = take(B), o_vtp = take(B), o_slen = take(B), o_pbc = take(N + 1), o_epoch = take(2);
+    uint32_t *base = nullptr;
+    int rc = dev_alloc(&base, words);
+    if (rc != LZ_OK) { delete t; return rc; }
+    cudaError_t e = cudaMemset(base, 0, words * 4);
+    if (e != cudaSuccess) { set_error("cudaMemset failed: %s", cudaGetErrorString(e)); cudaFree(base); delete t; return LZ_ECUDA; }
+    t->alloc_base = base;
+    p.edges = base + o_edges;
+    p.n_to_play = (int *)(base + o_ntp); p.n_best = (int *)(base + o_nbest);
+    p.legal = (int *)(base + o_legal); p.nlegal = (int *)(base + o_nlegal);
+    p.root_visit = (int *)(base + o_rvis); p.root_vsum = (float *)(base + o_rvsum); p.root_reward = (float *)(base + o_rrew);
+    p.mm_max = (float *)(base + o_mmax); p.mm_min = (float *)(base + o_mmin);
+    p.to_play = (int *)(base + o_tp); p.players_max = (int *)(base + o_players);
+    p.path_slot = (int *)(base + o_pslot); p.path_action = (int *)(base + o_pact); p.path_len = (int *)(base + o_plen);
+    p.vtp = (int *)(base + o_vtp); p.search_len = (int *)(base + o_slen);
+    t->d_pbc = (float *)(base + o_pbc); p.pbc = t->d_pbc;
+    p.rng_epoch = (unsigned long long *)(base + o_epoch);
+    p.rng_seed = 0x5eed5eedull;
+    *out = t;
+    return lz_tree_set_params(t, 19652, 1.25f, 0.997f, 0.01f);
+}
+
+int lz_tree_destroy(lz_tree *t)
+{
+    if (!t) return LZ_OK;
+    cudaFree(t->alloc_base);
+    delete t;
+    return LZ_OK;
+}
+
+int lz_tree_set_params(lz_tree *t, int pb_c_base, float pb_c_init, float discount, float value_delta_max)
+{
+    LZ_REQUIRE(t, LZ_EINVAL, "lz_tree_set_params: null tree");
+    LZ_REQUIRE(pb_c_base > 0, LZ_EINVAL, "lz_tree_set_params: pb_c_base must be > 0");
+    // cucb_score (cnode.cpp:672): pb_c = log((N + base + 1) / base) + init, all fp32, N = visit_count - 1.
+    // The argument only depends on the integer visit count, so the S+2 possible values are tabulated
+    // once on the host with the same libm logf the reference binary links against.
+    const int n = t->p.N + 1;
+    std::vector<float> tab(n);
+    const float base = (float)pb_c_base;
+    for (int i = 0; i < n; ++i) {
+        volatile float num = (float)i + base;
+        num = num + 1;
+        volatile float arg = num / base;
+        volatile float lg = logf(arg);
+        tab[i] = lg + pb_c_init;
+    }
+    LZ_CUDA_CHECK(cudaMemcpy(t->d_pbc, tab.data(), n * sizeof(float), cudaMemcpyHostToDevice));
+    t->p.discount = discount;
+    t->p.delta = value_delta_max;
+    t->params_set = true;
+    return LZ_OK;
+}
+
+int lz_tree_reset(lz_tree *t, const int32_t *d_legal, const int32_t *d_nlegal, lz_stream s)
+{
+    LZ_REQUIRE(t, LZ_EINVAL, "lz_tree_reset: null tree");
+    LZ_REQUIRE((d_legal == nullptr) == (d_nlegal == nullptr), LZ_EINVAL, "lz_tree_reset: pass both d_legal and d_nlegal or neither");
+    k_tree_reset<<<tree_grid(t->p.B), kTreeBlock, 0, (cudaStream_t)s>>>(t->p, d_legal, d_nlegal, nullptr);
+    LZ_KERNEL_CHECK();
+    t->prepared = false;
+    return LZ_OK;
+}
+
+int lz_tree_reset_mask(lz_tree *t, const uint8_t *d_mask, lz_stream s)
+{
+    LZ_REQUIRE(t, LZ_EINVAL, "lz_tree_reset_mask: null tree");
+    k_tree_reset<<<tree_grid(t->p.B), kTreeBlock, 0, (cudaStream_t)s>>>(t->p, nullptr, nullptr, d_mask);
+    LZ_KERNEL_CHECK();
+    t->prepared = false;
+    return LZ_OK;
+}
+
+int lz_tree_prepare(lz_tree *t, const float *d_logits, const float *d_noise, float noise_weight,
+                    const float *d_rewards, const int32_t *d_to_play, lz_stream s)
+{
+    LZ_REQUIRE(t && d_logits, LZ_EINVAL, "lz_tree_prepare: null argument");
+    k_tree_prepare<<<tree_grid(t->p.B), kTreeBlock, 0, (cudaStream_t)s>>>(t->p, d_logits, d_noise, noise_weight,
+                                                                         d_rewards, d_to_play);
+    LZ_KERNEL_CHECK();
+    t->prepared = true;
+    return LZ_OK;
+}
+
+int lz_tree_traverse(lz_tree *t, int deterministic, int32_t *d_ix, int32_t *d_iy, int32_t *d_last_action,
+                     int32_t *d_search_len, int32_t *d_virtual_to_play, lz_stream s)
+{
+    LZ_REQUIRE(t, LZ_EINVAL, "lz_tree_traverse: null tree");
+    LZ_REQUIRE(t->prepared, LZ_ESTATE, "lz_tree_traverse: roots not prepared (call lz_tree_prepare first)");
+    return tree_launch_traverse(t, deterministic, d_ix, d_iy, d_last_action, d_search_len, d_virtual_to_play,
+                                (cudaStream_t)s);
+}
+
+int lz_tree_backpropagate(lz_tree *t, int latent_index, const float *d_reward, const float *d_value,
+                          const float *d_logits, const int32_t *d_to_play, lz_stream s)
+{
+    LZ_REQUIRE(t && d_reward && d_value && d_logits, LZ_EINVAL, "lz_tree_backpropagate: null argument");
+    LZ_REQUIRE(t->prepared, LZ_ESTATE, "lz_tree_backpropagate: roots not prepared");
+    LZ_REQUIRE(latent_index >= 1 && latent_index <= t->max_sims, LZ_EINVAL,
+               "lz_tree_backpropagate: latent_index %d outside [1, %d]", latent_index, t->max_sims);
+    return tree_launch_backprop(t, latent_index, d_reward, d_value, d_logits, d_to_play, (cudaStream_t)s);
+}
+
+int lz_tree_results(lz_tree *t, int32_t *d_visits, float *d_values, int32_t *d_nlegal, int32_t *d_traj, lz_stream s)
+{
+    LZ_REQUIRE(t, LZ_EINVAL, "lz_tree_results: null tree");
+    k_tree_results<<<tree_grid(t->p.B), kTreeBlock, 0, (cudaStream_t)s>>>(t->p, d_visits, d_values, d_nlegal, d_traj);
+    LZ_KERNEL_CHECK();
+    return LZ_OK;
+}
+
+}  // extern "C"

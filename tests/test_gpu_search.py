@@ -1,0 +1,151 @@
+"""GPU tests of the fused search (one CUDA graph per search) through the MuZeroMCTSCtree mirror."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(B, A, S, seed=0, masks=False):
+    import lightzero_b200 as lzb
+    from oracle.model_ref import MuZeroModelRef, emulate_trained_
+    torch.manual_seed(seed)
+    ref = emulate_trained_(MuZeroModelRef((4, 84, 84), A), seed)
+    cu = lzb.MuZeroModel(observation_shape=(4, 84, 84), action_space_size=A).load_state_dict(ref.state_dict())
+    rng = np.random.default_rng(seed)
+    obs = torch.rand(B, 4, 84, 84)
+    mask = np.ones((B, A), np.uint8)
+    if masks:
+        mask = (rng.random((B, A)) < 0.6).astype(np.uint8)
+        mask[np.arange(B), rng.integers(0, A, B)] = 1
+    legal = [np.nonzero(mask[b])[0].tolist() for b in range(B)]
+    noises = [rng.dirichlet([0.3] * len(l)).astype(np.float32).tolist() for l in legal]
+    mcts = lzb.MuZeroMCTSCtree(dict(num_simulations=S, deterministic=True, discount_factor=0.997))
+    return ref, cu, obs, mask, legal, noises, mcts
+
+
+class _Recorder:
+    """Wraps the CUDA model so the step-wise search records what the network returned."""
+
+    def __init__(self, model):
+        self.model, self.calls = model, []
+
+    def eval(self):
+        return self
+
+    def recurrent_inference(self, latent, action):
+        out = self.model.recurrent_inference(latent, action)
+        self.calls.append((latent.clone(), action.clone(), out))
+        return out
+
+
+@pytest.mark.parametrize("B,A,S,masks", [(16, 6, 20, False), (300, 18, 50, True), (1024, 6, 50, False)])
+def test_fused_graph_search_equals_stepwise_search(B, A, S, masks):
+    """The single-graph search and the one-simulation-at-a-time drive of the same kernels must agree
+    exactly: visit counts, root values (bits), and repeated graph launches must be reproducible."""
+    ref, cu, obs, mask, legal, noises, mcts = _setup(B, A, S, masks=masks)
+    out = cu.initial_inference(obs.cuda())
+    results = []
+    for mode in ("fused", "fused", "step"):
+        roots = mcts.roots(B, legal)
+        roots.prepare(0.25, noises, [0.] * B, out.policy_logits, [-1] * B)
+        mcts.search(roots, cu if mode != "step" else _Recorder(cu), out.latent_state, [-1] * B)
+        results.append((roots.get_distributions(), np.asarray(roots.get_values(), np.float32).view(np.uint32).tolist()))
+        roots.clear()
+    assert results[0] == results[1] == results[2]
+    assert all(sum(d) == S for d in results[0][0])
+    assert mcts.last_num_kernels == 2 * S + 1
+
+
+def test_search_accepts_numpy_latents_and_host_lists():
+    """The reference passes latent_state_roots as np.ndarray and policy logits as nested lists
+    (policy/muzero.py:757-758,774-775); the mirror must take exactly that."""
+    B, A, S = 12, 6, 10
+    ref, cu, obs, mask, legal, noises, mcts = _setup(B, A, S)
+    out = cu.initial_inference(obs.cuda())
+    roots = mcts.roots(B, legal)
+    roots.prepare(0.25, noises, [0.] * B, out.policy_logits.cpu().numpy().tolist(), [-1] * B)
+    mcts.search(roots, cu, out.latent_state.cpu().numpy(), [-1] * B)
+    a = roots.get_distributions()
+    roots2 = mcts.roots(B, legal)
+    roots2.prepare(0.25, noises, [0.] * B, out.policy_logits, [-1] * B)
+    mcts.search(roots2, cu, out.latent_state, [-1] * B)
+    assert a == roots2.get_distributions()
+    assert len(a) == B and all(len(d) == A for d in a) and isinstance(roots.get_values()[0], float)
+
+
+@pytest.mark.parametrize("B,A,S,masks", [(64, 6, 25, False), (96, 18, 50, True)])
+def test_end_to_end_against_reference_pipeline(B, A, S, masks):
+    """Whole path vs the oracle pipeline (PyTorch-CPU fp32 model + reference ctree, deterministic).
+    Network outputs agree to ~1e-6, but PUCT is discontinuous (a flipped arg-max changes every later
+    simulation of that root), so identity of visit counts is asserted per root for the large majority
+    and the trees that do match must have root values within 1e-5."""
+    from oracle.search_ref import SearchRef, collect_step_ref, load_tree_module
+    ref, cu, obs, mask, legal, noises, mcts = _setup(B, A, S, seed=3, masks=masks)
+    tree, kind = load_tree_module()
+    sref = SearchRef(tree, num_simulations=S)
+    exp = collect_step_ref(sref, ref, obs, mask, [-1] * B, noises=noises)
+    out = cu.initial_inference(obs.cuda())
+    assert torch.allclose(out.policy_logits.cpu(), torch.from_numpy(exp["policy_logits"]), rtol=1e-5, atol=1e-5)
+    roots = mcts.roots(B, legal)
+    roots.prepare(0.25, noises, [0.] * B, out.policy_logits, [-1] * B)
+    mcts.search(roots, cu, out.latent_state, [-1] * B)
+    got_d, got_v = roots.get_distributions(), roots.get_values()
+    same = [g == e for g, e in zip(got_d, exp["distributions"])]
+    frac = sum(same) / B
+    print(f"identical visit distributions: {sum(same)}/{B} (tree oracle: {kind})")
+    assert frac >= 0.85, frac
+    for i in range(B):
+        if same[i]:
+            assert abs(got_v[i] - exp["values"][i]) <= 1e-5 + 2e-4 * abs(exp["values"][i])
+    assert all(sum(d) == S for d in got_d)
+
+
+def test_replay_of_reference_pipeline_is_bit_exact():
+    """Replay mode: feed the CUDA trees the network outputs the ORACLE pipeline
+    produced (recorded per simulation).  The trees must then reproduce the reference's visit counts
+    and root values bit for bit, on the same seeds."""
+    from lightzero_b200 import mz_tree
+    from oracle.search_ref import SearchRef, collect_step_ref, load_tree_module
+    B, A, S = 48, 18, 50
+    ref, cu, obs, mask, legal, noises, mcts = _setup(B, A, S, seed=5, masks=True)
+    tree, kind = load_tree_module()
+    rec = []
+    exp = collect_step_ref(SearchRef(tree, num_simulations=S), ref, obs, mask, [-1] * B, noises=noises, recorder=rec)
+    mz_tree.DEFAULT_MAX_SIMS = max(mz_tree.DEFAULT_MAX_SIMS, S)
+    roots = mz_tree.Roots(B, legal)
+    roots.prepare(0.25, noises, [0.] * B, exp["policy_logits"].tolist(), [-1] * B)
+    mm = mz_tree.MinMaxStatsList(B)
+    mm.set_delta(0.01)
+    for s in range(S):
+        res = mz_tree.ResultsWrapper(B)
+        ix, iy, la, vtp = mz_tree.batch_traverse(roots, 19652, 1.25, 0.997, mm, res, [-1] * B, True)
+        assert ix == rec[s]["ix"] and la == rec[s]["last_action"] and res.get_search_len() == rec[s]["search_len"]
+        mz_tree.batch_backpropagate(s + 1, 0.997, rec[s]["reward"], rec[s]["value"], rec[s]["policy"], mm, res, vtp)
+    assert roots.get_distributions() == exp["distributions"]
+    assert np.array_equal(np.asarray(roots.get_values(), np.float32).view(np.uint32),
+                          np.asarray(exp["values"], np.float32).view(np.uint32))
+
+
+def test_full_size_properties():
+    """BASELINE north-star size (1024 roots, 50 simulations, A=18): size-independent invariants."""
+    B, A, S = 1024, 18, 50
+    ref, cu, obs, mask, legal, noises, mcts = _setup(B, A, S, seed=9, masks=True)
+    out = cu.initial_inference(obs.cuda())
+    roots = mcts.roots(B, legal)
+    roots.prepare(0.25, noises, [0.] * B, out.policy_logits, [-1] * B)
+    mcts.search(roots, cu, out.latent_state, [-1] * B)
+    v, n = roots.get_distributions_tensor()
+    v, n = v.cpu().numpy(), n.cpu().numpy()
+    assert (n == mask.sum(1)).all()
+    for b in range(B):
+        assert (v[b, :n[b]] >= 0).all() and v[b, :n[b]].sum() == S and (v[b, n[b]:] == -1).all()
+    vals = np.asarray(roots.get_values())
+    assert np.isfinite(vals).all()
+    traj = roots.get_trajectories()
+    assert all(1 <= len(t) <= S for t in traj)
+    # idempotence: same inputs -> same search
+    roots2 = mcts.roots(B, legal)
+    roots2.prepare(0.25, noises, [0.] * B, out.policy_logits, [-1] * B)
+    mcts.search(roots2, cu, out.latent_state, [-1] * B)
+    assert np.array_equal(roots2.get_distributions_tensor()[0].cpu().numpy(), v)
