@@ -16,6 +16,7 @@ void set_error(const char *fmt, ...);
         cudaError_t _e = (expr);                                                               \
         if (_e != cudaSuccess) {                                                               \
             lz::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            (void)cudaGetLastError(); /* clear the non-sticky error so later calls do not re-report it */ \
             return LZ_ECUDA;                                                                   \
         }                                                                                      \
     } while (0)

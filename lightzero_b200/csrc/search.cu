@@ -21,6 +21,8 @@ struct lz_search {
     float *d_root_logits;        // [B][A]
     float *d_root_value;         // [B]
     cudaGraphExec_t exec[2];     // [deterministic]
+    cudaStream_t capture_stream; // library-owned: the caller's stream may be the legacy default stream,
+                                 // which cannot be captured; the instantiated graph launches on the caller's
     int num_kernels;
 };
 
@@ -59,9 +61,10 @@ static int run_graph(lz_search *q, int deterministic, cudaStream_t s)
     const int d = deterministic ? 1 : 0;
     if (!q->exec[d]) {
         cudaGraph_t graph = nullptr;
-        LZ_CUDA_CHECK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-        int rc = enqueue_search(q, deterministic, s);
-        cudaError_t e = cudaStreamEndCapture(s, &graph);
+        if (!q->capture_stream) LZ_CUDA_CHECK(cudaStreamCreateWithFlags(&q->capture_stream, cudaStreamNonBlocking));
+        LZ_CUDA_CHECK(cudaStreamBeginCapture(q->capture_stream, cudaStreamCaptureModeThreadLocal));
+        int rc = enqueue_search(q, deterministic, q->capture_stream);
+        cudaError_t e = cudaStreamEndCapture(q->capture_stream, &graph);
         if (rc != LZ_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
         if (e != cudaSuccess) { set_error("cudaStreamEndCapture failed: %s", cudaGetErrorString(e)); return LZ_ECUDA; }
         size_t n = 0;
@@ -105,6 +108,7 @@ int lz_search_destroy(lz_search *q)
 {
     if (!q) return LZ_OK;
     for (int d = 0; d < 2; ++d) if (q->exec[d]) cudaGraphExecDestroy(q->exec[d]);
+    if (q->capture_stream) cudaStreamDestroy(q->capture_stream);
     cudaFree(q->pool); cudaFree(q->d_ix); cudaFree(q->d_action); cudaFree(q->d_reward); cudaFree(q->d_value);
     cudaFree(q->d_policy); cudaFree(q->d_root_logits); cudaFree(q->d_root_value);
     delete q;

@@ -149,3 +149,47 @@ def test_full_size_properties():
     roots2.prepare(0.25, noises, [0.] * B, out.policy_logits, [-1] * B)
     mcts.search(roots2, cu, out.latent_state, [-1] * B)
     assert np.array_equal(roots2.get_distributions_tensor()[0].cpu().numpy(), v)
+
+
+def test_collect_policy_matches_manual_composition():
+    """lz_search_collect (initial_inference -> reset(mask) -> prepare(noise) -> graph) through the
+    _forward_collect mirror, from HOST buffers, equals the step-by-step composition of the public pieces."""
+    from lightzero_b200.collect import MuZeroCollectPolicy
+    B, A, S = 40, 18, 30
+    ref, cu, obs, mask, legal, noises, mcts = _setup(B, A, S, seed=11, masks=True)
+    nz = np.zeros((B, A), np.float32)
+    for b, n in enumerate(noises):
+        nz[b, :len(n)] = n
+    pol = MuZeroCollectPolicy(cu, dict(num_simulations=S, deterministic=True, discount_factor=0.997))
+    r = pol.search_batch(obs.pin_memory(), mask, nz, None)
+    out = cu.initial_inference(obs.cuda(), return_scalar_value=True)
+    roots = mcts.roots(B, legal)
+    roots.prepare(0.25, noises, [0.] * B, out.policy_logits, [-1] * B)
+    mcts.search(roots, cu, out.latent_state, [-1] * B)
+    dist = roots.get_distributions()
+    for b in range(B):
+        assert r["visits"][b, :r["nlegal"][b]].tolist() == dist[b]
+    assert np.array_equal(r["values"].numpy().view(np.uint32), np.asarray(roots.get_values(), np.float32).view(np.uint32))
+    assert torch.equal(r["policy_logits"], out.policy_logits.cpu())
+    assert torch.equal(r["pred_value"], out.value_scalar.cpu())
+
+
+def test_forward_collect_output_format():
+    """policy/muzero.py:801-808: per-env dict keys and types; actions are legal; eval is arg-max."""
+    from lightzero_b200.collect import MuZeroCollectPolicy
+    B, A, S = 10, 6, 12
+    ref, cu, obs, mask, legal, noises, mcts = _setup(B, A, S, seed=13, masks=True)
+    pol = MuZeroCollectPolicy(cu, dict(num_simulations=S, deterministic=True, discount_factor=0.997))
+    np.random.seed(0)
+    out = pol.forward_collect(obs, mask, temperature=1.0, to_play=[-1])
+    assert sorted(out.keys()) == list(range(B))
+    for i in range(B):
+        o = out[i]
+        assert set(o) == {'action', 'visit_count_distributions', 'visit_count_distribution_entropy',
+                          'searched_value', 'predicted_value', 'predicted_policy_logits'}
+        assert mask[i, o['action']] == 1 and sum(o['visit_count_distributions']) == S
+        assert len(o['visit_count_distributions']) == int(mask[i].sum()) and len(o['predicted_policy_logits']) == A
+    ev = pol.forward_eval(obs, mask, to_play=[-1])
+    for i in range(B):
+        d = ev[i]['visit_count_distributions']
+        assert ev[i]['action'] == np.nonzero(mask[i])[0][int(np.argmax(d))]
