@@ -111,6 +111,15 @@ int lz_model_destroy(lz_model *m);
 int lz_model_set_tensor(lz_model *m, const char *name, const float *h_data, int64_t numel);
 /* Folds eval-mode BatchNorm into per-channel scale/shift, packs weights for the kernels, uploads. */
 int lz_model_finalize(lz_model *m);
+/* Arithmetic of the latent-grid networks (recurrent_inference and the tail of initial_inference):
+ *   0 = fp32 FFMA on the CUDA cores;
+ *   1 = tcgen05 tensor cores with fp16 hi/lo operand splitting (3 MMAs per product, fp32 accumulate in
+ *       TMEM): fp32-accurate, the mode parity is stated for;
+ *   2 = tcgen05 single fp16 pass (fp32 accumulate): ~3x fewer MMAs, logits accurate to ~1e-3. */
+int lz_model_set_math(lz_model *m, int mode);
+/* Test hook: overrides the layer program of the tcgen05 kernels (see net_tc.cuh LF_* flags). */
+int lz_model_debug_tc_program(lz_model *m, int which, int nlayers, const int *layer_w, const int *layer_flags,
+                              int has_reward);
 int lz_model_latent_hw(const lz_model *m);   /* 6 for 84/96, 8 for 64 */
 int lz_model_support_size(const lz_model *m);
 

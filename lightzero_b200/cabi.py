@@ -40,6 +40,8 @@ SIGNATURES = {
     "lz_model_destroy": (c_int, [c_void_p]),
     "lz_model_set_tensor": (c_int, [c_void_p, c_char_p, c_void_p, c_int64]),
     "lz_model_finalize": (c_int, [c_void_p]),
+    "lz_model_set_math": (c_int, [c_void_p, c_int]),
+    "lz_model_debug_tc_program": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int]),
     "lz_model_latent_hw": (c_int, [c_void_p]),
     "lz_model_support_size": (c_int, [c_void_p]),
     "lz_model_initial_inference": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

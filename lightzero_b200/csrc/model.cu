@@ -331,6 +331,15 @@ static int model_prepare_launch()
 
 int model_recurrent(lz_model *m, const RecIO &io, cudaStream_t s)
 {
+    if (m->math != 0) {
+        TcIO t;
+        memset(&t, 0, sizeof(t));
+        t.B = io.B; t.npass = (m->math == 1) ? 3 : 1;
+        t.latent_base = io.latent_base; t.ix = io.ix; t.slot_stride = io.slot_stride; t.action = io.action;
+        t.latent_out = io.next_latent; t.reward = io.reward; t.value = io.value; t.policy_logits = io.policy_logits;
+        t.reward_logits = io.reward_logits; t.value_logits = io.value_logits;
+        return tc_launch(m->tc_rec, t, s);
+    }
     switch (pick_W(io.B)) {
         case 8: return launch_recurrent<8>(m->net, io, s);
         case 4: return launch_recurrent<4>(m->net, io, s);
@@ -408,6 +417,14 @@ int model_initial(lz_model *m, int B, const float *d_obs, const TailIO &io_in, c
     TailIO io = io_in;
     io.B = B;
     io.pre_latent = pre;
+    if (m->math != 0) {
+        TcIO t;
+        memset(&t, 0, sizeof(t));
+        t.B = B; t.npass = (m->math == 1) ? 3 : 1;
+        t.latent_base = pre; t.latent_out = io.latent; t.latent_out2 = io.latent2;
+        t.value = io.value; t.policy_logits = io.policy_logits; t.value_logits = io.value_logits;
+        return tc_launch(m->tc_tail, t, s);
+    }
     switch (pick_W(B)) {
         case 8: return launch_tail<8>(m->net, io, s);
         case 4: return launch_tail<4>(m->net, io, s);
@@ -499,6 +516,114 @@ static bool pack_head(lz_model *m, Packer &P, const std::string &conv, const std
     return true;
 }
 
+// ---- tcgen05 tables (net_tc.cu): fp16 hi/lo weights, folded BN, action-bias planes, layer programs ----
+static int pack_tc(lz_model *m, const NetDev &net)
+{
+    const lz_model_config &c = m->cfg;
+    const int A = c.action_space_size, n = c.num_res_blocks;
+    const int nconv = 1 + 6 * n;
+    const size_t conv_bytes = (size_t)tc_conv_layout_bytes();
+    const size_t off_convw = 0;
+    const size_t off_headw = off_convw + conv_bytes * nconv;
+    const size_t off_bn = off_headw + tc_head_layout_bytes();
+    const size_t off_headbn = off_bn + (size_t)nconv * 128 * 4;
+    const size_t off_abias = off_headbn + 96 * 4;
+    const size_t total = off_abias + (size_t)A * kC * kP * 4;
+    std::vector<unsigned char> host(total, 0);
+    float *bn = reinterpret_cast<float *>(host.data() + off_bn);
+    float *head_bn = reinterpret_cast<float *>(host.data() + off_headbn);
+    float *abias = reinterpret_cast<float *>(host.data() + off_abias);
+
+    std::vector<std::pair<std::string, std::string>> convs;   // (weight name, bn prefix)
+    const std::string D = "dynamics_network.", Q = "prediction_network.", R = "representation_network.";
+    convs.push_back({D + "conv.weight", D + "norm_common"});
+    for (const std::string &pre : {D, Q, R})
+        for (int i = 0; i < n; ++i) {
+            const std::string b = pre + "resblocks." + std::to_string(i);
+            convs.push_back({b + ".conv1.0.weight", b + ".conv1.1"});
+            convs.push_back({b + ".conv2.0.weight", b + ".conv2.1"});
+        }
+    for (int ci = 0; ci < nconv; ++ci) {
+        const int cin_total = (ci == 0) ? kC + A : kC;
+        auto w = find(m, convs[ci].first, (size_t)kC * cin_total * 9);
+        std::vector<float> scale, shift;
+        if (!w || !fold_bn(m, convs[ci].second, kC, scale, shift)) return LZ_EINVAL;
+        const float ws = tc_pack_conv3(w->data(), cin_total, kC, host.data() + off_convw + conv_bytes * ci);
+        for (int k = 0; k < kC; ++k) { bn[ci * 128 + k] = scale[k] / ws; bn[ci * 128 + 64 + k] = shift[k]; }
+        if (ci == 0) {   // one-hot action planes (muzero_model.py:341-369): border-aware tap sums, times the BN scale
+            for (int a = 0; a < A; ++a)
+                for (int co = 0; co < kC; ++co)
+                    for (int y = 0; y < kHW; ++y)
+                        for (int x = 0; x < kHW; ++x) {
+                            float acc = 0.0f;
+                            for (int ky = 0; ky < 3; ++ky)
+                                for (int kx = 0; kx < 3; ++kx) {
+                                    const int yy = y + ky - 1, xx = x + kx - 1;
+                                    if (yy < 0 || yy >= kHW || xx < 0 || xx >= kHW) continue;
+                                    acc += (*w)[((size_t)co * cin_total + kC + a) * 9 + ky * 3 + kx];
+                                }
+                            abias[((size_t)a * kC + co) * kP + y * kHW + x] = acc * scale[co];
+                        }
+        }
+    }
+    // 1x1 heads
+    struct HD { std::string conv, norm; int hc, nco, co_off; size_t hi, lo; int bn_off; };
+    const HD heads[3] = {
+        {D + "conv1x1_reward", D + "norm_reward", c.reward_head_channels, 16, 0, off_headw, off_headw + 2048, 0},
+        {Q + "conv1x1_value", Q + "norm_value", c.value_head_channels, 32, 0, off_headw + 4096, off_headw + 8192, 32},
+        {Q + "conv1x1_policy", Q + "norm_policy", c.policy_head_channels, 32, 16, off_headw + 4096, off_headw + 8192, 64},
+    };
+    for (const HD &h : heads) {
+        auto w1 = find(m, h.conv + ".weight", (size_t)h.hc * kC), b1 = find(m, h.conv + ".bias", h.hc);
+        std::vector<float> s1, t1;
+        if (!w1 || !b1 || !fold_bn(m, h.norm, h.hc, s1, t1)) return LZ_EINVAL;
+        const float ws = tc_pack_conv1(w1->data(), h.hc, h.nco, h.co_off, host.data() + h.hi, host.data() + h.lo);
+        for (int i = 0; i < h.hc; ++i) {
+            head_bn[h.bn_off + i] = s1[i] / ws;
+            head_bn[h.bn_off + 16 + i] = t1[i] + s1[i] * (*b1)[i];
+        }
+    }
+    if (m->d_tc) cudaFree(m->d_tc);
+    m->d_tc = nullptr;
+    int rc = dev_alloc(&m->d_tc, total);
+    if (rc != LZ_OK) return rc;
+    LZ_CUDA_CHECK(cudaMemcpy(m->d_tc, host.data(), total, cudaMemcpyHostToDevice));
+    TcNet base;
+    memset(&base, 0, sizeof(base));
+    base.convw = m->d_tc + off_convw; base.headw = m->d_tc + off_headw;
+    base.bn = reinterpret_cast<const float *>(m->d_tc + off_bn);
+    base.head_bn = reinterpret_cast<const float *>(m->d_tc + off_headbn);
+    base.abias = reinterpret_cast<const float *>(m->d_tc + off_abias);
+    base.reward = net.reward; base.value = net.value; base.policy = net.policy;
+    base.hc[0] = c.reward_head_channels; base.hc[1] = c.value_head_channels; base.hc[2] = c.policy_head_channels;
+    base.A = A; base.support_min = c.support_min; base.support_step = c.support_step;
+    // conv indices: 0 dyn conv | 1..2n dyn blocks | 2n+1..4n pred blocks | 4n+1..6n rep blocks
+    TcNet rec = base, tail = base;
+    int L = 0;
+    rec.layer_w[L] = 0; rec.layer_flags[L++] = LF_RES | LF_STORE_RES | LF_ACT_BIAS;
+    for (int i = 0; i < n; ++i) {
+        rec.layer_w[L] = 1 + 2 * i; rec.layer_flags[L++] = 0;
+        rec.layer_w[L] = 2 + 2 * i; rec.layer_flags[L++] = LF_RES | LF_STORE_RES | (i == n - 1 ? (LF_WRITE_LATENT | LF_HOOK_REWARD) : 0);
+    }
+    for (int i = 0; i < n; ++i) {
+        rec.layer_w[L] = 2 * n + 1 + 2 * i; rec.layer_flags[L++] = 0;
+        rec.layer_w[L] = 2 * n + 2 + 2 * i; rec.layer_flags[L++] = LF_RES | LF_STORE_RES | (i == n - 1 ? LF_HOOK_VALPOL : 0);
+    }
+    rec.nlayers = L; rec.has_reward = 1;
+    L = 0;
+    for (int i = 0; i < n; ++i) {
+        tail.layer_w[L] = 4 * n + 1 + 2 * i; tail.layer_flags[L++] = 0;
+        tail.layer_w[L] = 4 * n + 2 + 2 * i; tail.layer_flags[L++] = LF_RES | LF_STORE_RES | (i == n - 1 ? LF_WRITE_LATENT : 0);
+    }
+    for (int i = 0; i < n; ++i) {
+        tail.layer_w[L] = 2 * n + 1 + 2 * i; tail.layer_flags[L++] = 0;
+        tail.layer_w[L] = 2 * n + 2 + 2 * i; tail.layer_flags[L++] = LF_RES | LF_STORE_RES | (i == n - 1 ? LF_HOOK_VALPOL : 0);
+    }
+    tail.nlayers = L; tail.has_reward = 0;
+    m->tc_rec = rec; m->tc_tail = tail;
+    return tc_prepare_launch();
+}
+
 }  // namespace lz
 
 using namespace lz;
@@ -527,6 +652,7 @@ int lz_model_create(const lz_model_config *cfg, lz_model **out)
     m->hw = kHW; m->P = kP; m->K = K;
     m->ws[0] = m->ws[1] = m->ws[2] = nullptr;
     m->ws_floats = 0; m->ws_B = 0;
+    m->math = 0; m->d_tc = nullptr;
     *out = m;
     return LZ_OK;
 }
@@ -535,6 +661,7 @@ int lz_model_destroy(lz_model *m)
 {
     if (!m) return LZ_OK;
     cudaFree(m->d_weights);
+    cudaFree(m->d_tc);
     for (int i = 0; i < 3; ++i) cudaFree(m->ws[i]);
     delete m;
     return LZ_OK;
@@ -628,8 +755,28 @@ int lz_model_finalize(lz_model *m)
     LZ_REQUIRE(h4 == kHW, LZ_EINVAL, "lz_model_finalize: latent grid %d != %d", h4, kHW);
     rc = model_prepare_launch();
     if (rc != LZ_OK) return rc;
+    rc = pack_tc(m, net);
+    if (rc != LZ_OK) return rc;
     m->finalized = true;
     m->tensors.clear();
+    return LZ_OK;
+}
+
+int lz_model_set_math(lz_model *m, int mode)
+{
+    LZ_REQUIRE(m && mode >= 0 && mode <= 2, LZ_EINVAL, "lz_model_set_math: mode must be 0 (fp32 FFMA), 1 (tcgen05 3xFP16) or 2 (tcgen05 fp16)");
+    m->math = mode;
+    return LZ_OK;
+}
+
+/* debug: replace the layer program of the tcgen05 recurrent kernel (which == 0) or tail kernel (which == 1) */
+int lz_model_debug_tc_program(lz_model *m, int which, int nlayers, const int *layer_w, const int *layer_flags, int has_reward)
+{
+    LZ_REQUIRE(m && m->finalized && nlayers >= 1 && nlayers <= kTcMaxLayers, LZ_EINVAL, "lz_model_debug_tc_program: bad argument");
+    TcNet &n = which ? m->tc_tail : m->tc_rec;
+    n.nlayers = nlayers;
+    for (int i = 0; i < nlayers; ++i) { n.layer_w[i] = layer_w[i]; n.layer_flags[i] = layer_flags[i]; }
+    n.has_reward = has_reward;
     return LZ_OK;
 }
 

@@ -6,6 +6,7 @@
 
 #include "lz_common.cuh"
 #include "net6.cuh"
+#include "net_tc.cuh"
 
 namespace lz {
 
@@ -61,6 +62,9 @@ struct lz_model {
     lz::NetDev net;
     std::vector<lz::ConvG> tower;     // DownSample convs in execution order
     int hw, P, K;
+    int math;                         // 0 = fp32 FFMA (net6.cuh), 1 = tcgen05 3xFP16 (fp32-accurate), 2 = tcgen05 fp16 single pass
+    unsigned char *d_tc;              // packed fp16 hi/lo weights + tables of the tcgen05 path
+    lz::TcNet tc_rec, tc_tail;
     // workspace for initial inference (grown on demand, outside graph capture)
     float *ws[3];
     size_t ws_floats;

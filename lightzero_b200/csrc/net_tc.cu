@@ -1,0 +1,564 @@
+// net_tc.cu -- tcgen05 (5th-gen tensor core) path of the MuZero latent-grid networks for sm_100a.
+//
+// One CTA runs the WHOLE recurrent_inference (or the latent-grid tail of initial_inference) for up to 7
+// roots: five 3x3 convolutions + three 1x1 head convolutions as tcgen05.mma with fp32 accumulators in
+// TMEM, BatchNorm/residual/ReLU epilogues out of TMEM, and the small fully connected head layers +
+// softmax-expectation + inverse scalar transform on the CUDA cores.  Activations never leave the SM.
+//
+// fp32 accuracy on fp16 tensor cores ("3xFP16"): every fp32 operand v is split v = hi + lo with
+// hi = fp16(v), lo = fp16(v - hi) (22 significant bits); D += A_hi*B_hi + A_hi*B_lo + A_lo*B_hi with fp32
+// accumulation drops only the 2^-22 lo*lo term.  Same bytes per element as fp32 (2+2), three MMAs at
+// the fp16 rate.  Weights are pre-split on the host and pre-scaled by a power of two (exact; folded
+// back into the BatchNorm scale) so their lo parts stay in fp16's normal range.  Mode 2 ("fast")
+// issues only the hi*hi pass.
+//
+// Implicit GEMM without im2col: activations live in shared memory as [k-group of 8 channels][row][8
+// halves] (the UMMA K-major no-swizzle canonical layout with SBO = 128 B, so row r of the operand is at
+// start + 16*r bytes).  Rows are the pixels of a 7-wide padded grid (49 rows per root, column 6 and row
+// 6 zero), so the input of output row m for tap (dy,dx) is row m + 7*dy + dx: each of the 9 taps is the
+// SAME buffer addressed through a descriptor whose start address is shifted by (7*dy+dx)*16 bytes.  The
+// zero pad rows double as the conv padding between rows and between consecutive roots.  M tiles of 128
+// rows cut anywhere (every output row only depends on shifted input rows); all tiles of a layer
+// accumulate in TMEM before the epilogue rewrites the buffer IN PLACE; the ResBlock skip tensor is parked
+// in spare TMEM columns (tcgen05.st) instead of a second shared-memory buffer.
+//
+// Warp roles (192 threads): warps 0-3 = epilogue / loads / heads (thread t owns TMEM lane t),
+// warp 4 lane 0 = weight producer (cp.async.bulk global->shared ring, mbarrier complete_tx),
+// warp 5 lane 0 = MMA issuer (+ TMEM alloc/dealloc by warp 5).
+#include <cuda_fp16.h>
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "model.cuh"
+#include "net_tc.cuh"
+
+namespace lz {
+
+// ---------------------------------------------------------------------------------------------- PTX
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// bounded wait: a protocol bug must trap, never hang the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    const uint32_t a = smem_u32(bar);
+    for (uint32_t it = 0; it < (1u << 28); ++it) {
+        uint32_t ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+        if (ok) return;
+    }
+    printf("lz net_tc: mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+    asm volatile("trap;\n");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols)
+{
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], fp16 inputs, fp32 accumulate, issued by ONE thread
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+                 ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrives on the mbarrier once every MMA issued so far by this thread has completed
+__device__ __forceinline__ void umma_commit(uint64_t *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32])
+{
+    uint32_t r[32];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16])
+{
+    uint32_t r[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32])
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+                 "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+                 "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};\n"
+                 ::"r"(taddr),
+                   "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+                   "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+                   "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+                   "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15])),
+                   "r"(__float_as_uint(v[16])), "r"(__float_as_uint(v[17])), "r"(__float_as_uint(v[18])), "r"(__float_as_uint(v[19])),
+                   "r"(__float_as_uint(v[20])), "r"(__float_as_uint(v[21])), "r"(__float_as_uint(v[22])), "r"(__float_as_uint(v[23])),
+                   "r"(__float_as_uint(v[24])), "r"(__float_as_uint(v[25])), "r"(__float_as_uint(v[26])), "r"(__float_as_uint(v[27])),
+                   "r"(__float_as_uint(v[28])), "r"(__float_as_uint(v[29])), "r"(__float_as_uint(v[30])), "r"(__float_as_uint(v[31]))
+                 : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+}
+
+// K-major, SWIZZLE_NONE shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+// start address >> 4 in [0,14), leading byte offset >> 4 in [16,30) (between the two 16-byte K chunks of
+// one MMA), stride byte offset >> 4 in [32,46) (between 8-row core matrices), version = 1 in [46,48).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo16, uint32_t sbo16)
+{
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)(lbo16 & 0x3FFFu) << 16) | ((uint64_t)(sbo16 & 0x3FFFu) << 32) | (1ull << 46);
+}
+// instruction descriptor, kind::f16: D = F32 (bit 4), A = B = F16 (0), both K-major, N>>3 at [17,23), M>>4 at [24,29)
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) { return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24); }
+
+// ---------------------------------------------------------------------------------------------- geometry
+constexpr int kTcThreads = 192;
+constexpr int kPitch = 7, kRowsPerRoot = 49;     // padded 7x7 grid per root
+constexpr int kMaxRoots = 7, kMaxTiles = 3;      // 343 rows -> 3 tiles of 128
+constexpr int kMargin = 8;                       // |7*dy+dx| <= 8
+constexpr int kRowsAlloc = kMargin + kMaxTiles * 128 + kMargin;   // 400
+constexpr int kPlaneBytes = kRowsAlloc * 16;     // one k-group (8 fp16 channels) of all rows: 6400 B
+constexpr int kPartBytes = 8 * kPlaneBytes;      // 64 channels: 51200 B
+constexpr int kActBytes = 2 * kPartBytes;        // hi + lo: 102400 B
+constexpr int kTapBytes = 2 * 64 * 64 * 2;       // one 3x3 tap, hi + lo: 16384 B
+constexpr int kStages = 4;
+constexpr int kHeadWBytes = 3 * 2 * 16 * 64 * 2; // three 1x1 heads (hc <= 16), hi + lo: 12288 B
+constexpr int kSmemBytes = kActBytes + kStages * kTapBytes + kHeadWBytes + 1024;
+
+// TMEM columns
+constexpr int kColAcc = 0;        // 3 tiles x 64
+constexpr int kColRes = 192;      // 3 tiles x 64  (ResBlock skip tensor, fp32)
+constexpr int kColRew = 384;      // 3 tiles x 16  (reward 1x1)
+constexpr int kTmemCols = 512;
+
+struct TcBars {
+    uint64_t full[kStages], empty[kStages];
+    uint64_t acc_ready;     // MMA -> epilogue: this layer's accumulators are complete
+    uint64_t act_ready;     // epilogue -> MMA: activations (and TMEM) are ready for the next layer
+    uint64_t rew_ready;     // MMA -> heads: reward 1x1 accumulators complete (single phase)
+    uint64_t vp_ready;      // MMA -> heads: value/policy 1x1 accumulators complete (single phase)
+    uint32_t tmem_base;
+    uint32_t pad;
+};
+
+// split 8 floats into fp16 hi / lo and store them as two 16-byte vectors
+__device__ __forceinline__ void store_split8(unsigned char *hi_ptr, unsigned char *lo_ptr, const float *v)
+{
+    __half2 h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float a = v[2 * i], b = v[2 * i + 1];
+        a = fminf(fmaxf(a, -65504.0f), 65504.0f);
+        b = fminf(fmaxf(b, -65504.0f), 65504.0f);
+        __half ha = __float2half_rn(a), hb = __float2half_rn(b);
+        h[i] = __halves2half2(ha, hb);
+        l[i] = __halves2half2(__float2half_rn(a - __half2float(ha)), __float2half_rn(b - __half2float(hb)));
+    }
+    *reinterpret_cast<uint4 *>(hi_ptr) = *reinterpret_cast<uint4 *>(h);
+    *reinterpret_cast<uint4 *>(lo_ptr) = *reinterpret_cast<uint4 *>(l);
+}
+
+// ---------------------------------------------------------------------------------------------- kernel
+__global__ void __launch_bounds__(kTcThreads, 1) k_net_tc(TcNet net, TcIO io)
+{
+    extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned char *act = smem;                                   // [2 parts][8 planes][400 rows][16 B]
+    unsigned char *ring = smem + kActBytes;                      // [kStages][hi 8 KB | lo 8 KB]
+    unsigned char *headw = ring + kStages * kTapBytes;           // [3 heads][hi 2 KB | lo 2 KB]
+    TcBars *bars = reinterpret_cast<TcBars *>(headw + kHeadWBytes);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int R = io.roots_per_cta;
+    const int root0 = blockIdx.x * R;
+    const int nvalid = min(R, io.B - root0);                     // roots of this CTA that exist
+    const int rows_used = R * kRowsPerRoot;
+    const int NT = (rows_used + 127) >> 7;
+    const int npass = io.npass;
+    const int nlayers = net.nlayers;
+
+    // ---- one-time setup ----
+    if (tid == 0) {
+        for (int i = 0; i < kStages; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], 1); }
+        mbar_init(&bars->acc_ready, 1);
+        mbar_init(&bars->act_ready, 128);
+        mbar_init(&bars->rew_ready, 1);
+        mbar_init(&bars->vp_ready, 1);
+        fence_mbar_init();
+    }
+    // zero the margins once (pad rows inside the tiles are rewritten as zeros by every epilogue)
+    for (int i = tid; i < 2 * 8 * 2 * kMargin; i += kTcThreads) {
+        int part = i / (8 * 2 * kMargin), rem = i % (8 * 2 * kMargin), plane = rem / (2 * kMargin), r = rem % (2 * kMargin);
+        int row = r < kMargin ? r : kMargin + kMaxTiles * 128 + (r - kMargin);
+        *reinterpret_cast<uint4 *>(act + part * kPartBytes + plane * kPlaneBytes + row * 16) = make_uint4(0, 0, 0, 0);
+    }
+    if (warp == 5) tmem_alloc(&bars->tmem_base, kTmemCols);
+    // 1x1 head weights: plain copy (12 KB)
+    for (int i = tid; i < kHeadWBytes / 16; i += kTcThreads)
+        reinterpret_cast<uint4 *>(headw)[i] = __ldg(reinterpret_cast<const uint4 *>(net.headw) + i);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = bars->tmem_base;
+
+    if (warp == 4) {
+        // ================= weight producer =================
+        if (lane == 0) {
+            uint32_t n = 0;
+            for (int L = 0; L < nlayers; ++L) {
+                const unsigned char *src = net.convw + (size_t)net.layer_w[L] * (9 * kTapBytes);
+                for (int tap = 0; tap < 9; ++tap, ++n) {
+                    const int st = n % kStages;
+                    if (n >= kStages) mbar_wait(&bars->empty[st], ((n / kStages) - 1) & 1);
+                    mbar_expect_tx(&bars->full[st], kTapBytes);
+                    bulk_g2s(ring + st * kTapBytes, src + (size_t)tap * kTapBytes, kTapBytes, &bars->full[st]);
+                }
+            }
+        }
+    } else if (warp == 5) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            const uint32_t act_s = smem_u32(act), ring_s = smem_u32(ring), headw_s = smem_u32(headw);
+            const uint32_t idesc64 = make_idesc_f16(128, 64), idesc16 = make_idesc_f16(128, 16), idesc32 = make_idesc_f16(128, 32);
+            const bool sw = io.variant == 1;
+            const uint32_t a_lbo = sw ? 8 : (kPlaneBytes >> 4), a_sbo = sw ? (kPlaneBytes >> 4) : 8;
+            uint32_t n = 0;
+            for (int L = 0; L < nlayers; ++L) {
+                mbar_wait(&bars->act_ready, L & 1);              // inputs written, TMEM accumulators drained
+                tc_fence_after();
+                for (int tap = 0; tap < 9; ++tap, ++n) {
+                    const int st = n % kStages;
+                    mbar_wait(&bars->full[st], (n / kStages) & 1);
+                    tc_fence_after();
+                    const int shift = (tap / 3 - 1) * kPitch + (tap % 3 - 1);
+                    const uint32_t wbase = ring_s + st * kTapBytes;
+                    for (int t = 0; t < NT; ++t) {
+                        const uint32_t arow = act_s + (uint32_t)(kMargin + t * 128 + shift) * 16u;
+                        for (int ps = 0; ps < npass; ++ps) {
+                            const uint32_t apart = (ps == 2) ? kPartBytes : 0;          // (hi,hi) (hi,lo) (lo,hi)
+                            const uint32_t bpart = (ps == 1) ? (kTapBytes / 2) : 0;
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks) {
+                                const uint64_t ad = make_desc(arow + apart + ks * 2 * kPlaneBytes, a_lbo, a_sbo);
+                                const uint64_t bd = make_desc(wbase + bpart + ks * 2048, sw ? 8 : 64, sw ? 64 : 8);
+                                umma_f16(tmem + kColAcc + t * 64, ad, bd, idesc64, (tap | ps | ks) != 0);
+                            }
+                        }
+                    }
+                    umma_commit(&bars->empty[st]);               // frees this ring slot when the MMAs have read it
+                }
+                umma_commit(&bars->acc_ready);
+                const int flags = net.layer_flags[L];
+                if (flags & (LF_HOOK_REWARD | LF_HOOK_VALPOL)) {
+                    // 1x1 head convolutions on this layer's OUTPUT: wait for the epilogue to have written it (the same
+                    // phase the next layer waits for; waiting twice on a completed phase is immediate).  The
+                    // value/policy result reuses the drained conv accumulator columns, so that hook is only legal on
+                    // the LAST layer; the reward result has its own columns.
+                    mbar_wait(&bars->act_ready, (L + 1) & 1);
+                    tc_fence_after();
+                    for (int hook = 0; hook < 2; ++hook) {
+                        if (!(flags & (hook == 0 ? LF_HOOK_REWARD : LF_HOOK_VALPOL))) continue;
+                        for (int t = 0; t < NT; ++t) {
+                            const uint32_t arow = act_s + (uint32_t)(kMargin + t * 128) * 16u;
+                            for (int ps = 0; ps < npass; ++ps) {
+                                const uint32_t apart = (ps == 2) ? kPartBytes : 0;
+#pragma unroll
+                                for (int ks = 0; ks < 4; ++ks) {
+                                    const uint64_t ad = make_desc(arow + apart + ks * 2 * kPlaneBytes, a_lbo, a_sbo);
+                                    if (hook == 0) {   // reward head: N = 16, [kg][16 co][8]
+                                        const uint32_t wb = headw_s + ((ps == 1) ? 2048 : 0);
+                                        umma_f16(tmem + kColRew + t * 16, ad, make_desc(wb + ks * 512, sw ? 8 : 16, sw ? 16 : 8), idesc16, (ps | ks) != 0);
+                                    } else {           // value + policy heads as one N = 32 matrix, [kg][32 co][8]
+                                        const uint32_t wb = headw_s + 4096 + ((ps == 1) ? 4096 : 0);
+                                        umma_f16(tmem + kColAcc + t * 32, ad, make_desc(wb + ks * 1024, sw ? 8 : 32, sw ? 32 : 8), idesc32, (ps | ks) != 0);
+                                    }
+                                }
+                            }
+                        }
+                        umma_commit(hook == 0 ? &bars->rew_ready : &bars->vp_ready);
+                    }
+                }
+            }
+        }
+    } else {
+        // ================= epilogue warps (128 threads; thread tid owns TMEM lane tid) =================
+        const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+        // ---- load the input activation: gather NCHW latents, split to fp16 hi/lo, park fp32 copy in TMEM ----
+        for (int t = 0; t < NT; ++t) {
+            const int m = t * 128 + tid;
+            const int r = m / kRowsPerRoot, q = m - r * kRowsPerRoot, y = q / kPitch, x = q - y * kPitch;
+            const bool valid = (m < rows_used) && (r < nvalid) && (y < 6) && (x < 6);
+            const float *src = nullptr;
+            if (valid) {
+                const int b = root0 + r;
+                const size_t slot = io.ix ? (size_t)io.ix[b] : 0;
+                src = io.latent_base + slot * io.slot_stride + (size_t)b * (kC * kP) + (y * 6 + x);
+            }
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                float v[32];
+#pragma unroll
+                for (int c = 0; c < 32; ++c) v[c] = valid ? __ldg(src + (size_t)(half * 32 + c) * kP) : 0.0f;
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    unsigned char *p = act + (half * 4 + g) * kPlaneBytes + (kMargin + m) * 16;
+                    store_split8(p, p + kPartBytes, v + 8 * g);
+                }
+                tmem_st32(lane_base + kColRes + t * 64 + half * 32, v);
+            }
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        mbar_arrive(&bars->act_ready);                          // phase 0: layer 0 may start
+
+        int acc_par = 0;
+        for (int L = 0; L < nlayers; ++L) {
+            const int flags = net.layer_flags[L];
+            const float *bn = net.bn + (size_t)net.layer_w[L] * 128;      // [scale 64 | shift 64]
+            mbar_wait(&bars->acc_ready, acc_par);
+            acc_par ^= 1;
+            tc_fence_after();
+            for (int t = 0; t < NT; ++t) {
+                const int m = t * 128 + tid;
+                const int r = m / kRowsPerRoot, q = m - r * kRowsPerRoot, y = q / kPitch, x = q - y * kPitch;
+                const bool valid = (m < rows_used) && (r < nvalid) && (y < 6) && (x < 6);
+                const int b = root0 + r, p = y * 6 + x;
+                int action = 0;
+                if (valid && (flags & LF_ACT_BIAS)) action = min(max(io.action[b], 0), net.A - 1);
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    float v[32];
+                    tmem_ld32(lane_base + kColAcc + t * 64 + half * 32, v);
+                    if (flags & LF_RES) {
+                        float rs[32];
+                        tmem_ld32(lane_base + kColRes + t * 64 + half * 32, rs);
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) v[c] = fmaf(v[c], __ldg(bn + half * 32 + c), __ldg(bn + 64 + half * 32 + c)) + rs[c];
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) v[c] = fmaf(v[c], __ldg(bn + half * 32 + c), __ldg(bn + 64 + half * 32 + c));
+                    }
+                    if (flags & LF_ACT_BIAS) {
+                        if (valid) {
+                            const float *ab = net.abias + ((size_t)action * kC + half * 32) * kP + p;
+#pragma unroll
+                            for (int c = 0; c < 32; ++c) v[c] += __ldg(ab + (size_t)c * kP);
+                        }
+                    }
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) v[c] = valid ? fmaxf(v[c], 0.0f) : 0.0f;
+                    if (flags & LF_STORE_RES) tmem_st32(lane_base + kColRes + t * 64 + half * 32, v);
+                    if ((flags & LF_WRITE_LATENT) && valid) {
+                        if (io.latent_out) {
+                            float *dst = io.latent_out + (size_t)b * (kC * kP) + (size_t)(half * 32) * kP + p;
+#pragma unroll
+                            for (int c = 0; c < 32; ++c) dst[(size_t)c * kP] = v[c];
+                        }
+                        if (io.latent_out2) {
+                            float *dst = io.latent_out2 + (size_t)b * (kC * kP) + (size_t)(half * 32) * kP + p;
+#pragma unroll
+                            for (int c = 0; c < 32; ++c) dst[(size_t)c * kP] = v[c];
+                        }
+                    }
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        unsigned char *pp = act + (half * 4 + g) * kPlaneBytes + (kMargin + m) * 16;
+                        store_split8(pp, pp + kPartBytes, v + 8 * g);
+                    }
+                }
+            }
+            fence_proxy_async();
+            tc_fence_before();
+            mbar_arrive(&bars->act_ready);                      // phase L+1: next layer / this layer's hook may start
+        }
+        // all 1x1 head accumulators must be complete before the head stage reads them / reuses the buffer
+        if (net.has_reward) mbar_wait(&bars->rew_ready, 0);
+        mbar_wait(&bars->vp_ready, 0);
+        tc_fence_after();
+    }
+
+    // ================= heads: 1x1 accumulators -> BN/ReLU -> FC1 -> FC2 -> softmax expectation -> h^-1 =================
+    tc_fence_before();
+    __syncthreads();          // all MMAs committed & observed, activation buffer is free
+    tc_fence_after();
+    float *hflat = reinterpret_cast<float *>(act);                     // [3 heads][7 roots][576]
+    float *hidden = hflat + 3 * kMaxRoots * 576;                       // [3][7][32]
+    float *logits = hidden + 3 * kMaxRoots * 32;                       // [2][7][608] + [7][Apad]
+    const bool do_reward = net.has_reward;
+    if (warp < 4) {
+        const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+        for (int i = tid; i < 3 * kMaxRoots * 576; i += 128) hflat[i] = 0.0f;
+        asm volatile("bar.sync 1, 128;\n" ::: "memory");
+        for (int t = 0; t < NT; ++t) {
+            const int m = t * 128 + tid;
+            const int r = m / kRowsPerRoot, q = m - r * kRowsPerRoot, y = q / kPitch, x = q - y * kPitch;
+            const bool valid = (m < rows_used) && (r < nvalid) && (y < 6) && (x < 6);
+            const int p = y * 6 + x;
+            float v[16];
+            if (do_reward) {
+                tmem_ld16(lane_base + kColRew + t * 16, v);
+                if (valid)
+                    for (int c = 0; c < net.hc[0]; ++c)
+                        hflat[(0 * kMaxRoots + r) * 576 + c * kP + p] = fmaxf(fmaf(v[c], __ldg(net.head_bn + c), __ldg(net.head_bn + 16 + c)), 0.0f);
+            }
+            tmem_ld16(lane_base + kColAcc + t * 32, v);
+            if (valid)
+                for (int c = 0; c < net.hc[1]; ++c)
+                    hflat[(1 * kMaxRoots + r) * 576 + c * kP + p] = fmaxf(fmaf(v[c], __ldg(net.head_bn + 32 + c), __ldg(net.head_bn + 48 + c)), 0.0f);
+            tmem_ld16(lane_base + kColAcc + t * 32 + 16, v);
+            if (valid)
+                for (int c = 0; c < net.hc[2]; ++c)
+                    hflat[(2 * kMaxRoots + r) * 576 + c * kP + p] = fmaxf(fmaf(v[c], __ldg(net.head_bn + 64 + c), __ldg(net.head_bn + 80 + c)), 0.0f);
+        }
+        tc_fence_before();
+        asm volatile("bar.sync 1, 128;\n" ::: "memory");
+        const int A = net.A, Apad = (A + 31) & ~31;
+        float *lg_rew = logits, *lg_val = logits + kMaxRoots * 608, *lg_pol = logits + 2 * kMaxRoots * 608;
+        if (warp == 0) { if (do_reward) head_fc<kMaxRoots>(net.reward, hflat, 576, hidden, lg_rew, 608, lane); }
+        else if (warp == 1) head_fc<kMaxRoots>(net.value, hflat + kMaxRoots * 576, 576, hidden + kMaxRoots * 32, lg_val, 608, lane);
+        else if (warp == 2) head_fc<kMaxRoots>(net.policy, hflat + 2 * kMaxRoots * 576, 576, hidden + 2 * kMaxRoots * 32, lg_pol, Apad, lane);
+        asm volatile("bar.sync 1, 128;\n" ::: "memory");
+        for (int r = warp; r < nvalid; r += 4) {
+            const int b = root0 + r;
+            if (do_reward) {
+                float rv = categorical_to_scalar(lg_rew + r * 608, net.reward.K, net.support_min, net.support_step, lane);
+                if (lane == 0 && io.reward) io.reward[b] = rv;
+                if (io.reward_logits)
+                    for (int k = lane; k < net.reward.K; k += 32) io.reward_logits[(size_t)b * net.reward.K + k] = lg_rew[r * 608 + k];
+            }
+            float vv = categorical_to_scalar(lg_val + r * 608, net.value.K, net.support_min, net.support_step, lane);
+            if (lane == 0 && io.value) io.value[b] = vv;
+            if (io.value_logits)
+                for (int k = lane; k < net.value.K; k += 32) io.value_logits[(size_t)b * net.value.K + k] = lg_val[r * 608 + k];
+            if (io.policy_logits)
+                for (int a = lane; a < A; a += 32) io.policy_logits[(size_t)b * A + a] = lg_pol[r * Apad + a];
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5) {
+        __syncwarp();
+        tmem_dealloc(tmem, kTmemCols);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- host
+static void split_half(float v, float scale, __half &hi, __half &lo)
+{
+    float s = v * scale;
+    hi = __float2half_rn(s);
+    lo = __float2half_rn(s - __half2float(hi));
+}
+
+// One 3x3 conv -> 9 tap blocks of [hi | lo], each [kg = ci/8][co 64][ci % 8] fp16.  Returns the power-of-two
+// scale applied to the weights (exact), which the caller folds into the BatchNorm scale.
+float tc_pack_conv3(const float *w_torch /*[64][cin][3][3]*/, int cin_total, int cin_used, unsigned char *dst)
+{
+    float mx = 0.0f;
+    for (int co = 0; co < 64; ++co)
+        for (int ci = 0; ci < cin_used; ++ci)
+            for (int t = 0; t < 9; ++t) mx = std::max(mx, fabsf(w_torch[((size_t)co * cin_total + ci) * 9 + t]));
+    int e = 0;
+    if (mx > 0.0f) frexpf(mx, &e);               // mx = f * 2^e, f in [0.5, 1)
+    const float scale = ldexpf(1.0f, 13 - e);    // largest |w| lands in [4096, 8192)
+    __half *h = reinterpret_cast<__half *>(dst);
+    for (int t = 0; t < 9; ++t)
+        for (int co = 0; co < 64; ++co)
+            for (int ci = 0; ci < 64; ++ci) {
+                __half hi, lo;
+                split_half(w_torch[((size_t)co * cin_total + ci) * 9 + t], scale, hi, lo);
+                const size_t off = (size_t)t * (kTapBytes / 2) + ((size_t)(ci / 8) * 64 + co) * 8 + (ci % 8);
+                h[off] = hi;
+                h[off + kTapBytes / 4] = lo;      // lo block follows the 8 KB hi block (4096 halves)
+            }
+    return scale;
+}
+
+// 1x1 head conv [hc][64] -> [hi | lo] with nco rows (zero padded), [kg][co][8].
+float tc_pack_conv1(const float *w /*[hc][64]*/, int hc, int nco, int co_offset, unsigned char *dst_hi, unsigned char *dst_lo)
+{
+    float mx = 0.0f;
+    for (int i = 0; i < hc * 64; ++i) mx = std::max(mx, fabsf(w[i]));
+    int e = 0;
+    if (mx > 0.0f) frexpf(mx, &e);
+    const float scale = ldexpf(1.0f, 13 - e);
+    __half *hh = reinterpret_cast<__half *>(dst_hi), *hl = reinterpret_cast<__half *>(dst_lo);
+    for (int co = 0; co < hc; ++co)
+        for (int ci = 0; ci < 64; ++ci) {
+            __half hi, lo;
+            split_half(w[co * 64 + ci], scale, hi, lo);
+            const size_t off = ((size_t)(ci / 8) * nco + co + co_offset) * 8 + (ci % 8);
+            hh[off] = hi;
+            hl[off] = lo;
+        }
+    return scale;
+}
+
+int tc_head_layout_bytes() { return kHeadWBytes; }
+int tc_conv_layout_bytes() { return 9 * kTapBytes; }
+
+int tc_prepare_launch()
+{
+    LZ_CUDA_CHECK(cudaFuncSetAttribute(k_net_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    return LZ_OK;
+}
+
+int tc_pick_roots(int B)
+{
+    int r = (B + 147) / 148;
+    return std::min(std::max(r, 1), kMaxRoots);
+}
+
+int tc_launch(const TcNet &net, const TcIO &io_in, cudaStream_t s)
+{
+    TcIO io = io_in;
+    io.roots_per_cta = tc_pick_roots(io.B);
+    if (const char *e = getenv("LZ_TC_VARIANT")) io.variant = atoi(e);
+    if (const char *e = getenv("LZ_TC_ROOTS")) io.roots_per_cta = std::min(std::max(atoi(e), 1), kMaxRoots);
+    const int grid = (io.B + io.roots_per_cta - 1) / io.roots_per_cta;
+    k_net_tc<<<grid, kTcThreads, kSmemBytes, s>>>(net, io);
+    LZ_KERNEL_CHECK();
+    return LZ_OK;
+}
+
+}  // namespace lz

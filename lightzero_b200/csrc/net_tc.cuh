@@ -1,0 +1,51 @@
+// net_tc.cuh -- interface of the tcgen05 network path (net_tc.cu).
+#pragma once
+#include "lz_common.cuh"
+#include "net6.cuh"
+
+namespace lz {
+
+constexpr int kMaxResBlocksTc = 4;
+constexpr int kTcMaxLayers = 1 + 4 * kMaxResBlocksTc;
+
+struct TcNet {
+    const unsigned char *convw;    // [nconv][9 taps][hi 8 KB | lo 8 KB] fp16, K-major core-matrix layout
+    const float *bn;               // [nconv][scale 64 | shift 64] (weight power-of-two scale folded in)
+    const unsigned char *headw;    // [reward hi 2K | lo 2K][value+policy hi 4K | lo 4K]
+    const float *head_bn;          // [reward s16 t16 | value s16 t16 | policy s16 t16]
+    const float *abias;            // [A][64][36] action-plane contribution of the dynamics conv, x BN scale
+    Head reward, value, policy;    // FC parts (fp32, same tables as the SIMT path)
+    int hc[3];
+    int nlayers;
+    int layer_w[kTcMaxLayers];     // conv index into convw / bn
+    int layer_flags[kTcMaxLayers];
+    int has_reward;
+    int A;
+    float support_min, support_step;
+};
+
+struct TcIO {
+    int B;
+    int roots_per_cta;             // filled by tc_launch
+    int npass;                     // 3 = fp32-accurate (hi*hi + hi*lo + lo*hi), 1 = fast (hi*hi)
+    int variant;                   // debug (env LZ_TC_VARIANT): 1 swaps the LBO / SBO descriptor fields
+    const float *latent_base;      // input latents: base + ix[b]*slot_stride + b*2304 (NCHW [64][36])
+    const int *ix;                 // or nullptr
+    size_t slot_stride;
+    const int *action;             // [B] (recurrent) or nullptr
+    float *latent_out, *latent_out2;   // [B][64][36] or nullptr
+    float *reward, *value;         // [B] scalars
+    float *policy_logits;          // [B][A]
+    float *reward_logits, *value_logits;   // [B][K] or nullptr
+};
+
+enum : int { LF_RES = 1, LF_STORE_RES = 2, LF_WRITE_LATENT = 4, LF_ACT_BIAS = 8, LF_HOOK_REWARD = 16, LF_HOOK_VALPOL = 32 };
+
+float tc_pack_conv3(const float *w_torch, int cin_total, int cin_used, unsigned char *dst);
+float tc_pack_conv1(const float *w, int hc, int nco, int co_offset, unsigned char *dst_hi, unsigned char *dst_lo);
+int tc_head_layout_bytes();
+int tc_conv_layout_bytes();
+int tc_prepare_launch();
+int tc_launch(const TcNet &net, const TcIO &io, cudaStream_t s);
+
+}  // namespace lz
