@@ -120,6 +120,8 @@ int lz_model_set_math(lz_model *m, int mode);
 /* Test hook: overrides the layer program of the tcgen05 kernels (see net_tc.cuh LF_* flags). */
 int lz_model_debug_tc_program(lz_model *m, int which, int nlayers, const int *layer_w, const int *layer_flags,
                               int has_reward);
+/* Test hook: 64 clock64 stamps of CTA 0 of the last tcgen05 launch made with env LZ_TC_DEBUG=1. */
+int lz_debug_tc_stamps(unsigned long long *h_out);
 int lz_model_latent_hw(const lz_model *m);   /* 6 for 84/96, 8 for 64 */
 int lz_model_support_size(const lz_model *m);
 

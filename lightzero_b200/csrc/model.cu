@@ -652,7 +652,7 @@ int lz_model_create(const lz_model_config *cfg, lz_model **out)
     m->hw = kHW; m->P = kP; m->K = K;
     m->ws[0] = m->ws[1] = m->ws[2] = nullptr;
     m->ws_floats = 0; m->ws_B = 0;
-    m->math = 0; m->d_tc = nullptr;
+    m->math = 1; m->d_tc = nullptr;   // default: tcgen05 3xFP16 (fp32-accurate)
     *out = m;
     return LZ_OK;
 }
@@ -777,6 +777,14 @@ int lz_model_debug_tc_program(lz_model *m, int which, int nlayers, const int *la
     n.nlayers = nlayers;
     for (int i = 0; i < nlayers; ++i) { n.layer_w[i] = layer_w[i]; n.layer_flags[i] = layer_flags[i]; }
     n.has_reward = has_reward;
+    return LZ_OK;
+}
+
+/* debug: copies the 64 clock64 stamps of the last instrumented tcgen05 launch (env LZ_TC_DEBUG=1) to the host */
+int lz_debug_tc_stamps(unsigned long long *h_out)
+{
+    LZ_REQUIRE(h_out && tc_debug_buffer(), LZ_ESTATE, "lz_debug_tc_stamps: no instrumented launch yet");
+    LZ_CUDA_CHECK(cudaMemcpy(h_out, tc_debug_buffer(), 64 * 8, cudaMemcpyDeviceToHost));
     return LZ_OK;
 }
 

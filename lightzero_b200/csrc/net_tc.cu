@@ -22,9 +22,9 @@
 // accumulate in TMEM before the epilogue rewrites the buffer IN PLACE; the ResBlock skip tensor is parked
 // in spare TMEM columns (tcgen05.st) instead of a second shared-memory buffer.
 //
-// Warp roles (192 threads): warps 0-3 = epilogue / loads / heads (thread t owns TMEM lane t),
-// warp 4 lane 0 = weight producer (cp.async.bulk global->shared ring, mbarrier complete_tx),
-// warp 5 lane 0 = MMA issuer (+ TMEM alloc/dealloc by warp 5).
+// Warp roles (320 threads): warps 0-7 = epilogue / loads / heads (warp w owns TMEM lanes 32*(w%4).. and the
+// 32-column half w/4 of every accumulator), warp 8 lane 0 = weight producer (cp.async.bulk global->shared
+// ring, mbarrier complete_tx), warp 9 lane 0 = MMA issuer (+ TMEM alloc/dealloc by warp 9).
 #include <cuda_fp16.h>
 #include <math.h>
 #include <stdlib.h>
@@ -64,6 +64,25 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
     }
     printf("lz net_tc: mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x);
     asm volatile("trap;\n");
+}
+// Whole-warp wait: only lane 0 polls (with back-off) so that idle warps do not compete with the tensor
+// core's operand fetch for shared-memory bandwidth; the other lanes park at the warp barrier.
+__device__ __forceinline__ void mbar_wait_warp(uint64_t *bar, uint32_t parity)
+{
+    if ((threadIdx.x & 31) == 0) {
+        const uint32_t a = smem_u32(bar);
+        uint32_t ok = 0;
+        for (uint32_t it = 0; it < (1u << 26) && !ok; ++it) {
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                         : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+            if (!ok) __nanosleep(64);
+        }
+        if (!ok) {
+            printf("lz net_tc: mbarrier timeout (block %d warp %d)\n", blockIdx.x, threadIdx.x >> 5);
+            asm volatile("trap;\n");
+        }
+    }
+    __syncwarp();
 }
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
 {
@@ -152,7 +171,8 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo16, ui
 __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) { return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24); }
 
 // ---------------------------------------------------------------------------------------------- geometry
-constexpr int kTcThreads = 192;
+constexpr int kEpiWarps = 8, kEpiThreads = kEpiWarps * 32;   // two warps per TMEM lane quarter, one 32-column half each
+constexpr int kTcThreads = kEpiThreads + 64;
 constexpr int kPitch = 7, kRowsPerRoot = 49;     // padded 7x7 grid per root
 constexpr int kMaxRoots = 7, kMaxTiles = 3;      // 343 rows -> 3 tiles of 128
 constexpr int kMargin = 8;                       // |7*dy+dx| <= 8
@@ -220,7 +240,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_net_tc(TcNet net, TcIO io)
     if (tid == 0) {
         for (int i = 0; i < kStages; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], 1); }
         mbar_init(&bars->acc_ready, 1);
-        mbar_init(&bars->act_ready, 128);
+        mbar_init(&bars->act_ready, kEpiThreads);
         mbar_init(&bars->rew_ready, 1);
         mbar_init(&bars->vp_ready, 1);
         fence_mbar_init();
@@ -231,7 +251,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_net_tc(TcNet net, TcIO io)
         int row = r < kMargin ? r : kMargin + kMaxTiles * 128 + (r - kMargin);
         *reinterpret_cast<uint4 *>(act + part * kPartBytes + plane * kPlaneBytes + row * 16) = make_uint4(0, 0, 0, 0);
     }
-    if (warp == 5) tmem_alloc(&bars->tmem_base, kTmemCols);
+    if (warp == kEpiWarps + 1) tmem_alloc(&bars->tmem_base, kTmemCols);
     // 1x1 head weights: plain copy (12 KB)
     for (int i = tid; i < kHeadWBytes / 16; i += kTcThreads)
         reinterpret_cast<uint4 *>(headw)[i] = __ldg(reinterpret_cast<const uint4 *>(net.headw) + i);
@@ -241,7 +261,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_net_tc(TcNet net, TcIO io)
     tc_fence_after();
     const uint32_t tmem = bars->tmem_base;
 
-    if (warp == 4) {
+    if (warp == kEpiWarps) {
         // ================= weight producer =================
         if (lane == 0) {
             uint32_t n = 0;
@@ -255,39 +275,47 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_net_tc(TcNet net, TcIO io)
                 }
             }
         }
-    } else if (warp == 5) {
+    } else if (warp == kEpiWarps + 1) {
         // ================= MMA issuer =================
         if (lane == 0) {
             const uint32_t act_s = smem_u32(act), ring_s = smem_u32(ring), headw_s = smem_u32(headw);
             const uint32_t idesc64 = make_idesc_f16(128, 64), idesc16 = make_idesc_f16(128, 16), idesc32 = make_idesc_f16(128, 32);
-            const bool sw = io.variant == 1;
-            const uint32_t a_lbo = sw ? 8 : (kPlaneBytes >> 4), a_sbo = sw ? (kPlaneBytes >> 4) : 8;
+            const bool sw = false;
+            const uint32_t a_lbo = kPlaneBytes >> 4, a_sbo = 8;
+            const uint64_t a_desc0 = make_desc(act_s + kMargin * 16, a_lbo, a_sbo);   // row 0, hi part, k-step 0
+            const uint64_t b_desc0 = make_desc(ring_s, 64, 8);                        // stage 0, hi part, k-step 0
+            unsigned long long *dbg = (io.dbg && blockIdx.x == 0) ? io.dbg : nullptr;
             uint32_t n = 0;
             for (int L = 0; L < nlayers; ++L) {
                 mbar_wait(&bars->act_ready, L & 1);              // inputs written, TMEM accumulators drained
                 tc_fence_after();
+                if (dbg) dbg[32 + 2 * L] = clock64();
                 for (int tap = 0; tap < 9; ++tap, ++n) {
                     const int st = n % kStages;
                     mbar_wait(&bars->full[st], (n / kStages) & 1);
                     tc_fence_after();
                     const int shift = (tap / 3 - 1) * kPitch + (tap % 3 - 1);
-                    const uint32_t wbase = ring_s + st * kTapBytes;
+                    // descriptors differ only in the 14-bit start-address field: add 16-byte-unit offsets to a base
+                    const uint64_t b0 = b_desc0 + (uint64_t)((st * kTapBytes) >> 4);
                     for (int t = 0; t < NT; ++t) {
-                        const uint32_t arow = act_s + (uint32_t)(kMargin + t * 128 + shift) * 16u;
-                        for (int ps = 0; ps < npass; ++ps) {
-                            const uint32_t apart = (ps == 2) ? kPartBytes : 0;          // (hi,hi) (hi,lo) (lo,hi)
-                            const uint32_t bpart = (ps == 1) ? (kTapBytes / 2) : 0;
+                        const uint64_t a0 = a_desc0 + (uint64_t)(t * 128 + shift);
+                        const uint32_t d = tmem + kColAcc + t * 64;
 #pragma unroll
-                            for (int ks = 0; ks < 4; ++ks) {
-                                const uint64_t ad = make_desc(arow + apart + ks * 2 * kPlaneBytes, a_lbo, a_sbo);
-                                const uint64_t bd = make_desc(wbase + bpart + ks * 2048, sw ? 8 : 64, sw ? 64 : 8);
-                                umma_f16(tmem + kColAcc + t * 64, ad, bd, idesc64, (tap | ps | ks) != 0);
-                            }
+                        for (int ks = 0; ks < 4; ++ks)
+                            umma_f16(d, a0 + ks * (2 * kPlaneBytes >> 4), b0 + ks * (2048 >> 4), idesc64, (tap | ks) != 0);
+                        if (npass == 3) {
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks)      // A_hi * B_lo
+                                umma_f16(d, a0 + ks * (2 * kPlaneBytes >> 4), b0 + ((kTapBytes / 2) >> 4) + ks * (2048 >> 4), idesc64, 1);
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks)      // A_lo * B_hi
+                                umma_f16(d, a0 + (kPartBytes >> 4) + ks * (2 * kPlaneBytes >> 4), b0 + ks * (2048 >> 4), idesc64, 1);
                         }
                     }
                     umma_commit(&bars->empty[st]);               // frees this ring slot when the MMAs have read it
                 }
                 umma_commit(&bars->acc_ready);
+                if (dbg) dbg[33 + 2 * L] = clock64();
                 const int flags = net.layer_flags[L];
                 if (flags & (LF_HOOK_REWARD | LF_HOOK_VALPOL)) {
                     // 1x1 head convolutions on this layer's OUTPUT: wait for the epilogue to have written it (the same
@@ -321,11 +349,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_net_tc(TcNet net, TcIO io)
             }
         }
     } else {
-        // ================= epilogue warps (128 threads; thread tid owns TMEM lane tid) =================
-        const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+        // ================= epilogue warps: warp w owns TMEM lanes 32*(w%4).. and the 32-column half w/4 =================
+        const int q4 = warp & 3, half = warp >> 2, rowid = q4 * 32 + lane;
+        const uint32_t lane_base = tmem + ((uint32_t)(q4 * 32) << 16);
+        unsigned long long *dbg = (io.dbg && blockIdx.x == 0 && tid == 0) ? io.dbg : nullptr;
+        if (dbg) dbg[0] = clock64();
         // ---- load the input activation: gather NCHW latents, split to fp16 hi/lo, park fp32 copy in TMEM ----
         for (int t = 0; t < NT; ++t) {
-            const int m = t * 128 + tid;
+            const int m = t * 128 + rowid;
             const int r = m / kRowsPerRoot, q = m - r * kRowsPerRoot, y = q / kPitch, x = q - y * kPitch;
             const bool valid = (m < rows_used) && (r < nvalid) && (y < 6) && (x < 6);
             const float *src = nullptr;
@@ -334,87 +365,85 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_net_tc(TcNet net, TcIO io)
                 const size_t slot = io.ix ? (size_t)io.ix[b] : 0;
                 src = io.latent_base + slot * io.slot_stride + (size_t)b * (kC * kP) + (y * 6 + x);
             }
+            float v[32];
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                float v[32];
+            for (int c = 0; c < 32; ++c) v[c] = valid ? __ldg(src + (size_t)(half * 32 + c) * kP) : 0.0f;
 #pragma unroll
-                for (int c = 0; c < 32; ++c) v[c] = valid ? __ldg(src + (size_t)(half * 32 + c) * kP) : 0.0f;
-#pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    unsigned char *p = act + (half * 4 + g) * kPlaneBytes + (kMargin + m) * 16;
-                    store_split8(p, p + kPartBytes, v + 8 * g);
-                }
-                tmem_st32(lane_base + kColRes + t * 64 + half * 32, v);
+            for (int g = 0; g < 4; ++g) {
+                unsigned char *p = act + (half * 4 + g) * kPlaneBytes + (kMargin + m) * 16;
+                store_split8(p, p + kPartBytes, v + 8 * g);
             }
+            tmem_st32(lane_base + kColRes + t * 64 + half * 32, v);
         }
         fence_proxy_async();
         tc_fence_before();
         mbar_arrive(&bars->act_ready);                          // phase 0: layer 0 may start
+        if (dbg) dbg[1] = clock64();
 
         int acc_par = 0;
         for (int L = 0; L < nlayers; ++L) {
             const int flags = net.layer_flags[L];
             const float *bn = net.bn + (size_t)net.layer_w[L] * 128;      // [scale 64 | shift 64]
-            mbar_wait(&bars->acc_ready, acc_par);
+            mbar_wait_warp(&bars->acc_ready, acc_par);
             acc_par ^= 1;
             tc_fence_after();
+            if (dbg) dbg[2 + 2 * L] = clock64();
+            float bs[32], bt[32];                               // folded BatchNorm of this thread's 32 channels
+#pragma unroll
+            for (int c = 0; c < 32; ++c) { bs[c] = __ldg(bn + half * 32 + c); bt[c] = __ldg(bn + 64 + half * 32 + c); }
             for (int t = 0; t < NT; ++t) {
-                const int m = t * 128 + tid;
+                const int m = t * 128 + rowid;
                 const int r = m / kRowsPerRoot, q = m - r * kRowsPerRoot, y = q / kPitch, x = q - y * kPitch;
                 const bool valid = (m < rows_used) && (r < nvalid) && (y < 6) && (x < 6);
                 const int b = root0 + r, p = y * 6 + x;
-                int action = 0;
-                if (valid && (flags & LF_ACT_BIAS)) action = min(max(io.action[b], 0), net.A - 1);
+                float v[32];
+                tmem_ld32(lane_base + kColAcc + t * 64 + half * 32, v);
+                if (flags & LF_RES) {
+                    float rs[32];
+                    tmem_ld32(lane_base + kColRes + t * 64 + half * 32, rs);
 #pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    float v[32];
-                    tmem_ld32(lane_base + kColAcc + t * 64 + half * 32, v);
-                    if (flags & LF_RES) {
-                        float rs[32];
-                        tmem_ld32(lane_base + kColRes + t * 64 + half * 32, rs);
+                    for (int c = 0; c < 32; ++c) v[c] = fmaf(v[c], bs[c], bt[c]) + rs[c];
+                } else {
 #pragma unroll
-                        for (int c = 0; c < 32; ++c) v[c] = fmaf(v[c], __ldg(bn + half * 32 + c), __ldg(bn + 64 + half * 32 + c)) + rs[c];
-                    } else {
+                    for (int c = 0; c < 32; ++c) v[c] = fmaf(v[c], bs[c], bt[c]);
+                }
+                if ((flags & LF_ACT_BIAS) && valid) {
+                    const int action = min(max(io.action[b], 0), net.A - 1);
+                    const float *ab = net.abias + ((size_t)action * kC + half * 32) * kP + p;
 #pragma unroll
-                        for (int c = 0; c < 32; ++c) v[c] = fmaf(v[c], __ldg(bn + half * 32 + c), __ldg(bn + 64 + half * 32 + c));
+                    for (int c = 0; c < 32; ++c) v[c] += __ldg(ab + (size_t)c * kP);
+                }
+#pragma unroll
+                for (int c = 0; c < 32; ++c) v[c] = valid ? fmaxf(v[c], 0.0f) : 0.0f;
+                if (flags & LF_STORE_RES) tmem_st32(lane_base + kColRes + t * 64 + half * 32, v);
+                if ((flags & LF_WRITE_LATENT) && valid) {
+                    if (io.latent_out) {
+                        float *dst = io.latent_out + (size_t)b * (kC * kP) + (size_t)(half * 32) * kP + p;
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) dst[(size_t)c * kP] = v[c];
                     }
-                    if (flags & LF_ACT_BIAS) {
-                        if (valid) {
-                            const float *ab = net.abias + ((size_t)action * kC + half * 32) * kP + p;
+                    if (io.latent_out2) {
+                        float *dst = io.latent_out2 + (size_t)b * (kC * kP) + (size_t)(half * 32) * kP + p;
 #pragma unroll
-                            for (int c = 0; c < 32; ++c) v[c] += __ldg(ab + (size_t)c * kP);
-                        }
+                        for (int c = 0; c < 32; ++c) dst[(size_t)c * kP] = v[c];
                     }
+                }
 #pragma unroll
-                    for (int c = 0; c < 32; ++c) v[c] = valid ? fmaxf(v[c], 0.0f) : 0.0f;
-                    if (flags & LF_STORE_RES) tmem_st32(lane_base + kColRes + t * 64 + half * 32, v);
-                    if ((flags & LF_WRITE_LATENT) && valid) {
-                        if (io.latent_out) {
-                            float *dst = io.latent_out + (size_t)b * (kC * kP) + (size_t)(half * 32) * kP + p;
-#pragma unroll
-                            for (int c = 0; c < 32; ++c) dst[(size_t)c * kP] = v[c];
-                        }
-                        if (io.latent_out2) {
-                            float *dst = io.latent_out2 + (size_t)b * (kC * kP) + (size_t)(half * 32) * kP + p;
-#pragma unroll
-                            for (int c = 0; c < 32; ++c) dst[(size_t)c * kP] = v[c];
-                        }
-                    }
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        unsigned char *pp = act + (half * 4 + g) * kPlaneBytes + (kMargin + m) * 16;
-                        store_split8(pp, pp + kPartBytes, v + 8 * g);
-                    }
+                for (int g = 0; g < 4; ++g) {
+                    unsigned char *pp = act + (half * 4 + g) * kPlaneBytes + (kMargin + m) * 16;
+                    store_split8(pp, pp + kPartBytes, v + 8 * g);
                 }
             }
             fence_proxy_async();
             tc_fence_before();
             mbar_arrive(&bars->act_ready);                      // phase L+1: next layer / this layer's hook may start
+            if (dbg) dbg[3 + 2 * L] = clock64();
         }
         // all 1x1 head accumulators must be complete before the head stage reads them / reuses the buffer
-        if (net.has_reward) mbar_wait(&bars->rew_ready, 0);
-        mbar_wait(&bars->vp_ready, 0);
+        if (net.has_reward) mbar_wait_warp(&bars->rew_ready, 0);
+        mbar_wait_warp(&bars->vp_ready, 0);
         tc_fence_after();
+        if (dbg) dbg[24] = clock64();
     }
 
     // ================= heads: 1x1 accumulators -> BN/ReLU -> FC1 -> FC2 -> softmax expectation -> h^-1 =================
@@ -425,58 +454,129 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_net_tc(TcNet net, TcIO io)
     float *hidden = hflat + 3 * kMaxRoots * 576;                       // [3][7][32]
     float *logits = hidden + 3 * kMaxRoots * 32;                       // [2][7][608] + [7][Apad]
     const bool do_reward = net.has_reward;
-    if (warp < 4) {
-        const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
-        for (int i = tid; i < 3 * kMaxRoots * 576; i += 128) hflat[i] = 0.0f;
-        asm volatile("bar.sync 1, 128;\n" ::: "memory");
+    if (warp < kEpiWarps) {
+        const int q4 = warp & 3, half = warp >> 2, rowid = q4 * 32 + lane;
+        const uint32_t lane_base = tmem + ((uint32_t)(q4 * 32) << 16);
+        for (int i = tid; i < 3 * kMaxRoots * 576; i += kEpiThreads) hflat[i] = 0.0f;
+        asm volatile("bar.sync 1, %0;\n" ::"n"(kEpiThreads) : "memory");
         for (int t = 0; t < NT; ++t) {
-            const int m = t * 128 + tid;
+            const int m = t * 128 + rowid;
             const int r = m / kRowsPerRoot, q = m - r * kRowsPerRoot, y = q / kPitch, x = q - y * kPitch;
             const bool valid = (m < rows_used) && (r < nvalid) && (y < 6) && (x < 6);
             const int p = y * 6 + x;
             float v[16];
-            if (do_reward) {
-                tmem_ld16(lane_base + kColRew + t * 16, v);
+            if (half == 0) {                 // warps 0-3: reward + value features; warps 4-7: policy features
+                if (do_reward) {
+                    tmem_ld16(lane_base + kColRew + t * 16, v);
+                    if (valid)
+                        for (int c = 0; c < net.hc[0]; ++c)
+                            hflat[(0 * kMaxRoots + r) * 576 + c * kP + p] = fmaxf(fmaf(v[c], __ldg(net.head_bn + c), __ldg(net.head_bn + 16 + c)), 0.0f);
+                }
+                tmem_ld16(lane_base + kColAcc + t * 32, v);
                 if (valid)
-                    for (int c = 0; c < net.hc[0]; ++c)
-                        hflat[(0 * kMaxRoots + r) * 576 + c * kP + p] = fmaxf(fmaf(v[c], __ldg(net.head_bn + c), __ldg(net.head_bn + 16 + c)), 0.0f);
+                    for (int c = 0; c < net.hc[1]; ++c)
+                        hflat[(1 * kMaxRoots + r) * 576 + c * kP + p] = fmaxf(fmaf(v[c], __ldg(net.head_bn + 32 + c), __ldg(net.head_bn + 48 + c)), 0.0f);
+            } else {
+                tmem_ld16(lane_base + kColAcc + t * 32 + 16, v);
+                if (valid)
+                    for (int c = 0; c < net.hc[2]; ++c)
+                        hflat[(2 * kMaxRoots + r) * 576 + c * kP + p] = fmaxf(fmaf(v[c], __ldg(net.head_bn + 64 + c), __ldg(net.head_bn + 80 + c)), 0.0f);
             }
-            tmem_ld16(lane_base + kColAcc + t * 32, v);
-            if (valid)
-                for (int c = 0; c < net.hc[1]; ++c)
-                    hflat[(1 * kMaxRoots + r) * 576 + c * kP + p] = fmaxf(fmaf(v[c], __ldg(net.head_bn + 32 + c), __ldg(net.head_bn + 48 + c)), 0.0f);
-            tmem_ld16(lane_base + kColAcc + t * 32 + 16, v);
-            if (valid)
-                for (int c = 0; c < net.hc[2]; ++c)
-                    hflat[(2 * kMaxRoots + r) * 576 + c * kP + p] = fmaxf(fmaf(v[c], __ldg(net.head_bn + 64 + c), __ldg(net.head_bn + 80 + c)), 0.0f);
         }
         tc_fence_before();
-        asm volatile("bar.sync 1, 128;\n" ::: "memory");
+        asm volatile("bar.sync 1, %0;\n" ::"n"(kEpiThreads) : "memory");
+        if (io.dbg && blockIdx.x == 0 && tid == 0) io.dbg[25] = clock64();
         const int A = net.A, Apad = (A + 31) & ~31;
         float *lg_rew = logits, *lg_val = logits + kMaxRoots * 608, *lg_pol = logits + 2 * kMaxRoots * 608;
-        if (warp == 0) { if (do_reward) head_fc<kMaxRoots>(net.reward, hflat, 576, hidden, lg_rew, 608, lane); }
-        else if (warp == 1) head_fc<kMaxRoots>(net.value, hflat + kMaxRoots * 576, 576, hidden + kMaxRoots * 32, lg_val, 608, lane);
-        else if (warp == 2) head_fc<kMaxRoots>(net.policy, hflat + 2 * kMaxRoots * 576, 576, hidden + 2 * kMaxRoots * 32, lg_pol, Apad, lane);
-        asm volatile("bar.sync 1, 128;\n" ::: "memory");
-        for (int r = warp; r < nvalid; r += 4) {
+        float *part = lg_pol + kMaxRoots * Apad;                       // [kEpiWarps][3 heads][7 roots][32]
+        // ---- FC1 (576 -> 32, three heads, 7 roots): warp w takes a quarter of the 576 inputs, lane = hidden unit.
+        // Weight rows are 128-byte coalesced loads issued 8 at a time (the loop is L2-latency bound otherwise).
+        {
+            // all three heads have hc*36 <= 576 inputs; warp w takes inputs [72w, 72w+72), 24 weight rows in flight
+            constexpr int UB = 8;
+            for (int h = do_reward ? 0 : 1; h < 3; ++h) {
+                const Head &H = h == 0 ? net.reward : (h == 1 ? net.value : net.policy);
+                const int nin = H.hc * kP, qn = (nin + kEpiWarps - 1) / kEpiWarps, i0 = warp * qn, i1 = min(nin, i0 + qn);
+                float a[kMaxRoots];
+#pragma unroll
+                for (int r = 0; r < kMaxRoots; ++r) a[r] = 0.0f;
+                const float *hf = hflat + h * kMaxRoots * 576;
+                const float *wp = H.fc1 + lane;
+                const bool lane_on = lane < H.hid;
+                for (int i = i0; i < i1; i += 3 * UB) {
+                    float w[3 * UB];
+#pragma unroll
+                    for (int u = 0; u < 3 * UB; ++u) w[u] = (lane_on && i + u < i1) ? __ldg(wp + (size_t)(i + u) * H.hid) : 0.0f;
+#pragma unroll
+                    for (int u = 0; u < 3 * UB; ++u) {
+                        const int ii = min(i + u, nin - 1);
+#pragma unroll
+                        for (int r = 0; r < kMaxRoots; ++r) a[r] = fmaf(hf[r * 576 + ii], w[u], a[r]);
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < kMaxRoots; ++r) part[((warp * 3 + h) * kMaxRoots + r) * 32 + lane] = a[r];
+            }
+        }
+        asm volatile("bar.sync 1, %0;\n" ::"n"(kEpiThreads) : "memory");
+        for (int o = tid; o < 3 * kMaxRoots * 32; o += kEpiThreads) {
+            const int h = o / (kMaxRoots * 32), j = o & 31;
+            const Head &H = h == 0 ? net.reward : (h == 1 ? net.value : net.policy);
+            float v = 0.0f;
+#pragma unroll
+            for (int w8 = 0; w8 < kEpiWarps; ++w8) v += part[o + w8 * 3 * kMaxRoots * 32];
+            hidden[o] = (j < H.hid && (h > 0 || do_reward)) ? fmaxf(fmaf(v, __ldg(H.s2 + j), __ldg(H.t2 + j)), 0.0f) : 0.0f;
+        }
+        asm volatile("bar.sync 1, %0;\n" ::"n"(kEpiThreads) : "memory");
+        // ---- FC2 (32 -> K): thread = output k (strided by 128), weights [j][K] coalesced over k, 8 rows in flight
+        for (int h = do_reward ? 0 : 1; h < 3; ++h) {
+            const Head &H = h == 0 ? net.reward : (h == 1 ? net.value : net.policy);
+            float *lg = h == 0 ? lg_rew : (h == 1 ? lg_val : lg_pol);
+            const int ld = h == 2 ? Apad : 608;
+            const float *hid = hidden + h * kMaxRoots * 32;
+            for (int k = tid; k < H.K; k += kEpiThreads) {
+                float o[kMaxRoots];
+                const float bias = __ldg(H.b2 + k);
+#pragma unroll
+                for (int r = 0; r < kMaxRoots; ++r) o[r] = bias;
+                float w[32];
+#pragma unroll
+                for (int u = 0; u < 32; ++u) w[u] = (u < H.hid) ? __ldg(H.fc2 + (size_t)u * H.K + k) : 0.0f;
+#pragma unroll
+                for (int u = 0; u < 32; ++u) {
+#pragma unroll
+                    for (int r = 0; r < kMaxRoots; ++r) o[r] = fmaf(hid[r * 32 + u], w[u], o[r]);
+                }
+#pragma unroll
+                for (int r = 0; r < kMaxRoots; ++r) lg[r * ld + k] = o[r];
+            }
+        }
+        asm volatile("bar.sync 1, %0;\n" ::"n"(kEpiThreads) : "memory");
+        if (io.dbg && blockIdx.x == 0 && tid == 0) io.dbg[26] = clock64();
+        for (int task = warp; task < 2 * kMaxRoots; task += kEpiWarps) {
+            const int h = task / kMaxRoots, r = task - h * kMaxRoots;       // h: 0 reward, 1 value (+ policy copy)
+            if (r >= nvalid) continue;
             const int b = root0 + r;
-            if (do_reward) {
+            if (h == 0) {
+                if (!do_reward) continue;
                 float rv = categorical_to_scalar(lg_rew + r * 608, net.reward.K, net.support_min, net.support_step, lane);
                 if (lane == 0 && io.reward) io.reward[b] = rv;
                 if (io.reward_logits)
                     for (int k = lane; k < net.reward.K; k += 32) io.reward_logits[(size_t)b * net.reward.K + k] = lg_rew[r * 608 + k];
+            } else {
+                float vv = categorical_to_scalar(lg_val + r * 608, net.value.K, net.support_min, net.support_step, lane);
+                if (lane == 0 && io.value) io.value[b] = vv;
+                if (io.value_logits)
+                    for (int k = lane; k < net.value.K; k += 32) io.value_logits[(size_t)b * net.value.K + k] = lg_val[r * 608 + k];
+                if (io.policy_logits)
+                    for (int a = lane; a < A; a += 32) io.policy_logits[(size_t)b * A + a] = lg_pol[r * Apad + a];
             }
-            float vv = categorical_to_scalar(lg_val + r * 608, net.value.K, net.support_min, net.support_step, lane);
-            if (lane == 0 && io.value) io.value[b] = vv;
-            if (io.value_logits)
-                for (int k = lane; k < net.value.K; k += 32) io.value_logits[(size_t)b * net.value.K + k] = lg_val[r * 608 + k];
-            if (io.policy_logits)
-                for (int a = lane; a < A; a += 32) io.policy_logits[(size_t)b * A + a] = lg_pol[r * Apad + a];
         }
     }
+    if (io.dbg && blockIdx.x == 0 && tid == 0) io.dbg[27] = clock64();
     tc_fence_before();
     __syncthreads();
-    if (warp == 5) {
+    if (warp == kEpiWarps + 1) {
         __syncwarp();
         tmem_dealloc(tmem, kTmemCols);
     }
@@ -549,9 +649,16 @@ int tc_pick_roots(int B)
     return std::min(std::max(r, 1), kMaxRoots);
 }
 
+static unsigned long long *g_dbg = nullptr;
+unsigned long long *tc_debug_buffer() { return g_dbg; }
+
 int tc_launch(const TcNet &net, const TcIO &io_in, cudaStream_t s)
 {
     TcIO io = io_in;
+    if (getenv("LZ_TC_DEBUG")) {
+        if (!g_dbg) { cudaMalloc(&g_dbg, 64 * 8); cudaMemset(g_dbg, 0, 64 * 8); }
+        io.dbg = g_dbg;
+    }
     io.roots_per_cta = tc_pick_roots(io.B);
     if (const char *e = getenv("LZ_TC_VARIANT")) io.variant = atoi(e);
     if (const char *e = getenv("LZ_TC_ROOTS")) io.roots_per_cta = std::min(std::max(atoi(e), 1), kMaxRoots);

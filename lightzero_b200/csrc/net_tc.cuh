@@ -37,6 +37,7 @@ struct TcIO {
     float *reward, *value;         // [B] scalars
     float *policy_logits;          // [B][A]
     float *reward_logits, *value_logits;   // [B][K] or nullptr
+    unsigned long long *dbg;       // optional [64] clock64 stamps of CTA 0 (bring-up instrumentation)
 };
 
 enum : int { LF_RES = 1, LF_STORE_RES = 2, LF_WRITE_LATENT = 4, LF_ACT_BIAS = 8, LF_HOOK_REWARD = 16, LF_HOOK_VALPOL = 32 };
@@ -47,5 +48,6 @@ int tc_head_layout_bytes();
 int tc_conv_layout_bytes();
 int tc_prepare_launch();
 int tc_launch(const TcNet &net, const TcIO &io, cudaStream_t s);
+unsigned long long *tc_debug_buffer();   // device buffer [64] used when env LZ_TC_DEBUG=1
 
 }  // namespace lz

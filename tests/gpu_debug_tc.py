@@ -45,7 +45,7 @@ def main():
         exp_l0 = torch.relu(dyn.norm_common(dyn.conv(x0)) + latent)
         rb = dyn.resblocks[0]
         exp_c1 = rb.conv1(latent)          # relu(bn(conv(x)))
-    for variant in (0, 1):
+    for variant in (0,):
         os.environ["LZ_TC_VARIANT"] = str(variant)
         print(f"==== descriptor variant {variant} ====")
         cu.set_math("tc3")
@@ -106,5 +106,38 @@ def main():
         print(f"recurrent_inference B=1024 math={mode}: {a.elapsed_time(b) / 20 * 1e3:.1f} us per call (incl. logits outputs + torch allocs)")
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and not os.environ.get("DBG_PHASES"):
     main()
+
+
+def phase_breakdown():
+    """clock64 stamps of CTA 0 (env LZ_TC_DEBUG=1): where does a tcgen05 launch spend its cycles?"""
+    os.environ["LZ_TC_DEBUG"] = "1"
+    A = 6
+    torch.manual_seed(0)
+    ref = emulate_trained_(MuZeroModelRef((4, 84, 84), A), 0)
+    cu = lzb.MuZeroModel(observation_shape=(4, 84, 84), action_space_size=A).load_state_dict(ref.state_dict())
+    lib = cabi.load()
+    lat = torch.rand(1024, 64, 6, 6).cuda()
+    act = torch.randint(0, A, (1024,)).cuda()
+    for mode in ("tc3", "tc1"):
+        cu.set_math(mode)
+        for _ in range(3):
+            cu.recurrent_inference(lat, act)
+        torch.cuda.synchronize()
+        buf = (ctypes.c_ulonglong * 64)()
+        cabi.check(lib.lz_debug_tc_stamps(buf), "stamps")
+        s = list(buf)
+        t0 = s[0]
+        print(f"== phase breakdown, math={mode} (cycles since epilogue start)")
+        print(f"   load done            {s[1] - t0:8d}")
+        for L in range(5):
+            print(f"   L{L}: mma issue {s[32 + 2 * L] - t0:8d} -> {s[33 + 2 * L] - t0:8d} | acc ready {s[2 + 2 * L] - t0:8d}  epilogue done {s[3 + 2 * L] - t0:8d}")
+        print(f"   hooks ready          {s[24] - t0:8d}")
+        print(f"   hflat written        {s[25] - t0:8d}")
+        print(f"   fc done              {s[26] - t0:8d}")
+        print(f"   outputs done         {s[27] - t0:8d}")
+
+
+if __name__ == "__main__" and os.environ.get("DBG_PHASES"):
+    phase_breakdown()

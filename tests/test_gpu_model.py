@@ -108,3 +108,57 @@ def test_model_rejects_unsupported_configs():
     m = lzb.MuZeroModel()
     with pytest.raises(RuntimeError):
         m.initial_inference(torch.zeros(1, 4, 84, 84).cuda())
+
+
+# ------------------------------------------------------------------ tcgen05 path (lz_model_set_math)
+@pytest.mark.parametrize("B,A", [(7, 6), (50, 18), (1000, 6), (1024, 18)])
+def test_tensor_core_3xfp16_recurrent_matches_oracle(B, A):
+    """math='tc3': tcgen05 MMAs on fp16 hi/lo splits (3 passes), fp32 accumulation in TMEM -- must meet the
+    same 1e-5 bar as the fp32 FFMA path."""
+    ref, cu = _models(A, seed=4)
+    cu.set_math("tc3")
+    g = torch.Generator().manual_seed(B)
+    latent = torch.rand(B, 64, 6, 6, generator=g) * 2.0
+    action = torch.randint(0, A, (B,), generator=g)
+    with torch.no_grad():
+        exp = ref.recurrent_inference(latent, action)
+    out = cu.recurrent_inference(latent.cuda(), action.cuda(), return_scalars=True)
+    assert torch.allclose(out.latent_state.cpu(), exp.latent_state, **TOL)
+    assert torch.allclose(out.reward.cpu(), exp.reward, **TOL)
+    assert torch.allclose(out.value.cpu(), exp.value, **TOL)
+    assert torch.allclose(out.policy_logits.cpu(), exp.policy_logits, **TOL)
+    from oracle.model_ref import DiscreteSupport, InverseScalarTransform
+    inv = InverseScalarTransform(DiscreteSupport(-300., 301., 1.))
+    assert torch.allclose(out.value_scalar.cpu(), inv(exp.value).reshape(-1), rtol=2e-4, atol=2e-4)
+    assert torch.allclose(out.reward_scalar.cpu(), inv(exp.reward).reshape(-1), rtol=2e-4, atol=2e-4)
+
+
+@pytest.mark.parametrize("B,A,nres", [(5, 6, 1), (300, 18, 1), (9, 6, 2)])
+def test_tensor_core_3xfp16_initial_matches_oracle(B, A, nres):
+    ref, cu = _models(A, seed=5, nres=nres)
+    cu.set_math("tc3")
+    obs = torch.rand(B, 4, 84, 84)
+    with torch.no_grad():
+        exp = ref.initial_inference(obs)
+        exp2 = ref.recurrent_inference(exp.latent_state, torch.arange(B) % A)
+    out = cu.initial_inference(obs.cuda())
+    assert torch.allclose(out.latent_state.cpu(), exp.latent_state, **TOL)
+    assert torch.allclose(out.policy_logits.cpu(), exp.policy_logits, **TOL)
+    assert torch.allclose(out.value.cpu(), exp.value, **TOL)
+    out2 = cu.recurrent_inference(exp.latent_state.cuda(), (torch.arange(B) % A).cuda())
+    assert torch.allclose(out2.latent_state.cpu(), exp2.latent_state, **TOL)
+    assert torch.allclose(out2.reward.cpu(), exp2.reward, **TOL)
+
+
+def test_tensor_core_single_pass_is_close():
+    """math='tc1' (one fp16 pass): not the parity mode; logits within 1e-3 of fp32."""
+    ref, cu = _models(6, seed=6)
+    cu.set_math("tc1")
+    latent = torch.rand(64, 64, 6, 6) * 2.0
+    action = torch.randint(0, 6, (64,))
+    with torch.no_grad():
+        exp = ref.recurrent_inference(latent, action)
+    out = cu.recurrent_inference(latent.cuda(), action.cuda())
+    assert torch.allclose(out.latent_state.cpu(), exp.latent_state, rtol=5e-3, atol=5e-3)
+    assert torch.allclose(out.value.cpu(), exp.value, rtol=1e-3, atol=1e-3)
+    assert torch.allclose(out.policy_logits.cpu(), exp.policy_logits, rtol=1e-3, atol=1e-3)

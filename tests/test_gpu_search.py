@@ -6,12 +6,14 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def _setup(B, A, S, seed=0, masks=False):
+def _setup(B, A, S, seed=0, masks=False, math=None):
     import lightzero_b200 as lzb
     from oracle.model_ref import MuZeroModelRef, emulate_trained_
     torch.manual_seed(seed)
     ref = emulate_trained_(MuZeroModelRef((4, 84, 84), A), seed)
     cu = lzb.MuZeroModel(observation_shape=(4, 84, 84), action_space_size=A).load_state_dict(ref.state_dict())
+    if math is not None:
+        cu.set_math(math)
     rng = np.random.default_rng(seed)
     obs = torch.rand(B, 4, 84, 84)
     mask = np.ones((B, A), np.uint8)
@@ -39,11 +41,12 @@ class _Recorder:
         return out
 
 
+@pytest.mark.parametrize("math", ["fp32", "tc3"])
 @pytest.mark.parametrize("B,A,S,masks", [(16, 6, 20, False), (300, 18, 50, True), (1024, 6, 50, False)])
-def test_fused_graph_search_equals_stepwise_search(B, A, S, masks):
+def test_fused_graph_search_equals_stepwise_search(B, A, S, masks, math):
     """The single-graph search and the one-simulation-at-a-time drive of the same kernels must agree
     exactly: visit counts, root values (bits), and repeated graph launches must be reproducible."""
-    ref, cu, obs, mask, legal, noises, mcts = _setup(B, A, S, masks=masks)
+    ref, cu, obs, mask, legal, noises, mcts = _setup(B, A, S, masks=masks, math=math)
     out = cu.initial_inference(obs.cuda())
     results = []
     for mode in ("fused", "fused", "step"):
@@ -74,14 +77,15 @@ def test_search_accepts_numpy_latents_and_host_lists():
     assert len(a) == B and all(len(d) == A for d in a) and isinstance(roots.get_values()[0], float)
 
 
+@pytest.mark.parametrize("math", ["fp32", "tc3"])
 @pytest.mark.parametrize("B,A,S,masks", [(64, 6, 25, False), (96, 18, 50, True)])
-def test_end_to_end_against_reference_pipeline(B, A, S, masks):
+def test_end_to_end_against_reference_pipeline(B, A, S, masks, math):
     """Whole path vs the oracle pipeline (PyTorch-CPU fp32 model + reference ctree, deterministic).
     Network outputs agree to ~1e-6, but PUCT is discontinuous (a flipped arg-max changes every later
     simulation of that root), so identity of visit counts is asserted per root for the large majority
     and the trees that do match must have root values within 1e-5."""
     from oracle.search_ref import SearchRef, collect_step_ref, load_tree_module
-    ref, cu, obs, mask, legal, noises, mcts = _setup(B, A, S, seed=3, masks=masks)
+    ref, cu, obs, mask, legal, noises, mcts = _setup(B, A, S, seed=3, masks=masks, math=math)
     tree, kind = load_tree_module()
     sref = SearchRef(tree, num_simulations=S)
     exp = collect_step_ref(sref, ref, obs, mask, [-1] * B, noises=noises)
