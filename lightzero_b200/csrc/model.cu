@@ -11,6 +11,7 @@
 #include <algorithm>
 
 #include "model.cuh"
+#include "tc_ptx.cuh"
 
 namespace lz {
 
@@ -180,7 +181,7 @@ static inline size_t fused_smem_bytes(int W)
 template <int S>
 __global__ void __launch_bounds__(128)
 k_conv3x3_generic(ConvG L, const float *__restrict__ in, float *__restrict__ out, const float *__restrict__ res,
-                  int relu, int cic, int nrows_max)
+                  int relu, int cic, int nrows_max, Tcl tcl)
 {
     extern __shared__ __align__(16) float sm[];
     const int pitch = L.win + 2;
@@ -234,7 +235,21 @@ k_conv3x3_generic(ConvG L, const float *__restrict__ in, float *__restrict__ out
         }
         __syncthreads();
     }
-    if (valid) {
+    if (valid && tcl.base) {
+        // write the tensor-core layout of conv_tc.cuh (fp16 hi/lo, k-group planes over the padded grid)
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            v[j] = fmaf(acc[j], __ldg(L.scale + co0 + j), __ldg(L.shift + co0 + j));
+            if (relu) v[j] = fmaxf(v[j], 0.0f);
+        }
+        const int rho = (y + 1) * tcl.pitch + x;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            unsigned char *op = tcl.base + (size_t)b * tcl.img_stride + ((size_t)(co0 / 8 + g) * tcl.plane_rows + rho + 1) * 16;
+            store_split8(op, op + tcl.part_stride, v + 8 * g);
+        }
+    } else if (valid) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
             const size_t o = (((size_t)b * L.cout + co0 + j) * L.hout + y) * L.wout + x;
@@ -348,8 +363,12 @@ int model_recurrent(lz_model *m, const RecIO &io, cudaStream_t s)
     }
 }
 
-static int launch_convg(const ConvG &L, const float *in, float *out, const float *res, int relu, int B, cudaStream_t s)
+static int launch_convg(const ConvG &L, const float *in, float *out, const float *res, int relu, int B, cudaStream_t s,
+                        const Tcl *tcl = nullptr)
 {
+    Tcl t;
+    memset(&t, 0, sizeof(t));
+    if (tcl) t = *tcl;
     const int cic = std::min(8, L.cin);
     const int rows_out_max = std::min(L.hout, 127 / L.wout + 2);
     const int nrows_max = (rows_out_max - 1) * L.stride + 3;
@@ -357,8 +376,8 @@ static int launch_convg(const ConvG &L, const float *in, float *out, const float
     const size_t smem = ((((size_t)cic * nrows_max * pitch + 3) & ~(size_t)3) + (size_t)cic * 288) * sizeof(float);
     dim3 grid(ceil_div(L.hout * L.wout, 128), L.cout / 32, B);
     LZ_REQUIRE(smem <= 200 * 1024, LZ_EINVAL, "conv tower stage needs %zu B shared memory", smem);
-    if (L.stride == 1) k_conv3x3_generic<1><<<grid, 128, smem, s>>>(L, in, out, res, relu, cic, nrows_max);
-    else k_conv3x3_generic<2><<<grid, 128, smem, s>>>(L, in, out, res, relu, cic, nrows_max);
+    if (L.stride == 1) k_conv3x3_generic<1><<<grid, 128, smem, s>>>(L, in, out, res, relu, cic, nrows_max, t);
+    else k_conv3x3_generic<2><<<grid, 128, smem, s>>>(L, in, out, res, relu, cic, nrows_max, t);
     LZ_KERNEL_CHECK();
     return LZ_OK;
 }
@@ -386,7 +405,78 @@ int model_reserve(lz_model *m, int B)
     }
     m->ws_floats = per_root * B;
     m->ws_B = B;
+    // TCL activation workspace of the tcgen05 tower (zeroed once: pad rows / columns are never written non-zero)
+    {
+        const int h1 = m->tower[0].hout, h2 = m->tower[3].hout, h3 = (h2 - 1) / 2 + 1, c2 = kC / 2;
+        const size_t bT = tcl_bytes(B, c2, h1, h1, 1), bT2 = tcl_bytes(B, c2, h1 / 2, h1 / 2, 4);
+        const size_t bU = tcl_bytes(B, kC, h2, h2, 1), bV = tcl_bytes(B, kC, h3, h3, 1);
+        const size_t total = 2 * bT + bT2 + 3 * bU + 3 * bV;
+        if (m->tws) cudaFree(m->tws);
+        m->tws = nullptr;
+        int rc = dev_alloc(&m->tws, total);
+        if (rc != LZ_OK) return rc;
+        LZ_CUDA_CHECK(cudaMemset(m->tws, 0, total));
+        m->tws_bytes = total;
+        unsigned char *q = m->tws;
+        m->T0 = make_tcl(q, c2, h1, h1, 1); q += bT;
+        m->T1 = make_tcl(q, c2, h1, h1, 1); q += bT;
+        m->T2 = make_tcl(q, c2, h1 / 2, h1 / 2, 4); q += bT2;
+        m->U0 = make_tcl(q, kC, h2, h2, 1); q += bU;
+        m->U1 = make_tcl(q, kC, h2, h2, 1); q += bU;
+        m->U2 = make_tcl(q, kC, h2, h2, 1); q += bU;
+        m->V0 = make_tcl(q, kC, h3, h3, 1); q += bV;
+        m->V1 = make_tcl(q, kC, h3, h3, 1); q += bV;
+        m->V2 = make_tcl(q, kC, h3, h3, 1); q += bV;
+    }
     return LZ_OK;
+}
+
+// ---- tcgen05 tower ---------------------------------------------------------------------------
+// picks the band height (and, for whole small images, the images per CTA) that fits shared memory / TMEM
+// and wastes the fewest MMA rows
+static void pick_band(ConvTc &p)
+{
+    const int H = p.in.H, pitch = p.in.pitch, kg = p.in.C / 8;
+    double best = -1.0;
+    int best_h = 1, best_g = 1;
+    for (int G = 1; G <= 4; ++G)
+        for (int bh = (G > 1 ? H : 1); bh <= H; ++bh) {
+            const int rin = (bh + 2) * pitch + 2, mcount = (G - 1) * rin + bh * pitch, NT = (mcount + 127) / 128;
+            int PR = pitch + 1 + NT * 128 + pitch + 2;
+            if (PR < G * rin) PR = G * rin;
+            const size_t smem = (((size_t)PR * 16 * kg * 2 * p.in.nphase + 127) & ~(size_t)127) + 4 * (size_t)2 * kg * p.N * 16 + 1024;
+            if (smem > 227 * 1024 || NT * p.N > 512) continue;
+            const int nb = (H + bh - 1) / bh;
+            const double eff = (double)(G * H * (pitch - 1)) / ((double)nb * NT * 128);
+            if (eff > best + 1e-9) { best = eff; best_h = bh; best_g = G; }
+        }
+    p.band_h = best_h;
+    p.G = best_g;
+}
+
+static int tower_tc_run(lz_model *m, int B, const float *d_obs, float *pre_latent, cudaStream_t s)
+{
+    int rc;
+    const int npass = (m->math == 1) ? 3 : 1;
+    // stem: conv1 (Cin = 4/12, stride 2) on the CUDA cores, written straight into TCL
+    if ((rc = launch_convg(m->tower[0], d_obs, nullptr, nullptr, 1, B, s, &m->T0))) return rc;
+    auto run = [&](ConvTc p, const Tcl &in, const Tcl &o0, const Tcl *o1, const Tcl *res) {
+        p.in = in; p.out[0] = o0;
+        if (o1) p.out[1] = *o1;
+        if (res) p.res = *res; else p.res.base = nullptr;
+        p.B = B; p.npass = npass;
+        return conv_tc_launch(p, s);
+    };
+    if ((rc = run(m->tower_tc[0], m->T0, m->T1, nullptr, nullptr))) return rc;        // resblocks1.0.conv1
+    if ((rc = run(m->tower_tc[1], m->T1, m->T2, nullptr, &m->T0))) return rc;         // resblocks1.0.conv2 (+x) -> phase-split
+    if ((rc = run(m->tower_tc[2], m->T2, m->U0, &m->U1, nullptr))) return rc;         // downsample conv1 | conv3 (stride 2)
+    if ((rc = run(m->tower_tc[3], m->U0, m->U2, nullptr, &m->U1))) return rc;         // downsample conv2 + identity
+    if ((rc = run(m->tower_tc[4], m->U2, m->U0, nullptr, nullptr))) return rc;        // resblocks2.0.conv1
+    if ((rc = run(m->tower_tc[5], m->U0, m->U1, nullptr, &m->U2))) return rc;         // resblocks2.0.conv2 (+x)
+    if ((rc = pool_tcl_launch(m->U1, m->V0, B, s))) return rc;                        // pooling1
+    if ((rc = run(m->tower_tc_rb3[0], m->V0, m->V1, nullptr, nullptr))) return rc;    // resblocks3.0.conv1
+    if ((rc = run(m->tower_tc_rb3[1], m->V1, m->V2, nullptr, &m->V0))) return rc;     // resblocks3.0.conv2 (+x)
+    return pool_tcl_to_nchw_launch(m->V2, pre_latent, B, kHW, s);                    // pooling2 -> [B][64][6][6]
 }
 
 int model_initial(lz_model *m, int B, const float *d_obs, const TailIO &io_in, cudaStream_t s)
@@ -395,6 +485,16 @@ int model_initial(lz_model *m, int B, const float *d_obs, const TailIO &io_in, c
     float *a = m->ws[0], *b = m->ws[1], *c = m->ws[2];
     const std::vector<ConvG> &T = m->tower;
     int rc;
+    if (m->math != 0 && m->cfg.obs_h != 64 && !getenv("LZ_TOWER_SIMT")) {
+        if ((rc = tower_tc_run(m, B, d_obs, a, s))) return rc;
+        TailIO io = io_in;
+        TcIO t;
+        memset(&t, 0, sizeof(t));
+        t.B = B; t.npass = (m->math == 1) ? 3 : 1;
+        t.latent_base = a; t.latent_out = io.latent; t.latent_out2 = io.latent2;
+        t.value = io.value; t.policy_logits = io.policy_logits; t.value_logits = io.value_logits;
+        return tc_launch(m->tc_tail, t, s);
+    }
     // DownSample.forward, common.py:340-366
     if ((rc = launch_convg(T[0], d_obs, a, nullptr, 1, B, s))) return rc;          // conv1 + norm1 + relu
     if ((rc = launch_convg(T[1], a, b, nullptr, 1, B, s))) return rc;              // resblocks1.0
@@ -514,6 +614,88 @@ static bool pack_head(lz_model *m, Packer &P, const std::string &conv, const std
     o.s2 = P.add(s2); o.t2 = P.add(t2); o.fc2 = P.add(fc2); o.b2 = P.add(*B3);
     o.hc = hc; o.hid = hid; o.K = K;
     return true;
+}
+
+// ---- tcgen05 tower tables (conv_tc.cu) ----
+static int pack_tower_tc(lz_model *m)
+{
+    const std::string R = "representation_network.downsample_net.";
+    const int c2 = kC / 2;
+    const int h1 = m->tower[0].hout, h2 = m->tower[3].hout, h3 = (h2 - 1) / 2 + 1;
+    struct Item { std::string w, bn; int cin, cout; };
+    // layer table: 0 rb1.c1, 1 rb1.c2, 2 ds.c1 | ds.c3 (merged N=128), 3 ds.c2, 4 rb2.c1, 5 rb2.c2, 6 rb3.c1, 7 rb3.c2
+    const Item items[9] = {
+        {R + "resblocks1.0.conv1.0.weight", R + "resblocks1.0.conv1.1", c2, c2},
+        {R + "resblocks1.0.conv2.0.weight", R + "resblocks1.0.conv2.1", c2, c2},
+        {R + "downsample_block.conv1.0.weight", R + "downsample_block.conv1.1", c2, kC},
+        {R + "downsample_block.conv3.0.weight", "", c2, kC},
+        {R + "downsample_block.conv2.0.weight", R + "downsample_block.conv2.1", kC, kC},
+        {R + "resblocks2.0.conv1.0.weight", R + "resblocks2.0.conv1.1", kC, kC},
+        {R + "resblocks2.0.conv2.0.weight", R + "resblocks2.0.conv2.1", kC, kC},
+        {R + "resblocks3.0.conv1.0.weight", R + "resblocks3.0.conv1.1", kC, kC},
+        {R + "resblocks3.0.conv2.0.weight", R + "resblocks3.0.conv2.1", kC, kC},
+    };
+    // (layer index, item indices, N)
+    struct Lay { int it0, it1, cin, N; };
+    const Lay lays[8] = {{0, -1, c2, c2}, {1, -1, c2, c2}, {2, 3, c2, 2 * kC}, {4, -1, kC, kC},
+                         {5, -1, kC, kC}, {6, -1, kC, kC}, {7, -1, kC, kC}, {8, -1, kC, kC}};
+    size_t wbytes = 0;
+    for (const Lay &l : lays) wbytes += conv_tc_packed_bytes(l.cin, l.N);
+    size_t tab_off = (wbytes + 255) & ~(size_t)255;
+    std::vector<unsigned char> host(tab_off + 8 * 2 * 128 * sizeof(float), 0);
+    float *tab = reinterpret_cast<float *>(host.data() + tab_off);
+    size_t woff[8], off = 0;
+    for (int li = 0; li < 8; ++li) {
+        const Lay &l = lays[li];
+        woff[li] = off;
+        float *scale = tab + li * 256, *shift = scale + 128;
+        for (int part = 0; part < 2; ++part) {
+            const int it = part == 0 ? l.it0 : l.it1;
+            if (it < 0) continue;
+            const Item &I = items[it];
+            auto w = find(m, I.w, (size_t)I.cout * I.cin * 9);
+            if (!w) return LZ_EINVAL;
+            std::vector<float> sc(I.cout, 1.0f), sh(I.cout, 0.0f);
+            if (!I.bn.empty() && !fold_bn(m, I.bn, I.cout, sc, sh)) return LZ_EINVAL;
+            const int col0 = part * kC;
+            const float ws = conv_tc_pack(w->data(), I.cin, I.cout, l.N, col0, host.data() + off);
+            for (int k = 0; k < I.cout; ++k) { scale[col0 + k] = sc[k] / ws; shift[col0 + k] = sh[k]; }
+        }
+        off += conv_tc_packed_bytes(l.cin, l.N);
+    }
+    if (m->d_tower) cudaFree(m->d_tower);
+    m->d_tower = nullptr;
+    int rc = dev_alloc(&m->d_tower, host.size());
+    if (rc != LZ_OK) return rc;
+    LZ_CUDA_CHECK(cudaMemcpy(m->d_tower, host.data(), host.size(), cudaMemcpyHostToDevice));
+    const float *dtab = reinterpret_cast<const float *>(m->d_tower + tab_off);
+    auto base = [&](int li, int N, int H, int nphase_in, int C_in) {
+        ConvTc p;
+        memset(&p, 0, sizeof(p));
+        p.w = m->d_tower + woff[li];
+        p.scale = dtab + li * 256; p.shift = p.scale + 128;
+        p.N = N; p.relu[0] = 1; p.relu[1] = 0;
+        p.in = make_tcl(nullptr, C_in, H, H, nphase_in);
+        for (int t = 0; t < 9; ++t) {
+            const int ky = t / 3, kx = t % 3;
+            if (nphase_in == 1) { p.tap_phase[t] = 0; p.tap_shift[t] = (ky - 1) * p.in.pitch + (kx - 1); }
+            else {   // stride 2 on the 4-phase input: row 2y+ky-1 -> phase (ky+1)&1, offset -(ky==0)
+                p.tap_phase[t] = (((ky + 1) & 1) * 2) + ((kx + 1) & 1);
+                p.tap_shift[t] = (ky == 0 ? -p.in.pitch : 0) + (kx == 0 ? -1 : 0);
+            }
+        }
+        pick_band(p);
+        return p;
+    };
+    m->tower_tc[0] = base(0, c2, h1, 1, c2);
+    m->tower_tc[1] = base(1, c2, h1, 1, c2);
+    m->tower_tc[2] = base(2, 2 * kC, h2, 4, c2);
+    m->tower_tc[3] = base(3, kC, h2, 1, kC);
+    m->tower_tc[4] = base(4, kC, h2, 1, kC);
+    m->tower_tc[5] = base(5, kC, h2, 1, kC);
+    m->tower_tc_rb3[0] = base(6, kC, h3, 1, kC);
+    m->tower_tc_rb3[1] = base(7, kC, h3, 1, kC);
+    return conv_tc_prepare_launch();
 }
 
 // ---- tcgen05 tables (net_tc.cu): fp16 hi/lo weights, folded BN, action-bias planes, layer programs ----
@@ -653,6 +835,7 @@ int lz_model_create(const lz_model_config *cfg, lz_model **out)
     m->ws[0] = m->ws[1] = m->ws[2] = nullptr;
     m->ws_floats = 0; m->ws_B = 0;
     m->math = 1; m->d_tc = nullptr;   // default: tcgen05 3xFP16 (fp32-accurate)
+    m->d_tower = nullptr; m->tws = nullptr; m->tws_bytes = 0;
     *out = m;
     return LZ_OK;
 }
@@ -662,6 +845,8 @@ int lz_model_destroy(lz_model *m)
     if (!m) return LZ_OK;
     cudaFree(m->d_weights);
     cudaFree(m->d_tc);
+    cudaFree(m->d_tower);
+    cudaFree(m->tws);
     for (int i = 0; i < 3; ++i) cudaFree(m->ws[i]);
     delete m;
     return LZ_OK;
@@ -757,6 +942,10 @@ int lz_model_finalize(lz_model *m)
     if (rc != LZ_OK) return rc;
     rc = pack_tc(m, net);
     if (rc != LZ_OK) return rc;
+    if (c.obs_h != 64) {
+        rc = pack_tower_tc(m);
+        if (rc != LZ_OK) return rc;
+    }
     m->finalized = true;
     m->tensors.clear();
     return LZ_OK;

@@ -7,6 +7,7 @@
 #include "lz_common.cuh"
 #include "net6.cuh"
 #include "net_tc.cuh"
+#include "conv_tc.cuh"
 
 namespace lz {
 
@@ -65,6 +66,13 @@ struct lz_model {
     int math;                         // 0 = fp32 FFMA (net6.cuh), 1 = tcgen05 3xFP16 (fp32-accurate), 2 = tcgen05 fp16 single pass
     unsigned char *d_tc;              // packed fp16 hi/lo weights + tables of the tcgen05 path
     lz::TcNet tc_rec, tc_tail;
+    // tcgen05 DownSample tower: packed weights / folded BN per layer, TCL activation workspace
+    unsigned char *d_tower;           // weights + scale/shift tables
+    lz::ConvTc tower_tc[7];           // rb1.c1, rb1.c2, ds(c1+c3), ds.c2, rb2.c1, rb2.c2, rb3.c1 / rb3.c2 share [6]: see model.cu
+    lz::ConvTc tower_tc_rb3[2];
+    unsigned char *tws;               // TCL workspace (one allocation)
+    size_t tws_bytes;
+    lz::Tcl T0, T1, T2, U0, U1, U2, V0, V1, V2;
     // workspace for initial inference (grown on demand, outside graph capture)
     float *ws[3];
     size_t ws_floats;
