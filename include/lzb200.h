@@ -156,6 +156,14 @@ int lz_search_run(lz_search *q, const float *d_latent_roots, int deterministic, 
 int lz_search_collect(lz_search *q, const float *d_obs, const uint8_t *d_mask, const float *d_noise,
                       float noise_weight, const int32_t *d_to_play, int deterministic,
                       float *d_pred_value, float *d_policy_logits, lz_stream s);
+/* Same with HOST buffers (pinned memory recommended): h_obs f32 [B,obs_c,H,W], h_mask uint8 [B,A] or NULL,
+ * h_noise f32 [B,A] or NULL, h_to_play int32 [B] or NULL.  The observation batch is copied in `nchunks`
+ * (1..8) pieces on an internal copy stream so that the copy of chunk i+1 overlaps the representation
+ * network of chunk i; everything else is ordered on `s`.  The host buffers must stay valid until `s`
+ * reaches the end of the call's work. */
+int lz_search_collect_host(lz_search *q, const float *h_obs, const uint8_t *h_mask, const float *h_noise,
+                           float noise_weight, const int32_t *h_to_play, int deterministic, int nchunks,
+                           float *d_pred_value, float *d_policy_logits, lz_stream s);
 /* Number of kernel nodes one lz_search_run enqueues (for launch accounting). */
 int lz_search_num_kernels(const lz_search *q);
 /* Device pointer of the latent pool (NCHW per slot) for inspection in tests. */

@@ -54,6 +54,8 @@ SIGNATURES = {
     "lz_search_run": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
     "lz_search_collect": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_int, c_void_p,
                                   c_void_p, c_void_p]),
+    "lz_search_collect_host": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_int, c_int, c_void_p,
+                                       c_void_p, c_void_p]),
     "lz_search_num_kernels": (c_int, [c_void_p]),
     "lz_search_latent_pool": (c_void_p, [c_void_p]),
 }

@@ -39,6 +39,7 @@ class MuZeroCollectPolicy:
         self.cfg = self.mcts._cfg
         self.device = model.device
         self._buf = {}
+        self.h2d_chunks = 4      # host observation batches are copied in this many overlapped pieces
 
     # ---- device-resident fast path ---------------------------------------------------------------
     def _bufs(self, B, A):
@@ -66,34 +67,47 @@ class MuZeroCollectPolicy:
         dev = self.device
         det = self.mcts.deterministic if deterministic is None else bool(deterministic)
         with torch.cuda.device(dev):
-            if obs.is_cuda:
-                d_obs = obs.to(torch.float32).contiguous()
+            host_path = not obs.is_cuda
+            if host_path:
+                h_obs = obs.to(torch.float32).contiguous()
+                h_mask = (action_mask if isinstance(action_mask, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(action_mask))).to(torch.uint8).contiguous()
+                h_noise = None
+                if noises is not None:
+                    h_noise = (noises if isinstance(noises, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(noises, dtype=np.float32))).to(torch.float32).contiguous()
+                h_tp = None
+                if to_play is not None:
+                    h_tp = (to_play if isinstance(to_play, torch.Tensor) else torch.from_numpy(np.array(to_play, np.int32).reshape(-1))).to(torch.int32).contiguous()
+                assert not h_mask.is_cuda and (h_noise is None or not h_noise.is_cuda), "host observation batch needs host mask / noise"
+                self._keep_host = (h_obs, h_mask, h_noise, h_tp)
             else:
-                if bufs["obs"] is None or bufs["obs"].shape != obs.shape:
-                    bufs["obs"] = torch.empty(obs.shape, device=dev, dtype=torch.float32)
-                bufs["obs"].copy_(obs, non_blocking=True)
-                d_obs = bufs["obs"]
-            mask_t = action_mask if isinstance(action_mask, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(action_mask))
-            bufs["mask"].copy_(mask_t.to(torch.uint8), non_blocking=True)
-            d_noise = None
-            if noises is not None:
-                nz = noises if isinstance(noises, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(noises, dtype=np.float32))
-                bufs["noise"].copy_(nz, non_blocking=True)
-                d_noise = bufs["noise"]
-            d_tp = None
-            if to_play is not None:
-                tp = to_play if isinstance(to_play, torch.Tensor) else torch.from_numpy(np.asarray(to_play, np.int32).reshape(-1))
-                bufs["to_play"].copy_(tp.to(torch.int32), non_blocking=True)
-                d_tp = bufs["to_play"]
+                d_obs = obs.to(torch.float32).contiguous()
+                mask_t = action_mask if isinstance(action_mask, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(action_mask))
+                bufs["mask"].copy_(mask_t.to(torch.uint8), non_blocking=True)
+                d_noise = None
+                if noises is not None:
+                    nz = noises if isinstance(noises, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(noises, dtype=np.float32))
+                    bufs["noise"].copy_(nz, non_blocking=True)
+                    d_noise = bufs["noise"]
+                d_tp = None
+                if to_play is not None:
+                    tp = to_play if isinstance(to_play, torch.Tensor) else torch.from_numpy(np.array(to_play, np.int32).reshape(-1))
+                    bufs["to_play"].copy_(tp.to(torch.int32), non_blocking=True)
+                    d_tp = bufs["to_play"]
             tree = mz_tree.acquire_tree(dev, B, A, S)
             try:
                 tree.set_params(*self.mcts._params())
                 q = tree.search_for(self.model, S)
                 s = cabi.stream_ptr()
-                cabi.check(tree.lib.lz_search_collect(q, d_obs.data_ptr(), bufs["mask"].data_ptr(), cabi.ptr(d_noise),
-                                                      float(self.cfg.root_noise_weight), cabi.ptr(d_tp), int(det),
-                                                      bufs["pred_value"].data_ptr(), bufs["logits"].data_ptr(), s),
-                           "lz_search_collect")
+                if host_path:
+                    cabi.check(tree.lib.lz_search_collect_host(q, h_obs.data_ptr(), h_mask.data_ptr(), cabi.ptr(h_noise),
+                                                               float(self.cfg.root_noise_weight), cabi.ptr(h_tp), int(det),
+                                                               int(self.h2d_chunks), bufs["pred_value"].data_ptr(),
+                                                               bufs["logits"].data_ptr(), s), "lz_search_collect_host")
+                else:
+                    cabi.check(tree.lib.lz_search_collect(q, d_obs.data_ptr(), bufs["mask"].data_ptr(), cabi.ptr(d_noise),
+                                                          float(self.cfg.root_noise_weight), cabi.ptr(d_tp), int(det),
+                                                          bufs["pred_value"].data_ptr(), bufs["logits"].data_ptr(), s),
+                               "lz_search_collect")
                 cabi.check(tree.lib.lz_tree_results(tree.h, tree.visits.data_ptr(), tree.values.data_ptr(),
                                                     tree.nlegal.data_ptr(), None, s), "lz_tree_results")
                 self.last_num_kernels = tree.lib.lz_search_num_kernels(q)

@@ -14,8 +14,8 @@
 
 namespace lz {
 
-constexpr int kCvEpiWarps = 8, kCvEpiThreads = kCvEpiWarps * 32, kCvThreads = kCvEpiThreads + 64;
-constexpr int kCvStages = 4;
+constexpr int kCvEpiWarps = 4, kCvEpiThreads = kCvEpiWarps * 32, kCvThreads = kCvEpiThreads + 64;   // 192 threads: 2 CTAs / SM
+constexpr int kCvStages = 4;          // ring slots reserved in the barrier block; p.stages (2..4) are used
 
 struct CvBars {
     uint64_t full[kCvStages], empty[kCvStages];
@@ -44,18 +44,19 @@ __host__ __device__ inline CvGeom cv_geom(const ConvTc &p)
     g.phase = 2 * g.part;
     g.in_bytes = (g.phase * p.in.nphase + 127) & ~(size_t)127;
     g.tap_bytes = (size_t)2 * kg * p.N * 16;
-    g.smem = g.in_bytes + kCvStages * g.tap_bytes + 1024;
+    g.smem = g.in_bytes + p.stages * g.tap_bytes + 1024;
     return g;
 }
 
 template <int N>
-__global__ void __launch_bounds__(kCvThreads, 1) k_conv_tc(ConvTc p)
+__global__ void __launch_bounds__(kCvThreads, 2) k_conv_tc(ConvTc p)
 {
     extern __shared__ __align__(1024) unsigned char smem[];
     const CvGeom g = cv_geom(p);
     unsigned char *in_s = smem;
     unsigned char *ring = smem + g.in_bytes;
-    CvBars *bars = reinterpret_cast<CvBars *>(ring + kCvStages * g.tap_bytes);
+    CvBars *bars = reinterpret_cast<CvBars *>(ring + p.stages * g.tap_bytes);
+    const int nstages = p.stages;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int pitch = p.in.pitch, H = p.in.H, W = p.in.W, kg_in = p.in.C / 8;
     const int group = blockIdx.x / g.nbands, band = blockIdx.x - group * g.nbands;
@@ -63,7 +64,8 @@ __global__ void __launch_bounds__(kCvThreads, 1) k_conv_tc(ConvTc p)
     const int y0 = band * p.band_h;
     const int rin0 = y0 * pitch - 1;
     const int npass = p.npass;
-    constexpr uint32_t kTmemCols = 512;
+    uint32_t tmem_cols = 32;                         // power of two >= NT * N: lets two CTAs share the SM's 512 columns
+    while (tmem_cols < (uint32_t)(g.NT * N)) tmem_cols <<= 1;
 
     if (tid == 0) {
         for (int i = 0; i < kCvStages; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], 1); }
@@ -71,7 +73,7 @@ __global__ void __launch_bounds__(kCvThreads, 1) k_conv_tc(ConvTc p)
         mbar_init(&bars->acc_ready, 1);
         fence_mbar_init();
     }
-    if (warp == kCvEpiWarps + 1) tmem_alloc(&bars->tmem_base, kTmemCols);
+    if (warp == kCvEpiWarps + 1) tmem_alloc(&bars->tmem_base, tmem_cols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -94,8 +96,8 @@ __global__ void __launch_bounds__(kCvThreads, 1) k_conv_tc(ConvTc p)
                             bulk_g2s(dst, src, bytes, &bars->in_full);
                         }
             for (int tap = 0; tap < 9; ++tap) {
-                const int st = tap % kCvStages;
-                if (tap >= kCvStages) mbar_wait(&bars->empty[st], ((tap / kCvStages) - 1) & 1);
+                const int st = tap % nstages;
+                if (tap >= nstages) mbar_wait(&bars->empty[st], ((tap / nstages) - 1) & 1);
                 mbar_expect_tx(&bars->full[st], (uint32_t)g.tap_bytes);
                 bulk_g2s(ring + st * g.tap_bytes, p.w + (size_t)tap * g.tap_bytes, (uint32_t)g.tap_bytes, &bars->full[st]);
             }
@@ -113,8 +115,8 @@ __global__ void __launch_bounds__(kCvThreads, 1) k_conv_tc(ConvTc p)
             mbar_wait(&bars->in_full, 0);
             tc_fence_after();
             for (int tap = 0; tap < 9; ++tap) {
-                const int st = tap % kCvStages;
-                mbar_wait(&bars->full[st], (tap / kCvStages) & 1);
+                const int st = tap % nstages;
+                mbar_wait(&bars->full[st], (tap / nstages) & 1);
                 tc_fence_after();
                 const uint64_t b0 = b_desc0 + (uint64_t)((st * g.tap_bytes) >> 4);
                 const uint64_t a_tap = a_desc0 + (uint64_t)((p.tap_phase[tap] * g.phase) >> 4) + (uint64_t)(g.m_lo + p.tap_shift[tap]);
@@ -136,13 +138,8 @@ __global__ void __launch_bounds__(kCvThreads, 1) k_conv_tc(ConvTc p)
         }
     } else {
         // ================= epilogue: TMEM -> BN (+residual) (+ReLU) -> fp16 hi/lo -> next layer's TCL =================
-        const int q4 = warp & 3, half = warp >> 2, rowid = q4 * 32 + lane;
+        const int q4 = warp & 3, rowid = q4 * 32 + lane;
         const uint32_t lane_base = tmem + ((uint32_t)(q4 * 32) << 16);
-        constexpr int NC = N / 2;                        // columns per thread
-        const int grp = (N == 128) ? half : 0;           // output tensor of this thread's columns
-        const int ch_base = (N == 128) ? 0 : half * NC;  // first channel (within the output tensor)
-        const Tcl &o = p.out[grp];
-        const bool relu = p.relu[grp] != 0;
         const int yend = min(y0 + p.band_h, H);
         mbar_wait_warp(&bars->acc_ready, 0);
         tc_fence_after();
@@ -153,13 +150,16 @@ __global__ void __launch_bounds__(kCvThreads, 1) k_conv_tc(ConvTc p)
             const int yy = rho / pitch - 1, xx = rho - (yy + 1) * pitch;
             const bool in_band = (k < nimg) && (rho >= pitch) && (yy >= y0) && (yy < yend);
             const bool valid = in_band && (xx < W);
-            size_t obase = 0;
-            bool do_write = in_band;
-            if (in_band) {
-                if (o.nphase == 1) {
-                    obase = (size_t)(img0 + k) * o.img_stride + (size_t)(rho + 1) * 16;
-                } else {                                 // phase-split output for a stride-2 consumer
-                    if (valid) {
+#pragma unroll
+            for (int grp = 0; grp < (N == 128 ? 2 : 1); ++grp) {
+                const Tcl &o = p.out[grp];
+                const bool relu = p.relu[grp] != 0;
+                size_t obase = 0;
+                bool do_write = in_band;
+                if (in_band) {
+                    if (o.nphase == 1) {
+                        obase = (size_t)(img0 + k) * o.img_stride + (size_t)(rho + 1) * 16;
+                    } else if (valid) {                  // phase-split output for a stride-2 consumer
                         const int ph = (yy & 1) * 2 + (xx & 1);
                         const int rho2 = ((yy >> 1) + 1) * o.pitch + (xx >> 1);
                         obase = (size_t)(img0 + k) * o.img_stride + ph * o.phase_stride + (size_t)(rho2 + 1) * 16;
@@ -167,39 +167,40 @@ __global__ void __launch_bounds__(kCvThreads, 1) k_conv_tc(ConvTc p)
                         do_write = false;
                     }
                 }
-            }
+                constexpr int NCG = (N == 128) ? 64 : N;     // columns of this output tensor
 #pragma unroll
-            for (int c0 = 0; c0 < NC; c0 += 16) {
-                float v[16];
-                tmem_ld16(lane_base + t * N + half * NC + c0, v);
-                const int col = half * NC + c0;
+                for (int c0 = 0; c0 < NCG; c0 += 16) {
+                    float v[16];
+                    const int col = grp * 64 + c0;
+                    tmem_ld16(lane_base + t * N + col, v);
 #pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = fmaf(v[i], __ldg(p.scale + col + i), __ldg(p.shift + col + i));
-                if (p.res.base && grp == 0 && valid) {
+                    for (int i = 0; i < 16; ++i) v[i] = fmaf(v[i], __ldg(p.scale + col + i), __ldg(p.shift + col + i));
+                    if (p.res.base && grp == 0 && valid) {
 #pragma unroll
-                    for (int g2 = 0; g2 < 2; ++g2) {
-                        const int kgi = (ch_base + c0) / 8 + g2;
-                        const unsigned char *rp = p.res.base + (size_t)(img0 + k) * p.res.img_stride +
-                                                  ((size_t)kgi * p.res.plane_rows + rho + 1) * 16;
-                        const uint4 rh = __ldg(reinterpret_cast<const uint4 *>(rp));
-                        const uint4 rl = __ldg(reinterpret_cast<const uint4 *>(rp + p.res.part_stride));
-                        const __half2 *hh = reinterpret_cast<const __half2 *>(&rh), *hl = reinterpret_cast<const __half2 *>(&rl);
+                        for (int g2 = 0; g2 < 2; ++g2) {
+                            const int kgi = c0 / 8 + g2;
+                            const unsigned char *rp = p.res.base + (size_t)(img0 + k) * p.res.img_stride +
+                                                      ((size_t)kgi * p.res.plane_rows + rho + 1) * 16;
+                            const uint4 rh = __ldg(reinterpret_cast<const uint4 *>(rp));
+                            const uint4 rl = __ldg(reinterpret_cast<const uint4 *>(rp + p.res.part_stride));
+                            const __half2 *hh = reinterpret_cast<const __half2 *>(&rh), *hl = reinterpret_cast<const __half2 *>(&rl);
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const float2 a = __half22float2(hh[j]), b = __half22float2(hl[j]);
-                            v[g2 * 8 + 2 * j] += a.x + b.x;
-                            v[g2 * 8 + 2 * j + 1] += a.y + b.y;
+                            for (int j = 0; j < 4; ++j) {
+                                const float2 a = __half22float2(hh[j]), b = __half22float2(hl[j]);
+                                v[g2 * 8 + 2 * j] += a.x + b.x;
+                                v[g2 * 8 + 2 * j + 1] += a.y + b.y;
+                            }
                         }
                     }
-                }
 #pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = valid ? (relu ? fmaxf(v[i], 0.0f) : v[i]) : 0.0f;
-                if (do_write) {
+                    for (int i = 0; i < 16; ++i) v[i] = valid ? (relu ? fmaxf(v[i], 0.0f) : v[i]) : 0.0f;
+                    if (do_write) {
 #pragma unroll
-                    for (int g2 = 0; g2 < 2; ++g2) {
-                        const int kgi = (ch_base + c0) / 8 + g2;
-                        unsigned char *op = o.base + obase + (size_t)kgi * o.plane_rows * 16;
-                        store_split8(op, op + o.part_stride, v + 8 * g2);
+                        for (int g2 = 0; g2 < 2; ++g2) {
+                            const int kgi = c0 / 8 + g2;
+                            unsigned char *op = o.base + obase + (size_t)kgi * o.plane_rows * 16;
+                            store_split8(op, op + o.part_stride, v + 8 * g2);
+                        }
                     }
                 }
             }
@@ -209,7 +210,7 @@ __global__ void __launch_bounds__(kCvThreads, 1) k_conv_tc(ConvTc p)
     __syncthreads();
     if (warp == kCvEpiWarps + 1) {
         __syncwarp();
-        tmem_dealloc(tmem, kTmemCols);
+        tmem_dealloc(tmem, tmem_cols);
     }
 }
 

@@ -48,6 +48,7 @@ struct ConvTc {
     int relu[2];
     int N;                        // 32, 64 or 128
     int G, band_h;                // images per CTA (band_h == H when G > 1), image rows per band
+    int stages;                   // weight ring depth (2..4)
     int B, npass;
 };
 

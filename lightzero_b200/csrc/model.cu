@@ -438,20 +438,25 @@ static void pick_band(ConvTc &p)
 {
     const int H = p.in.H, pitch = p.in.pitch, kg = p.in.C / 8;
     double best = -1.0;
-    int best_h = 1, best_g = 1;
+    int best_h = 1, best_g = 1, best_st = 4;
     for (int G = 1; G <= 4; ++G)
-        for (int bh = (G > 1 ? H : 1); bh <= H; ++bh) {
-            const int rin = (bh + 2) * pitch + 2, mcount = (G - 1) * rin + bh * pitch, NT = (mcount + 127) / 128;
-            int PR = pitch + 1 + NT * 128 + pitch + 2;
-            if (PR < G * rin) PR = G * rin;
-            const size_t smem = (((size_t)PR * 16 * kg * 2 * p.in.nphase + 127) & ~(size_t)127) + 4 * (size_t)2 * kg * p.N * 16 + 1024;
-            if (smem > 227 * 1024 || NT * p.N > 512) continue;
-            const int nb = (H + bh - 1) / bh;
-            const double eff = (double)(G * H * (pitch - 1)) / ((double)nb * NT * 128);
-            if (eff > best + 1e-9) { best = eff; best_h = bh; best_g = G; }
-        }
+        for (int bh = (G > 1 ? H : 1); bh <= H; ++bh)
+            for (int st = 2; st <= 4; st += 2) {
+                const int rin = (bh + 2) * pitch + 2, mcount = (G - 1) * rin + bh * pitch, NT = (mcount + 127) / 128;
+                int PR = pitch + 1 + NT * 128 + pitch + 2;
+                if (PR < G * rin) PR = G * rin;
+                const size_t smem = (((size_t)PR * 16 * kg * 2 * p.in.nphase + 127) & ~(size_t)127) + st * (size_t)2 * kg * p.N * 16 + 1024;
+                if (smem > 227 * 1024 || NT * p.N > 512) continue;
+                const int nb = (H + bh - 1) / bh;
+                double score = (double)(G * H * (pitch - 1)) / ((double)nb * NT * 128);       // useful / issued MMA rows
+                const bool two_ctas = smem <= 113 * 1024 && NT * p.N <= 256;                // co-residency overlaps load / MMA / epilogue
+                score *= two_ctas ? 1.35 : 1.0;
+                score *= (st == 4) ? 1.0 : 0.97;
+                if (score > best + 1e-9) { best = score; best_h = bh; best_g = G; best_st = st; }
+            }
     p.band_h = best_h;
     p.G = best_g;
+    p.stages = best_st;
 }
 
 static int tower_tc_run(lz_model *m, int B, const float *d_obs, float *pre_latent, cudaStream_t s)

@@ -6,6 +6,8 @@
 // network through device memory and the network hands (reward, value, logits) back the same way.
 #include <string.h>
 
+#include <algorithm>
+
 #include "model.cuh"
 #include "tree.cuh"
 
@@ -24,6 +26,13 @@ struct lz_search {
     cudaStream_t capture_stream; // library-owned: the caller's stream may be the legacy default stream,
                                  // which cannot be captured; the instantiated graph launches on the caller's
     int num_kernels;
+    // host-buffer collect: staging + copy stream so the H2D of chunk i+1 overlaps the tower of chunk i
+    cudaStream_t copy_stream;
+    cudaEvent_t ev_chunk[8], ev_start;
+    float *d_obs_stage, *d_noise_stage;
+    uint8_t *d_mask_stage;
+    int32_t *d_tp_stage;
+    size_t obs_elems;            // floats per observation
 };
 
 using namespace lz;
@@ -109,6 +118,12 @@ int lz_search_destroy(lz_search *q)
     if (!q) return LZ_OK;
     for (int d = 0; d < 2; ++d) if (q->exec[d]) cudaGraphExecDestroy(q->exec[d]);
     if (q->capture_stream) cudaStreamDestroy(q->capture_stream);
+    if (q->copy_stream) {
+        cudaStreamDestroy(q->copy_stream);
+        for (int i = 0; i < 8; ++i) cudaEventDestroy(q->ev_chunk[i]);
+        cudaEventDestroy(q->ev_start);
+    }
+    cudaFree(q->d_obs_stage); cudaFree(q->d_noise_stage); cudaFree(q->d_mask_stage); cudaFree(q->d_tp_stage);
     cudaFree(q->pool); cudaFree(q->d_ix); cudaFree(q->d_action); cudaFree(q->d_reward); cudaFree(q->d_value);
     cudaFree(q->d_policy); cudaFree(q->d_root_logits); cudaFree(q->d_root_value);
     delete q;
@@ -139,6 +154,60 @@ int lz_search_collect(lz_search *q, const float *d_obs, const uint8_t *d_mask, c
     if ((rc = lz_tree_reset_mask(q->tree, d_mask, s))) return rc;                // :760,769
     if ((rc = lz_tree_prepare(q->tree, io.policy_logits, d_noise, noise_weight, nullptr, d_to_play, s))) return rc;   // :774
     return run_graph(q, deterministic, (cudaStream_t)s);                         // :775
+}
+
+int lz_search_collect_host(lz_search *q, const float *h_obs, const uint8_t *h_mask, const float *h_noise, float noise_weight,
+                           const int32_t *h_to_play, int deterministic, int nchunks, float *d_pred_value,
+                           float *d_policy_logits, lz_stream s_)
+{
+    LZ_REQUIRE(q && h_obs, LZ_EINVAL, "lz_search_collect_host: bad argument");
+    cudaStream_t s = (cudaStream_t)s_;
+    const lz_model_config &c = q->model->cfg;
+    const int B = q->B, A = q->A;
+    nchunks = nchunks < 1 ? 1 : (nchunks > 8 ? 8 : nchunks);
+    if (!q->copy_stream) {
+        q->obs_elems = (size_t)c.obs_c * c.obs_h * c.obs_w;
+        LZ_CUDA_CHECK(cudaStreamCreateWithFlags(&q->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 8; ++i) LZ_CUDA_CHECK(cudaEventCreateWithFlags(&q->ev_chunk[i], cudaEventDisableTiming));
+        LZ_CUDA_CHECK(cudaEventCreateWithFlags(&q->ev_start, cudaEventDisableTiming));
+        int rc = dev_alloc(&q->d_obs_stage, q->obs_elems * B);
+        if (rc == LZ_OK) rc = dev_alloc(&q->d_noise_stage, (size_t)B * A);
+        if (rc == LZ_OK) rc = dev_alloc(&q->d_mask_stage, (size_t)B * A);
+        if (rc == LZ_OK) rc = dev_alloc(&q->d_tp_stage, (size_t)B);
+        if (rc != LZ_OK) return rc;
+    }
+    // the copy stream may not overwrite the staging buffer before earlier work on `s` has consumed it
+    LZ_CUDA_CHECK(cudaEventRecord(q->ev_start, s));
+    LZ_CUDA_CHECK(cudaStreamWaitEvent(q->copy_stream, q->ev_start, 0));
+    const int per = (B + nchunks - 1) / nchunks;
+    for (int i = 0; i < nchunks; ++i) {
+        const int b0 = i * per, bc = std::min(per, B - b0);
+        if (bc <= 0) { nchunks = i; break; }
+        LZ_CUDA_CHECK(cudaMemcpyAsync(q->d_obs_stage + (size_t)b0 * q->obs_elems, h_obs + (size_t)b0 * q->obs_elems,
+                                      (size_t)bc * q->obs_elems * sizeof(float), cudaMemcpyHostToDevice, q->copy_stream));
+        LZ_CUDA_CHECK(cudaEventRecord(q->ev_chunk[i], q->copy_stream));
+    }
+    if (h_mask) LZ_CUDA_CHECK(cudaMemcpyAsync(q->d_mask_stage, h_mask, (size_t)B * A, cudaMemcpyHostToDevice, s));
+    if (h_noise) LZ_CUDA_CHECK(cudaMemcpyAsync(q->d_noise_stage, h_noise, (size_t)B * A * sizeof(float), cudaMemcpyHostToDevice, s));
+    if (h_to_play) LZ_CUDA_CHECK(cudaMemcpyAsync(q->d_tp_stage, h_to_play, (size_t)B * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    float *logits = d_policy_logits ? d_policy_logits : q->d_root_logits;
+    float *pred = d_pred_value ? d_pred_value : q->d_root_value;
+    for (int i = 0; i < nchunks; ++i) {
+        const int b0 = i * per, bc = std::min(per, B - b0);
+        LZ_CUDA_CHECK(cudaStreamWaitEvent(s, q->ev_chunk[i], 0));
+        TailIO io;
+        memset(&io, 0, sizeof(io));
+        io.latent2 = q->pool + (size_t)b0 * kC * kP;
+        io.policy_logits = logits + (size_t)b0 * A;
+        io.value = pred + b0;
+        int rc = model_initial(q->model, bc, q->d_obs_stage + (size_t)b0 * q->obs_elems, io, s);
+        if (rc) return rc;
+    }
+    int rc;
+    if ((rc = lz_tree_reset_mask(q->tree, h_mask ? q->d_mask_stage : nullptr, s))) return rc;
+    if ((rc = lz_tree_prepare(q->tree, logits, h_noise ? q->d_noise_stage : nullptr, noise_weight, nullptr,
+                              h_to_play ? q->d_tp_stage : nullptr, s))) return rc;
+    return run_graph(q, deterministic, s);
 }
 
 int lz_search_num_kernels(const lz_search *q) { return q ? q->num_kernels : 0; }
