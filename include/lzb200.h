@@ -105,6 +105,17 @@ typedef struct lz_model_config {
 } lz_model_config;
 
 int lz_model_create(const lz_model_config *cfg, lz_model **out);
+
+/* MuZeroModelMLP (lzero/model/muzero_model_mlp.py:21-295; vector observations, BASELINE config 1).  The
+ * handle is used with the same lz_model_* / lz_search_* calls: d_obs is f32 [B, obs_dim], latents are
+ * f32 [B, latent_dim].  State-dict names follow muzero_model_mlp.py / common.py:790-850,1218-1292. */
+typedef struct lz_mlp_config {
+    int obs_dim, action_space_size, latent_dim;         /* 4, 2, 128 for CartPole */
+    int reward_hidden, value_hidden, policy_hidden;     /* one hidden layer each: 32 */
+    int res_connection_in_dynamics;                     /* policy default True (policy/muzero.py:68) */
+    float support_min, support_max, support_step;
+} lz_mlp_config;
+int lz_model_create_mlp(const lz_mlp_config *cfg, lz_model **out);
 int lz_model_destroy(lz_model *m);
 /* Feed one tensor of the reference state_dict (names as produced by MuZeroModel.state_dict(),
  * SURVEY.md App. B.4; fp32, contiguous, HOST memory).  Unknown names are ignored (returns 1). */

@@ -346,6 +346,7 @@ static int model_prepare_launch()
 
 int model_recurrent(lz_model *m, const RecIO &io, cudaStream_t s)
 {
+    if (m->kind == 1) return mlp_recurrent(m, io, s);
     if (m->math != 0) {
         TcIO t;
         memset(&t, 0, sizeof(t));
@@ -393,7 +394,7 @@ static int launch_pool(const float *in, float *out, int planes, int hin, int hou
 
 int model_reserve(lz_model *m, int B)
 {
-    if (B <= m->ws_B) return LZ_OK;
+    if (m->kind == 1 || B <= m->ws_B) return LZ_OK;
     size_t per_root = 0;
     for (const ConvG &L : m->tower) per_root = std::max(per_root, (size_t)L.cout * L.hout * L.wout);
     per_root = std::max(per_root, (size_t)kActFloats);
@@ -486,6 +487,7 @@ static int tower_tc_run(lz_model *m, int B, const float *d_obs, float *pre_laten
 
 int model_initial(lz_model *m, int B, const float *d_obs, const TailIO &io_in, cudaStream_t s)
 {
+    if (m->kind == 1) return mlp_initial(m, B, d_obs, io_in, s);
     LZ_REQUIRE(B <= m->ws_B, LZ_ESTATE, "model_initial: workspace sized for %d roots, got %d (call model_reserve outside capture)", m->ws_B, B);
     float *a = m->ws[0], *b = m->ws[1], *c = m->ws[2];
     const std::vector<ConvG> &T = m->tower;
@@ -834,6 +836,9 @@ int lz_model_create(const lz_model_config *cfg, lz_model **out)
     LZ_REQUIRE(ndev > 0, LZ_ECUDA, "lz_model_create: no CUDA device (this library has no CPU fallback)");
     lz_model *m = new lz_model();
     m->cfg = *cfg;
+    m->kind = 0;
+    m->latent_floats = kC * kP;
+    memset(&m->mcfg, 0, sizeof(m->mcfg));
     m->finalized = false;
     m->d_weights = nullptr;
     m->hw = kHW; m->P = kP; m->K = K;
@@ -873,6 +878,7 @@ int lz_model_set_tensor(lz_model *m, const char *name, const float *h_data, int6
 int lz_model_finalize(lz_model *m)
 {
     LZ_REQUIRE(m, LZ_EINVAL, "lz_model_finalize: null model");
+    if (m->kind == 1) return mlp_finalize(m);
     const lz_model_config &c = m->cfg;
     const int A = c.action_space_size, n = c.num_res_blocks;
     Packer P;
@@ -959,6 +965,7 @@ int lz_model_finalize(lz_model *m)
 int lz_model_set_math(lz_model *m, int mode)
 {
     LZ_REQUIRE(m && mode >= 0 && mode <= 2, LZ_EINVAL, "lz_model_set_math: mode must be 0 (fp32 FFMA), 1 (tcgen05 3xFP16) or 2 (tcgen05 fp16)");
+    LZ_REQUIRE(m->kind == 0 || mode == 0, LZ_EINVAL, "lz_model_set_math: the MLP model only has the fp32 path");
     m->math = mode;
     return LZ_OK;
 }

@@ -30,6 +30,20 @@ struct ConvG {                        // generic 3x3 conv of the DownSample towe
     int cin, cout, stride, hin, win, hout, wout;
 };
 
+struct Dense {                        // y = act(scale * (W x) + shift); wt is input-major [in][out]
+    const float *wt, *scale, *shift;
+    int in, out, act, nact;           // act: 0 none, 1 ReLU, 2 GELU(tanh); nact: trailing one-hot action inputs
+};
+
+struct MlpNet {                       // MuZeroModelMLP (muzero_model_mlp.py)
+    Dense e0, e1;                     // representation: Linear+BN+GELU, Linear (+ LayerNorm)
+    Dense d1a, d1b, d2a, d2b;         // dynamics: fc_dynamics_1 (or fc_dynamics), fc_dynamics_2
+    Dense r0, r1, pc0, pc1, v0, v1, p0, p1;
+    const float *ln_w, *ln_b;
+    int latent, obs_dim, A, res;
+    float support_min, support_step;
+};
+
 struct RecIO {
     int B;
     const float *latent_base;         // latent source: base + ix[b]*slot_stride + b*C*P  (ix == nullptr: slot 0)
@@ -55,6 +69,10 @@ struct TailIO {
 }  // namespace lz
 
 struct lz_model {
+    int kind;                         // 0 = conv MuZeroModel, 1 = MuZeroModelMLP
+    int latent_floats;                // floats per root latent (64*36 or latent_dim)
+    lz_mlp_config mcfg;
+    lz::MlpNet mlp;
     lz_model_config cfg;
     std::map<std::string, std::vector<float>> tensors;   // raw reference state_dict (host)
     bool finalized;
@@ -83,4 +101,7 @@ namespace lz {
 int model_recurrent(lz_model *m, const RecIO &io, cudaStream_t s);
 int model_initial(lz_model *m, int B, const float *d_obs, const TailIO &io, cudaStream_t s);
 int model_reserve(lz_model *m, int B);   // sizes the initial-inference workspace (synchronous)
+int mlp_recurrent(lz_model *m, const RecIO &io, cudaStream_t s);
+int mlp_initial(lz_model *m, int B, const float *d_obs, const TailIO &io, cudaStream_t s);
+int mlp_finalize(lz_model *m);
 }  // namespace lz

@@ -98,7 +98,7 @@ int lz_search_create(lz_tree *t, lz_model *m, int num_simulations, lz_search **o
     lz_search *q = new lz_search();
     memset(q, 0, sizeof(*q));
     q->tree = t; q->model = m; q->S = num_simulations; q->B = t->p.B; q->A = t->p.A;
-    q->slot_stride = (size_t)q->B * kC * kP;
+    q->slot_stride = (size_t)q->B * m->latent_floats;
     int rc = dev_alloc(&q->pool, q->slot_stride * (size_t)(q->S + 1));
     if (rc == LZ_OK) rc = dev_alloc(&q->d_ix, (size_t)q->B);
     if (rc == LZ_OK) rc = dev_alloc(&q->d_action, (size_t)q->B);
@@ -164,9 +164,10 @@ int lz_search_collect_host(lz_search *q, const float *h_obs, const uint8_t *h_ma
     cudaStream_t s = (cudaStream_t)s_;
     const lz_model_config &c = q->model->cfg;
     const int B = q->B, A = q->A;
+    const size_t obs_elems = q->model->kind == 1 ? (size_t)q->model->mcfg.obs_dim : (size_t)c.obs_c * c.obs_h * c.obs_w;
     nchunks = nchunks < 1 ? 1 : (nchunks > 8 ? 8 : nchunks);
     if (!q->copy_stream) {
-        q->obs_elems = (size_t)c.obs_c * c.obs_h * c.obs_w;
+        q->obs_elems = obs_elems;
         LZ_CUDA_CHECK(cudaStreamCreateWithFlags(&q->copy_stream, cudaStreamNonBlocking));
         for (int i = 0; i < 8; ++i) LZ_CUDA_CHECK(cudaEventCreateWithFlags(&q->ev_chunk[i], cudaEventDisableTiming));
         LZ_CUDA_CHECK(cudaEventCreateWithFlags(&q->ev_start, cudaEventDisableTiming));
@@ -197,7 +198,7 @@ int lz_search_collect_host(lz_search *q, const float *h_obs, const uint8_t *h_ma
         LZ_CUDA_CHECK(cudaStreamWaitEvent(s, q->ev_chunk[i], 0));
         TailIO io;
         memset(&io, 0, sizeof(io));
-        io.latent2 = q->pool + (size_t)b0 * kC * kP;
+        io.latent2 = q->pool + (size_t)b0 * q->model->latent_floats;
         io.policy_logits = logits + (size_t)b0 * A;
         io.value = pred + b0;
         int rc = model_initial(q->model, bc, q->d_obs_stage + (size_t)b0 * q->obs_elems, io, s);

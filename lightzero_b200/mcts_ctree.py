@@ -22,6 +22,7 @@ import torch
 
 from . import cabi, mz_tree
 from .muzero_model import MuZeroModel
+from .muzero_model_mlp import MuZeroModelMLP
 from .scaling_transform import DiscreteSupport, InverseScalarTransform
 
 
@@ -101,7 +102,7 @@ class MuZeroMCTSCtree(object):
             lat = latent_state_roots.to(dev, torch.float32, non_blocking=True).contiguous()
         else:
             lat = torch.from_numpy(np.ascontiguousarray(latent_state_roots, dtype=np.float32)).to(dev, non_blocking=True)
-        if isinstance(model, MuZeroModel):
+        if isinstance(model, (MuZeroModel, MuZeroModelMLP)):
             q = t.search_for(model, S)
             with torch.cuda.device(dev):
                 cabi.check(t.lib.lz_search_run(q, lat.data_ptr(), int(self.deterministic), cabi.stream_ptr()),

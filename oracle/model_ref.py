@@ -310,3 +310,156 @@ def inverse_scalar_transform(logits, scalar_support, epsilon=0.001, categorical_
         value = logits
     return torch.sign(value) * (
         ((torch.sqrt(1 + 4 * epsilon * (torch.abs(value) + 1 + epsilon)) - 1) / (2 * epsilon)) ** 2 - 1)
+
+
+# --------------------------------------------------------------------------------------------------
+# MuZeroModelMLP (vector observations; BASELINE config 1: CartPole, latent 128, A=2)
+# --------------------------------------------------------------------------------------------------
+def DingMLP(in_channels, hidden_channels, out_channels, layer_num, output_activation=True, output_norm=True):
+    """DI-engine ``ding.torch_utils.MLP`` with norm_type='BN', activation=ReLU as called at
+    muzero_model_mlp.py:367-404: ``layer_num`` Linear layers [in] + [hidden]*(layer_num-1) + [out], each
+    followed by BatchNorm1d + ReLU (last layer per output_norm / output_activation).  Sequential indices
+    for layer_num=2: 0 Linear, 1 BN, 2 ReLU, 3 Linear, 4 BN, 5 ReLU."""
+    chans = [in_channels] + [hidden_channels] * (layer_num - 1) + [out_channels]
+    block = []
+    for i in range(layer_num):
+        last = i == layer_num - 1
+        block.append(nn.Linear(chans[i], chans[i + 1]))
+        if (not last) or output_norm:
+            block.append(nn.BatchNorm1d(chans[i + 1]))
+        if (not last) or output_activation:
+            block.append(nn.ReLU())
+    return nn.Sequential(*block)
+
+
+def MLP_V2_general(in_channels, hidden_channels, out_channels, activation, output_activation, output_norm,
+                   last_linear_layer_init_zero):
+    """lzero/model/common.py:28-99 with norm_type='BN'."""
+    layers = []
+    chans = [in_channels] + list(hidden_channels) + [out_channels]
+    n = len(chans) - 1
+    for i in range(n):
+        layers.append(nn.Linear(chans[i], chans[i + 1]))
+        if i != n - 1:
+            layers.append(nn.BatchNorm1d(chans[i + 1]))
+            layers.append(activation())
+        else:
+            if output_norm:
+                layers.append(nn.BatchNorm1d(chans[i + 1]))
+            if output_activation:
+                layers.append(activation())
+    if last_linear_layer_init_zero:
+        last = [l for l in layers if isinstance(l, nn.Linear)][-1]
+        nn.init.zeros_(last.weight)
+        nn.init.zeros_(last.bias)
+    return nn.Sequential(*layers)
+
+
+class RepresentationNetworkMLP(nn.Module):
+    """lzero/model/common.py:790-850: Linear -> BN1d -> GELU(tanh) -> Linear(zero-init) -> LayerNorm
+    (MuZeroModelMLP passes no activation, so the default nn.GELU(approximate='tanh') applies,
+    muzero_model_mlp.py:104-106)."""
+
+    def __init__(self, observation_shape, hidden_channels):
+        super().__init__()
+        self.fc_representation = MLP_V2_general(observation_shape, [hidden_channels], hidden_channels,
+                                                lambda: nn.GELU(approximate='tanh'), False, False, True)
+        self.norm = nn.LayerNorm(hidden_channels)
+
+    def forward(self, x):
+        return self.norm(self.fc_representation(x.float()))
+
+
+class DynamicsNetworkMLP(nn.Module):
+    """lzero/model/muzero_model_mlp.py:328-442"""
+
+    def __init__(self, action_encoding_dim, latent_dim, reward_hidden, support_size, res_connection, last_zero=True):
+        super().__init__()
+        self.action_encoding_dim = action_encoding_dim
+        self.res_connection_in_dynamics = res_connection
+        nc = latent_dim + action_encoding_dim
+        if res_connection:
+            self.fc_dynamics_1 = DingMLP(nc, latent_dim, latent_dim, 2)
+            self.fc_dynamics_2 = DingMLP(latent_dim, latent_dim, latent_dim, 2)
+        else:
+            self.fc_dynamics = DingMLP(nc, latent_dim, latent_dim, 2)
+        self.fc_reward_head = MLP_V2_general(latent_dim, list(reward_hidden), support_size, nn.ReLU, False, False, last_zero)
+
+    def forward(self, sa):
+        if self.res_connection_in_dynamics:
+            latent = sa[:, :-self.action_encoding_dim]
+            nxt = self.fc_dynamics_1(sa) + latent
+            enc = self.fc_dynamics_2(nxt)
+        else:
+            nxt = self.fc_dynamics(sa)
+            enc = nxt
+        return nxt, self.fc_reward_head(enc)
+
+
+class PredictionNetworkMLP(nn.Module):
+    """lzero/model/common.py:1218-1292"""
+
+    def __init__(self, action_space_size, latent_dim, value_hidden, policy_hidden, support_size, last_zero=True):
+        super().__init__()
+        self.fc_prediction_common = MLP_V2_general(latent_dim, [latent_dim], latent_dim, nn.ReLU, True, True, False)
+        self.fc_value_head = MLP_V2_general(latent_dim, list(value_hidden), support_size, nn.ReLU, False, False, last_zero)
+        self.fc_policy_head = MLP_V2_general(latent_dim, list(policy_hidden), action_space_size, nn.ReLU, False, False, last_zero)
+
+    def forward(self, latent):
+        x = self.fc_prediction_common(latent)
+        return self.fc_policy_head(x), self.fc_value_head(x)
+
+
+class MuZeroModelMLPRef(nn.Module):
+    """lzero/model/muzero_model_mlp.py:21-295 (one_hot actions, categorical, BN, state_norm=False)."""
+
+    def __init__(self, observation_shape: int = 4, action_space_size: int = 2, latent_state_dim: int = 128,
+                 reward_head_hidden_channels=(32,), value_head_hidden_channels=(32,), policy_head_hidden_channels=(32,),
+                 reward_support_range=(-300., 301., 1.), value_support_range=(-300., 301., 1.),
+                 res_connection_in_dynamics: bool = True, last_linear_layer_init_zero: bool = True):
+        super().__init__()
+        self.action_space_size = action_space_size
+        self.latent_state_dim = latent_state_dim
+        self.reward_support_size = len(torch.arange(*reward_support_range))
+        self.value_support_size = len(torch.arange(*value_support_range))
+        self.representation_network = RepresentationNetworkMLP(observation_shape, latent_state_dim)
+        self.dynamics_network = DynamicsNetworkMLP(action_space_size, latent_state_dim, reward_head_hidden_channels,
+                                                   self.reward_support_size, res_connection_in_dynamics,
+                                                   last_linear_layer_init_zero)
+        self.prediction_network = PredictionNetworkMLP(action_space_size, latent_state_dim, value_head_hidden_channels,
+                                                       policy_head_hidden_channels, self.value_support_size,
+                                                       last_linear_layer_init_zero)
+
+    def initial_inference(self, obs):
+        latent = self.representation_network(obs)
+        policy_logits, value = self.prediction_network(latent)
+        return MZNetworkOutput(value, [0. for _ in range(obs.size(0))], policy_logits, latent)
+
+    def recurrent_inference(self, latent_state, action):
+        if action.dim() == 1:
+            action = action.unsqueeze(-1)
+        one_hot = torch.zeros(action.shape[0], self.action_space_size, device=action.device)
+        one_hot.scatter_(1, action.long(), 1)
+        nxt, reward = self.dynamics_network(torch.cat((latent_state, one_hot.float()), dim=1))
+        policy_logits, value = self.prediction_network(nxt)
+        return MZNetworkOutput(value, reward, policy_logits, nxt)
+
+
+def emulate_trained_mlp_(model: nn.Module, seed: int = 0) -> nn.Module:
+    """Same idea as emulate_trained_: un-zero every zero-initialised last layer, randomise norm statistics."""
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for m in model.modules():
+            if isinstance(m, nn.BatchNorm1d):
+                m.running_mean.copy_(torch.randn(m.running_mean.shape, generator=g) * 0.1)
+                m.running_var.copy_(torch.rand(m.running_var.shape, generator=g) + 0.5)
+                m.weight.copy_(1.0 + 0.1 * torch.randn(m.weight.shape, generator=g))
+                m.bias.copy_(0.1 * torch.randn(m.bias.shape, generator=g))
+            if isinstance(m, nn.LayerNorm):
+                m.weight.copy_(1.0 + 0.1 * torch.randn(m.weight.shape, generator=g))
+                m.bias.copy_(0.1 * torch.randn(m.bias.shape, generator=g))
+            if isinstance(m, nn.Linear) and float(m.weight.abs().sum()) == 0.0:
+                m.weight.copy_(torch.randn(m.weight.shape, generator=g) * 0.05)
+                m.bias.copy_(torch.randn(m.bias.shape, generator=g) * 0.05)
+    model.eval()
+    return model
