@@ -799,6 +799,7 @@ static int pack_tc(lz_model *m, const NetDev &net)
         rec.layer_w[L] = 2 * n + 2 + 2 * i; rec.layer_flags[L++] = LF_RES | LF_STORE_RES | (i == n - 1 ? LF_HOOK_VALPOL : 0);
     }
     rec.nlayers = L; rec.has_reward = 1;
+    rec.has_reward_early = (A <= 608 && !getenv("LZ_TC_LATE_REWARD")) ? 1 : 0;   // scratch sized for ldl = 608
     L = 0;
     for (int i = 0; i < n; ++i) {
         tail.layer_w[L] = 4 * n + 1 + 2 * i; tail.layer_flags[L++] = 0;
@@ -978,6 +979,7 @@ int lz_model_debug_tc_program(lz_model *m, int which, int nlayers, const int *la
     n.nlayers = nlayers;
     for (int i = 0; i < nlayers; ++i) { n.layer_w[i] = layer_w[i]; n.layer_flags[i] = layer_flags[i]; }
     n.has_reward = has_reward;
+    n.has_reward_early = 0;
     return LZ_OK;
 }
 

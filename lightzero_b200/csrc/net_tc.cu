@@ -51,7 +51,9 @@ constexpr int kActBytes = 2 * kPartBytes;        // hi + lo: 102400 B
 constexpr int kTapBytes = 2 * 64 * 64 * 2;       // one 3x3 tap, hi + lo: 16384 B
 constexpr int kStages = 4;
 constexpr int kHeadWBytes = 3 * 2 * 16 * 64 * 2; // three 1x1 heads (hc <= 16), hi + lo: 12288 B
-constexpr int kSmemBytes = kActBytes + kStages * kTapBytes + kHeadWBytes + 1024;
+constexpr int kSmemMain = kActBytes + kStages * kTapBytes + kHeadWBytes + 1024;
+constexpr int kHeadScratch = (kMaxRoots * (576 + 32 + 608) + 8 * kMaxRoots * 32) * 4;   // one head: features, hidden, logits, partials
+constexpr int kSmemBytes = kSmemMain + kHeadScratch;
 
 // TMEM columns
 constexpr int kColAcc = 0;        // 3 tiles x 64
@@ -68,6 +70,136 @@ struct TcBars {
     uint32_t tmem_base;
     uint32_t pad;
 };
+
+// ---------------------------------------------------------------------------------------------- heads
+// 1x1-conv accumulators (TMEM) -> BN/ReLU features -> FC1 -> BN/ReLU -> FC2 -> softmax expectation -> h^-1 for the
+// heads in `hmask` (bit 0 reward, 1 value, 2 policy).  Executed by the kEpiThreads epilogue threads together
+// (named barrier 1).  scr: [nh][7][576] features | [nh][7][32] hidden | [nh][7][ldl] logits | [8][nh][7][32] partials.
+__device__ __forceinline__ void head_stage(const TcNet &net, const TcIO &io, int hmask, float *scr, uint32_t tmem, int NT,
+                                           int rows_used, int nvalid, int root0)
+{
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int q4 = warp & 3, half = warp >> 2, rowid = q4 * 32 + lane;
+    const uint32_t lane_base = tmem + ((uint32_t)(q4 * 32) << 16);
+    const int A = net.A, ldl = max(608, (A + 31) & ~31);
+    const int nh = __popc(hmask);
+    int slot[3];
+    slot[0] = 0; slot[1] = hmask & 1; slot[2] = (hmask & 1) + ((hmask >> 1) & 1);
+    float *hflat = scr, *hidden = hflat + nh * kMaxRoots * 576, *logits = hidden + nh * kMaxRoots * 32;
+    float *part = logits + nh * kMaxRoots * ldl;
+    for (int i = tid; i < nh * kMaxRoots * 576; i += kEpiThreads) hflat[i] = 0.0f;
+    asm volatile("bar.sync 1, %0;\n" ::"n"(kEpiThreads) : "memory");
+    for (int t = 0; t < NT; ++t) {
+        const int m = t * 128 + rowid;
+        const int r = m / kRowsPerRoot, q = m - r * kRowsPerRoot, y = q / kPitch, x = q - y * kPitch;
+        const bool valid = (m < rows_used) && (r < nvalid) && (y < 6) && (x < 6);
+        const int p = y * 6 + x;
+        float v[16];
+        // warps 0-3 scatter reward + value features, warps 4-7 policy features (any warp may read its lane quarter)
+        if (half == 0 && (hmask & 1)) {
+            tmem_ld16(lane_base + kColRew + t * 16, v);
+            if (valid)
+                for (int c = 0; c < net.hc[0]; ++c)
+                    hflat[(slot[0] * kMaxRoots + r) * 576 + c * kP + p] = fmaxf(fmaf(v[c], __ldg(net.head_bn + c), __ldg(net.head_bn + 16 + c)), 0.0f);
+        }
+        if (half == 0 && (hmask & 2)) {
+            tmem_ld16(lane_base + kColAcc + t * 32, v);
+            if (valid)
+                for (int c = 0; c < net.hc[1]; ++c)
+                    hflat[(slot[1] * kMaxRoots + r) * 576 + c * kP + p] = fmaxf(fmaf(v[c], __ldg(net.head_bn + 32 + c), __ldg(net.head_bn + 48 + c)), 0.0f);
+        }
+        if (half == 1 && (hmask & 4)) {
+            tmem_ld16(lane_base + kColAcc + t * 32 + 16, v);
+            if (valid)
+                for (int c = 0; c < net.hc[2]; ++c)
+                    hflat[(slot[2] * kMaxRoots + r) * 576 + c * kP + p] = fmaxf(fmaf(v[c], __ldg(net.head_bn + 64 + c), __ldg(net.head_bn + 80 + c)), 0.0f);
+        }
+    }
+    tc_fence_before();
+    asm volatile("bar.sync 1, %0;\n" ::"n"(kEpiThreads) : "memory");
+    // ---- FC1 (hc*36 -> hid): warp w takes an eighth of the inputs, lane = hidden unit; 24 coalesced weight rows in flight
+    for (int h = 0; h < 3; ++h) {
+        if (!((hmask >> h) & 1)) continue;
+        const Head &H = h == 0 ? net.reward : (h == 1 ? net.value : net.policy);
+        const int nin = H.hc * kP, qn = (nin + kEpiWarps - 1) / kEpiWarps, i0 = warp * qn, i1 = min(nin, i0 + qn);
+        float a[kMaxRoots];
+#pragma unroll
+        for (int r = 0; r < kMaxRoots; ++r) a[r] = 0.0f;
+        const float *hf = hflat + slot[h] * kMaxRoots * 576;
+        const float *wp = H.fc1 + lane;
+        const bool lane_on = lane < H.hid;
+        for (int i = i0; i < i1; i += 24) {
+            float w[24];
+#pragma unroll
+            for (int u = 0; u < 24; ++u) w[u] = (lane_on && i + u < i1) ? __ldg(wp + (size_t)(i + u) * H.hid) : 0.0f;
+#pragma unroll
+            for (int u = 0; u < 24; ++u) {
+                const int ii = min(i + u, nin - 1);
+#pragma unroll
+                for (int r = 0; r < kMaxRoots; ++r) a[r] = fmaf(hf[r * 576 + ii], w[u], a[r]);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < kMaxRoots; ++r) part[((warp * nh + slot[h]) * kMaxRoots + r) * 32 + lane] = a[r];
+    }
+    asm volatile("bar.sync 1, %0;\n" ::"n"(kEpiThreads) : "memory");
+    for (int o = tid; o < nh * kMaxRoots * 32; o += kEpiThreads) {
+        const int sl = o / (kMaxRoots * 32), j = o & 31;
+        const int h = (sl == slot[0] && (hmask & 1)) ? 0 : ((sl == slot[1] && (hmask & 2)) ? 1 : 2);
+        const Head &H = h == 0 ? net.reward : (h == 1 ? net.value : net.policy);
+        float v = 0.0f;
+#pragma unroll
+        for (int w8 = 0; w8 < kEpiWarps; ++w8) v += part[o + w8 * nh * kMaxRoots * 32];
+        hidden[o] = (j < H.hid) ? fmaxf(fmaf(v, __ldg(H.s2 + j), __ldg(H.t2 + j)), 0.0f) : 0.0f;
+    }
+    asm volatile("bar.sync 1, %0;\n" ::"n"(kEpiThreads) : "memory");
+    // ---- FC2 (hid -> K): thread = output k, weights [j][K] coalesced over k, all 32 rows in flight
+    for (int h = 0; h < 3; ++h) {
+        if (!((hmask >> h) & 1)) continue;
+        const Head &H = h == 0 ? net.reward : (h == 1 ? net.value : net.policy);
+        float *lg = logits + slot[h] * kMaxRoots * ldl;
+        const float *hid = hidden + slot[h] * kMaxRoots * 32;
+        for (int k = tid; k < H.K; k += kEpiThreads) {
+            float o[kMaxRoots];
+            const float bias = __ldg(H.b2 + k);
+#pragma unroll
+            for (int r = 0; r < kMaxRoots; ++r) o[r] = bias;
+            float w[32];
+#pragma unroll
+            for (int u = 0; u < 32; ++u) w[u] = (u < H.hid) ? __ldg(H.fc2 + (size_t)u * H.K + k) : 0.0f;
+#pragma unroll
+            for (int u = 0; u < 32; ++u) {
+#pragma unroll
+                for (int r = 0; r < kMaxRoots; ++r) o[r] = fmaf(hid[r * 32 + u], w[u], o[r]);
+            }
+#pragma unroll
+            for (int r = 0; r < kMaxRoots; ++r) lg[r * ldl + k] = o[r];
+        }
+    }
+    asm volatile("bar.sync 1, %0;\n" ::"n"(kEpiThreads) : "memory");
+    // ---- softmax expectation + inverse transform: one warp per (categorical head, root)
+    for (int task = warp; task < 2 * kMaxRoots; task += kEpiWarps) {
+        const int h = task / kMaxRoots, r = task - h * kMaxRoots;       // h: 0 reward, 1 value (+ policy copy)
+        if (r >= nvalid || !((hmask >> h) & 1)) continue;
+        const int b = root0 + r;
+        const float *lg = logits + (slot[h] * kMaxRoots + r) * ldl;
+        if (h == 0) {
+            const float rv = categorical_to_scalar(lg, net.reward.K, net.support_min, net.support_step, lane);
+            if (lane == 0 && io.reward) io.reward[b] = rv;
+            if (io.reward_logits)
+                for (int k = lane; k < net.reward.K; k += 32) io.reward_logits[(size_t)b * net.reward.K + k] = lg[k];
+        } else {
+            const float vv = categorical_to_scalar(lg, net.value.K, net.support_min, net.support_step, lane);
+            if (lane == 0 && io.value) io.value[b] = vv;
+            if (io.value_logits)
+                for (int k = lane; k < net.value.K; k += 32) io.value_logits[(size_t)b * net.value.K + k] = lg[k];
+            if (io.policy_logits && (hmask & 4)) {
+                const float *lp = logits + (slot[2] * kMaxRoots + r) * ldl;
+                for (int a = lane; a < A; a += 32) io.policy_logits[(size_t)b * A + a] = lp[a];
+            }
+        }
+    }
+}
 
 // ---------------------------------------------------------------------------------------------- kernel
 __global__ void __launch_bounds__(kTcThreads, 1) k_net_tc(TcNet net, TcIO io)
@@ -289,9 +421,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_net_tc(TcNet net, TcIO io)
             tc_fence_before();
             mbar_arrive(&bars->act_ready);                      // phase L+1: next layer / this layer's hook may start
             if (dbg) dbg[3 + 2 * L] = clock64();
+            if ((flags & LF_HOOK_REWARD) && net.has_reward_early) {
+                // the reward head (FC1, FC2, softmax, h^-1) runs here, underneath the NEXT layer's MMAs
+                mbar_wait_warp(&bars->rew_ready, 0);
+                tc_fence_after();
+                head_stage(net, io, 1, reinterpret_cast<float *>(smem + kSmemMain), tmem, NT, rows_used, nvalid, root0);
+                if (dbg) dbg[28] = clock64();
+            }
         }
         // all 1x1 head accumulators must be complete before the head stage reads them / reuses the buffer
-        if (net.has_reward) mbar_wait_warp(&bars->rew_ready, 0);
+        if (net.has_reward && !net.has_reward_early) mbar_wait_warp(&bars->rew_ready, 0);
         mbar_wait_warp(&bars->vp_ready, 0);
         tc_fence_after();
         if (dbg) dbg[24] = clock64();
@@ -301,129 +440,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_net_tc(TcNet net, TcIO io)
     tc_fence_before();
     __syncthreads();          // all MMAs committed & observed, activation buffer is free
     tc_fence_after();
-    float *hflat = reinterpret_cast<float *>(act);                     // [3 heads][7 roots][576]
-    float *hidden = hflat + 3 * kMaxRoots * 576;                       // [3][7][32]
-    float *logits = hidden + 3 * kMaxRoots * 32;                       // [2][7][608] + [7][Apad]
-    const bool do_reward = net.has_reward;
-    if (warp < kEpiWarps) {
-        const int q4 = warp & 3, half = warp >> 2, rowid = q4 * 32 + lane;
-        const uint32_t lane_base = tmem + ((uint32_t)(q4 * 32) << 16);
-        for (int i = tid; i < 3 * kMaxRoots * 576; i += kEpiThreads) hflat[i] = 0.0f;
-        asm volatile("bar.sync 1, %0;\n" ::"n"(kEpiThreads) : "memory");
-        for (int t = 0; t < NT; ++t) {
-            const int m = t * 128 + rowid;
-            const int r = m / kRowsPerRoot, q = m - r * kRowsPerRoot, y = q / kPitch, x = q - y * kPitch;
-            const bool valid = (m < rows_used) && (r < nvalid) && (y < 6) && (x < 6);
-            const int p = y * 6 + x;
-            float v[16];
-            if (half == 0) {                 // warps 0-3: reward + value features; warps 4-7: policy features
-                if (do_reward) {
-                    tmem_ld16(lane_base + kColRew + t * 16, v);
-                    if (valid)
-                        for (int c = 0; c < net.hc[0]; ++c)
-                            hflat[(0 * kMaxRoots + r) * 576 + c * kP + p] = fmaxf(fmaf(v[c], __ldg(net.head_bn + c), __ldg(net.head_bn + 16 + c)), 0.0f);
-                }
-                tmem_ld16(lane_base + kColAcc + t * 32, v);
-                if (valid)
-                    for (int c = 0; c < net.hc[1]; ++c)
-                        hflat[(1 * kMaxRoots + r) * 576 + c * kP + p] = fmaxf(fmaf(v[c], __ldg(net.head_bn + 32 + c), __ldg(net.head_bn + 48 + c)), 0.0f);
-            } else {
-                tmem_ld16(lane_base + kColAcc + t * 32 + 16, v);
-                if (valid)
-                    for (int c = 0; c < net.hc[2]; ++c)
-                        hflat[(2 * kMaxRoots + r) * 576 + c * kP + p] = fmaxf(fmaf(v[c], __ldg(net.head_bn + 64 + c), __ldg(net.head_bn + 80 + c)), 0.0f);
-            }
-        }
-        tc_fence_before();
-        asm volatile("bar.sync 1, %0;\n" ::"n"(kEpiThreads) : "memory");
-        if (io.dbg && blockIdx.x == 0 && tid == 0) io.dbg[25] = clock64();
-        const int A = net.A, Apad = (A + 31) & ~31;
-        float *lg_rew = logits, *lg_val = logits + kMaxRoots * 608, *lg_pol = logits + 2 * kMaxRoots * 608;
-        float *part = lg_pol + kMaxRoots * Apad;                       // [kEpiWarps][3 heads][7 roots][32]
-        // ---- FC1 (576 -> 32, three heads, 7 roots): warp w takes a quarter of the 576 inputs, lane = hidden unit.
-        // Weight rows are 128-byte coalesced loads issued 8 at a time (the loop is L2-latency bound otherwise).
-        {
-            // all three heads have hc*36 <= 576 inputs; warp w takes inputs [72w, 72w+72), 24 weight rows in flight
-            constexpr int UB = 8;
-            for (int h = do_reward ? 0 : 1; h < 3; ++h) {
-                const Head &H = h == 0 ? net.reward : (h == 1 ? net.value : net.policy);
-                const int nin = H.hc * kP, qn = (nin + kEpiWarps - 1) / kEpiWarps, i0 = warp * qn, i1 = min(nin, i0 + qn);
-                float a[kMaxRoots];
-#pragma unroll
-                for (int r = 0; r < kMaxRoots; ++r) a[r] = 0.0f;
-                const float *hf = hflat + h * kMaxRoots * 576;
-                const float *wp = H.fc1 + lane;
-                const bool lane_on = lane < H.hid;
-                for (int i = i0; i < i1; i += 3 * UB) {
-                    float w[3 * UB];
-#pragma unroll
-                    for (int u = 0; u < 3 * UB; ++u) w[u] = (lane_on && i + u < i1) ? __ldg(wp + (size_t)(i + u) * H.hid) : 0.0f;
-#pragma unroll
-                    for (int u = 0; u < 3 * UB; ++u) {
-                        const int ii = min(i + u, nin - 1);
-#pragma unroll
-                        for (int r = 0; r < kMaxRoots; ++r) a[r] = fmaf(hf[r * 576 + ii], w[u], a[r]);
-                    }
-                }
-#pragma unroll
-                for (int r = 0; r < kMaxRoots; ++r) part[((warp * 3 + h) * kMaxRoots + r) * 32 + lane] = a[r];
-            }
-        }
-        asm volatile("bar.sync 1, %0;\n" ::"n"(kEpiThreads) : "memory");
-        for (int o = tid; o < 3 * kMaxRoots * 32; o += kEpiThreads) {
-            const int h = o / (kMaxRoots * 32), j = o & 31;
-            const Head &H = h == 0 ? net.reward : (h == 1 ? net.value : net.policy);
-            float v = 0.0f;
-#pragma unroll
-            for (int w8 = 0; w8 < kEpiWarps; ++w8) v += part[o + w8 * 3 * kMaxRoots * 32];
-            hidden[o] = (j < H.hid && (h > 0 || do_reward)) ? fmaxf(fmaf(v, __ldg(H.s2 + j), __ldg(H.t2 + j)), 0.0f) : 0.0f;
-        }
-        asm volatile("bar.sync 1, %0;\n" ::"n"(kEpiThreads) : "memory");
-        // ---- FC2 (32 -> K): thread = output k (strided by 128), weights [j][K] coalesced over k, 8 rows in flight
-        for (int h = do_reward ? 0 : 1; h < 3; ++h) {
-            const Head &H = h == 0 ? net.reward : (h == 1 ? net.value : net.policy);
-            float *lg = h == 0 ? lg_rew : (h == 1 ? lg_val : lg_pol);
-            const int ld = h == 2 ? Apad : 608;
-            const float *hid = hidden + h * kMaxRoots * 32;
-            for (int k = tid; k < H.K; k += kEpiThreads) {
-                float o[kMaxRoots];
-                const float bias = __ldg(H.b2 + k);
-#pragma unroll
-                for (int r = 0; r < kMaxRoots; ++r) o[r] = bias;
-                float w[32];
-#pragma unroll
-                for (int u = 0; u < 32; ++u) w[u] = (u < H.hid) ? __ldg(H.fc2 + (size_t)u * H.K + k) : 0.0f;
-#pragma unroll
-                for (int u = 0; u < 32; ++u) {
-#pragma unroll
-                    for (int r = 0; r < kMaxRoots; ++r) o[r] = fmaf(hid[r * 32 + u], w[u], o[r]);
-                }
-#pragma unroll
-                for (int r = 0; r < kMaxRoots; ++r) lg[r * ld + k] = o[r];
-            }
-        }
-        asm volatile("bar.sync 1, %0;\n" ::"n"(kEpiThreads) : "memory");
-        if (io.dbg && blockIdx.x == 0 && tid == 0) io.dbg[26] = clock64();
-        for (int task = warp; task < 2 * kMaxRoots; task += kEpiWarps) {
-            const int h = task / kMaxRoots, r = task - h * kMaxRoots;       // h: 0 reward, 1 value (+ policy copy)
-            if (r >= nvalid) continue;
-            const int b = root0 + r;
-            if (h == 0) {
-                if (!do_reward) continue;
-                float rv = categorical_to_scalar(lg_rew + r * 608, net.reward.K, net.support_min, net.support_step, lane);
-                if (lane == 0 && io.reward) io.reward[b] = rv;
-                if (io.reward_logits)
-                    for (int k = lane; k < net.reward.K; k += 32) io.reward_logits[(size_t)b * net.reward.K + k] = lg_rew[r * 608 + k];
-            } else {
-                float vv = categorical_to_scalar(lg_val + r * 608, net.value.K, net.support_min, net.support_step, lane);
-                if (lane == 0 && io.value) io.value[b] = vv;
-                if (io.value_logits)
-                    for (int k = lane; k < net.value.K; k += 32) io.value_logits[(size_t)b * net.value.K + k] = lg_val[r * 608 + k];
-                if (io.policy_logits)
-                    for (int a = lane; a < A; a += 32) io.policy_logits[(size_t)b * A + a] = lg_pol[r * Apad + a];
-            }
-        }
-    }
+    if (warp < kEpiWarps)
+        head_stage(net, io, net.has_reward_early ? 6 : (net.has_reward ? 7 : 6), reinterpret_cast<float *>(act), tmem, NT, rows_used, nvalid, root0);
     if (io.dbg && blockIdx.x == 0 && tid == 0) io.dbg[27] = clock64();
     tc_fence_before();
     __syncthreads();

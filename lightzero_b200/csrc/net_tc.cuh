@@ -20,6 +20,7 @@ struct TcNet {
     int layer_w[kTcMaxLayers];     // conv index into convw / bn
     int layer_flags[kTcMaxLayers];
     int has_reward;
+    int has_reward_early;          // reward head evaluated right after its hook, under the next layer's MMAs
     int A;
     float support_min, support_step;
 };

@@ -133,10 +133,9 @@ def phase_breakdown():
         print(f"   load done            {s[1] - t0:8d}")
         for L in range(5):
             print(f"   L{L}: mma issue {s[32 + 2 * L] - t0:8d} -> {s[33 + 2 * L] - t0:8d} | acc ready {s[2 + 2 * L] - t0:8d}  epilogue done {s[3 + 2 * L] - t0:8d}")
-        print(f"   hooks ready          {s[24] - t0:8d}")
-        print(f"   hflat written        {s[25] - t0:8d}")
-        print(f"   fc done              {s[26] - t0:8d}")
-        print(f"   outputs done         {s[27] - t0:8d}")
+        print(f"   early reward head done {s[28] - t0:8d}   (runs under the next layer's MMAs)")
+        print(f"   hooks ready            {s[24] - t0:8d}")
+        print(f"   heads + outputs done   {s[27] - t0:8d}")
 
 
 if __name__ == "__main__" and os.environ.get("DBG_PHASES"):
