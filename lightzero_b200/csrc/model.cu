@@ -354,6 +354,7 @@ int model_recurrent(lz_model *m, const RecIO &io, cudaStream_t s)
         t.latent_base = io.latent_base; t.ix = io.ix; t.slot_stride = io.slot_stride; t.action = io.action;
         t.latent_out = io.next_latent; t.reward = io.reward; t.value = io.value; t.policy_logits = io.policy_logits;
         t.reward_logits = io.reward_logits; t.value_logits = io.value_logits;
+        t.pdl = io.pdl;
         return tc_launch(m->tc_rec, t, s);
     }
     switch (pick_W(io.B)) {

@@ -54,6 +54,7 @@ struct RecIO {
     float *reward, *value;            // [B] scalars or nullptr
     float *policy_logits;             // [B][A] or nullptr
     float *reward_logits, *value_logits;   // [B][K] or nullptr
+    int pdl;                          // programmatic dependent launch (search graph)
 };
 
 struct TailIO {

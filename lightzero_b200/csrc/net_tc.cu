@@ -219,6 +219,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_net_tc(TcNet net, TcIO io)
     const int npass = io.npass;
     const int nlayers = net.nlayers;
 
+    pdl_launch_dependents();      // the next tree kernel may become resident; it blocks in pdl_wait() until this grid is done
     // ---- one-time setup ----
     if (tid == 0) {
         for (int i = 0; i < kStages; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], 1); }
@@ -337,6 +338,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_net_tc(TcNet net, TcIO io)
         const uint32_t lane_base = tmem + ((uint32_t)(q4 * 32) << 16);
         unsigned long long *dbg = (io.dbg && blockIdx.x == 0 && tid == 0) ? io.dbg : nullptr;
         if (dbg) dbg[0] = clock64();
+        pdl_wait();                   // ix / action / the latent pool come from the preceding kernels
         // ---- load the input activation: gather NCHW latents, split to fp16 hi/lo, park fp32 copy in TMEM ----
         for (int t = 0; t < NT; ++t) {
             const int m = t * 128 + rowid;
@@ -532,8 +534,14 @@ int tc_launch(const TcNet &net, const TcIO &io_in, cudaStream_t s)
     if (const char *e = getenv("LZ_TC_VARIANT")) io.variant = atoi(e);
     if (const char *e = getenv("LZ_TC_ROOTS")) io.roots_per_cta = std::min(std::max(atoi(e), 1), kMaxRoots);
     const int grid = (io.B + io.roots_per_cta - 1) / io.roots_per_cta;
-    k_net_tc<<<grid, kTcThreads, kSmemBytes, s>>>(net, io);
-    LZ_KERNEL_CHECK();
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kTcThreads); cfg.dynamicSmemBytes = kSmemBytes; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = io_in.pdl ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    LZ_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_net_tc, net, io));
     return LZ_OK;
 }
 

@@ -4,6 +4,7 @@
 // :326-329, a duplicated recurrent_inference :338/:345, four blocking D2H copies :347-350 and three
 // .tolist() conversions :355-357) has no counterpart here: the tree hands (slot, action) to the
 // network through device memory and the network hands (reward, value, logits) back the same way.
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -42,6 +43,8 @@ static int enqueue_search(lz_search *q, int deterministic, cudaStream_t s)
     int rc;
     lz_tree *t = q->tree;
     t->step_counter = 0;
+    const bool pdl = q->model->kind == 0 && q->model->math != 0 && !getenv("LZ_NO_PDL");
+    t->pdl = pdl;
     if ((rc = tree_launch_traverse(t, deterministic, q->d_ix, nullptr, q->d_action, nullptr, nullptr, s))) return rc;
     for (int sim = 0; sim < q->S; ++sim) {
         RecIO io;
@@ -55,13 +58,15 @@ static int enqueue_search(lz_search *q, int deterministic, cudaStream_t s)
         io.reward = q->d_reward;
         io.value = q->d_value;
         io.policy_logits = q->d_policy;
-        if ((rc = model_recurrent(q->model, io, s))) return rc;
+        io.pdl = pdl ? 1 : 0;
+        if ((rc = model_recurrent(q->model, io, s))) { t->pdl = false; return rc; }
         if (sim + 1 < q->S)
             rc = tree_launch_backprop_traverse(t, sim + 1, q->d_reward, q->d_value, q->d_policy, deterministic, q->d_ix, q->d_action, s);
         else
             rc = tree_launch_backprop(t, sim + 1, q->d_reward, q->d_value, q->d_policy, nullptr, s);
-        if (rc) return rc;
+        if (rc) { t->pdl = false; return rc; }
     }
+    t->pdl = false;
     return LZ_OK;
 }
 

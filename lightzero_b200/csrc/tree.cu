@@ -7,6 +7,7 @@
 
 #include "lz_common.cuh"
 #include "tree.cuh"
+#include "tc_ptx.cuh"
 
 namespace lz {
 
@@ -101,6 +102,8 @@ k_tree_traverse(TreeParams p, int deterministic, unsigned step, int32_t *ix, int
                 int32_t *len, int32_t *vtp)
 {
     const int b = blockIdx.x * (kTreeBlock / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    pdl_launch_dependents();
+    pdl_wait();
     if (b >= p.B) return;
     tree_traverse(p, b, lane, deterministic, step, ix, iy, act, len, vtp);
 }
@@ -110,6 +113,8 @@ k_tree_backprop(TreeParams p, int latent_index, const float *reward, const float
                 const int32_t *to_play)
 {
     const int b = blockIdx.x * (kTreeBlock / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    pdl_launch_dependents();
+    pdl_wait();
     if (b >= p.B) return;
     tree_backprop(p, b, lane, latent_index, reward[b], value[b], logits + (size_t)b * p.A, to_play);
 }
@@ -119,6 +124,8 @@ k_tree_backprop_traverse(TreeParams p, int latent_index, const float *reward, co
                          const float *logits, int deterministic, unsigned step, int32_t *ix, int32_t *act)
 {
     const int b = blockIdx.x * (kTreeBlock / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    pdl_launch_dependents();      // lets the next network kernel set up (TMEM, barriers, first weight taps) meanwhile
+    pdl_wait();                   // reward / value / logits come from the preceding network kernel
     if (b >= p.B) return;
     tree_backprop(p, b, lane, latent_index, reward[b], value[b], logits + (size_t)b * p.A, nullptr);
     tree_traverse(p, b, lane, deterministic, step, ix, nullptr, act, nullptr, nullptr);
@@ -161,21 +168,32 @@ k_tree_results(TreeParams p, int32_t *visits, float *values, int32_t *nlegal, in
 
 static inline dim3 tree_grid(int B) { return dim3(ceil_div(B, kTreeBlock / 32)); }
 
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, cudaStream_t s, bool pdl, Args... args)
+{
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = dim3(kTreeBlock); cfg.dynamicSmemBytes = 0; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 int tree_launch_traverse(lz_tree *t, int deterministic, int32_t *d_ix, int32_t *d_iy, int32_t *d_action,
                          int32_t *d_len, int32_t *d_vtp, cudaStream_t s)
 {
-    k_tree_traverse<<<tree_grid(t->p.B), kTreeBlock, 0, s>>>(t->p, deterministic, t->step_counter++, d_ix, d_iy,
-                                                            d_action, d_len, d_vtp);
-    LZ_KERNEL_CHECK();
+    LZ_CUDA_CHECK(launch_pdl(k_tree_traverse, tree_grid(t->p.B), s, t->pdl, t->p, deterministic, t->step_counter++, d_ix, d_iy,
+                             d_action, d_len, d_vtp));
     return LZ_OK;
 }
 
 int tree_launch_backprop(lz_tree *t, int latent_index, const float *d_reward, const float *d_value,
                          const float *d_logits, const int32_t *d_to_play, cudaStream_t s)
 {
-    k_tree_backprop<<<tree_grid(t->p.B), kTreeBlock, 0, s>>>(t->p, latent_index, d_reward, d_value, d_logits,
-                                                            d_to_play);
-    LZ_KERNEL_CHECK();
+    LZ_CUDA_CHECK(launch_pdl(k_tree_backprop, tree_grid(t->p.B), s, t->pdl, t->p, latent_index, d_reward, d_value, d_logits,
+                             d_to_play));
     return LZ_OK;
 }
 
@@ -183,10 +201,8 @@ int tree_launch_backprop_traverse(lz_tree *t, int latent_index, const float *d_r
                                   const float *d_logits, int deterministic, int32_t *d_ix, int32_t *d_action,
                                   cudaStream_t s)
 {
-    k_tree_backprop_traverse<<<tree_grid(t->p.B), kTreeBlock, 0, s>>>(t->p, latent_index, d_reward, d_value,
-                                                                     d_logits, deterministic, t->step_counter++,
-                                                                     d_ix, d_action);
-    LZ_KERNEL_CHECK();
+    LZ_CUDA_CHECK(launch_pdl(k_tree_backprop_traverse, tree_grid(t->p.B), s, t->pdl, t->p, latent_index, d_reward, d_value,
+                             d_logits, deterministic, t->step_counter++, d_ix, d_action));
     return LZ_OK;
 }
 

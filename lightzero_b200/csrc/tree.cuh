@@ -369,6 +369,7 @@ struct lz_tree {
     int max_sims;
     unsigned step_counter;
     bool params_set, prepared;
+    bool pdl;                    // launch tree kernels with programmatic stream serialization (set by the search graph)
     void *alloc_base;
 };
 
