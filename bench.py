@@ -23,6 +23,7 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+_emit = print
 
 METRIC = "MCTS simulations/sec (batched search+infer)"
 UNIT = "simulations/s"
@@ -105,7 +106,7 @@ def reference_arm(args, rank, world):
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    _emit(json.dumps(line))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -194,8 +195,13 @@ def ours(args, rank, local_rank, world):
     h_noise = torch.from_numpy(rng.dirichlet([0.3] * A, size=B).astype(np.float32)).pin_memory()
     d_mask, d_noise = h_mask.to(dev), h_noise.to(dev)
 
+    from lightzero_b200.dist import gather_search_results
+
     def device_step(i):
-        return policy.search_batch(d_obs[i % NBUF], d_mask, d_noise, None, deterministic=True, read_back=False)
+        r = policy.search_batch(d_obs[i % NBUF], d_mask, d_noise, None, deterministic=True, read_back=False)
+        if world > 1:   # the only collective of the path: all-gather of the finished results (82 KB per rank) over NCCL
+            gather_search_results(r["visits"], r["values"], B * world)
+        return r
 
     def e2e_step(i):
         return policy.search_batch(h_obs[i % NBUF], h_mask, h_noise, None, deterministic=True, read_back=True)
@@ -296,7 +302,7 @@ def ours(args, rank, local_rank, world):
             "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32 (fp16x2-split tensor MMAs, fp32 accumulate)", "data": "synthetic",
             "config": {"workload": WORKLOAD, "roots_per_gpu": B, "global_roots": total_roots, "num_simulations": S,
-                       "actions": A, "obs": list(OBS), "parallelism": f"roots sharded x{world}, no data-path collective",
+                       "actions": A, "obs": list(OBS), "parallelism": f"roots sharded x{world}, no data-path collective; one NCCL all-gather of visits/values per step",
                        "step": "initial_inference + prepare + S x (traverse, recurrent_inference, backpropagate) + results",
                        "deterministic": True,
                        "math": "tcgen05 fp16 hi/lo split (3 MMAs per product, fp32 accumulate in TMEM): fp32-accurate, the 1e-5 parity mode",
@@ -323,13 +329,23 @@ def ours(args, rank, local_rank, world):
         if not args.no_cpu_baseline and world == 1:
             r = run_reference_pipeline(args.cpu_sample_roots, S, 1, 0)
             line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
-        print(json.dumps(line), flush=True)
+        _emit(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
 def main():
+    # stdout must carry exactly ONE JSON line: libraries (e.g. NCCL's version banner) write to fd 1, so park the
+    # real stdout and point fd 1 at stderr until the result is printed
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    global _emit
+
+    def _emit(line):
+        sys.stdout.flush()
+        os.write(real_stdout, (line + "\n").encode())
     args = parse()
     rank = int(os.environ.get("RANK", 0))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
