@@ -39,7 +39,7 @@ class MuZeroCollectPolicy:
         self.cfg = self.mcts._cfg
         self.device = model.device
         self._buf = {}
-        self.h2d_chunks = 4      # host observation batches are copied in this many overlapped pieces
+        self.h2d_chunks = 2      # host observation batches are copied in this many overlapped pieces
 
     # ---- device-resident fast path ---------------------------------------------------------------
     def _bufs(self, B, A):

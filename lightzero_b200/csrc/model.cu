@@ -486,6 +486,25 @@ static int tower_tc_run(lz_model *m, int B, const float *d_obs, float *pre_laten
     return pool_tcl_to_nchw_launch(m->V2, pre_latent, B, kHW, s);                    // pooling2 -> [B][64][6][6]
 }
 
+// tcgen05 path only: the DownSample tower alone (obs -> pre-latent [B][64][36]) ...
+int model_initial_tower(lz_model *m, int B, const float *d_obs, float *pre_latent, cudaStream_t s)
+{
+    LZ_REQUIRE(m->kind == 0 && m->math != 0 && m->cfg.obs_h != 64, LZ_ESTATE, "model_initial_tower: tensor-core conv model only");
+    LZ_REQUIRE(B <= m->ws_B, LZ_ESTATE, "model_initial_tower: workspace sized for %d roots, got %d", m->ws_B, B);
+    return tower_tc_run(m, B, d_obs, pre_latent, s);
+}
+
+// ... and the latent-grid tail (representation ResBlocks -> latent -> prediction network)
+int model_initial_tail(lz_model *m, int B, const float *pre_latent, const TailIO &io_in, cudaStream_t s)
+{
+    TcIO t;
+    memset(&t, 0, sizeof(t));
+    t.B = B; t.npass = (m->math == 1) ? 3 : 1;
+    t.latent_base = pre_latent; t.latent_out = io_in.latent; t.latent_out2 = io_in.latent2;
+    t.value = io_in.value; t.policy_logits = io_in.policy_logits; t.value_logits = io_in.value_logits;
+    return tc_launch(m->tc_tail, t, s);
+}
+
 int model_initial(lz_model *m, int B, const float *d_obs, const TailIO &io_in, cudaStream_t s)
 {
     if (m->kind == 1) return mlp_initial(m, B, d_obs, io_in, s);
@@ -495,13 +514,7 @@ int model_initial(lz_model *m, int B, const float *d_obs, const TailIO &io_in, c
     int rc;
     if (m->math != 0 && m->cfg.obs_h != 64 && !getenv("LZ_TOWER_SIMT")) {
         if ((rc = tower_tc_run(m, B, d_obs, a, s))) return rc;
-        TailIO io = io_in;
-        TcIO t;
-        memset(&t, 0, sizeof(t));
-        t.B = B; t.npass = (m->math == 1) ? 3 : 1;
-        t.latent_base = a; t.latent_out = io.latent; t.latent_out2 = io.latent2;
-        t.value = io.value; t.policy_logits = io.policy_logits; t.value_logits = io.value_logits;
-        return tc_launch(m->tc_tail, t, s);
+        return model_initial_tail(m, B, a, io_in, s);
     }
     // DownSample.forward, common.py:340-366
     if ((rc = launch_convg(T[0], d_obs, a, nullptr, 1, B, s))) return rc;          // conv1 + norm1 + relu

@@ -101,6 +101,8 @@ struct lz_model {
 namespace lz {
 int model_recurrent(lz_model *m, const RecIO &io, cudaStream_t s);
 int model_initial(lz_model *m, int B, const float *d_obs, const TailIO &io, cudaStream_t s);
+int model_initial_tower(lz_model *m, int B, const float *d_obs, float *pre_latent, cudaStream_t s);
+int model_initial_tail(lz_model *m, int B, const float *pre_latent, const TailIO &io, cudaStream_t s);
 int model_reserve(lz_model *m, int B);   // sizes the initial-inference workspace (synchronous)
 int mlp_recurrent(lz_model *m, const RecIO &io, cudaStream_t s);
 int mlp_initial(lz_model *m, int B, const float *d_obs, const TailIO &io, cudaStream_t s);

@@ -28,9 +28,9 @@ struct lz_search {
                                  // which cannot be captured; the instantiated graph launches on the caller's
     int num_kernels;
     // host-buffer collect: staging + copy stream so the H2D of chunk i+1 overlaps the tower of chunk i
-    cudaStream_t copy_stream;
+    cudaStream_t copy_stream, copy_stream2;   // chunks alternate between two copy streams (two DMA engines)
     cudaEvent_t ev_chunk[8], ev_start;
-    float *d_obs_stage, *d_noise_stage;
+    float *d_obs_stage, *d_noise_stage, *d_pre_stage;
     uint8_t *d_mask_stage;
     int32_t *d_tp_stage;
     size_t obs_elems;            // floats per observation
@@ -125,10 +125,11 @@ int lz_search_destroy(lz_search *q)
     if (q->capture_stream) cudaStreamDestroy(q->capture_stream);
     if (q->copy_stream) {
         cudaStreamDestroy(q->copy_stream);
+        cudaStreamDestroy(q->copy_stream2);
         for (int i = 0; i < 8; ++i) cudaEventDestroy(q->ev_chunk[i]);
         cudaEventDestroy(q->ev_start);
     }
-    cudaFree(q->d_obs_stage); cudaFree(q->d_noise_stage); cudaFree(q->d_mask_stage); cudaFree(q->d_tp_stage);
+    cudaFree(q->d_obs_stage); cudaFree(q->d_noise_stage); cudaFree(q->d_pre_stage); cudaFree(q->d_mask_stage); cudaFree(q->d_tp_stage);
     cudaFree(q->pool); cudaFree(q->d_ix); cudaFree(q->d_action); cudaFree(q->d_reward); cudaFree(q->d_value);
     cudaFree(q->d_policy); cudaFree(q->d_root_logits); cudaFree(q->d_root_value);
     delete q;
@@ -174,10 +175,12 @@ int lz_search_collect_host(lz_search *q, const float *h_obs, const uint8_t *h_ma
     if (!q->copy_stream) {
         q->obs_elems = obs_elems;
         LZ_CUDA_CHECK(cudaStreamCreateWithFlags(&q->copy_stream, cudaStreamNonBlocking));
+        LZ_CUDA_CHECK(cudaStreamCreateWithFlags(&q->copy_stream2, cudaStreamNonBlocking));
         for (int i = 0; i < 8; ++i) LZ_CUDA_CHECK(cudaEventCreateWithFlags(&q->ev_chunk[i], cudaEventDisableTiming));
         LZ_CUDA_CHECK(cudaEventCreateWithFlags(&q->ev_start, cudaEventDisableTiming));
         int rc = dev_alloc(&q->d_obs_stage, q->obs_elems * B);
         if (rc == LZ_OK) rc = dev_alloc(&q->d_noise_stage, (size_t)B * A);
+        if (rc == LZ_OK) rc = dev_alloc(&q->d_pre_stage, (size_t)B * q->model->latent_floats);
         if (rc == LZ_OK) rc = dev_alloc(&q->d_mask_stage, (size_t)B * A);
         if (rc == LZ_OK) rc = dev_alloc(&q->d_tp_stage, (size_t)B);
         if (rc != LZ_OK) return rc;
@@ -185,28 +188,47 @@ int lz_search_collect_host(lz_search *q, const float *h_obs, const uint8_t *h_ma
     // the copy stream may not overwrite the staging buffer before earlier work on `s` has consumed it
     LZ_CUDA_CHECK(cudaEventRecord(q->ev_start, s));
     LZ_CUDA_CHECK(cudaStreamWaitEvent(q->copy_stream, q->ev_start, 0));
+    LZ_CUDA_CHECK(cudaStreamWaitEvent(q->copy_stream2, q->ev_start, 0));
+    const bool two = !getenv("LZ_ONE_COPY_STREAM");
     const int per = (B + nchunks - 1) / nchunks;
     for (int i = 0; i < nchunks; ++i) {
         const int b0 = i * per, bc = std::min(per, B - b0);
         if (bc <= 0) { nchunks = i; break; }
+        cudaStream_t cs = (two && (i & 1)) ? q->copy_stream2 : q->copy_stream;
         LZ_CUDA_CHECK(cudaMemcpyAsync(q->d_obs_stage + (size_t)b0 * q->obs_elems, h_obs + (size_t)b0 * q->obs_elems,
-                                      (size_t)bc * q->obs_elems * sizeof(float), cudaMemcpyHostToDevice, q->copy_stream));
-        LZ_CUDA_CHECK(cudaEventRecord(q->ev_chunk[i], q->copy_stream));
+                                      (size_t)bc * q->obs_elems * sizeof(float), cudaMemcpyHostToDevice, cs));
+        LZ_CUDA_CHECK(cudaEventRecord(q->ev_chunk[i], cs));
     }
     if (h_mask) LZ_CUDA_CHECK(cudaMemcpyAsync(q->d_mask_stage, h_mask, (size_t)B * A, cudaMemcpyHostToDevice, s));
     if (h_noise) LZ_CUDA_CHECK(cudaMemcpyAsync(q->d_noise_stage, h_noise, (size_t)B * A * sizeof(float), cudaMemcpyHostToDevice, s));
     if (h_to_play) LZ_CUDA_CHECK(cudaMemcpyAsync(q->d_tp_stage, h_to_play, (size_t)B * sizeof(int32_t), cudaMemcpyHostToDevice, s));
     float *logits = d_policy_logits ? d_policy_logits : q->d_root_logits;
     float *pred = d_pred_value ? d_pred_value : q->d_root_value;
+    const bool split = q->model->kind == 0 && q->model->math != 0 && c.obs_h != 64;   // tower per chunk, tail once
     for (int i = 0; i < nchunks; ++i) {
         const int b0 = i * per, bc = std::min(per, B - b0);
         LZ_CUDA_CHECK(cudaStreamWaitEvent(s, q->ev_chunk[i], 0));
+        int rc;
+        if (split) {
+            rc = model_initial_tower(q->model, bc, q->d_obs_stage + (size_t)b0 * q->obs_elems,
+                                     q->d_pre_stage + (size_t)b0 * q->model->latent_floats, s);
+        } else {
+            TailIO io;
+            memset(&io, 0, sizeof(io));
+            io.latent2 = q->pool + (size_t)b0 * q->model->latent_floats;
+            io.policy_logits = logits + (size_t)b0 * A;
+            io.value = pred + b0;
+            rc = model_initial(q->model, bc, q->d_obs_stage + (size_t)b0 * q->obs_elems, io, s);
+        }
+        if (rc) return rc;
+    }
+    if (split) {
         TailIO io;
         memset(&io, 0, sizeof(io));
-        io.latent2 = q->pool + (size_t)b0 * q->model->latent_floats;
-        io.policy_logits = logits + (size_t)b0 * A;
-        io.value = pred + b0;
-        int rc = model_initial(q->model, bc, q->d_obs_stage + (size_t)b0 * q->obs_elems, io, s);
+        io.latent2 = q->pool;
+        io.policy_logits = logits;
+        io.value = pred;
+        int rc = model_initial_tail(q->model, B, q->d_pre_stage, io, s);
         if (rc) return rc;
     }
     int rc;

@@ -37,3 +37,19 @@ for ch in (1, 2, 4, 8):
     call_ms = (time.perf_counter() - t0) * 1e3
     torch.cuda.synchronize()
     print("host step, chunks=%d:      dev %.3f ms wall %.3f ms  (launch-call returns after %.3f ms)" % (ch, *timeit(lambda: pol.search_batch(h_obs, mask, noise, None, deterministic=True, read_back=True)), call_ms))
+
+print("---- same under a non-default (non-blocking) torch stream")
+st = torch.cuda.Stream()
+with torch.cuda.stream(st):
+    for ch in (1, 2, 4):
+        pol.h2d_chunks = ch
+        for _ in range(2):
+            pol.search_batch(h_obs, mask, noise, None, deterministic=True, read_back=True)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(st)
+        for _ in range(5):
+            pol.search_batch(h_obs, mask, noise, None, deterministic=True, read_back=True)
+        b.record(st)
+        torch.cuda.synchronize()
+        print("side stream, chunks=%d: dev %.3f ms" % (ch, a.elapsed_time(b) / 5))
