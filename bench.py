@@ -315,6 +315,7 @@ def ours(args, rank, local_rank, world):
                     "ms_per_step": e2e_ms, "device_ms_per_step": e2e_dev_ms / args.steps,
                     "api": "lightzero_b200.collect.MuZeroCollectPolicy.search_batch (pinned host obs/mask/noise in, pinned host visits/values out)"},
             "gpu_launches": args.steps * (13 + 2 + num_kernels_search + 1),
+            "search_graph_kernels": num_kernels_search,
             "roofline": {"bound": "tensor", "kernel": "k_net_tc (fused recurrent_inference, tcgen05)", "achieved": achieved_tf,
                          "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf, "traffic": None,
                          "peak_source": peak_note, "kernel_ms": k_avg_ms, "kernel_ms_min": k_ms[0],

@@ -35,6 +35,7 @@
 #include "model.cuh"
 #include "net_tc.cuh"
 #include "tc_ptx.cuh"
+#include "tree.cuh"
 
 namespace lz {
 
@@ -202,7 +203,7 @@ __device__ __forceinline__ void head_stage(const TcNet &net, const TcIO &io, int
 }
 
 // ---------------------------------------------------------------------------------------------- kernel
-__global__ void __launch_bounds__(kTcThreads, 1) k_net_tc(TcNet net, TcIO io)
+__global__ void __launch_bounds__(kTcThreads, 1) k_net_tc(TcNet net, TcIO io, TreeParams tp)
 {
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char *act = smem;                                   // [2 parts][8 planes][400 rows][16 B]
@@ -218,6 +219,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_net_tc(TcNet net, TcIO io)
     const int NT = (rows_used + 127) >> 7;
     const int npass = io.npass;
     const int nlayers = net.nlayers;
+    const int nsims = io.nsims > 0 ? io.nsims : 1;     // > 1 (or persistent): the whole search loop runs inside this launch
+    const bool persistent = io.persistent != 0;
 
     pdl_launch_dependents();      // the next tree kernel may become resident; it blocks in pdl_wait() until this grid is done
     // ---- one-time setup ----
@@ -228,12 +231,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_net_tc(TcNet net, TcIO io)
         mbar_init(&bars->rew_ready, 1);
         mbar_init(&bars->vp_ready, 1);
         fence_mbar_init();
-    }
-    // zero the margins once (pad rows inside the tiles are rewritten as zeros by every epilogue)
-    for (int i = tid; i < 2 * 8 * 2 * kMargin; i += kTcThreads) {
-        int part = i / (8 * 2 * kMargin), rem = i % (8 * 2 * kMargin), plane = rem / (2 * kMargin), r = rem % (2 * kMargin);
-        int row = r < kMargin ? r : kMargin + kMaxTiles * 128 + (r - kMargin);
-        *reinterpret_cast<uint4 *>(act + part * kPartBytes + plane * kPlaneBytes + row * 16) = make_uint4(0, 0, 0, 0);
     }
     if (warp == kEpiWarps + 1) tmem_alloc(&bars->tmem_base, kTmemCols);
     // 1x1 head weights: plain copy (12 KB)
@@ -249,15 +246,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_net_tc(TcNet net, TcIO io)
         // ================= weight producer =================
         if (lane == 0) {
             uint32_t n = 0;
-            for (int L = 0; L < nlayers; ++L) {
-                const unsigned char *src = net.convw + (size_t)net.layer_w[L] * (9 * kTapBytes);
-                for (int tap = 0; tap < 9; ++tap, ++n) {
-                    const int st = n % kStages;
-                    if (n >= kStages) mbar_wait(&bars->empty[st], ((n / kStages) - 1) & 1);
-                    mbar_expect_tx(&bars->full[st], kTapBytes);
-                    bulk_g2s(ring + st * kTapBytes, src + (size_t)tap * kTapBytes, kTapBytes, &bars->full[st]);
+            for (int sim = 0; sim < nsims; ++sim)       // runs ahead of the MMAs: the next simulation's first taps are
+                for (int L = 0; L < nlayers; ++L) {     // already in the ring while heads / tree work is going on
+                    const unsigned char *src = net.convw + (size_t)net.layer_w[L] * (9 * kTapBytes);
+                    for (int tap = 0; tap < 9; ++tap, ++n) {
+                        const int st = n % kStages;
+                        if (n >= kStages) mbar_wait(&bars->empty[st], ((n / kStages) - 1) & 1);
+                        mbar_expect_tx(&bars->full[st], kTapBytes);
+                        bulk_g2s(ring + st * kTapBytes, src + (size_t)tap * kTapBytes, kTapBytes, &bars->full[st]);
+                    }
                 }
-            }
         }
     } else if (warp == kEpiWarps + 1) {
         // ================= MMA issuer =================
@@ -270,10 +268,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_net_tc(TcNet net, TcIO io)
             const uint64_t b_desc0 = make_desc(ring_s, 64, 8);                        // stage 0, hi part, k-step 0
             unsigned long long *dbg = (io.dbg && blockIdx.x == 0) ? io.dbg : nullptr;
             uint32_t n = 0;
+            for (int sim = 0; sim < nsims; ++sim)
             for (int L = 0; L < nlayers; ++L) {
-                mbar_wait(&bars->act_ready, L & 1);              // inputs written, TMEM accumulators drained
+                const uint32_t ev = (uint32_t)sim * (nlayers + 1) + L;   // act_ready event index: 1 load + nlayers epilogues per simulation
+                mbar_wait(&bars->act_ready, ev & 1);             // inputs written, TMEM accumulators drained
                 tc_fence_after();
-                if (dbg) dbg[32 + 2 * L] = clock64();
+                if (dbg && sim == 0) dbg[32 + 2 * L] = clock64();
                 for (int tap = 0; tap < 9; ++tap, ++n) {
                     const int st = n % kStages;
                     mbar_wait(&bars->full[st], (n / kStages) & 1);
@@ -299,14 +299,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_net_tc(TcNet net, TcIO io)
                     umma_commit(&bars->empty[st]);               // frees this ring slot when the MMAs have read it
                 }
                 umma_commit(&bars->acc_ready);
-                if (dbg) dbg[33 + 2 * L] = clock64();
+                if (dbg && sim == 0) dbg[33 + 2 * L] = clock64();
                 const int flags = net.layer_flags[L];
                 if (flags & (LF_HOOK_REWARD | LF_HOOK_VALPOL)) {
                     // 1x1 head convolutions on this layer's OUTPUT: wait for the epilogue to have written it (the same
                     // phase the next layer waits for; waiting twice on a completed phase is immediate).  The
                     // value/policy result reuses the drained conv accumulator columns, so that hook is only legal on
                     // the LAST layer; the reward result has its own columns.
-                    mbar_wait(&bars->act_ready, (L + 1) & 1);
+                    mbar_wait(&bars->act_ready, (ev + 1) & 1);
                     tc_fence_after();
                     for (int hook = 0; hook < 2; ++hook) {
                         if (!(flags & (hook == 0 ? LF_HOOK_REWARD : LF_HOOK_VALPOL))) continue;
@@ -339,112 +339,140 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_net_tc(TcNet net, TcIO io)
         unsigned long long *dbg = (io.dbg && blockIdx.x == 0 && tid == 0) ? io.dbg : nullptr;
         if (dbg) dbg[0] = clock64();
         pdl_wait();                   // ix / action / the latent pool come from the preceding kernels
-        // ---- load the input activation: gather NCHW latents, split to fp16 hi/lo, park fp32 copy in TMEM ----
-        for (int t = 0; t < NT; ++t) {
-            const int m = t * 128 + rowid;
-            const int r = m / kRowsPerRoot, q = m - r * kRowsPerRoot, y = q / kPitch, x = q - y * kPitch;
-            const bool valid = (m < rows_used) && (r < nvalid) && (y < 6) && (x < 6);
-            const float *src = nullptr;
-            if (valid) {
-                const int b = root0 + r;
-                const size_t slot = io.ix ? (size_t)io.ix[b] : 0;
-                src = io.latent_base + slot * io.slot_stride + (size_t)b * (kC * kP) + (y * 6 + x);
-            }
-            float v[32];
-#pragma unroll
-            for (int c = 0; c < 32; ++c) v[c] = valid ? __ldg(src + (size_t)(half * 32 + c) * kP) : 0.0f;
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-                unsigned char *p = act + (half * 4 + g) * kPlaneBytes + (kMargin + m) * 16;
-                store_split8(p, p + kPartBytes, v + 8 * g);
-            }
-            tmem_st32(lane_base + kColRes + t * 64 + half * 32, v);
-        }
-        fence_proxy_async();
-        tc_fence_before();
-        mbar_arrive(&bars->act_ready);                          // phase 0: layer 0 may start
-        if (dbg) dbg[1] = clock64();
-
         int acc_par = 0;
-        for (int L = 0; L < nlayers; ++L) {
-            const int flags = net.layer_flags[L];
-            const float *bn = net.bn + (size_t)net.layer_w[L] * 128;      // [scale 64 | shift 64]
-            mbar_wait_warp(&bars->acc_ready, acc_par);
-            acc_par ^= 1;
-            tc_fence_after();
-            if (dbg) dbg[2 + 2 * L] = clock64();
-            float bs[32], bt[32];                               // folded BatchNorm of this thread's 32 channels
-#pragma unroll
-            for (int c = 0; c < 32; ++c) { bs[c] = __ldg(bn + half * 32 + c); bt[c] = __ldg(bn + 64 + half * 32 + c); }
+        for (int sim = 0; sim < nsims; ++sim) {
+            if (persistent) {
+                // ---- tree phase: one warp per root of this CTA (roots never interact, so the whole search of these roots
+                // lives in this CTA): back up the previous simulation, then descend to the next leaf.  cnode.cpp:480-500,754-825
+                if (warp < nvalid) {
+                    const int b = root0 + warp;
+                    if (sim > 0)
+                        tree_backprop(tp, b, lane, io.sim0 + sim, io.reward[b], io.value[b], io.policy_logits + (size_t)b * net.A, nullptr);
+                    tree_traverse(tp, b, lane, io.deterministic, (unsigned)(io.sim0 + sim), io.ix_rw, nullptr, io.action_rw, nullptr, nullptr);
+                }
+                __threadfence_block();
+                asm volatile("bar.sync 1, %0;\n" ::"n"(kEpiThreads) : "memory");
+            }
+            float *latent_out = persistent ? (io.latent_pool_rw + (size_t)(io.sim0 + sim + 1) * io.slot_stride) : io.latent_out;
+            // zero the margins (the head scratch of the previous simulation overlays them; pad rows inside the tiles are
+            // rewritten as zeros by every load / epilogue)
+            for (int i = tid; i < 2 * 8 * 2 * kMargin; i += kEpiThreads) {
+                int part = i / (8 * 2 * kMargin), rem = i % (8 * 2 * kMargin), plane = rem / (2 * kMargin), r = rem % (2 * kMargin);
+                int row = r < kMargin ? r : kMargin + kMaxTiles * 128 + (r - kMargin);
+                *reinterpret_cast<uint4 *>(act + part * kPartBytes + plane * kPlaneBytes + row * 16) = make_uint4(0, 0, 0, 0);
+            }
+            // ---- load the input activation: gather NCHW latents, split to fp16 hi/lo, park fp32 copy in TMEM ----
             for (int t = 0; t < NT; ++t) {
                 const int m = t * 128 + rowid;
                 const int r = m / kRowsPerRoot, q = m - r * kRowsPerRoot, y = q / kPitch, x = q - y * kPitch;
                 const bool valid = (m < rows_used) && (r < nvalid) && (y < 6) && (x < 6);
-                const int b = root0 + r, p = y * 6 + x;
+                const float *src = nullptr;
+                if (valid) {
+                    const int b = root0 + r;
+                    const size_t slot = io.ix ? (size_t)io.ix[b] : 0;
+                    src = io.latent_base + slot * io.slot_stride + (size_t)b * (kC * kP) + (y * 6 + x);
+                }
                 float v[32];
-                tmem_ld32(lane_base + kColAcc + t * 64 + half * 32, v);
-                if (flags & LF_RES) {
-                    float rs[32];
-                    tmem_ld32(lane_base + kColRes + t * 64 + half * 32, rs);
-#pragma unroll
-                    for (int c = 0; c < 32; ++c) v[c] = fmaf(v[c], bs[c], bt[c]) + rs[c];
-                } else {
-#pragma unroll
-                    for (int c = 0; c < 32; ++c) v[c] = fmaf(v[c], bs[c], bt[c]);
-                }
-                if ((flags & LF_ACT_BIAS) && valid) {
-                    const int action = min(max(io.action[b], 0), net.A - 1);
-                    const float *ab = net.abias + ((size_t)action * kC + half * 32) * kP + p;
-#pragma unroll
-                    for (int c = 0; c < 32; ++c) v[c] += __ldg(ab + (size_t)c * kP);
-                }
-#pragma unroll
-                for (int c = 0; c < 32; ++c) v[c] = valid ? fmaxf(v[c], 0.0f) : 0.0f;
-                if (flags & LF_STORE_RES) tmem_st32(lane_base + kColRes + t * 64 + half * 32, v);
-                if ((flags & LF_WRITE_LATENT) && valid) {
-                    if (io.latent_out) {
-                        float *dst = io.latent_out + (size_t)b * (kC * kP) + (size_t)(half * 32) * kP + p;
-#pragma unroll
-                        for (int c = 0; c < 32; ++c) dst[(size_t)c * kP] = v[c];
-                    }
-                    if (io.latent_out2) {
-                        float *dst = io.latent_out2 + (size_t)b * (kC * kP) + (size_t)(half * 32) * kP + p;
-#pragma unroll
-                        for (int c = 0; c < 32; ++c) dst[(size_t)c * kP] = v[c];
-                    }
-                }
-#pragma unroll
+    #pragma unroll
+                for (int c = 0; c < 32; ++c) v[c] = valid ? src[(size_t)(half * 32 + c) * kP] : 0.0f   /* plain load: the pool is written by this launch in persistent mode */;
+    #pragma unroll
                 for (int g = 0; g < 4; ++g) {
-                    unsigned char *pp = act + (half * 4 + g) * kPlaneBytes + (kMargin + m) * 16;
-                    store_split8(pp, pp + kPartBytes, v + 8 * g);
+                    unsigned char *p = act + (half * 4 + g) * kPlaneBytes + (kMargin + m) * 16;
+                    store_split8(p, p + kPartBytes, v + 8 * g);
                 }
+                tmem_st32(lane_base + kColRes + t * 64 + half * 32, v);
             }
             fence_proxy_async();
             tc_fence_before();
-            mbar_arrive(&bars->act_ready);                      // phase L+1: next layer / this layer's hook may start
-            if (dbg) dbg[3 + 2 * L] = clock64();
-            if ((flags & LF_HOOK_REWARD) && net.has_reward_early) {
-                // the reward head (FC1, FC2, softmax, h^-1) runs here, underneath the NEXT layer's MMAs
-                mbar_wait_warp(&bars->rew_ready, 0);
+            mbar_arrive(&bars->act_ready);                          // phase 0: layer 0 may start
+            if (dbg) dbg[1] = clock64();
+
+
+            for (int L = 0; L < nlayers; ++L) {
+                const int flags = net.layer_flags[L];
+                const float *bn = net.bn + (size_t)net.layer_w[L] * 128;      // [scale 64 | shift 64]
+                mbar_wait_warp(&bars->acc_ready, acc_par);
+                acc_par ^= 1;                                       // one commit per layer, across simulations
                 tc_fence_after();
-                head_stage(net, io, 1, reinterpret_cast<float *>(smem + kSmemMain), tmem, NT, rows_used, nvalid, root0);
-                if (dbg) dbg[28] = clock64();
+                if (dbg) dbg[2 + 2 * L] = clock64();
+                float bs[32], bt[32];                               // folded BatchNorm of this thread's 32 channels
+    #pragma unroll
+                for (int c = 0; c < 32; ++c) { bs[c] = __ldg(bn + half * 32 + c); bt[c] = __ldg(bn + 64 + half * 32 + c); }
+                for (int t = 0; t < NT; ++t) {
+                    const int m = t * 128 + rowid;
+                    const int r = m / kRowsPerRoot, q = m - r * kRowsPerRoot, y = q / kPitch, x = q - y * kPitch;
+                    const bool valid = (m < rows_used) && (r < nvalid) && (y < 6) && (x < 6);
+                    const int b = root0 + r, p = y * 6 + x;
+                    float v[32];
+                    tmem_ld32(lane_base + kColAcc + t * 64 + half * 32, v);
+                    if (flags & LF_RES) {
+                        float rs[32];
+                        tmem_ld32(lane_base + kColRes + t * 64 + half * 32, rs);
+    #pragma unroll
+                        for (int c = 0; c < 32; ++c) v[c] = fmaf(v[c], bs[c], bt[c]) + rs[c];
+                    } else {
+    #pragma unroll
+                        for (int c = 0; c < 32; ++c) v[c] = fmaf(v[c], bs[c], bt[c]);
+                    }
+                    if ((flags & LF_ACT_BIAS) && valid) {
+                        const int action = min(max(io.action[b], 0), net.A - 1);
+                        const float *ab = net.abias + ((size_t)action * kC + half * 32) * kP + p;
+    #pragma unroll
+                        for (int c = 0; c < 32; ++c) v[c] += __ldg(ab + (size_t)c * kP);
+                    }
+    #pragma unroll
+                    for (int c = 0; c < 32; ++c) v[c] = valid ? fmaxf(v[c], 0.0f) : 0.0f;
+                    if (flags & LF_STORE_RES) tmem_st32(lane_base + kColRes + t * 64 + half * 32, v);
+                    if ((flags & LF_WRITE_LATENT) && valid) {
+                        if (latent_out) {
+                            float *dst = latent_out + (size_t)b * (kC * kP) + (size_t)(half * 32) * kP + p;
+    #pragma unroll
+                            for (int c = 0; c < 32; ++c) dst[(size_t)c * kP] = v[c];
+                        }
+                        if (io.latent_out2) {
+                            float *dst = io.latent_out2 + (size_t)b * (kC * kP) + (size_t)(half * 32) * kP + p;
+    #pragma unroll
+                            for (int c = 0; c < 32; ++c) dst[(size_t)c * kP] = v[c];
+                        }
+                    }
+    #pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        unsigned char *pp = act + (half * 4 + g) * kPlaneBytes + (kMargin + m) * 16;
+                        store_split8(pp, pp + kPartBytes, v + 8 * g);
+                    }
+                }
+                fence_proxy_async();
+                tc_fence_before();
+                mbar_arrive(&bars->act_ready);                      // phase L+1: next layer / this layer's hook may start
+                if (dbg) dbg[3 + 2 * L] = clock64();
+                if ((flags & LF_HOOK_REWARD) && net.has_reward_early) {
+                    // the reward head (FC1, FC2, softmax, h^-1) runs here, underneath the NEXT layer's MMAs
+                    mbar_wait_warp(&bars->rew_ready, sim & 1);
+                    tc_fence_after();
+                    head_stage(net, io, 1, reinterpret_cast<float *>(smem + kSmemMain), tmem, NT, rows_used, nvalid, root0);
+                    if (dbg) dbg[28] = clock64();
+                }
             }
+
+            // all 1x1 head accumulators must be complete before the head stage reads them / reuses the buffer
+            if (net.has_reward && !net.has_reward_early) mbar_wait_warp(&bars->rew_ready, sim & 1);
+            mbar_wait_warp(&bars->vp_ready, sim & 1);
+            tc_fence_after();
+            if (dbg) dbg[24] = clock64();
+            // ---- heads: 1x1 accumulators -> BN/ReLU -> FC1 -> FC2 -> softmax expectation -> h^-1 (scratch overlays the
+            // activation buffer: every conv MMA of this simulation has completed)
+            head_stage(net, io, net.has_reward_early ? 6 : (net.has_reward ? 7 : 6), reinterpret_cast<float *>(act), tmem, NT, rows_used, nvalid, root0);
+            if (dbg) dbg[27] = clock64();
+            dbg = nullptr;
+            __threadfence_block();
+            asm volatile("bar.sync 1, %0;\n" ::"n"(kEpiThreads) : "memory");
         }
-        // all 1x1 head accumulators must be complete before the head stage reads them / reuses the buffer
-        if (net.has_reward && !net.has_reward_early) mbar_wait_warp(&bars->rew_ready, 0);
-        mbar_wait_warp(&bars->vp_ready, 0);
-        tc_fence_after();
-        if (dbg) dbg[24] = clock64();
+        if (persistent && warp < nvalid) {        // back up the last simulation (mcts_ctree.py:365-368)
+            const int b = root0 + warp;
+            tree_backprop(tp, b, lane, io.sim0 + nsims, io.reward[b], io.value[b], io.policy_logits + (size_t)b * net.A, nullptr);
+        }
     }
 
-    // ================= heads: 1x1 accumulators -> BN/ReLU -> FC1 -> FC2 -> softmax expectation -> h^-1 =================
-    tc_fence_before();
-    __syncthreads();          // all MMAs committed & observed, activation buffer is free
-    tc_fence_after();
-    if (warp < kEpiWarps)
-        head_stage(net, io, net.has_reward_early ? 6 : (net.has_reward ? 7 : 6), reinterpret_cast<float *>(act), tmem, NT, rows_used, nvalid, root0);
-    if (io.dbg && blockIdx.x == 0 && tid == 0) io.dbg[27] = clock64();
     tc_fence_before();
     __syncthreads();
     if (warp == kEpiWarps + 1) {
@@ -523,9 +551,13 @@ int tc_pick_roots(int B)
 static unsigned long long *g_dbg = nullptr;
 unsigned long long *tc_debug_buffer() { return g_dbg; }
 
-int tc_launch(const TcNet &net, const TcIO &io_in, cudaStream_t s)
+int tc_launch(const TcNet &net, const TcIO &io_in, cudaStream_t s, const TreeParams *tp_in)
 {
     TcIO io = io_in;
+    TreeParams tp;
+    memset(&tp, 0, sizeof(tp));
+    if (tp_in) tp = *tp_in;
+    LZ_REQUIRE(!io.persistent || (tp_in && net.has_reward_early), LZ_EINVAL, "tc_launch: persistent search needs tree parameters and the early reward head");
     if (getenv("LZ_TC_DEBUG")) {
         if (!g_dbg) { cudaMalloc(&g_dbg, 64 * 8); cudaMemset(g_dbg, 0, 64 * 8); }
         io.dbg = g_dbg;
@@ -541,7 +573,7 @@ int tc_launch(const TcNet &net, const TcIO &io_in, cudaStream_t s)
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = io_in.pdl ? 1 : 0;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    LZ_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_net_tc, net, io));
+    LZ_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_net_tc, net, io, tp));
     return LZ_OK;
 }
 

@@ -2,6 +2,7 @@
 #pragma once
 #include "lz_common.cuh"
 #include "net6.cuh"
+#include "tree.cuh"
 
 namespace lz {
 
@@ -39,6 +40,10 @@ struct TcIO {
     float *reward, *value;         // [B] scalars
     float *policy_logits;          // [B][A]
     float *reward_logits, *value_logits;   // [B][K] or nullptr
+    // persistent search (the whole num_simulations loop in one launch; tree + network per CTA of 7 roots)
+    int persistent, nsims, sim0, deterministic;
+    int *ix_rw, *action_rw;        // [B] tree -> network hand-off (same arrays as ix / action)
+    float *latent_pool_rw;         // == latent_base; slot s+1 receives the latents of simulation s
     unsigned long long *dbg;       // optional [64] clock64 stamps of CTA 0 (bring-up instrumentation)
 };
 
@@ -49,7 +54,7 @@ float tc_pack_conv1(const float *w, int hc, int nco, int co_offset, unsigned cha
 int tc_head_layout_bytes();
 int tc_conv_layout_bytes();
 int tc_prepare_launch();
-int tc_launch(const TcNet &net, const TcIO &io, cudaStream_t s);
+int tc_launch(const TcNet &net, const TcIO &io, cudaStream_t s, const TreeParams *tp = nullptr);
 unsigned long long *tc_debug_buffer();   // device buffer [64] used when env LZ_TC_DEBUG=1
 
 }  // namespace lz

@@ -43,6 +43,18 @@ static int enqueue_search(lz_search *q, int deterministic, cudaStream_t s)
     int rc;
     lz_tree *t = q->tree;
     t->step_counter = 0;
+    // Persistent search: roots never interact, so the CTA that owns 7 roots can run their whole search -- tree
+    // back-up / descent and the network -- for all num_simulations inside ONE launch of the tcgen05 kernel.
+    if (q->model->kind == 0 && q->model->math != 0 && q->model->tc_rec.has_reward_early && !getenv("LZ_NO_PERSIST")) {
+        TcIO io;
+        memset(&io, 0, sizeof(io));
+        io.B = q->B; io.npass = (q->model->math == 1) ? 3 : 1;
+        io.latent_base = q->pool; io.latent_pool_rw = q->pool; io.slot_stride = q->slot_stride;
+        io.ix = q->d_ix; io.ix_rw = q->d_ix; io.action = q->d_action; io.action_rw = q->d_action;
+        io.reward = q->d_reward; io.value = q->d_value; io.policy_logits = q->d_policy;
+        io.persistent = 1; io.nsims = q->S; io.sim0 = 0; io.deterministic = deterministic;
+        return tc_launch(q->model->tc_rec, io, s, &t->p);
+    }
     const bool pdl = q->model->kind == 0 && q->model->math != 0 && getenv("LZ_PDL");   // opt-in: measured slower (6.26 vs 5.90 ms per 50-sim search)
     t->pdl = pdl;
     if ((rc = tree_launch_traverse(t, deterministic, q->d_ix, nullptr, q->d_action, nullptr, nullptr, s))) return rc;
