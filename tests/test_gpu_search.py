@@ -198,3 +198,21 @@ def test_forward_collect_output_format():
     for i in range(B):
         d = ev[i]['visit_count_distributions']
         assert ev[i]['action'] == np.nonzero(mask[i])[0][int(np.argmax(d))]
+
+
+def test_config3_shard_200_simulations():
+    """BASELINE config 3 per-GPU shard: 1024 roots over 8 GPUs = 128 roots, num_simulations=200 (deep trees, 201 latent
+    slots): persistent search == step-wise drive, bit for bit."""
+    B, A, S = 128, 18, 200
+    ref, cu, obs, mask, legal, noises, mcts = _setup(B, A, S, seed=21, masks=True, math="tc3")
+    out = cu.initial_inference(obs.cuda())
+    res = []
+    for mode in ("fused", "step"):
+        roots = mcts.roots(B, legal)
+        roots.prepare(0.25, noises, [0.] * B, out.policy_logits, [-1] * B)
+        mcts.search(roots, cu if mode == "fused" else _Recorder(cu), out.latent_state, [-1] * B)
+        res.append((roots.get_distributions(), np.asarray(roots.get_values(), np.float32).view(np.uint32).tolist(),
+                    roots.get_trajectories()))
+        roots.clear()
+    assert res[0] == res[1]
+    assert all(sum(d) == S for d in res[0][0])
