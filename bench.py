@@ -246,6 +246,21 @@ def ours(args, rank, local_rank, world):
         q = t.search_for(model, S)
         cabi.check(lib.lz_search_run(q, out0.latent_state.data_ptr(), 1, cabi.stream_ptr()), "lz_search_run")
     so_ms, _ = timed(search_only, args.steps, 3)
+
+    # the dominant kernel: the persistent search launch (50 x [tree + recurrent_inference]); CUDA events around the graph
+    # launch alone, on the launching stream
+    q_search = roots._tree.search_for(model, S)
+    g_ev = []
+    for i in range(3 + args.steps):
+        roots._materialize(S, mcts._params())
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        cabi.check(lib.lz_search_run(q_search, None, 1, cabi.stream_ptr()), "lz_search_run")
+        b.record()
+        g_ev.append((a, b))
+    torch.cuda.synchronize()
+    graph_ms = sorted(x.elapsed_time(y) for x, y in g_ev[3:])
+    graph_avg_ms = sum(graph_ms) / len(graph_ms)
     num_kernels_search = lib.lz_search_num_kernels(roots._tree.search_for(model, S))
 
     # dominant kernel (k_recurrent) timed live with CUDA events on the launching stream: the same
@@ -275,10 +290,10 @@ def ours(args, rank, local_rank, world):
     k_avg_ms = sum(k_ms) / len(k_ms)
 
     # max over ranks
-    vals = torch.tensor([dev_ms, wall_ms, e2e_dev_ms, e2e_wall_ms, so_ms, k_avg_ms], device=dev, dtype=torch.float64)
+    vals = torch.tensor([dev_ms, wall_ms, e2e_dev_ms, e2e_wall_ms, so_ms, k_avg_ms, graph_avg_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(vals, op=dist.ReduceOp.MAX)
-    dev_ms, wall_ms, e2e_dev_ms, e2e_wall_ms, so_ms, k_avg_ms = vals.tolist()
+    dev_ms, wall_ms, e2e_dev_ms, e2e_wall_ms, so_ms, k_avg_ms, graph_avg_ms = vals.tolist()
 
     if rank == 0:
         peaks = {}
@@ -316,17 +331,22 @@ def ours(args, rank, local_rank, world):
                     "api": "lightzero_b200.collect.MuZeroCollectPolicy.search_batch (pinned host obs/mask/noise in, pinned host visits/values out)"},
             "gpu_launches": args.steps * (13 + 2 + num_kernels_search + 1),
             "search_graph_kernels": num_kernels_search,
-            "roofline": {"bound": "tensor", "kernel": "k_net_tc (fused recurrent_inference, tcgen05)", "achieved": achieved_tf,
-                         "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf, "traffic": None,
-                         "peak_source": peak_note, "kernel_ms": k_avg_ms, "kernel_ms_min": k_ms[0],
-                         "kernel_share_of_step": S * k_avg_ms / ms_per_step,
-                         "flop_per_launch": B * FLOP_RECURRENT,
-                         "issued_flop_per_launch": int(B * FLOP_RECURRENT * 3 * 384 / 252),
-                         "note": "achieved = algorithmic FLOPs (SURVEY 8d, 14,427,392 per root per simulation, counted ONCE) / CUDA-event "
-                                 "duration of one launch, against the measured bf16 peak.  The kernel issues 3 fp16 MMAs per product "
-                                 "(fp32-accurate hi/lo split) on 384 padded rows per 252 real ones, i.e. 4.6x the algorithmic FLOPs: "
-                                 "the ceiling of this formulation is 1/4.6 = 21.9% of the tensor peak"},
-        }
+            "roofline": {"bound": "tensor",
+                         "kernel": "k_net_tc, persistent launch = num_simulations x [tree back-up/descent + fused recurrent_inference] (tcgen05)",
+                         "achieved": B * S * FLOP_RECURRENT / (graph_avg_ms * 1e-3) / 1e12,
+                         "peak": peak_tf, "unit": "TFLOP/s",
+                         "frac": B * S * FLOP_RECURRENT / (graph_avg_ms * 1e-3) / 1e12 / peak_tf,
+                         "traffic": 496454656 if (B, S, A) == (1024, 50, 18) else None,
+                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one persistent launch, ncu --set full (profiles/r01c_summary.md); algorithmic bytes 50 x 19.0 MB = 950 MB (reads of fresh latents hit L2)",
+                         "peak_source": peak_note, "kernel_ms": graph_avg_ms, "kernel_ms_min": graph_ms[0],
+                         "kernel_share_of_step": graph_avg_ms / ms_per_step,
+                         "flop_per_launch": B * S * FLOP_RECURRENT,
+                         "issued_flop_per_launch": int(B * S * FLOP_RECURRENT * 3 * 384 / 252),
+                         "single_simulation_launch_ms": k_avg_ms,
+                         "note": "achieved = algorithmic FLOPs (SURVEY 8d, 14,427,392 per root per simulation, counted ONCE) x roots x "
+                                 "simulations / CUDA-event duration of the persistent launch (which also contains the tree phases), against "
+                                 "the measured bf16 peak.  The kernel issues 3 fp16 MMAs per product (fp32-accurate hi/lo split) on 384 padded "
+                                 "rows per 252 real ones = 4.57x the algorithmic FLOPs: the ceiling of this formulation is 21.9% of the tensor peak"},
         if not args.no_cpu_baseline and world == 1:
             r = run_reference_pipeline(args.cpu_sample_roots, S, 1, 0)
             line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
