@@ -1,4 +1,4 @@
-"""Build the UNMODIFIED reference MuZero ctree (Cython + C++) into oracle/_ref/.
+"""Build the UNMODIFIED reference MuZero and EfficientZero ctrees (Cython + C++) into oracle/_ref/.
 
 TEST INFRASTRUCTURE ONLY.  Nothing under oracle/ is imported by the product
 package `lightzero_b200`; only tests/, __graft_entry__.smoke() and bench.py's
@@ -13,6 +13,7 @@ Reference files compiled:
   lzero/mcts/ctree/ctree_muzero/mz_tree.pyx (+ mz_tree.pxd)
   lzero/mcts/ctree/ctree_muzero/lib/cnode.cpp, cnode.h   (textually included by the .pxd)
   lzero/mcts/ctree/common_lib/cminimax.cpp, cminimax.h, utils.cpp
+  lzero/mcts/ctree/ctree_efficientzero/ez_tree.pyx (+ .pxd, lib/cnode.cpp, cnode.h), same common_lib
 Flags mirror the reference setup.py:58,89-91 (-std=c++11, distutils -O2 -DNDEBUG).
 Quirk: cnode.h:6 includes "./../common_lib/cminimax.h", which only
 resolves with -I <ctree_muzero> on the include path.
@@ -30,40 +31,58 @@ REF = os.environ.get("LZ_REFERENCE", "/root/reference")
 CTREE = os.path.join(REF, "lzero", "mcts", "ctree")
 
 
-def ref_module_path():
+def ref_module_path(name: str = "mz_tree"):
     suffix = sysconfig.get_config_var("EXT_SUFFIX")
-    return os.path.join(OUT, "mz_tree" + suffix)
+    return os.path.join(OUT, name + suffix)
 
 
-def build(force: bool = False) -> str:
+# module name -> reference sub-directory.  ez_tree (EfficientZero) has no `deterministic` flag: cselect_child always
+# draws `rand() % ties` (ctree_efficientzero/lib/cnode.cpp:691) after reseeding from the wall clock
+# (common_lib/utils.cpp:12-26).  To make the UNMODIFIED sources reproducible the module is linked with
+# oracle/rand_shim.c, whose hidden-visibility `rand()` returns 0: index 0 of the tie list is the first position
+# attaining the exact maximum (cnode.cpp:676-688), i.e. exactly the `deterministic=True` rule of the MuZero tree.
+MODULES = {"mz_tree": ("ctree_muzero", False), "ez_tree": ("ctree_efficientzero", True)}
+
+
+def build(force: bool = False, name: str = "mz_tree") -> str:
     """Returns the path of the built module, or '' if the reference tree is absent."""
-    target = ref_module_path()
+    subdir, shim = MODULES[name]
+    target = ref_module_path(name)
     if os.path.exists(target) and not force:
         return target
-    src_dir = os.path.join(CTREE, "ctree_muzero")
+    src_dir = os.path.join(CTREE, subdir)
     if not os.path.isdir(src_dir):
         return ""
     import numpy
     os.makedirs(OUT, exist_ok=True)
     with tempfile.TemporaryDirectory() as tmp:
-        gen_cpp = os.path.join(tmp, "mz_tree.cpp")
+        gen_cpp = os.path.join(tmp, name + ".cpp")
         # cython reads the .pyx/.pxd in place; only the generated C++ goes to tmp
         subprocess.check_call(
             [sys.executable, "-m", "cython", "--cplus", "-3", "-I", src_dir,
-             os.path.join(src_dir, "mz_tree.pyx"), "-o", gen_cpp])
+             os.path.join(src_dir, name + ".pyx"), "-o", gen_cpp])
         inc = sysconfig.get_paths()["include"]
+        extra = []
+        if shim:
+            shim_o = os.path.join(tmp, "rand_shim.o")
+            subprocess.check_call(["gcc", "-O2", "-fPIC", "-c", os.path.join(HERE, "rand_shim.c"), "-o", shim_o])
+            extra = [shim_o]
         cmd = ["g++", "-std=c++11", "-O2", "-DNDEBUG", "-fPIC", "-shared", "-w",
                "-I", inc, "-I", numpy.get_include(),
                "-I", src_dir,                      # resolves "lib/cnode.cpp" from the pxd
                "-I", os.path.join(src_dir, "lib"),
                "-I", CTREE,                        # cnode.h:6 quirk: ./../common_lib
-               gen_cpp, "-o", target]
-        # cnode.h includes "./../common_lib/cminimax.h" relative to ctree_muzero/lib -> ctree_muzero/common_lib
-        # (does not exist). g++ then searches -I dirs: <ctree_muzero>/./../common_lib == ctree/common_lib.
+               gen_cpp] + extra + ["-o", target]
+        # cnode.h includes "./../common_lib/cminimax.h" relative to <subdir>/lib -> <subdir>/common_lib
+        # (does not exist). g++ then searches -I dirs: <subdir>/./../common_lib == ctree/common_lib.
         subprocess.check_call(cmd)
     return target
 
 
+def build_all(force: bool = False):
+    return [build(force, n) for n in MODULES]
+
+
 if __name__ == "__main__":
-    p = build(force="--force" in sys.argv)
-    print(p if p else "reference tree not present; nothing built")
+    for p in build_all(force="--force" in sys.argv):
+        print(p if p else "reference tree not present; nothing built")

@@ -1,5 +1,6 @@
-"""Generate the committed golden fixtures for the MuZero ctree path by RUNNING THE COMPILED,
-UNMODIFIED REFERENCE (oracle/_ref/mz_tree, built from /root/reference by oracle/build_ref.py).
+"""Generate the committed golden fixtures for the MuZero and EfficientZero ctree paths by RUNNING THE COMPILED,
+UNMODIFIED REFERENCE (oracle/_ref/mz_tree and ez_tree, built from /root/reference by oracle/build_ref.py; ez_tree
+is linked with oracle/rand_shim.c so that its rand()-based tie-break is reproducible).
 
 Run in the build container (the GPU box has no /root/reference; it uses the committed .npz files):
     python tests/golden/make_golden.py
@@ -95,6 +96,79 @@ def make_case(mz, B, A, S, masks, noise, two_player, scale, seed):
                 delta=np.float32(DELTA), noise_w=np.float32(NOISE_W))
 
 
+EZ_CASES = [
+    # name,             B,  A,  S,  masks, noise, two_player, scale, seed, lstm_horizon_len
+    ("ez_atari_a6",     32,  6, 50, 0, 1, 0, 1.0, 11, 5),
+    ("ez_atari_a18",    32, 18, 50, 1, 1, 0, 2.0, 12, 5),
+    ("ez_deep_s120",     8, 18, 120, 0, 1, 0, 0.5, 13, 3),
+    ("ez_board_2p_a9",  16,  9, 40, 1, 1, 1, 1.0, 14, 4),
+]
+
+
+def make_case_ez(ez, B, A, S, masks, noise, two_player, scale, seed, horizon):
+    """EfficientZero tree (oracle/_ref/ez_tree = unmodified ctree_efficientzero + rand()==0 shim): the driver protocol of
+    mcts_ctree.py:782-876 -- value prefixes instead of rewards, is_reset = (search_len % lstm_horizon_len == 0)."""
+    rng = np.random.default_rng(seed)
+    if masks:
+        legal = []
+        for _ in range(B):
+            m = rng.random(A) < 0.6
+            if not m.any():
+                m[rng.integers(A)] = True
+            legal.append(np.nonzero(m)[0].tolist())
+    else:
+        legal = [list(range(A)) for _ in range(B)]
+    pol = (rng.standard_normal((B, A)) * scale).astype(np.float32)
+    to_play = rng.integers(1, 3, size=B).astype(np.int32) if two_player else np.full(B, -1, np.int32)
+    roots = ez.Roots(B, legal)
+    noises = np.zeros((B, A), np.float32)
+    if noise:
+        nz = []
+        for b, l in enumerate(legal):
+            d = rng.dirichlet([0.3] * len(l)).astype(np.float32)
+            noises[b, :len(l)] = d
+            nz.append(d.tolist())
+        roots.prepare(NOISE_W, nz, [0.] * B, pol.tolist(), to_play.tolist())
+    else:
+        roots.prepare_no_noise([0.] * B, pol.tolist(), to_play.tolist())
+    mm = ez.MinMaxStatsList(B)
+    mm.set_delta(DELTA)
+    vp = np.zeros((S, B), np.float32); val = np.zeros((S, B), np.float32)
+    pols = np.zeros((S, B, A), np.float32)
+    ix = np.zeros((S, B), np.int32); iy = np.zeros((S, B), np.int32)
+    la = np.zeros((S, B), np.int32); sl = np.zeros((S, B), np.int32); vtp = np.zeros((S, B), np.int32)
+    rs = np.zeros((S, B), np.int32)
+    for s in range(S):
+        res = ez.ResultsWrapper(B)
+        a, b_, c, d = ez.batch_traverse(roots, PB_C_BASE, PB_C_INIT, DISCOUNT, mm, res, copy.deepcopy(to_play.tolist()))
+        ix[s], iy[s], la[s], vtp[s] = a, b_, c, d
+        sl[s] = res.get_search_len()
+        vp[s] = (rng.standard_normal(B) * scale).astype(np.float32)
+        val[s] = (rng.standard_normal(B) * scale).astype(np.float32)
+        pols[s] = (rng.standard_normal((B, A)) * scale).astype(np.float32)
+        rs[s] = (sl[s] % horizon == 0).astype(np.int32)
+        ez.batch_backpropagate(s + 1, DISCOUNT, vp[s].tolist(), val[s].tolist(), pols[s].tolist(), mm, res,
+                               rs[s].tolist(), d)
+    dist = np.full((B, A), -1, np.int32)
+    for b, dd in enumerate(roots.get_distributions()):
+        dist[b, :len(dd)] = dd
+    values = np.asarray(roots.get_values(), np.float32)
+    traj = np.full((B, S + 1), -1, np.int32)
+    for b, t in enumerate(roots.get_trajectories()):
+        traj[b, :len(t)] = t
+    legal_arr = np.full((B, A), -1, np.int32)
+    nlegal = np.zeros(B, np.int32)
+    for b, l in enumerate(legal):
+        legal_arr[b, :len(l)] = l
+        nlegal[b] = len(l)
+    return dict(B=B, A=A, S=S, use_noise=noise, legal=legal_arr, nlegal=nlegal, root_logits=pol,
+                noises=noises, to_play=to_play, rewards=vp, values_in=val, policies=pols, is_reset=rs,
+                ix=ix, iy=iy, last_action=la, search_len=sl, virtual_to_play=vtp,
+                distributions=dist, root_values_bits=values.view(np.uint32), trajectories=traj,
+                pb_c_base=PB_C_BASE, pb_c_init=np.float32(PB_C_INIT), discount=np.float32(DISCOUNT),
+                delta=np.float32(DELTA), noise_w=np.float32(NOISE_W), lstm_horizon_len=horizon)
+
+
 def main():
     import mz_tree
     for name, *args in CASES:
@@ -112,6 +186,14 @@ def main():
         acts.append(la[0])
     assert acts == [0] * 5, acts
     print("reference KAT ok", acts)
+    import ez_tree
+    for name, *args in EZ_CASES:
+        case = make_case_ez(ez_tree, *args)
+        again = make_case_ez(ez_tree, *args)     # the shimmed reference must be reproducible
+        assert all(np.array_equal(case[k], again[k]) for k in case), name
+        np.savez_compressed(os.path.join(HERE, f"tree_{name}.npz"), **case)
+        print(name, "sum visits ok:", bool((np.where(case["distributions"] < 0, 0, case["distributions"]).sum(1) == case["S"]).all()),
+              "resets:", int(case["is_reset"].sum()))
 
 
 if __name__ == "__main__":
