@@ -86,6 +86,21 @@ int lz_tree_traverse(lz_tree *t, int deterministic, int32_t *d_ix, int32_t *d_iy
 int lz_tree_backpropagate(lz_tree *t, int latent_index, const float *d_reward, const float *d_value,
                           const float *d_logits, const int32_t *d_to_play, lz_stream s);
 
+/* ---- EfficientZero tree (lzero/mcts/ctree/ctree_efficientzero/lib/cnode.cpp, ez_tree.pyx) ----
+ * lz_tree_set_ez switches a tree to value-prefix semantics before lz_tree_prepare: the reward slot carries the child's
+ * value prefix, every expanded node carries is_reset, the reward of a step is the prefix difference unless the parent
+ * was reset (cnode.cpp:185-195, 496-573, 786-790).  lstm_horizon_len (mcts_ctree.py:857) is used by the fused search
+ * and by lz_tree_traverse_ez to derive is_reset = (search_len % lstm_horizon_len == 0).
+ * The reference tie-break is rand() % len(ties) with no deterministic switch (cnode.cpp:691); these entry points use
+ * the first-maximum rule, which is that draw with rand() == 0 (how the parity oracle builds the reference). */
+int lz_tree_set_ez(lz_tree *t, int efficientzero, int lstm_horizon_len);
+/* cbatch_traverse (ctree_efficientzero cnode.cpp:876-958); d_is_reset int32 [B] out (may be NULL). */
+int lz_tree_traverse_ez(lz_tree *t, int32_t *d_ix, int32_t *d_iy, int32_t *d_last_action, int32_t *d_search_len,
+                        int32_t *d_virtual_to_play, int32_t *d_is_reset, lz_stream s);
+/* cbatch_backpropagate (ctree_efficientzero cnode.cpp:577-601): value prefixes instead of rewards + is_reset_list. */
+int lz_tree_backpropagate_ez(lz_tree *t, int latent_index, const float *d_value_prefix, const float *d_value,
+                             const float *d_logits, const int32_t *d_is_reset, const int32_t *d_to_play, lz_stream s);
+
 /* get_distributions / get_values / get_trajectories (cnode.cpp:237-277,369-417).
  * d_visits int32 [B,A] in legal order, -1 padded; d_values f32 [B]; d_nlegal int32 [B];
  * d_traj int32 [B, max_sims+1] -1 padded.  Any pointer may be NULL. */

@@ -60,6 +60,7 @@ k_tree_reset(TreeParams p, const int32_t *legal, const int32_t *nlegal, const ui
         p.mm_min[b] = kFloatMax;
         p.path_len[b] = 0;
         p.search_len[b] = 0;
+        p.n_reset[(size_t)b * p.N] = 0;      // the root is never reset (ctree_efficientzero cnode.cpp:54,75)
     }
 }
 
@@ -97,38 +98,46 @@ k_tree_prepare(TreeParams p, const float *logits, const float *noise, float nois
     }
 }
 
+template <bool EZ>
 __global__ void __launch_bounds__(kTreeBlock)
 k_tree_traverse(TreeParams p, int deterministic, unsigned step, int32_t *ix, int32_t *iy, int32_t *act,
-                int32_t *len, int32_t *vtp)
+                int32_t *len, int32_t *vtp, int32_t *is_reset)
 {
     const int b = blockIdx.x * (kTreeBlock / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     pdl_launch_dependents();
     pdl_wait();
     if (b >= p.B) return;
-    tree_traverse(p, b, lane, deterministic, step, ix, iy, act, len, vtp);
+    tree_traverse<EZ>(p, b, lane, deterministic, step, ix, iy, act, len, vtp);
+    // mcts_ctree.py:856-861: the LSTM state of a leaf is reset every lstm_horizon_len steps of depth
+    if (EZ && is_reset && lane == 0) is_reset[b] = (p.search_len[b] % p.lstm_horizon == 0) ? 1 : 0;
 }
 
+template <bool EZ>
 __global__ void __launch_bounds__(kTreeBlock)
 k_tree_backprop(TreeParams p, int latent_index, const float *reward, const float *value, const float *logits,
-                const int32_t *to_play)
+                const int32_t *to_play, const int32_t *is_reset)
 {
     const int b = blockIdx.x * (kTreeBlock / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     pdl_launch_dependents();
     pdl_wait();
     if (b >= p.B) return;
-    tree_backprop(p, b, lane, latent_index, reward[b], value[b], logits + (size_t)b * p.A, to_play);
+    tree_backprop<EZ>(p, b, lane, latent_index, reward[b], value[b], logits + (size_t)b * p.A, to_play,
+                      (EZ && is_reset) ? is_reset[b] : 0);
 }
 
+template <bool EZ>
 __global__ void __launch_bounds__(kTreeBlock)
 k_tree_backprop_traverse(TreeParams p, int latent_index, const float *reward, const float *value,
-                         const float *logits, int deterministic, unsigned step, int32_t *ix, int32_t *act)
+                         const float *logits, int deterministic, unsigned step, int32_t *ix, int32_t *act, int32_t *is_reset)
 {
     const int b = blockIdx.x * (kTreeBlock / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     pdl_launch_dependents();      // lets the next network kernel set up (TMEM, barriers, first weight taps) meanwhile
     pdl_wait();                   // reward / value / logits come from the preceding network kernel
     if (b >= p.B) return;
-    tree_backprop(p, b, lane, latent_index, reward[b], value[b], logits + (size_t)b * p.A, nullptr);
-    tree_traverse(p, b, lane, deterministic, step, ix, nullptr, act, nullptr, nullptr);
+    tree_backprop<EZ>(p, b, lane, latent_index, reward[b], value[b], logits + (size_t)b * p.A, nullptr,
+                      (EZ && is_reset) ? is_reset[b] : 0);
+    tree_traverse<EZ>(p, b, lane, deterministic, step, ix, nullptr, act, nullptr, nullptr);
+    if (EZ && is_reset && lane == 0) is_reset[b] = (p.search_len[b] % p.lstm_horizon == 0) ? 1 : 0;
 }
 
 // get_distributions / get_values / get_trajectories (cnode.cpp:237-277,369-417)
@@ -182,27 +191,39 @@ static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, cudaStream_t 
 }
 
 int tree_launch_traverse(lz_tree *t, int deterministic, int32_t *d_ix, int32_t *d_iy, int32_t *d_action,
-                         int32_t *d_len, int32_t *d_vtp, cudaStream_t s)
+                         int32_t *d_len, int32_t *d_vtp, cudaStream_t s, int32_t *d_is_reset)
 {
-    LZ_CUDA_CHECK(launch_pdl(k_tree_traverse, tree_grid(t->p.B), s, t->pdl, t->p, deterministic, t->step_counter++, d_ix, d_iy,
-                             d_action, d_len, d_vtp));
+    if (t->p.ez)
+        LZ_CUDA_CHECK(launch_pdl(k_tree_traverse<true>, tree_grid(t->p.B), s, t->pdl, t->p, deterministic, t->step_counter++, d_ix, d_iy,
+                                 d_action, d_len, d_vtp, d_is_reset));
+    else
+        LZ_CUDA_CHECK(launch_pdl(k_tree_traverse<false>, tree_grid(t->p.B), s, t->pdl, t->p, deterministic, t->step_counter++, d_ix, d_iy,
+                                 d_action, d_len, d_vtp, d_is_reset));
     return LZ_OK;
 }
 
 int tree_launch_backprop(lz_tree *t, int latent_index, const float *d_reward, const float *d_value,
-                         const float *d_logits, const int32_t *d_to_play, cudaStream_t s)
+                         const float *d_logits, const int32_t *d_to_play, cudaStream_t s, const int32_t *d_is_reset)
 {
-    LZ_CUDA_CHECK(launch_pdl(k_tree_backprop, tree_grid(t->p.B), s, t->pdl, t->p, latent_index, d_reward, d_value, d_logits,
-                             d_to_play));
+    if (t->p.ez)
+        LZ_CUDA_CHECK(launch_pdl(k_tree_backprop<true>, tree_grid(t->p.B), s, t->pdl, t->p, latent_index, d_reward, d_value, d_logits,
+                                 d_to_play, d_is_reset));
+    else
+        LZ_CUDA_CHECK(launch_pdl(k_tree_backprop<false>, tree_grid(t->p.B), s, t->pdl, t->p, latent_index, d_reward, d_value, d_logits,
+                                 d_to_play, d_is_reset));
     return LZ_OK;
 }
 
 int tree_launch_backprop_traverse(lz_tree *t, int latent_index, const float *d_reward, const float *d_value,
                                   const float *d_logits, int deterministic, int32_t *d_ix, int32_t *d_action,
-                                  cudaStream_t s)
+                                  cudaStream_t s, int32_t *d_is_reset)
 {
-    LZ_CUDA_CHECK(launch_pdl(k_tree_backprop_traverse, tree_grid(t->p.B), s, t->pdl, t->p, latent_index, d_reward, d_value,
-                             d_logits, deterministic, t->step_counter++, d_ix, d_action));
+    if (t->p.ez)
+        LZ_CUDA_CHECK(launch_pdl(k_tree_backprop_traverse<true>, tree_grid(t->p.B), s, t->pdl, t->p, latent_index, d_reward, d_value,
+                                 d_logits, deterministic, t->step_counter++, d_ix, d_action, d_is_reset));
+    else
+        LZ_CUDA_CHECK(launch_pdl(k_tree_backprop_traverse<false>, tree_grid(t->p.B), s, t->pdl, t->p, latent_index, d_reward, d_value,
+                                 d_logits, deterministic, t->step_counter++, d_ix, d_action, d_is_reset));
     return LZ_OK;
 }
 
@@ -231,7 +252,7 @@ int lz_tree_create(int B, int A, int max_sims, lz_tree **out)
     size_t words = 0;
     auto take = [&](size_t n) { size_t o = words; words += (n + 31) & ~(size_t)31; return o; };
     size_t o_edges = take((size_t)B * N * kEdgeFields * A);
-    size_t o_ntp = take((size_t)B * N), o_nbest = take((size_t)B * N);
+    size_t o_ntp = take((size_t)B * N), o_nbest = take((size_t)B * N), o_nreset = take((size_t)B * N);
     size_t o_legal = take((size_t)B * A), o_nlegal = take(B);
     size_t o_rvis = take(B), o_rvsum = take(B), o_rrew = take(B), o_mmax = take(B), o_mmin = take(B);
     size_t o_tp = take(B), o_players = take(1), o_pslot = take((size_t)B * N), o_pact = take((size_t)B * N);
@@ -243,7 +264,8 @@ int lz_tree_create(int B, int A, int max_sims, lz_tree **out)
     if (e != cudaSuccess) { set_error("cudaMemset failed: %s", cudaGetErrorString(e)); cudaFree(base); delete t; return LZ_ECUDA; }
     t->alloc_base = base;
     p.edges = base + o_edges;
-    p.n_to_play = (int *)(base + o_ntp); p.n_best = (int *)(base + o_nbest);
+    p.n_to_play = (int *)(base + o_ntp); p.n_best = (int *)(base + o_nbest); p.n_reset = (int *)(base + o_nreset);
+    p.ez = 0; p.lstm_horizon = 5;
     p.legal = (int *)(base + o_legal); p.nlegal = (int *)(base + o_nlegal);
     p.root_visit = (int *)(base + o_rvis); p.root_vsum = (float *)(base + o_rvsum); p.root_reward = (float *)(base + o_rrew);
     p.mm_max = (float *)(base + o_mmax); p.mm_min = (float *)(base + o_mmin);
@@ -324,6 +346,7 @@ int lz_tree_traverse(lz_tree *t, int deterministic, int32_t *d_ix, int32_t *d_iy
 {
     LZ_REQUIRE(t, LZ_EINVAL, "lz_tree_traverse: null tree");
     LZ_REQUIRE(t->prepared, LZ_ESTATE, "lz_tree_traverse: roots not prepared (call lz_tree_prepare first)");
+    LZ_REQUIRE(!t->p.ez, LZ_ESTATE, "lz_tree_traverse: tree is in EfficientZero mode, use lz_tree_traverse_ez");
     return tree_launch_traverse(t, deterministic, d_ix, d_iy, d_last_action, d_search_len, d_virtual_to_play,
                                 (cudaStream_t)s);
 }
@@ -333,9 +356,38 @@ int lz_tree_backpropagate(lz_tree *t, int latent_index, const float *d_reward, c
 {
     LZ_REQUIRE(t && d_reward && d_value && d_logits, LZ_EINVAL, "lz_tree_backpropagate: null argument");
     LZ_REQUIRE(t->prepared, LZ_ESTATE, "lz_tree_backpropagate: roots not prepared");
+    LZ_REQUIRE(!t->p.ez, LZ_ESTATE, "lz_tree_backpropagate: tree is in EfficientZero mode, use lz_tree_backpropagate_ez");
     LZ_REQUIRE(latent_index >= 1 && latent_index <= t->max_sims, LZ_EINVAL,
                "lz_tree_backpropagate: latent_index %d outside [1, %d]", latent_index, t->max_sims);
     return tree_launch_backprop(t, latent_index, d_reward, d_value, d_logits, d_to_play, (cudaStream_t)s);
+}
+
+int lz_tree_set_ez(lz_tree *t, int efficientzero, int lstm_horizon_len)
+{
+    LZ_REQUIRE(t, LZ_EINVAL, "lz_tree_set_ez: null tree");
+    LZ_REQUIRE(!efficientzero || lstm_horizon_len > 0, LZ_EINVAL, "lz_tree_set_ez: lstm_horizon_len must be > 0 (mcts_ctree.py:857)");
+    t->p.ez = efficientzero ? 1 : 0;
+    if (efficientzero) t->p.lstm_horizon = lstm_horizon_len;
+    return LZ_OK;
+}
+
+int lz_tree_traverse_ez(lz_tree *t, int32_t *d_ix, int32_t *d_iy, int32_t *d_last_action, int32_t *d_search_len,
+                        int32_t *d_virtual_to_play, int32_t *d_is_reset, lz_stream s)
+{
+    LZ_REQUIRE(t && t->p.ez, LZ_ESTATE, "lz_tree_traverse_ez: tree is not in EfficientZero mode (lz_tree_set_ez)");
+    LZ_REQUIRE(t->prepared, LZ_ESTATE, "lz_tree_traverse_ez: roots not prepared (call lz_tree_prepare first)");
+    return tree_launch_traverse(t, 1, d_ix, d_iy, d_last_action, d_search_len, d_virtual_to_play, (cudaStream_t)s, d_is_reset);
+}
+
+int lz_tree_backpropagate_ez(lz_tree *t, int latent_index, const float *d_value_prefix, const float *d_value,
+                             const float *d_logits, const int32_t *d_is_reset, const int32_t *d_to_play, lz_stream s)
+{
+    LZ_REQUIRE(t && d_value_prefix && d_value && d_logits && d_is_reset, LZ_EINVAL, "lz_tree_backpropagate_ez: null argument");
+    LZ_REQUIRE(t->p.ez, LZ_ESTATE, "lz_tree_backpropagate_ez: tree is not in EfficientZero mode (lz_tree_set_ez)");
+    LZ_REQUIRE(t->prepared, LZ_ESTATE, "lz_tree_backpropagate_ez: roots not prepared");
+    LZ_REQUIRE(latent_index >= 1 && latent_index <= t->max_sims, LZ_EINVAL,
+               "lz_tree_backpropagate_ez: latent_index %d outside [1, %d]", latent_index, t->max_sims);
+    return tree_launch_backprop(t, latent_index, d_value_prefix, d_value, d_logits, d_to_play, (cudaStream_t)s, d_is_reset);
 }
 
 int lz_tree_results(lz_tree *t, int32_t *d_visits, float *d_values, int32_t *d_nlegal, int32_t *d_traj, lz_stream s)

@@ -43,6 +43,10 @@ struct TreeParams {
     float discount, delta;
     unsigned long long rng_seed;
     unsigned long long *rng_epoch;   // [1] bumped by every reset so graph replays draw fresh ties
+    // EfficientZero mode (ctree_efficientzero): the edge "reward" word holds the child's VALUE PREFIX, every expanded node
+    // carries is_reset, and a step's reward is the prefix difference unless the parent was reset
+    int ez, lstm_horizon;
+    int *n_reset;                // [B][N]
 };
 
 __device__ __forceinline__ float u2f(uint32_t u) { return __uint_as_float(u); }
@@ -75,10 +79,11 @@ __device__ __forceinline__ float mm_normalize(float value, float mmax, float mmi
     return norm_value;
 }
 
-// cucb_score (cnode.cpp:654-698) for the child held by this lane.
+// cucb_score (cnode.cpp:654-698; EZ: ctree_efficientzero/lib/cnode.cpp:756-814) for the child held by this lane.
+template <bool EZ = false>
 __device__ __forceinline__ float ucb_score(const uint32_t *nb, int A, int a, bool active, float pbc, float sq,
                                            float mean_q, float discount, int players, float mmax,
-                                           float mmin, float delta_max)
+                                           float mmin, float delta_max, float parent_vp = 0.0f, int parent_reset = 0)
 {
     if (!active) return -INFINITY;
     int vis = (int)nb[F_VISIT * A + a];
@@ -90,6 +95,7 @@ __device__ __forceinline__ float ucb_score(const uint32_t *nb, int A, int a, boo
         value_score = mean_q;
     } else {
         float rw = u2f(nb[F_REWARD * A + a]);
+        if (EZ && parent_reset != 1) rw = __fsub_rn(rw, parent_vp);   // true_reward = child prefix - parent prefix
         float v = __fdiv_rn(u2f(nb[F_VSUM * A + a]), (float)vis);
         value_score = __fadd_rn(rw, __fmul_rn(discount, players == 1 ? v : -v));
     }
@@ -101,6 +107,8 @@ __device__ __forceinline__ float ucb_score(const uint32_t *nb, int A, int a, boo
 
 // One PUCT descent of tree b by the calling warp: cbatch_traverse body (cnode.cpp:783-824) with
 // compute_mean_q (169-203) and cselect_child (551-595).  Records the path for the backup.
+// EZ = true: ctree_efficientzero/lib/cnode.cpp:876-958, 173-210, 651-697 (its rand() tie-break == deterministic for rand() == 0).
+template <bool EZ = false>
 __device__ __forceinline__ void tree_traverse(const TreeParams &p, int b, int lane, int deterministic,
                                               unsigned step, int *out_ix, int *out_iy, int *out_action,
                                               int *out_len, int *out_vtp)
@@ -118,6 +126,8 @@ __device__ __forceinline__ void tree_traverse(const TreeParams &p, int b, int la
     int vtp = p.to_play[b];
     bool is_root = true;
     float parent_q = 0.0f;
+    float cur_vp = EZ ? p.root_reward[b] : 0.0f;      // value prefix / is_reset of the node being scanned
+    int cur_reset = EZ ? p.n_reset[(size_t)b * N] : 0;
 
     while (true) {
         const uint32_t *nb = tree_edges + (size_t)slot * kEdgeFields * A;
@@ -133,7 +143,9 @@ __device__ __forceinline__ void tree_traverse(const TreeParams &p, int b, int la
             float q = 0.0f;
             if (vis > 0) {
                 float v = __fdiv_rn(u2f(nb[F_VSUM * A + a]), (float)vis);
-                q = __fadd_rn(u2f(nb[F_REWARD * A + a]), __fmul_rn(discount, v));
+                float rw = u2f(nb[F_REWARD * A + a]);
+                if (EZ && cur_reset != 1) rw = __fsub_rn(rw, cur_vp);
+                q = __fadd_rn(rw, __fmul_rn(discount, v));
             }
             unsigned m = __ballot_sync(0xffffffffu, vis > 0);
             while (m) {
@@ -157,7 +169,7 @@ __device__ __forceinline__ void tree_traverse(const TreeParams &p, int b, int la
             int k = c0 + lane;
             bool act = k < n;
             int a = act ? (is_root ? lg[k] : k) : 0;
-            float sc = ucb_score(nb, A, a, act, pbc, sq, mean_q, discount, players, mmax, mmin, delta_max);
+            float sc = ucb_score<EZ>(nb, A, a, act, pbc, sq, mean_q, discount, players, mmax, mmin, delta_max, cur_vp, cur_reset);
             float cmax = warp_max_exact(sc);
             if (best < cmax) {
                 best = cmax;
@@ -173,7 +185,7 @@ __device__ __forceinline__ void tree_traverse(const TreeParams &p, int b, int la
                 int k = c0 + lane;
                 bool act = k < n;
                 int a = act ? (is_root ? lg[k] : k) : 0;
-                float sc = ucb_score(nb, A, a, act, pbc, sq, mean_q, discount, players, mmax, mmin, delta_max);
+                float sc = ucb_score<EZ>(nb, A, a, act, pbc, sq, mean_q, discount, players, mmax, mmin, delta_max, cur_vp, cur_reset);
                 count += __popc(__ballot_sync(0xffffffffu, act && k > best_k && sc >= thr));
             }
             if (count > 1) {
@@ -185,7 +197,7 @@ __device__ __forceinline__ void tree_traverse(const TreeParams &p, int b, int la
                         int k = c0 + lane;
                         bool act = k < n;
                         int a = act ? (is_root ? lg[k] : k) : 0;
-                        float sc = ucb_score(nb, A, a, act, pbc, sq, mean_q, discount, players, mmax, mmin, delta_max);
+                        float sc = ucb_score<EZ>(nb, A, a, act, pbc, sq, mean_q, discount, players, mmax, mmin, delta_max, cur_vp, cur_reset);
                         unsigned m = __ballot_sync(0xffffffffu, act && k > best_k && sc >= thr);
                         int c = __popc(m);
                         if (seen < r && r <= seen + c) {
@@ -216,6 +228,7 @@ __device__ __forceinline__ void tree_traverse(const TreeParams &p, int b, int la
         is_root = false;
         parent_q = mean_q;
         if (cs < 0 || plen >= N) break;
+        if (EZ) { cur_vp = u2f(nb[F_REWARD * A + action]); cur_reset = p.n_reset[(size_t)b * N + cs]; }
         slot = cs;
     }
     if (lane == 0) {
@@ -270,9 +283,11 @@ __device__ __forceinline__ void expand_block(uint32_t *nb, int A, const float *l
 
 // cbatch_backpropagate body for tree b (cnode.cpp:495-499): expand the leaf reached by the last
 // traverse into slot `latent_index`, then cbackpropagate (cnode.cpp:419-478) along the recorded path.
+// EZ = true: ctree_efficientzero/lib/cnode.cpp:577-601 + 482-575; `reward` is the value prefix, `leaf_reset` the leaf's is_reset.
+template <bool EZ = false>
 __device__ __forceinline__ void tree_backprop(const TreeParams &p, int b, int lane, int latent_index,
                                               float reward, float value, const float *logits,
-                                              const int *to_play_override)
+                                              const int *to_play_override, int leaf_reset = 0)
 {
     const int A = p.A, N = p.N;
     const int plen = p.path_len[b];
@@ -288,6 +303,7 @@ __device__ __forceinline__ void tree_backprop(const TreeParams &p, int b, int la
     if (lane == 0) {
         p.n_to_play[(size_t)b * N + latent_index] = tp;
         p.n_best[(size_t)b * N + latent_index] = -1;
+        if (EZ) p.n_reset[(size_t)b * N + latent_index] = leaf_reset;
         leaf_nb[F_CSLOT * A + leaf_pa] = (uint32_t)latent_index;
         leaf_nb[F_REWARD * A + leaf_pa] = f2u(reward);
     }
@@ -298,10 +314,14 @@ __device__ __forceinline__ void tree_backprop(const TreeParams &p, int b, int la
     for (int hi = plen; hi >= 0; hi -= 32) {
         const int i = hi - lane;
         const bool act = i >= 0;
-        float vs = 0.0f, rw = 0.0f;
-        int vc = 0, ntp = 0;
+        float vs = 0.0f, rw = 0.0f, pvp = 0.0f;     // pvp / prs: value prefix and is_reset of the PARENT path node (EZ)
+        int vc = 0, ntp = 0, prs = 0;
         uint32_t *enb = nullptr;
         int ea = 0;
+        if (EZ && act && i >= 1) {
+            pvp = (i == 1) ? p.root_reward[b] : u2f(tree_edges[(size_t)pslot[i - 2] * kEdgeFields * A + F_REWARD * A + pact[i - 2]]);
+            prs = p.n_reset[(size_t)b * N + pslot[i - 1]];
+        }
         if (act) {
             if (i == plen) {               // the leaf: unvisited edge, reward just predicted
                 rw = reward; ntp = tp;
@@ -327,7 +347,18 @@ __device__ __forceinline__ void tree_backprop(const TreeParams &p, int b, int la
             float rw_l = __shfl_sync(0xffffffffu, rw, l);
             int ntp_l = __shfl_sync(0xffffffffu, ntp, l);
             float nvs, upd;
-            if (tp == -1) {                // cnode.cpp:432-449
+            if (EZ) {                      // ctree_efficientzero cnode.cpp:496-573
+                const float pvp_l = __shfl_sync(0xffffffffu, pvp, l);
+                const int prs_l = __shfl_sync(0xffffffffu, prs, l);
+                const bool same = (tp == -1) || (ntp_l == tp);
+                nvs = __fadd_rn(vs_l, same ? G : -G);
+                const float nodeval = __fdiv_rn(nvs, (float)(vc_l + 1));
+                float true_reward = __fsub_rn(rw_l, pvp_l);
+                upd = __fadd_rn(true_reward, __fmul_rn(discount, nodeval));   // MinMax sees the un-reset difference and +value
+                if (prs_l == 1) true_reward = rw_l;
+                if (tp == -1) G = __fadd_rn(true_reward, __fmul_rn(discount, G));
+                else G = same ? __fadd_rn(-true_reward, __fmul_rn(discount, G)) : __fadd_rn(true_reward, __fmul_rn(discount, G));
+            } else if (tp == -1) {         // cnode.cpp:432-449
                 nvs = __fadd_rn(vs_l, G);
                 float nodeval = __fdiv_rn(nvs, (float)(vc_l + 1));
                 upd = __fadd_rn(rw_l, __fmul_rn(discount, nodeval));
@@ -375,11 +406,11 @@ struct lz_tree {
 
 namespace lz {
 int tree_launch_traverse(lz_tree *t, int deterministic, int32_t *d_ix, int32_t *d_iy, int32_t *d_action,
-                         int32_t *d_len, int32_t *d_vtp, cudaStream_t s);
+                         int32_t *d_len, int32_t *d_vtp, cudaStream_t s, int32_t *d_is_reset = nullptr);
 int tree_launch_backprop(lz_tree *t, int latent_index, const float *d_reward, const float *d_value,
-                         const float *d_logits, const int32_t *d_to_play, cudaStream_t s);
+                         const float *d_logits, const int32_t *d_to_play, cudaStream_t s, const int32_t *d_is_reset = nullptr);
 // fused: backup of simulation (latent_index - 1) followed by the descent of the next simulation
 int tree_launch_backprop_traverse(lz_tree *t, int latent_index, const float *d_reward, const float *d_value,
                                   const float *d_logits, int deterministic, int32_t *d_ix, int32_t *d_action,
-                                  cudaStream_t s);
+                                  cudaStream_t s, int32_t *d_is_reset = nullptr);
 }  // namespace lz

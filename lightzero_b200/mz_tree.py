@@ -134,6 +134,7 @@ class Roots:
             self._legal_lists = [list(l) for l in legal_actions_list]
             assert len(self._legal_lists) == root_num
         self._pending = None      # prepare() arguments until the tree is materialised
+        self._ez, self._lstm_horizon = False, 5     # EfficientZero value-prefix semantics (set by ez_tree.Roots)
         self._tree: Optional[TreeHandle] = None
         self._delta_reset = None
 
@@ -232,6 +233,7 @@ class Roots:
         s = None
         with torch.cuda.device(self.device):
             s = cabi.stream_ptr()
+            cabi.check(t.lib.lz_tree_set_ez(t.h, int(self._ez), int(self._lstm_horizon)), "lz_tree_set_ez")
             if self._mask is not None:
                 m = _to_dev(self._mask, torch.uint8, self.device, (self.root_num, A))
                 cabi.check(t.lib.lz_tree_reset_mask(t.h, m.data_ptr(), s), "lz_tree_reset_mask")
