@@ -8,8 +8,8 @@ carries ``is_reset`` and a step's reward is the prefix difference unless the par
 (ctree_efficientzero/lib/cnode.cpp:185-195, 496-573, 786-790).
 
 Tie-breaking: the reference draws ``rand() % len(ties)`` reseeded from the wall clock (cnode.cpp:691) and offers no
-deterministic switch; this module always takes the first maximum, which is that draw with ``rand() == 0`` -- the
-configuration the parity oracle compiles the unmodified reference in (oracle/rand_shim.c).
+deterministic switch; this module always takes the first maximum, which is that draw with ``rand() == 0`` (the
+configuration in which the parity tests build the unmodified reference).
 """
 import torch
 
