@@ -3,14 +3,19 @@
 TEST INFRASTRUCTURE ONLY: the parity checker for the CUDA network kernels.  Never imported by
 the product package ``lightzero_b200``.
 
-PARITY UNPINNED for the conv-net arithmetic: the reference model cannot be imported in this
-container (``lzero/model/muzero_model.py:10-11`` and ``common.py:20-22`` import DI-engine ``ding``,
-pinned ``DI-engine>=0.5.3`` in requirements.txt:1, which is neither installed nor under
-/root/reference) and the reference's own model tests (``lzero/model/tests/test_muzero_model.py:49-142``)
-assert shapes only.  What IS pinned: ``InverseScalarTransform`` against the reference's
-``inverse_scalar_transform`` (policy/tests/test_scaling_transform.py:7-19 states both agree
-bit-for-bit; tests/test_oracle_model.py repeats that check here) and the layer graph / state_dict
-key layout, which follow the reference files cited on each class.
+Pinning: tests/golden/make_model_golden.py imports the reference's OWN model classes
+(lzero/model/{muzero_model,efficientzero_model,muzero_model_mlp,common}.py from /root/reference, without executing
+lzero/__init__.py) and asserts that every class below reproduces them BIT FOR BIT on seeded inputs with identical
+state_dicts (initial_inference and recurrent_inference: value / reward or value_prefix / policy logits / latents / LSTM
+state) before it writes the committed fixtures tests/golden/model_*.npz; tests/test_oracle_model.py re-checks the
+restatement against those vectors anywhere.  The reference's two third-party imports that are absent here (DI-engine
+``ding`` -- pinned ``DI-engine>=0.5.3`` in requirements.txt:1 -- and ``ditk``) are served by tests/golden/ding_stub, which
+restates ``ding.torch_utils.{MLP,ResBlock}`` / ``build_normalization`` from their published v0.5.x semantics: those two
+building blocks are the only part of the model arithmetic that is NOT executed from reference source ("parity unpinned"
+for them; everything lzero/model does with them is pinned).  (4,84,84) observations: the reference MuZeroModel itself
+raises for them (muzero_model.py:122-128 defines latent_size for 96 and 64 only); the restatement follows
+sampled_muzero_model.py:144-145.  ``InverseScalarTransform`` is pinned against the reference's
+``inverse_scalar_transform`` (policy/tests/test_scaling_transform.py:7-19).
 
 DI-engine pieces restated from DI-engine v0.5.x ``ding/torch_utils/network/{res_block,nn_module}.py``
 semantics: ``conv2d_block`` = nn.Sequential(Conv2d[, norm][, act]) and
@@ -243,6 +248,105 @@ class MuZeroModelRef(nn.Module):
         next_latent_state, reward = self.dynamics_network(torch.cat((latent_state, enc), dim=1))
         policy_logits, value = self.prediction_network(next_latent_state)
         return MZNetworkOutput(value, reward, policy_logits, next_latent_state)
+
+
+@dataclass
+class EZNetworkOutput:
+    """lzero/model/common.py:119-128"""
+    value: torch.Tensor
+    value_prefix: torch.Tensor
+    policy_logits: torch.Tensor
+    latent_state: torch.Tensor
+    reward_hidden_state: tuple
+
+
+class DynamicsNetworkEZ(nn.Module):
+    """lzero/model/efficientzero_model.py:427-570: the MuZero dynamics trunk, then conv1x1_reward -> BN -> ReLU ->
+    flatten -> nn.LSTM(flatten, lstm_hidden) (one step) -> BatchNorm1d -> ReLU -> DI-engine MLP(lstm_hidden -> hidden ->
+    support) = Linear, BN, ReLU, Linear (efficientzero_model.py:515-525)."""
+
+    def __init__(self, action_encoding_dim, num_res_blocks, num_channels, reward_head_channels,
+                 reward_head_hidden_channels, output_support_size, flatten_size, lstm_hidden_size=512, last_zero=True):
+        super().__init__()
+        self.action_encoding_dim = action_encoding_dim
+        self.flatten_size = flatten_size
+        self.conv = nn.Conv2d(num_channels + action_encoding_dim, num_channels, 3, 1, 1, bias=False)
+        self.norm_common = nn.BatchNorm2d(num_channels)
+        self.resblocks = nn.ModuleList([ResBlock(num_channels) for _ in range(num_res_blocks)])
+        self.conv1x1_reward = nn.Conv2d(num_channels, reward_head_channels, 1)
+        self.norm_reward = nn.BatchNorm2d(reward_head_channels)
+        self.lstm = nn.LSTM(input_size=flatten_size, hidden_size=lstm_hidden_size)
+        self.norm_value_prefix = nn.BatchNorm1d(lstm_hidden_size)
+        self.fc_reward_head = DingMLP(lstm_hidden_size, reward_head_hidden_channels[0], output_support_size,
+                                      len(reward_head_hidden_channels) + 1, output_activation=False, output_norm=False)
+        if last_zero:
+            last = [l for l in self.fc_reward_head if isinstance(l, nn.Linear)][-1]
+            nn.init.zeros_(last.weight)
+            nn.init.zeros_(last.bias)
+
+    def forward(self, state_action_encoding, reward_hidden_state):
+        state_encoding = state_action_encoding[:, :-self.action_encoding_dim, :, :]
+        x = self.norm_common(self.conv(state_action_encoding))
+        x = x + state_encoding
+        x = torch.relu(x)
+        for b in self.resblocks:
+            x = b(x)
+        next_latent_state = x
+        x = torch.relu(self.norm_reward(self.conv1x1_reward(next_latent_state)))
+        x = x.reshape(-1, self.flatten_size).unsqueeze(0)
+        value_prefix, next_reward_hidden_state = self.lstm(x, reward_hidden_state)
+        value_prefix = torch.relu(self.norm_value_prefix(value_prefix.squeeze(0)))
+        return next_latent_state, next_reward_hidden_state, self.fc_reward_head(value_prefix)
+
+
+class EfficientZeroModelRef(nn.Module):
+    """lzero/model/efficientzero_model.py:20-272 (conv, downsample=True, BN, one_hot, categorical, state_norm=False);
+    the SSL projection heads (:184-201) are training-only and not restated."""
+
+    def __init__(self, observation_shape: Sequence[int] = (4, 96, 96), action_space_size: int = 6,
+                 num_res_blocks: int = 1, num_channels: int = 64, lstm_hidden_size: int = 512,
+                 reward_head_channels: int = 16, value_head_channels: int = 16, policy_head_channels: int = 16,
+                 reward_head_hidden_channels=(32,), value_head_hidden_channels=(32,),
+                 policy_head_hidden_channels=(32,), reward_support_range=(-300., 301., 1.),
+                 value_support_range=(-300., 301., 1.), last_linear_layer_init_zero: bool = True):
+        super().__init__()
+        self.action_space_size = action_space_size
+        self.lstm_hidden_size = lstm_hidden_size
+        self.reward_support_size = len(torch.arange(*reward_support_range))
+        self.value_support_size = len(torch.arange(*value_support_range))
+        hw = latent_hw(observation_shape[1])
+        latent_size = hw * hw
+        self.latent_hw = hw
+        self.representation_network = RepresentationNetwork(observation_shape, num_res_blocks, num_channels)
+        self.dynamics_network = DynamicsNetworkEZ(
+            action_space_size, num_res_blocks, num_channels, reward_head_channels,
+            list(reward_head_hidden_channels), self.reward_support_size,
+            reward_head_channels * latent_size, lstm_hidden_size, last_linear_layer_init_zero)
+        self.prediction_network = PredictionNetwork(
+            action_space_size, num_res_blocks, num_channels, value_head_channels, policy_head_channels,
+            list(value_head_hidden_channels), list(policy_head_hidden_channels), self.value_support_size,
+            value_head_channels * latent_size, policy_head_channels * latent_size,
+            last_linear_layer_init_zero)
+
+    def initial_inference(self, obs):
+        """efficientzero_model.py:203-238: zero reward hidden state (h, c)"""
+        B = obs.size(0)
+        latent_state = self.representation_network(obs)
+        policy_logits, value = self.prediction_network(latent_state)
+        hidden = (torch.zeros(1, B, self.lstm_hidden_size, device=obs.device), torch.zeros(1, B, self.lstm_hidden_size, device=obs.device))
+        return EZNetworkOutput(value, [0. for _ in range(B)], policy_logits, latent_state, hidden)
+
+    def recurrent_inference(self, latent_state, reward_hidden_state, action):
+        """efficientzero_model.py:240-272 with _dynamics one-hot encoding (:310-381)"""
+        if action.dim() == 1:
+            action = action.unsqueeze(-1)
+        one_hot = torch.zeros(action.shape[0], self.action_space_size, device=action.device)
+        one_hot.scatter_(1, action.long(), 1)
+        enc = one_hot.unsqueeze(-1).unsqueeze(-1).expand(
+            latent_state.shape[0], self.action_space_size, latent_state.shape[2], latent_state.shape[3])
+        next_latent_state, hidden, value_prefix = self.dynamics_network(torch.cat((latent_state, enc), dim=1), reward_hidden_state)
+        policy_logits, value = self.prediction_network(next_latent_state)
+        return EZNetworkOutput(value, value_prefix, policy_logits, next_latent_state, hidden)
 
 
 def emulate_trained_(model: nn.Module, seed: int = 0) -> nn.Module:
