@@ -107,7 +107,7 @@ int lz_tree_backpropagate_ez(lz_tree *t, int latent_index, const float *d_value_
 int lz_tree_results(lz_tree *t, int32_t *d_visits, float *d_values, int32_t *d_nlegal,
                     int32_t *d_traj, lz_stream s);
 
-/* ------------------------------------------------------------------ model (muzero_model.py) */
+/* ------------------------------------------------------------------ model (muzero_model.py, efficientzero_model.py) */
 
 typedef struct lz_model_config {
     int obs_c, obs_h, obs_w;       /* observation planes and size: (4|12, 64|84|96, same) */
@@ -117,6 +117,10 @@ typedef struct lz_model_config {
     int reward_head_channels, value_head_channels, policy_head_channels;   /* 16 */
     int reward_hidden, value_hidden, policy_hidden;                         /* one hidden layer: 32 */
     float support_min, support_max, support_step;                           /* -300, 301, 1 (value == reward) */
+    /* EfficientZeroModel (lzero/model/efficientzero_model.py:20-272): the reward head becomes conv1x1 -> BN -> ReLU ->
+     * LSTM(hc*36 -> lstm_hidden_size) -> BN1d -> ReLU -> MLP and predicts a VALUE PREFIX; 0 = MuZeroModel */
+    int efficientzero;
+    int lstm_hidden_size;          /* 512 (must be a multiple of 16, <= 512) */
 } lz_model_config;
 
 int lz_model_create(const lz_model_config *cfg, lz_model **out);
@@ -163,6 +167,17 @@ int lz_model_initial_inference(lz_model *m, int B, const float *d_obs, float *d_
 int lz_model_recurrent_inference(lz_model *m, int B, const float *d_latent, const int32_t *d_action,
                                  float *d_next_latent, float *d_reward_logits, float *d_value_logits,
                                  float *d_policy_logits, float *d_reward, float *d_value, lz_stream s);
+/* EfficientZeroModel.recurrent_inference (efficientzero_model.py:240-272).  The reward hidden state is the tuple the
+ * reference passes to nn.LSTM: d_hidden0 = element 0 (LSTM h), d_hidden1 = element 1 (LSTM c), each f32 [B, lstm_hidden_size]
+ * (the leading sequence dimension of 1 dropped).  Outputs as lz_model_recurrent_inference with the value prefix in place of
+ * the reward, plus the next hidden state (un-reset: resetting every lstm_horizon_len steps is the search driver's job,
+ * mcts_ctree.py:856-861).  initial_inference is lz_model_initial_inference (the hidden state starts as zeros). */
+int lz_model_recurrent_inference_ez(lz_model *m, int B, const float *d_latent, const float *d_hidden0, const float *d_hidden1,
+                                    const int32_t *d_action, float *d_next_latent, float *d_next_hidden0, float *d_next_hidden1,
+                                    float *d_value_prefix_logits, float *d_value_logits, float *d_policy_logits,
+                                    float *d_value_prefix, float *d_value, lz_stream s);
+int lz_model_lstm_hidden_size(const lz_model *m);   /* 0 for a MuZero model */
+
 /* InverseScalarTransform (scaling_transform.py:82-92) on its own: logits f32 [B,support] -> f32 [B]. */
 int lz_inverse_scalar_transform(lz_model *m, int B, const float *d_logits, float *d_out, lz_stream s);
 
@@ -175,6 +190,10 @@ int lz_search_destroy(lz_search *q);
 /* MuZeroMCTSCtree.search (mcts_ctree.py:267-368) on roots already prepared with lz_tree_prepare.
  * d_latent_roots f32 [B,C,h,w].  One graph launch, zero host syncs. */
 int lz_search_run(lz_search *q, const float *d_latent_roots, int deterministic, lz_stream s);
+/* EfficientZeroMCTSCtree.search (mcts_ctree.py:671-876) for a search created from an EfficientZero model and a tree in
+ * EfficientZero mode.  d_hidden{0,1}_roots: f32 [B, lstm_hidden_size] = reward_hidden_state_roots[0] / [1] (NULL = zeros,
+ * what initial_inference returns).  The LSTM state of a leaf is zeroed every lstm_horizon_len steps of depth (:856-861). */
+int lz_search_run_ez(lz_search *q, const float *d_latent_roots, const float *d_hidden0_roots, const float *d_hidden1_roots, lz_stream s);
 /* The search-feeding part of _forward_collect (policy/muzero.py:749-779): initial_inference ->
  * reset(mask) -> prepare(noise) -> search.  d_obs f32 [B,obs_c,H,W]; d_mask uint8 [B,A] or NULL;
  * d_noise f32 [B,A] legal-order rows or NULL; d_to_play int32 [B] or NULL (-1).
@@ -194,6 +213,8 @@ int lz_search_collect_host(lz_search *q, const float *h_obs, const uint8_t *h_ma
 int lz_search_num_kernels(const lz_search *q);
 /* Device pointer of the latent pool (NCHW per slot) for inspection in tests. */
 const float *lz_search_latent_pool(const lz_search *q);
+/* EfficientZero: device LSTM-state pool [(S+1)][B][H], which = 0 / 1 for tuple element 0 / 1 (NULL for MuZero). */
+const float *lz_search_hidden_pool(const lz_search *q, int which);
 
 #ifdef __cplusplus
 }

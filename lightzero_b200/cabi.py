@@ -20,7 +20,7 @@ class ModelConfig(ctypes.Structure):
                 ("num_res_blocks", c_int), ("num_channels", c_int), ("reward_head_channels", c_int),
                 ("value_head_channels", c_int), ("policy_head_channels", c_int), ("reward_hidden", c_int),
                 ("value_hidden", c_int), ("policy_hidden", c_int), ("support_min", c_float),
-                ("support_max", c_float), ("support_step", c_float)]
+                ("support_max", c_float), ("support_step", c_float), ("efficientzero", c_int), ("lstm_hidden_size", c_int)]
 
 
 class MlpConfig(ctypes.Structure):
@@ -59,6 +59,8 @@ SIGNATURES = {
     "lz_model_initial_inference": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "lz_model_recurrent_inference": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                              c_void_p, c_void_p, c_void_p, c_void_p]),
+    "lz_model_recurrent_inference_ez": (c_int, [c_void_p, c_int] + [c_void_p] * 12 + [c_void_p]),
+    "lz_model_lstm_hidden_size": (c_int, [c_void_p]),
     "lz_inverse_scalar_transform": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "lz_search_create": (c_int, [c_void_p, c_void_p, c_int, ctypes.POINTER(c_void_p)]),
     "lz_search_destroy": (c_int, [c_void_p]),
@@ -69,6 +71,8 @@ SIGNATURES = {
                                        c_void_p, c_void_p]),
     "lz_search_num_kernels": (c_int, [c_void_p]),
     "lz_search_latent_pool": (c_void_p, [c_void_p]),
+    "lz_search_run_ez": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "lz_search_hidden_pool": (c_void_p, [c_void_p, c_int]),
 }
 
 

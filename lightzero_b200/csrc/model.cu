@@ -355,6 +355,20 @@ int model_recurrent(lz_model *m, const RecIO &io, cudaStream_t s)
         t.latent_out = io.next_latent; t.reward = io.reward; t.value = io.value; t.policy_logits = io.policy_logits;
         t.reward_logits = io.reward_logits; t.value_logits = io.value_logits;
         t.pdl = io.pdl;
+        if (m->cfg.efficientzero) {
+            // conv trunk + prediction heads on the tensor cores; the reward features go through the LSTM head (ez.cu)
+            LZ_REQUIRE(io.B <= m->ez_B, LZ_ESTATE, "model_recurrent: EfficientZero scratch sized for %d roots, got %d (model_reserve)", m->ez_B, io.B);
+            LZ_REQUIRE(io.h_base && io.c_base, LZ_EINVAL, "model_recurrent: EfficientZero needs the reward hidden state");
+            t.reward = nullptr; t.reward_logits = nullptr; t.ez_feat = m->ez_feat;
+            int rc = tc_launch(m->tc_rec, t, s);
+            if (rc) return rc;
+            EzIO e;
+            memset(&e, 0, sizeof(e));
+            e.B = io.B; e.feat = m->ez_feat; e.h_base = io.h_base; e.c_base = io.c_base; e.ix = io.ix; e.slot_stride = io.hslot_stride;
+            e.h_out = io.h_out; e.c_out = io.c_out; e.is_reset = io.is_reset; e.h_tmp = m->ez_htmp;
+            e.value_prefix = io.reward; e.vp_logits = io.reward_logits;
+            return ez_launch(m->ez, e, s);
+        }
         return tc_launch(m->tc_rec, t, s);
     }
     switch (pick_W(io.B)) {
@@ -395,6 +409,14 @@ static int launch_pool(const float *in, float *out, int planes, int hin, int hou
 
 int model_reserve(lz_model *m, int B)
 {
+    if (m->kind == 0 && m->cfg.efficientzero && B > m->ez_B) {
+        cudaFree(m->ez_feat); cudaFree(m->ez_htmp);
+        m->ez_feat = m->ez_htmp = nullptr;
+        int rc = dev_alloc(&m->ez_feat, (size_t)B * m->cfg.reward_head_channels * kP);
+        if (rc == LZ_OK) rc = dev_alloc(&m->ez_htmp, (size_t)B * m->cfg.lstm_hidden_size);
+        if (rc != LZ_OK) return rc;
+        m->ez_B = B;
+    }
     if (m->kind == 1 || B <= m->ws_B) return LZ_OK;
     size_t per_root = 0;
     for (const ConvG &L : m->tower) per_root = std::max(per_root, (size_t)L.cout * L.hout * L.wout);
@@ -620,6 +642,12 @@ static bool pack_head(lz_model *m, Packer &P, const std::string &conv, const std
     std::vector<float> s1, t1, s2, t2;
     if (!fold_bn(m, norm, hc, s1, t1)) return false;
     for (int i = 0; i < hc; ++i) t1[i] += s1[i] * (*b1)[i];
+    if (fc.empty()) {               // EfficientZero reward head: only the 1x1 conv part lives here (the rest is ez.cu)
+        o.w1 = P.add(*w1); o.s1 = P.add(s1); o.t1 = P.add(t1);
+        o.fc1 = o.s2 = o.t2 = o.fc2 = o.b2 = o.w1;
+        o.hc = hc; o.hid = 0; o.K = K;
+        return true;
+    }
     auto W0 = find(m, fc + ".0.weight", (size_t)hid * hc * Pix), B0 = find(m, fc + ".0.bias", hid);
     auto W3 = find(m, fc + ".3.weight", (size_t)K * hid), B3 = find(m, fc + ".3.bias", K);
     if (!W0 || !B0 || !W3 || !B3) return false;
@@ -849,8 +877,11 @@ int lz_model_create(const lz_model_config *cfg, lz_model **out)
     int ndev = 0;
     LZ_CUDA_CHECK(cudaGetDeviceCount(&ndev));
     LZ_REQUIRE(ndev > 0, LZ_ECUDA, "lz_model_create: no CUDA device (this library has no CPU fallback)");
+    LZ_REQUIRE(!cfg->efficientzero || (cfg->lstm_hidden_size > 0 && cfg->lstm_hidden_size <= 512 && cfg->lstm_hidden_size % 16 == 0),
+               LZ_EINVAL, "lz_model_create: lstm_hidden_size must be a multiple of 16 in [16, 512] (got %d)", cfg->lstm_hidden_size);
     lz_model *m = new lz_model();
     m->cfg = *cfg;
+    m->ez_feat = m->ez_htmp = nullptr; m->ez_B = 0;
     m->kind = 0;
     m->latent_floats = kC * kP;
     memset(&m->mcfg, 0, sizeof(m->mcfg));
@@ -872,6 +903,7 @@ int lz_model_destroy(lz_model *m)
     cudaFree(m->d_tc);
     cudaFree(m->d_tower);
     cudaFree(m->tws);
+    cudaFree(m->ez_feat); cudaFree(m->ez_htmp);
     for (int i = 0; i < 3; ++i) cudaFree(m->ws[i]);
     delete m;
     return LZ_OK;
@@ -924,10 +956,39 @@ int lz_model_finalize(lz_model *m)
              pack_conv3(m, P, "representation_network.resblocks." + si + ".conv2.0.weight", "representation_network.resblocks." + si + ".conv2.1", kC, kC, rep_res[2 * i + 1]);
     }
     if (!ok) return LZ_EINVAL;
-    ok = pack_head(m, P, D + "conv1x1_reward", D + "norm_reward", D + "fc_reward_head", c.reward_head_channels, c.reward_hidden, m->K, kP, hr) &&
+    ok = pack_head(m, P, D + "conv1x1_reward", D + "norm_reward", c.efficientzero ? std::string() : D + "fc_reward_head", c.reward_head_channels, c.reward_hidden, m->K, kP, hr) &&
          pack_head(m, P, Q + "conv1x1_value", Q + "norm_value", Q + "fc_value", c.value_head_channels, c.value_hidden, m->K, kP, hv) &&
          pack_head(m, P, Q + "conv1x1_policy", Q + "norm_policy", Q + "fc_policy", c.policy_head_channels, c.policy_hidden, A, kP, hp);
     if (!ok) return LZ_EINVAL;
+    // ---- EfficientZero value-prefix head (efficientzero_model.py:511-525, 556-569)
+    size_t ez_wcat = 0, ez_bias = 0, ez_vps = 0, ez_vpt = 0, ez_fc1 = 0, ez_s2 = 0, ez_t2 = 0, ez_fc2 = 0, ez_b2 = 0;
+    if (c.efficientzero) {
+        const int H = c.lstm_hidden_size, nin = c.reward_head_channels * kP, hid = c.reward_hidden, K = m->K;
+        auto Wih = find(m, D + "lstm.weight_ih_l0", (size_t)4 * H * nin), Whh = find(m, D + "lstm.weight_hh_l0", (size_t)4 * H * H);
+        auto bih = find(m, D + "lstm.bias_ih_l0", (size_t)4 * H), bhh = find(m, D + "lstm.bias_hh_l0", (size_t)4 * H);
+        auto W0 = find(m, D + "fc_reward_head.0.weight", (size_t)hid * H), B0 = find(m, D + "fc_reward_head.0.bias", hid);
+        auto W3 = find(m, D + "fc_reward_head.3.weight", (size_t)K * hid), B3 = find(m, D + "fc_reward_head.3.bias", K);
+        std::vector<float> vs, vt, s2, t2;
+        if (!Wih || !Whh || !bih || !bhh || !W0 || !B0 || !W3 || !B3 || !fold_bn(m, D + "norm_value_prefix", H, vs, vt) ||
+            !fold_bn(m, D + "fc_reward_head.1", hid, s2, t2))
+            return LZ_EINVAL;
+        for (int j = 0; j < hid; ++j) t2[j] += s2[j] * (*B0)[j];
+        // torch.nn.LSTM stacks the gates (i, f, g, o) along dim 0; column n = unit * 4 + gate
+        std::vector<float> wcat((size_t)(nin + H) * 4 * H), bias((size_t)4 * H), fc1((size_t)H * hid), fc2((size_t)hid * K);
+        for (int g = 0; g < 4; ++g)
+            for (int u = 0; u < H; ++u) {
+                const size_t row = (size_t)g * H + u, col = (size_t)u * 4 + g;
+                for (int k = 0; k < nin; ++k) wcat[(size_t)k * 4 * H + col] = (*Wih)[row * nin + k];
+                for (int k = 0; k < H; ++k) wcat[(size_t)(nin + k) * 4 * H + col] = (*Whh)[row * H + k];
+                bias[col] = (*bih)[row] + (*bhh)[row];
+            }
+        for (int j = 0; j < hid; ++j)
+            for (int i = 0; i < H; ++i) fc1[(size_t)i * hid + j] = (*W0)[(size_t)j * H + i];
+        for (int k = 0; k < K; ++k)
+            for (int j = 0; j < hid; ++j) fc2[(size_t)j * K + k] = (*W3)[(size_t)k * hid + j];
+        ez_wcat = P.add(wcat); ez_bias = P.add(bias); ez_vps = P.add(vs); ez_vpt = P.add(vt); ez_fc1 = P.add(fc1);
+        ez_s2 = P.add(s2); ez_t2 = P.add(t2); ez_fc2 = P.add(fc2); ez_b2 = P.add(*B3);
+    }
 
     if (m->d_weights) cudaFree(m->d_weights);
     m->d_weights = nullptr;
@@ -948,6 +1009,14 @@ int lz_model_finalize(lz_model *m)
     net.reward = mkh(hr); net.value = mkh(hv); net.policy = mkh(hp);
     net.nres = n; net.A = A;
     net.support_min = c.support_min; net.support_step = c.support_step;
+    memset(&m->ez, 0, sizeof(m->ez));
+    if (c.efficientzero) {
+        EzNet &e = m->ez;
+        e.wcat = base + ez_wcat; e.bias = base + ez_bias; e.vp_s = base + ez_vps; e.vp_t = base + ez_vpt;
+        e.fc1 = base + ez_fc1; e.s2 = base + ez_s2; e.t2 = base + ez_t2; e.fc2 = base + ez_fc2; e.b2 = base + ez_b2;
+        e.nin = c.reward_head_channels * kP; e.H = c.lstm_hidden_size; e.hid = c.reward_hidden; e.K = m->K;
+        e.support_min = c.support_min; e.support_step = c.support_step;
+    }
 
     // DownSample geometry: conv s2 p1: h -> (h-1)/2+1
     const int h0 = c.obs_h, h1 = (h0 - 1) / 2 + 1, h2 = (h1 - 1) / 2 + 1, h3 = (h2 - 1) / 2 + 1;
@@ -981,6 +1050,7 @@ int lz_model_set_math(lz_model *m, int mode)
 {
     LZ_REQUIRE(m && mode >= 0 && mode <= 2, LZ_EINVAL, "lz_model_set_math: mode must be 0 (fp32 FFMA), 1 (tcgen05 3xFP16) or 2 (tcgen05 fp16)");
     LZ_REQUIRE(m->kind == 0 || mode == 0, LZ_EINVAL, "lz_model_set_math: the MLP model only has the fp32 path");
+    LZ_REQUIRE(!(m->kind == 0 && m->cfg.efficientzero && mode == 0), LZ_EINVAL, "lz_model_set_math: the EfficientZero model runs its conv stack on the tcgen05 path only (mode 1 or 2)");
     m->math = mode;
     return LZ_OK;
 }
@@ -1036,6 +1106,28 @@ int lz_model_recurrent_inference(lz_model *m, int B, const float *d_latent, cons
     io.reward_logits = d_reward_logits; io.value_logits = d_value_logits;
     return model_recurrent(m, io, (cudaStream_t)s);
 }
+
+int lz_model_recurrent_inference_ez(lz_model *m, int B, const float *d_latent, const float *d_hidden0, const float *d_hidden1,
+                                    const int32_t *d_action, float *d_next_latent, float *d_next_hidden0, float *d_next_hidden1,
+                                    float *d_value_prefix_logits, float *d_value_logits, float *d_policy_logits,
+                                    float *d_value_prefix, float *d_value, lz_stream s)
+{
+    LZ_REQUIRE(m && d_latent && d_hidden0 && d_hidden1 && d_action && d_next_latent && B > 0, LZ_EINVAL, "lz_model_recurrent_inference_ez: bad argument");
+    LZ_REQUIRE(m->finalized && m->kind == 0 && m->cfg.efficientzero, LZ_ESTATE, "lz_model_recurrent_inference_ez: not a finalized EfficientZero model");
+    if (B > m->ez_B) {
+        int rc = model_reserve(m, B);
+        if (rc != LZ_OK) return rc;
+    }
+    RecIO io;
+    memset(&io, 0, sizeof(io));
+    io.B = B; io.latent_base = d_latent; io.action = d_action;
+    io.next_latent = d_next_latent; io.reward = d_value_prefix; io.value = d_value; io.policy_logits = d_policy_logits;
+    io.reward_logits = d_value_prefix_logits; io.value_logits = d_value_logits;
+    io.h_base = d_hidden0; io.c_base = d_hidden1; io.h_out = d_next_hidden0; io.c_out = d_next_hidden1;
+    return model_recurrent(m, io, (cudaStream_t)s);
+}
+
+int lz_model_lstm_hidden_size(const lz_model *m) { return (m && m->kind == 0 && m->cfg.efficientzero) ? m->cfg.lstm_hidden_size : 0; }
 
 int lz_inverse_scalar_transform(lz_model *m, int B, const float *d_logits, float *d_out, lz_stream s)
 {

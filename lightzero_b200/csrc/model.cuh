@@ -8,6 +8,7 @@
 #include "net6.cuh"
 #include "net_tc.cuh"
 #include "conv_tc.cuh"
+#include "ez.cuh"
 
 namespace lz {
 
@@ -55,6 +56,11 @@ struct RecIO {
     float *policy_logits;             // [B][A] or nullptr
     float *reward_logits, *value_logits;   // [B][K] or nullptr
     int pdl;                          // programmatic dependent launch (search graph)
+    // EfficientZero (reward == value prefix): LSTM state in / out, see ez.cuh
+    const float *h_base, *c_base;     // base + ix[b]*hslot_stride + b*H
+    size_t hslot_stride;
+    float *h_out, *c_out;
+    const int *is_reset;
 };
 
 struct TailIO {
@@ -70,7 +76,10 @@ struct TailIO {
 }  // namespace lz
 
 struct lz_model {
-    int kind;                         // 0 = conv MuZeroModel, 1 = MuZeroModelMLP
+    int kind;                         // 0 = conv MuZeroModel / EfficientZeroModel (cfg.efficientzero), 1 = MuZeroModelMLP
+    lz::EzNet ez;                     // EfficientZero value-prefix head tables (device pointers into d_weights)
+    float *ez_feat, *ez_htmp;         // [ws_B][hc*36], [ws_B][H] scratch between the conv kernel and the LSTM kernels
+    int ez_B;
     int latent_floats;                // floats per root latent (64*36 or latent_dim)
     lz_mlp_config mcfg;
     lz::MlpNet mlp;

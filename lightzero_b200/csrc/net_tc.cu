@@ -118,6 +118,16 @@ __device__ __forceinline__ void head_stage(const TcNet &net, const TcIO &io, int
     }
     tc_fence_before();
     asm volatile("bar.sync 1, %0;\n" ::"n"(kEpiThreads) : "memory");
+    if (hmask == 1 && io.ez_feat) {
+        // EfficientZero (efficientzero_model.py:556-562): the flattened reward features feed an LSTM that is evaluated as
+        // one batched GEMM over all roots by the next kernel (ez.cu)
+        const int nin = net.hc[0] * kP;
+        for (int i = tid; i < nvalid * nin; i += kEpiThreads) {
+            const int r = i / nin, j = i - r * nin;
+            io.ez_feat[(size_t)(root0 + r) * nin + j] = hflat[r * 576 + j];
+        }
+        return;
+    }
     // ---- FC1 (hc*36 -> hid): warp w takes an eighth of the inputs, lane = hidden unit; 24 coalesced weight rows in flight
     for (int h = 0; h < 3; ++h) {
         if (!((hmask >> h) & 1)) continue;

@@ -44,6 +44,7 @@ struct TcIO {
     int persistent, nsims, sim0, deterministic;
     int *ix_rw, *action_rw;        // [B] tree -> network hand-off (same arrays as ix / action)
     float *latent_pool_rw;         // == latent_base; slot s+1 receives the latents of simulation s
+    float *ez_feat;                // EfficientZero: the reward head stops after conv1x1+BN+ReLU and writes [B][hc*36] here
     unsigned long long *dbg;       // optional [64] clock64 stamps of CTA 0 (bring-up instrumentation)
 };
 

@@ -23,6 +23,11 @@ struct lz_search {
     float *d_policy;             // [B][A]
     float *d_root_logits;        // [B][A]
     float *d_root_value;         // [B]
+    // EfficientZero: LSTM state pools [(S+1)][B][H] (tuple element 0 / 1 of reward_hidden_state, mcts_ctree.py:775-776)
+    // and the per-leaf is_reset flags handed from the traverse to the LSTM kernel and the back-up (:856-861)
+    float *hpool, *cpool;
+    size_t hslot_stride;
+    int32_t *d_is_reset;
     cudaGraphExec_t exec[2];     // [deterministic]
     cudaStream_t capture_stream; // library-owned: the caller's stream may be the legacy default stream,
                                  // which cannot be captured; the instantiated graph launches on the caller's
@@ -45,6 +50,29 @@ static int enqueue_search(lz_search *q, int deterministic, cudaStream_t s)
     t->step_counter = 0;
     // Persistent search: roots never interact, so the CTA that owns 7 roots can run their whole search -- tree
     // back-up / descent and the network -- for all num_simulations inside ONE launch of the tcgen05 kernel.
+    const bool ez = q->model->kind == 0 && q->model->cfg.efficientzero;
+    if (ez) {
+        // EfficientZeroMCTSCtree.search (mcts_ctree.py:671-876): the LSTM step is a GEMM over all roots, so the network
+        // is several launches per simulation and the loop stays a multi-kernel graph
+        if ((rc = tree_launch_traverse(t, 1, q->d_ix, nullptr, q->d_action, nullptr, nullptr, s, q->d_is_reset))) return rc;
+        for (int sim = 0; sim < q->S; ++sim) {
+            RecIO io;
+            memset(&io, 0, sizeof(io));
+            io.B = q->B; io.latent_base = q->pool; io.ix = q->d_ix; io.slot_stride = q->slot_stride; io.action = q->d_action;
+            io.next_latent = q->pool + (size_t)(sim + 1) * q->slot_stride;
+            io.reward = q->d_reward; io.value = q->d_value; io.policy_logits = q->d_policy;
+            io.h_base = q->hpool; io.c_base = q->cpool; io.hslot_stride = q->hslot_stride;
+            io.h_out = q->hpool + (size_t)(sim + 1) * q->hslot_stride; io.c_out = q->cpool + (size_t)(sim + 1) * q->hslot_stride;
+            io.is_reset = q->d_is_reset;
+            if ((rc = model_recurrent(q->model, io, s))) return rc;
+            if (sim + 1 < q->S)
+                rc = tree_launch_backprop_traverse(t, sim + 1, q->d_reward, q->d_value, q->d_policy, 1, q->d_ix, q->d_action, s, q->d_is_reset);
+            else
+                rc = tree_launch_backprop(t, sim + 1, q->d_reward, q->d_value, q->d_policy, nullptr, s, q->d_is_reset);
+            if (rc) return rc;
+        }
+        return LZ_OK;
+    }
     if (q->model->kind == 0 && q->model->math != 0 && q->model->tc_rec.has_reward_early && !getenv("LZ_NO_PERSIST")) {
         TcIO io;
         memset(&io, 0, sizeof(io));
@@ -112,6 +140,9 @@ int lz_search_create(lz_tree *t, lz_model *m, int num_simulations, lz_search **o
     LZ_REQUIRE(m->finalized, LZ_ESTATE, "lz_search_create: model not finalized");
     LZ_REQUIRE(num_simulations <= t->max_sims, LZ_EINVAL, "lz_search_create: num_simulations %d > tree capacity %d", num_simulations, t->max_sims);
     LZ_REQUIRE(t->p.A == m->cfg.action_space_size, LZ_EINVAL, "lz_search_create: tree has %d actions, model %d", t->p.A, m->cfg.action_space_size);
+    const bool ez = m->kind == 0 && m->cfg.efficientzero;
+    LZ_REQUIRE(ez == (t->p.ez != 0), LZ_EINVAL, "lz_search_create: %s model needs a tree in %s mode (lz_tree_set_ez)",
+               ez ? "an EfficientZero" : "a MuZero", ez ? "EfficientZero" : "MuZero");
     lz_search *q = new lz_search();
     memset(q, 0, sizeof(*q));
     q->tree = t; q->model = m; q->S = num_simulations; q->B = t->p.B; q->A = t->p.A;
@@ -124,6 +155,12 @@ int lz_search_create(lz_tree *t, lz_model *m, int num_simulations, lz_search **o
     if (rc == LZ_OK) rc = dev_alloc(&q->d_policy, (size_t)q->B * q->A);
     if (rc == LZ_OK) rc = dev_alloc(&q->d_root_logits, (size_t)q->B * q->A);
     if (rc == LZ_OK) rc = dev_alloc(&q->d_root_value, (size_t)q->B);
+    if (rc == LZ_OK && ez) {
+        q->hslot_stride = (size_t)q->B * m->cfg.lstm_hidden_size;
+        rc = dev_alloc(&q->hpool, q->hslot_stride * (size_t)(q->S + 1));
+        if (rc == LZ_OK) rc = dev_alloc(&q->cpool, q->hslot_stride * (size_t)(q->S + 1));
+        if (rc == LZ_OK) rc = dev_alloc(&q->d_is_reset, (size_t)q->B);
+    }
     if (rc == LZ_OK) rc = model_reserve(m, q->B);
     if (rc != LZ_OK) { lz_search_destroy(q); return rc; }
     *out = q;
@@ -144,13 +181,36 @@ int lz_search_destroy(lz_search *q)
     cudaFree(q->d_obs_stage); cudaFree(q->d_noise_stage); cudaFree(q->d_pre_stage); cudaFree(q->d_mask_stage); cudaFree(q->d_tp_stage);
     cudaFree(q->pool); cudaFree(q->d_ix); cudaFree(q->d_action); cudaFree(q->d_reward); cudaFree(q->d_value);
     cudaFree(q->d_policy); cudaFree(q->d_root_logits); cudaFree(q->d_root_value);
+    cudaFree(q->hpool); cudaFree(q->cpool); cudaFree(q->d_is_reset);
     delete q;
     return LZ_OK;
+}
+
+static int ez_root_hidden(lz_search *q, const float *d_hidden0, const float *d_hidden1, cudaStream_t s)
+{
+    const size_t bytes = q->hslot_stride * sizeof(float);
+    if (d_hidden0) LZ_CUDA_CHECK(cudaMemcpyAsync(q->hpool, d_hidden0, bytes, cudaMemcpyDeviceToDevice, s));
+    else LZ_CUDA_CHECK(cudaMemsetAsync(q->hpool, 0, bytes, s));        // efficientzero_model.py:231-236: zeros after initial_inference
+    if (d_hidden1) LZ_CUDA_CHECK(cudaMemcpyAsync(q->cpool, d_hidden1, bytes, cudaMemcpyDeviceToDevice, s));
+    else LZ_CUDA_CHECK(cudaMemsetAsync(q->cpool, 0, bytes, s));
+    return LZ_OK;
+}
+
+int lz_search_run_ez(lz_search *q, const float *d_latent_roots, const float *d_hidden0_roots, const float *d_hidden1_roots, lz_stream s)
+{
+    LZ_REQUIRE(q && q->hpool, LZ_EINVAL, "lz_search_run_ez: not an EfficientZero search");
+    LZ_REQUIRE(q->tree->prepared, LZ_ESTATE, "lz_search_run_ez: roots not prepared (call lz_tree_prepare first)");
+    if (d_latent_roots && d_latent_roots != q->pool)
+        LZ_CUDA_CHECK(cudaMemcpyAsync(q->pool, d_latent_roots, q->slot_stride * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)s));
+    int rc = ez_root_hidden(q, d_hidden0_roots, d_hidden1_roots, (cudaStream_t)s);
+    if (rc) return rc;
+    return run_graph(q, 1, (cudaStream_t)s);
 }
 
 int lz_search_run(lz_search *q, const float *d_latent_roots, int deterministic, lz_stream s)
 {
     LZ_REQUIRE(q, LZ_EINVAL, "lz_search_run: null search");
+    LZ_REQUIRE(!q->hpool, LZ_ESTATE, "lz_search_run: EfficientZero search, use lz_search_run_ez");
     LZ_REQUIRE(q->tree->prepared, LZ_ESTATE, "lz_search_run: roots not prepared (call lz_tree_prepare first)");
     if (d_latent_roots && d_latent_roots != q->pool)
         LZ_CUDA_CHECK(cudaMemcpyAsync(q->pool, d_latent_roots, q->slot_stride * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)s));
@@ -171,6 +231,7 @@ int lz_search_collect(lz_search *q, const float *d_obs, const uint8_t *d_mask, c
     if (rc) return rc;
     if ((rc = lz_tree_reset_mask(q->tree, d_mask, s))) return rc;                // :760,769
     if ((rc = lz_tree_prepare(q->tree, io.policy_logits, d_noise, noise_weight, nullptr, d_to_play, s))) return rc;   // :774
+    if (q->hpool && (rc = ez_root_hidden(q, nullptr, nullptr, (cudaStream_t)s))) return rc;
     return run_graph(q, deterministic, (cudaStream_t)s);                         // :775
 }
 
@@ -247,10 +308,12 @@ int lz_search_collect_host(lz_search *q, const float *h_obs, const uint8_t *h_ma
     if ((rc = lz_tree_reset_mask(q->tree, h_mask ? q->d_mask_stage : nullptr, s))) return rc;
     if ((rc = lz_tree_prepare(q->tree, logits, h_noise ? q->d_noise_stage : nullptr, noise_weight, nullptr,
                               h_to_play ? q->d_tp_stage : nullptr, s))) return rc;
+    if (q->hpool && (rc = ez_root_hidden(q, nullptr, nullptr, s))) return rc;
     return run_graph(q, deterministic, s);
 }
 
 int lz_search_num_kernels(const lz_search *q) { return q ? q->num_kernels : 0; }
 const float *lz_search_latent_pool(const lz_search *q) { return q ? q->pool : nullptr; }
+const float *lz_search_hidden_pool(const lz_search *q, int which) { return q ? (which ? q->cpool : q->hpool) : nullptr; }
 
 }  // extern "C"

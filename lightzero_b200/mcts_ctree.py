@@ -20,7 +20,8 @@ from typing import Any, List, Optional, Union
 import numpy as np
 import torch
 
-from . import cabi, mz_tree
+from . import cabi, ez_tree, mz_tree
+from .efficientzero_model import EfficientZeroModel
 from .muzero_model import MuZeroModel
 from .muzero_model_mlp import MuZeroModelMLP
 from .scaling_transform import DiscreteSupport, InverseScalarTransform
@@ -102,6 +103,8 @@ class MuZeroMCTSCtree(object):
             lat = latent_state_roots.to(dev, torch.float32, non_blocking=True).contiguous()
         else:
             lat = torch.from_numpy(np.ascontiguousarray(latent_state_roots, dtype=np.float32)).to(dev, non_blocking=True)
+        if isinstance(model, EfficientZeroModel):
+            raise TypeError("MuZeroMCTSCtree.search: an EfficientZeroModel needs EfficientZeroMCTSCtree")
         if isinstance(model, (MuZeroModel, MuZeroModelMLP)):
             q = t.search_for(model, S)
             with torch.cuda.device(dev):
@@ -138,3 +141,85 @@ class MuZeroMCTSCtree(object):
                 cabi.check(t.lib.lz_tree_backpropagate(t.h, sim + 1, reward.data_ptr(), value.data_ptr(),
                                                        pol.data_ptr(), None, cabi.stream_ptr()),
                            "lz_tree_backpropagate")
+
+
+class EfficientZeroMCTSCtree(MuZeroMCTSCtree):
+    """Mirror of ``lzero.mcts.tree_search.mcts_ctree.EfficientZeroMCTSCtree`` (mcts_ctree.py:671-876): same config keys
+    (+ ``lstm_horizon_len``, read at :857), ``roots(n, legal_actions)`` and
+    ``search(roots, model, latent_state_roots, reward_hidden_state_roots, to_play_batch)``.
+
+    With a ``lightzero_b200.EfficientZeroModel`` the whole loop is one CUDA-graph launch (``lz_search_run_ez``): per
+    simulation the descent (which also derives ``is_reset = search_len % lstm_horizon_len == 0``, :856-861), the conv
+    trunk + prediction heads, the LSTM value-prefix head over all roots, and the back-up.  Any other model object is
+    driven step-wise around the device trees.  Ties: first maximum (the reference's ``rand() % len(ties)`` with
+    ``rand() == 0``; the EfficientZero tree has no deterministic switch, cnode.cpp:691)."""
+
+    def __init__(self, cfg=None) -> None:
+        super().__init__(cfg)
+        self._cfg.setdefault("lstm_horizon_len", 5)
+
+    @classmethod
+    def roots(cls, active_collect_env_num: int, legal_actions: List[Any]) -> "ez_tree.Roots":
+        """mcts_ctree.py:715-727"""
+        return ez_tree.Roots(active_collect_env_num, legal_actions)
+
+    def search(self, roots: "ez_tree.Roots", model, latent_state_roots, reward_hidden_state_roots,
+               to_play_batch: Union[int, List[Any]]) -> None:
+        S, H = int(self._cfg.num_simulations), int(self._cfg.lstm_horizon_len)
+        assert H > 0                                   # mcts_ctree.py:857
+        roots._ez, roots._lstm_horizon = True, H
+        roots._materialize(S, self._params())
+        t = roots._tree
+        dev = roots.device
+
+        def dev_f32(x):
+            if isinstance(x, torch.Tensor):
+                return x.to(dev, torch.float32, non_blocking=True).contiguous()
+            return torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).to(dev, non_blocking=True)
+        lat = dev_f32(latent_state_roots)
+        B = roots.num
+        h0 = dev_f32(reward_hidden_state_roots[0]).reshape(B, -1)
+        h1 = dev_f32(reward_hidden_state_roots[1]).reshape(B, -1)
+        if isinstance(model, EfficientZeroModel):
+            q = t.search_for(model, S, (1, H))
+            with torch.cuda.device(dev):
+                cabi.check(t.lib.lz_search_run_ez(q, lat.data_ptr(), h0.data_ptr(), h1.data_ptr(), cabi.stream_ptr()),
+                           "lz_search_run_ez")
+            self.last_num_kernels = t.lib.lz_search_num_kernels(q)
+            return
+        self._search_stepwise_ez(roots, model, lat, h0, h1, S, H)
+
+    def _search_stepwise_ez(self, roots, model, lat, h0, h1, S, H):
+        t = roots._tree
+        dev = roots.device
+        if self._inv is None:
+            m = self._cfg.get("model", None)
+            rng = tuple(m.value_support_range) if m is not None and "value_support_range" in m else (-300., 301., 1.)
+            self._inv = InverseScalarTransform(DiscreteSupport(*rng, device=dev))
+        B = roots.num
+        pool = torch.empty((S + 1,) + tuple(lat.shape), device=dev, dtype=torch.float32)
+        hp0 = torch.zeros((S + 1, B, h0.shape[1]), device=dev)
+        hp1 = torch.zeros((S + 1, B, h1.shape[1]), device=dev)
+        pool[0], hp0[0], hp1[0] = lat, h0, h1
+        rows = torch.arange(B, device=dev)
+        reset = torch.empty(B, dtype=torch.int32, device=dev)
+        with torch.no_grad(), torch.cuda.device(dev):
+            if hasattr(model, "eval"):
+                model.eval()
+            for sim in range(S):
+                cabi.check(t.lib.lz_tree_traverse_ez(t.h, t.ix.data_ptr(), t.iy.data_ptr(), t.action.data_ptr(),
+                                                     t.search_len.data_ptr(), t.vtp.data_ptr(), reset.data_ptr(),
+                                                     cabi.stream_ptr()), "lz_tree_traverse_ez")
+                ix = t.ix.long()
+                hidden = (hp0[ix, rows].unsqueeze(0), hp1[ix, rows].unsqueeze(0))          # mcts_ctree.py:819-831
+                out = model.recurrent_inference(pool[ix, rows], hidden, t.action.long())
+                pool[sim + 1] = out.latent_state
+                keep = (reset == 0).to(torch.float32).unsqueeze(1)                          # :856-863
+                hp0[sim + 1] = out.reward_hidden_state[0].reshape(B, -1) * keep
+                hp1[sim + 1] = out.reward_hidden_state[1].reshape(B, -1) * keep
+                value = self._inv(out.value).reshape(-1).contiguous()
+                vprefix = self._inv(out.value_prefix).reshape(-1).contiguous()
+                pol = out.policy_logits.to(torch.float32).contiguous()
+                cabi.check(t.lib.lz_tree_backpropagate_ez(t.h, sim + 1, vprefix.data_ptr(), value.data_ptr(), pol.data_ptr(),
+                                                          reset.data_ptr(), None, cabi.stream_ptr()),
+                           "lz_tree_backpropagate_ez")

@@ -53,7 +53,8 @@ class MuZeroModel:
                                num_res_blocks, num_channels, reward_head_channels, value_head_channels,
                                policy_head_channels, reward_head_hidden_channels[0], value_head_hidden_channels[0],
                                policy_head_hidden_channels[0], value_support_range[0], value_support_range[1],
-                               value_support_range[2])
+                               value_support_range[2], int(bool(kwargs.get("_efficientzero", False))),
+                               int(kwargs.get("lstm_hidden_size", 0) if kwargs.get("_efficientzero", False) else 0))
         self._cfg = cfg
         h = cabi.c_void_p()
         with torch.cuda.device(self.device):

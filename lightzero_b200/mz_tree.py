@@ -49,8 +49,8 @@ class TreeHandle:
                 cabi.check(self.lib.lz_tree_set_params(self.h, *p), "lz_tree_set_params")
             self.params = p
 
-    def search_for(self, model, num_simulations):
-        key = (id(model), num_simulations)
+    def search_for(self, model, num_simulations, mode=()):
+        key = (id(model), num_simulations) + tuple(mode)     # mode: (ez, lstm_horizon_len) -- both are baked into the graph
         if key not in self.searches:
             q = cabi.c_void_p()
             with torch.cuda.device(self.device):
