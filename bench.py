@@ -27,14 +27,35 @@ _emit = print
 
 METRIC = "MCTS simulations/sec (batched search+infer)"
 UNIT = "simulations/s"
-ROOTS_PER_GPU = 1024
-NUM_SIMULATIONS = 50
-ACTIONS = 18
-OBS = (4, 84, 84)
-WORKLOAD = "Atari 84x84 MuZero ResNet (64ch, 1 res block, support 601), num_simulations=50, 1024 roots per GPU, 18 actions"
-# algorithmic FLOPs: per root per simulation at P=36, A=18; initial inference once per root
-FLOP_RECURRENT = 14_427_392
-FLOP_INITIAL = 227_867_584
+# --workload muzero (default): SURVEY.md 8(d) config 3, the north star.  --workload efficientzero: BASELINE.json configs[1]
+#  -- 96x96 frames: the reference EfficientZeroModel cannot be constructed for 84x84 with
+# downsample=True (efficientzero_model.py:120-126 defines latent_size for 96 and 64 only).
+WORKLOADS = {
+    "muzero": dict(
+        roots=1024, sims=50, actions=18, obs=(4, 84, 84), ez=False,
+        name="Atari 84x84 MuZero ResNet (64ch, 1 res block, support 601), num_simulations=50, 1024 roots per GPU, 18 actions",
+        # algorithmic FLOPs: per root per simulation at P=36, A=18
+        flop_recurrent=14_427_392),
+    "efficientzero": dict(
+        roots=256, sims=50, actions=6, obs=(4, 96, 96), ez=True, lstm_horizon_len=5,
+        name="Atari 96x96 EfficientZero ResNet (64ch, 1 res block, LSTM 512, support 601), num_simulations=50, 256 roots per GPU, "
+             "6 actions, lstm_horizon_len=5",
+        # MuZero count at A=6 (13,928,960) with the reward FC1 (576x32 MAC) replaced by the LSTM step ((576+512) x 2048 MAC)
+        # and Linear(512, 32): 2 x (6,964,480 - 18,432 + 2,228,224 + 16,384)
+        flop_recurrent=18_381_312),
+}
+WL = WORKLOADS["muzero"]
+ROOTS_PER_GPU = NUM_SIMULATIONS = ACTIONS = OBS = WORKLOAD = FLOP_RECURRENT = None
+
+
+def select_workload(name):
+    global WL, ROOTS_PER_GPU, NUM_SIMULATIONS, ACTIONS, OBS, WORKLOAD, FLOP_RECURRENT
+    WL = WORKLOADS[name]
+    ROOTS_PER_GPU, NUM_SIMULATIONS, ACTIONS, OBS = WL["roots"], WL["sims"], WL["actions"], WL["obs"]
+    WORKLOAD, FLOP_RECURRENT = WL["name"], WL["flop_recurrent"]
+
+
+select_workload("muzero")
 
 
 def parse():
@@ -43,18 +64,24 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--roots", type=int, default=ROOTS_PER_GPU)
-    ap.add_argument("--sims", type=int, default=NUM_SIMULATIONS)
+    ap.add_argument("--workload", default="muzero", choices=sorted(WORKLOADS))
+    ap.add_argument("--roots", type=int, default=None)
+    ap.add_argument("--sims", type=int, default=None)
     ap.add_argument("--cpu-sample-roots", type=int, default=128)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    return ap.parse_args()
+    args = ap.parse_args()
+    select_workload(args.workload)
+    args.roots = args.roots or ROOTS_PER_GPU
+    args.sims = args.sims or NUM_SIMULATIONS
+    return args
 
 
 def make_reference_model(seed=0):
     import torch
-    from oracle.model_ref import MuZeroModelRef, emulate_trained_
+    from oracle.model_ref import EfficientZeroModelRef, MuZeroModelRef, emulate_trained_
     torch.manual_seed(seed)
-    return emulate_trained_(MuZeroModelRef(OBS, ACTIONS), seed)
+    cls = EfficientZeroModelRef if WL["ez"] else MuZeroModelRef
+    return emulate_trained_(cls(OBS, ACTIONS), seed)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -63,15 +90,20 @@ def make_reference_model(seed=0):
 def run_reference_pipeline(roots, sims, steps, warmup, threads=None):
     import numpy as np
     import torch
-    from oracle.search_ref import SearchRef, collect_step_ref, load_tree_module
+    from oracle.search_ref import SearchRef, SearchRefEZ, collect_step_ref, collect_step_ref_ez, load_tree_module
     if threads:
         torch.set_num_threads(threads)
     cores = torch.get_num_threads()
-    tree, kind = load_tree_module(prefer_ref=True)
+    tree, kind = load_tree_module(prefer_ref=True, name="ez_tree" if WL["ez"] else "mz_tree")
     model = make_reference_model()
     # as the reference runs it: stochastic tie-break is irrelevant for timing; keep deterministic.  The
-    # duplicated recurrent_inference of mcts_ctree.py:338/:345 is part of the unmodified reference.
-    search = SearchRef(tree, num_simulations=sims, duplicate_inference=True)
+    # duplicated recurrent_inference of mcts_ctree.py:338/:345 is part of the unmodified MuZero driver (the
+    # EfficientZero driver, :729-876, calls the network once).
+    if WL["ez"]:
+        search = SearchRefEZ(tree, lstm_horizon_len=WL["lstm_horizon_len"], num_simulations=sims)
+        collect_step_ref = collect_step_ref_ez
+    else:
+        search = SearchRef(tree, num_simulations=sims, duplicate_inference=True)
     rng = np.random.default_rng(0)
     torch.manual_seed(0)
     times = []
@@ -87,8 +119,9 @@ def run_reference_pipeline(roots, sims, steps, warmup, threads=None):
     mean = sum(times) / len(times)
     return dict(value=roots * sims / mean, seconds_per_step=mean, cores=cores, kind="reference" if kind == "reference" else "port",
                 sample=f"{roots} roots x {sims} simulations per step ({steps} timed steps after {warmup} warm-up), "
-                       f"{'compiled reference mz_tree (oracle/_ref)' if kind == 'reference' else 'C port of the ctree'} + "
-                       f"PyTorch-CPU fp32 model restatement, duplicate recurrent_inference kept (mcts_ctree.py:338,345), "
+                       f"{'compiled reference ' + ('ez_tree' if WL['ez'] else 'mz_tree') + ' (oracle/_ref)' if kind == 'reference' else 'C port of the ctree'} + "
+                       f"PyTorch-CPU fp32 model restatement, "
+                       f"{'one recurrent_inference per simulation (mcts_ctree.py:834)' if WL['ez'] else 'duplicate recurrent_inference kept (mcts_ctree.py:338,345)'}, "
                        f"torch threads={cores}")
 
 
@@ -175,12 +208,17 @@ def ours(args, rank, local_rank, world):
         dist.init_process_group("nccl", device_id=dev)
     import lightzero_b200 as lzb
     from lightzero_b200 import cabi, mz_tree
-    from lightzero_b200.collect import MuZeroCollectPolicy
+    from lightzero_b200.collect import EfficientZeroCollectPolicy, MuZeroCollectPolicy
 
     B, S, A = args.roots, args.sims, ACTIONS
+    EZ = WL["ez"]
     ref = make_reference_model()
-    model = lzb.MuZeroModel(observation_shape=OBS, action_space_size=A, device=dev).load_state_dict(ref.state_dict())
-    policy = MuZeroCollectPolicy(model, dict(num_simulations=S, deterministic=True, discount_factor=0.997))
+    if EZ:
+        model = lzb.EfficientZeroModel(observation_shape=OBS, action_space_size=A, device=dev).load_state_dict(ref.state_dict())
+        policy = EfficientZeroCollectPolicy(model, dict(num_simulations=S, discount_factor=0.997, lstm_horizon_len=WL["lstm_horizon_len"]))
+    else:
+        model = lzb.MuZeroModel(observation_shape=OBS, action_space_size=A, device=dev).load_state_dict(ref.state_dict())
+        policy = MuZeroCollectPolicy(model, dict(num_simulations=S, deterministic=True, discount_factor=0.997))
     lib = cabi.load()
 
     # synthetic inputs: rotating observation batches (3 x 115 MB) so no step re-reads a cached batch;
@@ -238,56 +276,65 @@ def ours(args, rank, local_rank, world):
     out0 = model.initial_inference(d_obs[0])
     mcts = policy.mcts
     roots = mcts.roots(B, torch.from_numpy(mask))
+    if EZ:
+        roots._lstm_horizon = WL["lstm_horizon_len"]
     roots.prepare(0.25, d_noise, None, out0.policy_logits, None)
+    mode = (1, WL["lstm_horizon_len"]) if EZ else ()
+
+    def run_search(q):
+        if EZ:
+            cabi.check(lib.lz_search_run_ez(q, out0.latent_state.data_ptr(), None, None, cabi.stream_ptr()), "lz_search_run_ez")
+        else:
+            cabi.check(lib.lz_search_run(q, out0.latent_state.data_ptr(), 1, cabi.stream_ptr()), "lz_search_run")
 
     def search_only(i):
         roots._materialize(S, mcts._params())
-        t = roots._tree
-        q = t.search_for(model, S)
-        cabi.check(lib.lz_search_run(q, out0.latent_state.data_ptr(), 1, cabi.stream_ptr()), "lz_search_run")
+        run_search(roots._tree.search_for(model, S, mode))
     so_ms, _ = timed(search_only, args.steps, 3)
 
     # the dominant kernel: the persistent search launch (50 x [tree + recurrent_inference]); CUDA events around the graph
     # launch alone, on the launching stream
-    q_search = roots._tree.search_for(model, S)
+    q_search = roots._tree.search_for(model, S, mode)
     g_ev = []
     for i in range(3 + args.steps):
         roots._materialize(S, mcts._params())
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        cabi.check(lib.lz_search_run(q_search, out0.latent_state.data_ptr(), 1, cabi.stream_ptr()), "lz_search_run")
+        run_search(q_search)
         b.record()
         g_ev.append((a, b))
     torch.cuda.synchronize()
     graph_ms = sorted(x.elapsed_time(y) for x, y in g_ev[3:])
     graph_avg_ms = sum(graph_ms) / len(graph_ms)
-    num_kernels_search = lib.lz_search_num_kernels(roots._tree.search_for(model, S))
+    num_kernels_search = lib.lz_search_num_kernels(roots._tree.search_for(model, S, mode))
 
-    # dominant kernel (k_recurrent) timed live with CUDA events on the launching stream: the same
-    # simulation loop driven one launch at a time through the C ABI, events around the network launch
-    t = roots._tree
-    roots._materialize(S, mcts._params())
-    pool = torch.empty(S + 1, B, 64, 6, 6, device=dev)
-    pool[0] = out0.latent_state
-    rows = torch.arange(B, device=dev)
-    rew, val = torch.empty(B, device=dev), torch.empty(B, device=dev)
-    pol, nxt = torch.empty(B, A, device=dev), torch.empty(B, 64, 6, 6, device=dev)
-    kev = []
-    stream = cabi.stream_ptr()
-    for sim in range(S):
-        cabi.check(lib.lz_tree_traverse(t.h, 1, t.ix.data_ptr(), t.iy.data_ptr(), t.action.data_ptr(), None, None, stream), "traverse")
-        lat = pool[t.ix.long(), rows].contiguous()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        cabi.check(lib.lz_model_recurrent_inference(model._h, B, lat.data_ptr(), t.action.data_ptr(), nxt.data_ptr(), None, None,
-                                                    pol.data_ptr(), rew.data_ptr(), val.data_ptr(), stream), "recurrent")
-        b.record()
-        kev.append((a, b))
-        pool[sim + 1] = nxt
-        cabi.check(lib.lz_tree_backpropagate(t.h, sim + 1, rew.data_ptr(), val.data_ptr(), pol.data_ptr(), None, stream), "backprop")
-    torch.cuda.synchronize()
-    k_ms = sorted(x.elapsed_time(y) for x, y in kev)
-    k_avg_ms = sum(k_ms) / len(k_ms)
+    k_avg_ms = 0.0
+    if not EZ:
+        # dominant kernel (k_recurrent) timed live with CUDA events on the launching stream: the same
+        # simulation loop driven one launch at a time through the C ABI, events around the network launch
+        t = roots._tree
+        roots._materialize(S, mcts._params())
+        pool = torch.empty(S + 1, B, 64, 6, 6, device=dev)
+        pool[0] = out0.latent_state
+        rows = torch.arange(B, device=dev)
+        rew, val = torch.empty(B, device=dev), torch.empty(B, device=dev)
+        pol, nxt = torch.empty(B, A, device=dev), torch.empty(B, 64, 6, 6, device=dev)
+        kev = []
+        stream = cabi.stream_ptr()
+        for sim in range(S):
+            cabi.check(lib.lz_tree_traverse(t.h, 1, t.ix.data_ptr(), t.iy.data_ptr(), t.action.data_ptr(), None, None, stream), "traverse")
+            lat = pool[t.ix.long(), rows].contiguous()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            cabi.check(lib.lz_model_recurrent_inference(model._h, B, lat.data_ptr(), t.action.data_ptr(), nxt.data_ptr(), None, None,
+                                                        pol.data_ptr(), rew.data_ptr(), val.data_ptr(), stream), "recurrent")
+            b.record()
+            kev.append((a, b))
+            pool[sim + 1] = nxt
+            cabi.check(lib.lz_tree_backpropagate(t.h, sim + 1, rew.data_ptr(), val.data_ptr(), pol.data_ptr(), None, stream), "backprop")
+        torch.cuda.synchronize()
+        k_ms = sorted(x.elapsed_time(y) for x, y in kev)
+        k_avg_ms = sum(k_ms) / len(k_ms)
 
     # max over ranks
     vals = torch.tensor([dev_ms, wall_ms, e2e_dev_ms, e2e_wall_ms, so_ms, k_avg_ms, graph_avg_ms], device=dev, dtype=torch.float64)
@@ -317,21 +364,25 @@ def ours(args, rank, local_rank, world):
             "vs_baseline": None, "dtype": "f32 (fp16x2-split tensor MMAs, fp32 accumulate)", "data": "synthetic",
             "config": {"workload": WORKLOAD, "roots_per_gpu": B, "global_roots": total_roots, "num_simulations": S,
                        "actions": A, "obs": list(OBS), "parallelism": f"roots sharded x{world}, no data-path collective; one NCCL all-gather of visits/values per step",
-                       "step": "initial_inference + prepare + S x (traverse, recurrent_inference, backpropagate) + results",
+                       "step": "initial_inference + prepare + S x (traverse, recurrent_inference, backpropagate) + results"
+                               + (" (EfficientZero: value-prefix trees, LSTM state reset every lstm_horizon_len steps)" if EZ else ""),
                        "deterministic": True,
                        "math": "tcgen05 fp16 hi/lo split (3 MMAs per product, fp32 accumulate in TMEM): fp32-accurate, the 1e-5 parity mode",
-                       "l2": "no explicit flush: per-step working set = rotating 3 x 115 MB observation batches + 481 MB latent pool > 126 MB L2",
+                       "l2": f"no explicit flush: per-step working set = rotating 3 x {h_obs[0].numel() * 4 / 1e6:.0f} MB observation batches + "
+                             f"{(S + 1) * B * (2304 + (1024 if EZ else 0)) * 4 / 1e6:.0f} MB latent / LSTM-state pools > 126 MB L2",
                        "search_only_ms": so_ms / args.steps,
                        "search_only_sims_per_s": total_roots * S / (so_ms / args.steps * 1e-3),
                        "wall_ms_per_step": wall_ms / args.steps},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms, "device_ms_per_step": e2e_dev_ms / args.steps,
-                    "api": "lightzero_b200.collect.MuZeroCollectPolicy.search_batch (pinned host obs/mask/noise in, pinned host visits/values out)"},
+                    "api": f"lightzero_b200.collect.{type(policy).__name__}.search_batch (pinned host obs/mask/noise in, pinned host visits/values out)"},
             "gpu_launches": args.steps * (13 + 2 + num_kernels_search + 1),
             "search_graph_kernels": num_kernels_search,
             "roofline": {"bound": "tensor",
-                         "kernel": "k_net_tc, persistent launch = num_simulations x [tree back-up/descent + fused recurrent_inference] (tcgen05)",
+                         "kernel": ("search graph = 1 + num_simulations x [k_net_tc conv trunk + prediction heads (tcgen05), k_ez_lstm (fp32 GEMM over "
+                                    "all roots + cell update), k_ez_head, tree back-up + descent]" if EZ else
+                                    "k_net_tc, persistent launch = num_simulations x [tree back-up/descent + fused recurrent_inference] (tcgen05)"),
                          "achieved": B * S * FLOP_RECURRENT / (graph_avg_ms * 1e-3) / 1e12,
                          "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": B * S * FLOP_RECURRENT / (graph_avg_ms * 1e-3) / 1e12 / peak_tf,
@@ -340,9 +391,11 @@ def ours(args, rank, local_rank, world):
                          "peak_source": peak_note, "kernel_ms": graph_avg_ms, "kernel_ms_min": graph_ms[0],
                          "kernel_share_of_step": graph_avg_ms / ms_per_step,
                          "flop_per_launch": B * S * FLOP_RECURRENT,
-                         "issued_flop_per_launch": int(B * S * FLOP_RECURRENT * 3 * 384 / 252),
-                         "single_simulation_launch_ms": k_avg_ms,
-                         "note": "achieved = algorithmic FLOPs (SURVEY 8d, 14,427,392 per root per simulation, counted ONCE) x roots x "
+                         "issued_flop_per_launch": int(B * S * FLOP_RECURRENT * 3 * 384 / 252) if not EZ else None,
+                         "single_simulation_launch_ms": k_avg_ms if not EZ else None,
+                         "note": ("achieved = algorithmic FLOPs (18,381,312 per root per simulation: the MuZero count at A=6 with the reward FC1 replaced "
+                                  "by the LSTM step and Linear(512,32)) x roots x simulations / CUDA-event duration of the whole search graph, against the "
+                                  "measured bf16 peak; the LSTM GEMM is fp32 FFMA in this round (24% of the algorithmic FLOPs, CUDA cores)") if EZ else "achieved = algorithmic FLOPs (SURVEY 8d, 14,427,392 per root per simulation, counted ONCE) x roots x "
                                  "simulations / CUDA-event duration of the persistent launch (which also contains the tree phases), against "
                                  "the measured bf16 peak.  The kernel issues 3 fp16 MMAs per product (fp32-accurate hi/lo split) on 384 padded "
                                  "rows per 252 real ones = 4.57x the algorithmic FLOPs: the ceiling of this formulation is 21.9% of the tensor peak"},

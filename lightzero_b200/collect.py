@@ -14,7 +14,8 @@ import numpy as np
 import torch
 
 from . import cabi, mz_tree
-from .mcts_ctree import MuZeroMCTSCtree
+from .efficientzero_model import EfficientZeroModel
+from .mcts_ctree import EfficientZeroMCTSCtree, MuZeroMCTSCtree
 from .muzero_model import MuZeroModel
 
 
@@ -40,6 +41,7 @@ class MuZeroCollectPolicy:
         self.device = model.device
         self._buf = {}
         self.h2d_chunks = 2      # host observation batches are copied in this many overlapped pieces
+        self._tree_mode = (0, 5)   # (EfficientZero value-prefix trees?, lstm_horizon_len)
 
     # ---- device-resident fast path ---------------------------------------------------------------
     def _bufs(self, B, A):
@@ -96,7 +98,8 @@ class MuZeroCollectPolicy:
             tree = mz_tree.acquire_tree(dev, B, A, S)
             try:
                 tree.set_params(*self.mcts._params())
-                q = tree.search_for(self.model, S)
+                cabi.check(tree.lib.lz_tree_set_ez(tree.h, *self._tree_mode), "lz_tree_set_ez")
+                q = tree.search_for(self.model, S, self._tree_mode if self._tree_mode[0] else ())
                 s = cabi.stream_ptr()
                 if host_path:
                     cabi.check(tree.lib.lz_search_collect_host(q, h_obs.data_ptr(), h_mask.data_ptr(), cabi.ptr(h_noise),
@@ -170,3 +173,15 @@ class MuZeroCollectPolicy:
                 'predicted_policy_logits': logits[i].tolist(),
             }
         return output
+
+
+class EfficientZeroCollectPolicy(MuZeroCollectPolicy):
+    """The same for ``EfficientZeroPolicy._forward_collect`` / ``_forward_eval`` (lzero/policy/efficientzero.py:539-640,
+    690-760): value-prefix trees, the reward hidden state starts as zeros after ``initial_inference`` (:580-590) and is reset
+    every ``lstm_horizon_len`` steps of search depth.  Same output dict."""
+
+    def __init__(self, model: EfficientZeroModel, cfg: Optional[dict] = None):
+        super().__init__(model, cfg)
+        self.mcts = EfficientZeroMCTSCtree(cfg or {})
+        self.cfg = self.mcts._cfg
+        self._tree_mode = (1, int(self.cfg.lstm_horizon_len))
