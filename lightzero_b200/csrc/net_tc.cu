@@ -88,6 +88,10 @@ __device__ __forceinline__ void head_stage(const TcNet &net, const TcIO &io, int
     slot[0] = 0; slot[1] = hmask & 1; slot[2] = (hmask & 1) + ((hmask >> 1) & 1);
     float *hflat = scr, *hidden = hflat + nh * kMaxRoots * 576, *logits = hidden + nh * kMaxRoots * 32;
     float *part = logits + nh * kMaxRoots * ldl;
+    // The scratch may overlay the activation buffer the epilogue has just written (value/policy stage).  Those writes are
+    // already ordered before this point through act_ready -> MMA issuer -> vp_ready, but an explicit barrier among the
+    // epilogue threads costs nothing and keeps compute-sanitizer's racecheck (which does not follow mbarriers) quiet.
+    asm volatile("bar.sync 1, %0;\n" ::"n"(kEpiThreads) : "memory");
     for (int i = tid; i < nh * kMaxRoots * 576; i += kEpiThreads) hflat[i] = 0.0f;
     asm volatile("bar.sync 1, %0;\n" ::"n"(kEpiThreads) : "memory");
     for (int t = 0; t < NT; ++t) {

@@ -31,5 +31,20 @@ roots = mcts.roots(5, [[0, 1]] * 5)
 roots.prepare_no_noise([0.] * 5, o.policy_logits, [1, 2, 1, 2, 1])     # two-player sign flips
 mcts.search(roots, mcu, o.latent_state, [1, 2, 1, 2, 1])
 print("mlp ok", roots.get_distributions(), roots.get_trajectories()[:2])
+# EfficientZero: value-prefix trees, LSTM value-prefix head, multi-kernel search graph, collect from host buffers
+from lightzero_b200.collect import EfficientZeroCollectPolicy
+from oracle.model_ref import EfficientZeroModelRef
+eref = emulate_trained_(EfficientZeroModelRef((4, 96, 96), A), 1)
+ecu = lzb.EfficientZeroModel(observation_shape=(4, 96, 96), action_space_size=A).load_state_dict(eref.state_dict())
+epol = EfficientZeroCollectPolicy(ecu, dict(num_simulations=8, discount_factor=0.997, lstm_horizon_len=2))
+eobs = torch.rand(B, 4, 96, 96)
+r = epol.search_batch(eobs.pin_memory(), mask, noise, None)
+assert int(r["visits"].clamp(min=0).sum()) == B * 8
+emcts = lzb.EfficientZeroMCTSCtree(dict(num_simulations=8, lstm_horizon_len=2))
+eo = ecu.initial_inference(eobs.cuda())
+eroots = emcts.roots(B, [list(range(A))] * B)
+eroots.prepare(0.25, noise, [0.] * B, eo.policy_logits, [1, 2] * (B // 2) + [1])     # two-player branch
+emcts.search(eroots, ecu, eo.latent_state, eo.reward_hidden_state, [1, 2] * (B // 2) + [1])
+print("efficientzero ok", r["values"][:3].tolist(), eroots.get_distributions()[:2])
 torch.cuda.synchronize()
 print("sanitize script finished")
