@@ -11,13 +11,14 @@
 
 namespace lz {
 
-constexpr int kGM = 64, kGN = 64, kGK = 16;
+constexpr int kGM = 64, kGN = 32, kGK = 16;      // 64 roots x 32 gate columns (= 8 hidden units) per CTA: 64 x ceil(B/64) CTAs
+constexpr int kGThreads = 128;                   // thread = 4 roots x 4 gates of one hidden unit
 
-__global__ void __launch_bounds__(256) k_ez_lstm(EzNet net, EzIO io)
+__global__ void __launch_bounds__(kGThreads) k_ez_lstm(EzNet net, EzIO io)
 {
     __shared__ float As[kGK][kGM + 4];
     __shared__ float Bs[kGK][kGN];
-    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int tid = threadIdx.x, tx = tid & 7, ty = tid >> 3;          // tx: hidden unit within the tile, ty: 4-row group
     const int n0 = blockIdx.x * kGN, m0 = blockIdx.y * kGM;
     const int H = net.H, nin = net.nin, KT = nin + H, N = 4 * H;
     float acc[4][4];
@@ -25,29 +26,34 @@ __global__ void __launch_bounds__(256) k_ez_lstm(EzNet net, EzIO io)
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
-    // A-tile loader: thread -> (row = tid / 4, 4 consecutive k)
-    const int ar = tid >> 2, ak = (tid & 3) * 4;
+    // A-tile loader: thread -> (row = tid / 2, 8 consecutive k); B-tile loader: thread -> (k = tid / 8, 4 consecutive n)
+    const int ar = tid >> 1, ak = (tid & 1) * 8;
     const int arow = m0 + ar;
-    const float *hsrc = nullptr;
-    if (arow < io.B) hsrc = io.h_base + (io.ix ? (size_t)io.ix[arow] * io.slot_stride : 0) + (size_t)arow * H;
-    const float *fsrc = io.feat + (size_t)min(arow, io.B - 1) * nin;
-    // B-tile loader: thread -> (k = tid / 16, 4 consecutive n)
-    const int bk = tid >> 4, bn = (tid & 15) * 4;
-    for (int k0 = 0; k0 < KT; k0 += kGK) {
-        float a4[4];
+    const bool arow_on = arow < io.B;
+    const float *hsrc = io.h_base + (arow_on && io.ix ? (size_t)io.ix[arow] * io.slot_stride : 0) + (size_t)(arow_on ? arow : 0) * H;
+    const float *fsrc = io.feat + (size_t)(arow_on ? arow : 0) * nin;
+    const int bk = tid >> 3, bn = (tid & 7) * 4;
+    float4 a4[2];
+    float4 b4;
+    auto fetch = [&](int k0) {       // global -> registers (in flight while the previous tile is being multiplied)
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int k = k0 + ak + u;
-            float v = 0.0f;
-            if (arow < io.B && k < KT) v = k < nin ? fsrc[k] : hsrc[k - nin];
-            a4[u] = v;
+        for (int v = 0; v < 2; ++v) {        // nin and H are multiples of 4, so a 16-byte load never straddles feat | h
+            const int k = k0 + ak + 4 * v;
+            a4[v] = (arow_on && k < KT) ? *reinterpret_cast<const float4 *>(k < nin ? fsrc + k : hsrc + (k - nin)) : make_float4(0, 0, 0, 0);
         }
-        const float4 b4 = (k0 + bk < KT) ? *reinterpret_cast<const float4 *>(net.wcat + (size_t)(k0 + bk) * N + n0 + bn) : make_float4(0, 0, 0, 0);
+        b4 = (k0 + bk < KT) ? __ldg(reinterpret_cast<const float4 *>(net.wcat + (size_t)(k0 + bk) * N + n0 + bn)) : make_float4(0, 0, 0, 0);
+    };
+    fetch(0);
+    for (int k0 = 0; k0 < KT; k0 += kGK) {
         __syncthreads();
 #pragma unroll
-        for (int u = 0; u < 4; ++u) As[ak + u][ar] = a4[u];
+        for (int v = 0; v < 2; ++v) {
+            As[ak + 4 * v + 0][ar] = a4[v].x; As[ak + 4 * v + 1][ar] = a4[v].y;
+            As[ak + 4 * v + 2][ar] = a4[v].z; As[ak + 4 * v + 3][ar] = a4[v].w;
+        }
         *reinterpret_cast<float4 *>(&Bs[bk][bn]) = b4;
         __syncthreads();
+        if (k0 + kGK < KT) fetch(k0 + kGK);
 #pragma unroll
         for (int k = 0; k < kGK; ++k) {
             const float4 a = *reinterpret_cast<const float4 *>(&As[k][ty * 4]);
@@ -78,7 +84,7 @@ __global__ void __launch_bounds__(256) k_ez_lstm(EzNet net, EzIO io)
     }
 }
 
-constexpr int kHR = 8;        // roots per CTA of the head kernel
+constexpr int kHR = 2;        // roots per CTA of the head kernel (the FC weights are 64 KB + 77 KB, L2-resident)
 constexpr int kHMaxH = 512, kHMaxHid = 32, kHLd = 608;
 
 __global__ void __launch_bounds__(256) k_ez_head(EzNet net, EzIO io)
@@ -95,23 +101,29 @@ __global__ void __launch_bounds__(256) k_ez_head(EzNet net, EzIO io)
         x[r][u] = r < nr ? fmaxf(fmaf(io.h_tmp[(size_t)(r0 + r) * H + u], net.vp_s[u], net.vp_t[u]), 0.0f) : 0.0f;
     }
     __syncthreads();
-    {   // Linear(H -> hid): warp w sums its eighth of the inputs, lane = hidden unit
+    {   // Linear(H -> hid): warp w sums its eighth of the inputs, lane = hidden unit; 16 weight rows in flight per batch
         const int per = (H + 7) / 8, i0 = warp * per, i1 = min(H, i0 + per);
         float a[kHR];
 #pragma unroll
         for (int r = 0; r < kHR; ++r) a[r] = 0.0f;
-        if (lane < hid)
-            for (int i = i0; i < i1; ++i) {
-                const float w = __ldg(net.fc1 + (size_t)i * hid + lane);
+        const bool lane_on = lane < hid;
+        for (int i = i0; i < i1; i += 16) {
+            float w[16];
 #pragma unroll
-                for (int r = 0; r < kHR; ++r) a[r] = fmaf(x[r][i], w, a[r]);
+            for (int u = 0; u < 16; ++u) w[u] = (lane_on && i + u < i1) ? __ldg(net.fc1 + (size_t)(i + u) * hid + lane) : 0.0f;
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+                const int ii = min(i + u, H - 1);
+#pragma unroll
+                for (int r = 0; r < kHR; ++r) a[r] = fmaf(x[r][ii], w[u], a[r]);
             }
+        }
 #pragma unroll
         for (int r = 0; r < kHR; ++r) part[warp][r][lane] = a[r];
     }
     __syncthreads();
-    {
-        const int r = tid >> 5, j = tid & 31;      // 8 roots x 32 hidden units
+    if (tid < kHR * 32) {
+        const int r = tid >> 5, j = tid & 31;      // kHR roots x 32 hidden units
         float v = 0.0f;
 #pragma unroll
         for (int w = 0; w < 8; ++w) v += part[w][r][j];
@@ -123,10 +135,13 @@ __global__ void __launch_bounds__(256) k_ez_head(EzNet net, EzIO io)
         const float bias = __ldg(net.b2 + k);
 #pragma unroll
         for (int r = 0; r < kHR; ++r) o[r] = bias;
-        for (int j = 0; j < hid; ++j) {
-            const float w = __ldg(net.fc2 + (size_t)j * K + k);
+        float w[kHMaxHid];
 #pragma unroll
-            for (int r = 0; r < kHR; ++r) o[r] = fmaf(hidden[r][j], w, o[r]);
+        for (int j = 0; j < kHMaxHid; ++j) w[j] = j < hid ? __ldg(net.fc2 + (size_t)j * K + k) : 0.0f;     // all rows in flight
+#pragma unroll
+        for (int j = 0; j < kHMaxHid; ++j) {
+#pragma unroll
+            for (int r = 0; r < kHR; ++r) o[r] = fmaf(hidden[r][j], w[j], o[r]);
         }
 #pragma unroll
         for (int r = 0; r < kHR; ++r) logits[r][k] = o[r];
@@ -143,10 +158,10 @@ __global__ void __launch_bounds__(256) k_ez_head(EzNet net, EzIO io)
 
 int ez_launch(const EzNet &net, const EzIO &io, cudaStream_t s)
 {
-    LZ_REQUIRE(net.H <= kHMaxH && net.hid <= kHMaxHid && net.K <= kHLd && (net.H % 16) == 0, LZ_EINVAL,
+    LZ_REQUIRE(net.H <= kHMaxH && net.hid <= kHMaxHid && net.K <= kHLd && (net.H % 8) == 0, LZ_EINVAL,
                "ez_launch: unsupported LSTM / head size (H=%d hid=%d K=%d)", net.H, net.hid, net.K);
     dim3 grid(4 * net.H / kGN, (io.B + kGM - 1) / kGM);
-    k_ez_lstm<<<grid, 256, 0, s>>>(net, io);
+    k_ez_lstm<<<grid, kGThreads, 0, s>>>(net, io);
     LZ_KERNEL_CHECK();
     k_ez_head<<<(io.B + kHR - 1) / kHR, 256, 0, s>>>(net, io);
     LZ_KERNEL_CHECK();
