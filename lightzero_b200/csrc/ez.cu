@@ -6,8 +6,15 @@
 // of a thread holds (i, f, g, o) of one hidden unit for 4 roots.  torch.nn.LSTM gate order i, f, g, o; c' = sig(f) c +
 // sig(i) tanh(g); h' = sig(o) tanh(c').
 // k_ez_head: per root relu(bn(h')) -> Linear(H, hid) + BN + ReLU -> Linear(hid, K) -> softmax expectation -> h^-1.
+#include <cuda_fp16.h>
+#include <math.h>
+#include <stdlib.h>
+
+#include <algorithm>
+
 #include "ez.cuh"
 #include "lz_common.cuh"
+#include "tc_ptx.cuh"
 
 namespace lz {
 
@@ -156,12 +163,186 @@ __global__ void __launch_bounds__(256) k_ez_head(EzNet net, EzIO io)
     }
 }
 
-int ez_launch(const EzNet &net, const EzIO &io, cudaStream_t s)
+// ---------------------------------------------------------------------------------------------- tcgen05 LSTM step
+// gates = [feat | h] * W as a tcgen05 GEMM with fp32 accuracy ("3xFP16": A_hi*W_hi + A_hi*W_lo + A_lo*W_hi, fp32
+// accumulation in TMEM).  CTA tile: 128 roots x 64 gate columns (16 hidden units), K = nin + H in chunks of 64 through a
+// 3-stage ring.  Warps 0-3: gather the fp32 A rows (features, then the leaf parent's h through ix), split them to fp16
+// hi / lo into the UMMA K-major layout [k-group][row][8 halves] -- then become the epilogue (tcgen05.ld, LSTM cell update,
+// reset).  Warp 4 lane 0: bulk-copies the pre-split weight chunks.  Warp 5 lane 0: MMA issue (+ TMEM alloc by warp 5).
+constexpr int kTM = 128, kTN = 64, kTK = 64, kTStages = 3;
+constexpr int kTAPart = 8 * kTM * 16;            // one hi or lo part of an A stage: [8 k-groups][128 rows][16 B] = 16 KB
+constexpr int kTWPart = 8 * kTN * 16;            // one hi or lo part of a W stage: 8 KB
+constexpr int kTStageBytes = 2 * kTAPart + 2 * kTWPart;     // 48 KB
+constexpr int kTSmem = kTStages * kTStageBytes + 256;
+constexpr int kTGroups = 3;                      // A-producer groups of 128 threads; group g converts chunks g, g+3, ... (3 chunks of L2 latency in flight)
+constexpr int kTThreads = 192 + (kTGroups - 1) * 128;
+
+struct EzTcBars {
+    uint64_t full_a[kTStages], full_w[kTStages], empty[kTStages];
+    uint64_t acc_ready;
+    uint32_t tmem_base, pad;
+};
+
+__global__ void __launch_bounds__(kTThreads, 1) k_ez_lstm_tc(EzNet net, EzIO io)
+{
+    extern __shared__ __align__(1024) unsigned char smem[];
+    EzTcBars *bars = reinterpret_cast<EzTcBars *>(smem + kTStages * kTStageBytes);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nt = blockIdx.x, m0 = blockIdx.y * kTM;
+    const int H = net.H, nin = net.nin, KT = nin + H, nchunks = KT / kTK;
+
+    if (tid == 0) {
+        for (int i = 0; i < kTStages; ++i) { mbar_init(&bars->full_a[i], 128); mbar_init(&bars->full_w[i], 1); mbar_init(&bars->empty[i], 1); }
+        mbar_init(&bars->acc_ready, 1);
+        fence_mbar_init();
+    }
+    if (warp == 5) tmem_alloc(&bars->tmem_base, 64);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = bars->tmem_base;
+
+    if (warp == 4) {
+        if (lane == 0) {
+            const unsigned char *src = net.wtc + (size_t)nt * nchunks * (2 * kTWPart);
+            for (int c = 0; c < nchunks; ++c) {
+                const int st = c % kTStages;
+                if (c >= kTStages) mbar_wait(&bars->empty[st], ((c / kTStages) - 1) & 1);
+                mbar_expect_tx(&bars->full_w[st], 2 * kTWPart);
+                bulk_g2s(smem + st * kTStageBytes + 2 * kTAPart, src + (size_t)c * (2 * kTWPart), 2 * kTWPart, &bars->full_w[st]);
+            }
+        }
+    } else if (warp == 5) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_f16(kTM, kTN);
+            for (int c = 0; c < nchunks; ++c) {
+                const int st = c % kTStages;
+                mbar_wait(&bars->full_a[st], (c / kTStages) & 1);
+                mbar_wait(&bars->full_w[st], (c / kTStages) & 1);
+                tc_fence_after();
+                const uint32_t a_s = smem_u32(smem + st * kTStageBytes), w_s = a_s + 2 * kTAPart;
+                const uint64_t a_hi = make_desc(a_s, (kTM * 16) >> 4, 8), a_lo = make_desc(a_s + kTAPart, (kTM * 16) >> 4, 8);
+                const uint64_t w_hi = make_desc(w_s, (kTN * 16) >> 4, 8), w_lo = make_desc(w_s + kTWPart, (kTN * 16) >> 4, 8);
+#pragma unroll
+                for (int ks = 0; ks < kTK / 16; ++ks) {
+                    const uint64_t ao = (uint64_t)(ks * 2 * kTM * 16 >> 4), wo = (uint64_t)(ks * 2 * kTN * 16 >> 4);
+                    umma_f16(tmem, a_hi + ao, w_hi + wo, idesc, (c | ks) != 0);
+                    umma_f16(tmem, a_hi + ao, w_lo + wo, idesc, 1);
+                    umma_f16(tmem, a_lo + ao, w_hi + wo, idesc, 1);
+                }
+                umma_commit(&bars->empty[st]);
+            }
+            umma_commit(&bars->acc_ready);
+        }
+    } else {
+        // ---- A producers: thread = one root row of the tile; warps 0-3 are group 0, warps 6-9 group 1, warps 10-13 group 2
+        const int grp = warp < 4 ? 0 : (warp - 6) / 4 + 1;
+        const int row = warp < 4 ? tid : (tid - 192) & 127, b = m0 + row;
+        const bool on = b < io.B;
+        const float *fsrc = io.feat + (size_t)(on ? b : 0) * nin;
+        const size_t hoff = (on && io.ix ? (size_t)io.ix[b] * io.slot_stride : 0) + (size_t)(on ? b : 0) * H;
+        const float *hsrc = io.h_base + hoff;
+        for (int c = grp; c < nchunks; c += kTGroups) {
+            const int st = c % kTStages;
+            const int k0 = c * kTK;
+            const float *src = k0 < nin ? fsrc + k0 : hsrc + (k0 - nin);      // nin is a multiple of 64: a chunk never straddles
+            float4 v[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) v[u] = on ? *reinterpret_cast<const float4 *>(src + 4 * u) : make_float4(0, 0, 0, 0);
+            if (c >= kTStages) mbar_wait(&bars->empty[st], ((c / kTStages) - 1) & 1);
+            unsigned char *a_hi = smem + st * kTStageBytes + row * 16;
+#pragma unroll
+            for (int kg = 0; kg < 8; ++kg) {
+                const float f[8] = {v[2 * kg].x, v[2 * kg].y, v[2 * kg].z, v[2 * kg].w, v[2 * kg + 1].x, v[2 * kg + 1].y, v[2 * kg + 1].z, v[2 * kg + 1].w};
+                store_split8(a_hi + kg * (kTM * 16), a_hi + kTAPart + kg * (kTM * 16), f);
+            }
+            fence_proxy_async();
+            mbar_arrive(&bars->full_a[st]);
+        }
+        if (grp != 0) goto done;
+        // ---- epilogue (group 0): 64 accumulator columns of this thread's row = 16 hidden units x (i, f, g, o)
+        mbar_wait_warp(&bars->acc_ready, 0);
+        tc_fence_after();
+        const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+        const float inv = net.wtc_inv_scale;
+        const float *c_in = io.c_base + hoff;
+        const bool reset = on && io.is_reset && io.is_reset[b] != 0;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            float g[32];
+            tmem_ld32(lane_base + half * 32, g);
+            if (!on) continue;
+            const int u0 = nt * 16 + half * 8;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const float4 bias = *reinterpret_cast<const float4 *>(net.bias + (size_t)(u0 + u) * 4);
+                const float gi = fmaf(g[4 * u], inv, bias.x), gf = fmaf(g[4 * u + 1], inv, bias.y);
+                const float gg = fmaf(g[4 * u + 2], inv, bias.z), go = fmaf(g[4 * u + 3], inv, bias.w);
+                const float si = 1.0f / (1.0f + expf(-gi)), sf = 1.0f / (1.0f + expf(-gf)), so = 1.0f / (1.0f + expf(-go));
+                const float c_new = sf * c_in[u0 + u] + si * tanhf(gg);
+                const float h_new = so * tanhf(c_new);
+                io.h_tmp[(size_t)b * H + u0 + u] = h_new;
+                if (io.h_out) io.h_out[(size_t)b * H + u0 + u] = reset ? 0.0f : h_new;
+                if (io.c_out) io.c_out[(size_t)b * H + u0 + u] = reset ? 0.0f : c_new;
+            }
+        }
+    }
+done:
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5) {
+        __syncwarp();
+        tmem_dealloc(tmem, 64);
+    }
+}
+
+size_t ez_wtc_bytes(int nin, int H) { return (size_t)(4 * H / kTN) * ((nin + H) / kTK) * (2 * kTWPart); }
+
+// W_ih [4H][nin], W_hh [4H][H] (torch gate order i, f, g, o along dim 0) -> per (n-tile, k-chunk) [hi | lo] blocks of
+// [k-group][n][8 halves]; column n = unit * 4 + gate as in the fp32 path.  Returns the power-of-two scale applied.
+float ez_pack_wtc(const float *w_ih, const float *w_hh, int nin, int H, unsigned char *dst)
+{
+    const int KT = nin + H, N = 4 * H, nchunks = KT / kTK;
+    float mx = 0.0f;
+    for (size_t i = 0; i < (size_t)N * nin; ++i) mx = std::max(mx, fabsf(w_ih[i]));
+    for (size_t i = 0; i < (size_t)N * H; ++i) mx = std::max(mx, fabsf(w_hh[i]));
+    int e = 0;
+    if (mx > 0.0f) frexpf(mx, &e);
+    const float scale = ldexpf(1.0f, 13 - e);    // largest |w| lands in [4096, 8192): lo parts stay normal fp16
+    __half *h = reinterpret_cast<__half *>(dst);
+    for (int n = 0; n < N; ++n) {
+        const int unit = n >> 2, gate = n & 3, row = gate * H + unit, nt = n / kTN, nn = n % kTN;
+        for (int k = 0; k < KT; ++k) {
+            const float w = (k < nin ? w_ih[(size_t)row * nin + k] : w_hh[(size_t)row * H + (k - nin)]) * scale;
+            const __half hi = __float2half_rn(w), lo = __float2half_rn(w - __half2float(hi));
+            const int c = k / kTK, kk = k % kTK;
+            const size_t blk = ((size_t)nt * nchunks + c) * (2 * kTWPart / 2);      // in halves
+            const size_t off = blk + ((size_t)(kk / 8) * kTN + nn) * 8 + (kk % 8);
+            h[off] = hi;
+            h[off + kTWPart / 2] = lo;
+        }
+    }
+    return scale;
+}
+
+int ez_prepare_launch()
+{
+    LZ_CUDA_CHECK(cudaFuncSetAttribute(k_ez_lstm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, kTSmem));
+    return LZ_OK;
+}
+
+int ez_launch(const EzNet &net, const EzIO &io, cudaStream_t s, int math)
 {
     LZ_REQUIRE(net.H <= kHMaxH && net.hid <= kHMaxHid && net.K <= kHLd && (net.H % 8) == 0, LZ_EINVAL,
                "ez_launch: unsupported LSTM / head size (H=%d hid=%d K=%d)", net.H, net.hid, net.K);
-    dim3 grid(4 * net.H / kGN, (io.B + kGM - 1) / kGM);
-    k_ez_lstm<<<grid, kGThreads, 0, s>>>(net, io);
+    const bool tc_ok = net.wtc && (net.nin % kTK) == 0 && (net.H % kTK) == 0 && !getenv("LZ_EZ_FP32");
+    if (math != 0 && tc_ok) {
+        dim3 grid(4 * net.H / kTN, (io.B + kTM - 1) / kTM);
+        k_ez_lstm_tc<<<grid, kTThreads, kTSmem, s>>>(net, io);
+    } else {
+        dim3 grid(4 * net.H / kGN, (io.B + kGM - 1) / kGM);
+        k_ez_lstm<<<grid, kGThreads, 0, s>>>(net, io);
+    }
     LZ_KERNEL_CHECK();
     k_ez_head<<<(io.B + kHR - 1) / kHR, 256, 0, s>>>(net, io);
     LZ_KERNEL_CHECK();

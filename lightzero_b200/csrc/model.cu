@@ -367,7 +367,7 @@ int model_recurrent(lz_model *m, const RecIO &io, cudaStream_t s)
             e.B = io.B; e.feat = m->ez_feat; e.h_base = io.h_base; e.c_base = io.c_base; e.ix = io.ix; e.slot_stride = io.hslot_stride;
             e.h_out = io.h_out; e.c_out = io.c_out; e.is_reset = io.is_reset; e.h_tmp = m->ez_htmp;
             e.value_prefix = io.reward; e.vp_logits = io.reward_logits;
-            return ez_launch(m->ez, e, s);
+            return ez_launch(m->ez, e, s, m->math);
         }
         return tc_launch(m->tc_rec, t, s);
     }
@@ -881,7 +881,7 @@ int lz_model_create(const lz_model_config *cfg, lz_model **out)
                LZ_EINVAL, "lz_model_create: lstm_hidden_size must be a multiple of 16 in [16, 512] (got %d)", cfg->lstm_hidden_size);
     lz_model *m = new lz_model();
     m->cfg = *cfg;
-    m->ez_feat = m->ez_htmp = nullptr; m->ez_B = 0;
+    m->ez_feat = m->ez_htmp = nullptr; m->ez_B = 0; m->d_ez_wtc = nullptr;
     m->kind = 0;
     m->latent_floats = kC * kP;
     memset(&m->mcfg, 0, sizeof(m->mcfg));
@@ -903,7 +903,7 @@ int lz_model_destroy(lz_model *m)
     cudaFree(m->d_tc);
     cudaFree(m->d_tower);
     cudaFree(m->tws);
-    cudaFree(m->ez_feat); cudaFree(m->ez_htmp);
+    cudaFree(m->ez_feat); cudaFree(m->ez_htmp); cudaFree(m->d_ez_wtc);
     for (int i = 0; i < 3; ++i) cudaFree(m->ws[i]);
     delete m;
     return LZ_OK;
@@ -961,6 +961,7 @@ int lz_model_finalize(lz_model *m)
          pack_head(m, P, Q + "conv1x1_policy", Q + "norm_policy", Q + "fc_policy", c.policy_head_channels, c.policy_hidden, A, kP, hp);
     if (!ok) return LZ_EINVAL;
     // ---- EfficientZero value-prefix head (efficientzero_model.py:511-525, 556-569)
+    float ez_scale = 1.0f;
     size_t ez_wcat = 0, ez_bias = 0, ez_vps = 0, ez_vpt = 0, ez_fc1 = 0, ez_s2 = 0, ez_t2 = 0, ez_fc2 = 0, ez_b2 = 0;
     if (c.efficientzero) {
         const int H = c.lstm_hidden_size, nin = c.reward_head_channels * kP, hid = c.reward_hidden, K = m->K;
@@ -986,6 +987,15 @@ int lz_model_finalize(lz_model *m)
             for (int i = 0; i < H; ++i) fc1[(size_t)i * hid + j] = (*W0)[(size_t)j * H + i];
         for (int k = 0; k < K; ++k)
             for (int j = 0; j < hid; ++j) fc2[(size_t)j * K + k] = (*W3)[(size_t)k * hid + j];
+        {   // tcgen05 copy of the LSTM weights (fp16 hi / lo, power-of-two scaled), own allocation
+            std::vector<unsigned char> wtc(ez_wtc_bytes(nin, H));
+            ez_scale = ez_pack_wtc(Wih->data(), Whh->data(), nin, H, wtc.data());
+            if (m->d_ez_wtc) cudaFree(m->d_ez_wtc);
+            m->d_ez_wtc = nullptr;
+            int rc2 = dev_alloc(&m->d_ez_wtc, wtc.size());
+            if (rc2 != LZ_OK) return rc2;
+            LZ_CUDA_CHECK(cudaMemcpy(m->d_ez_wtc, wtc.data(), wtc.size(), cudaMemcpyHostToDevice));
+        }
         ez_wcat = P.add(wcat); ez_bias = P.add(bias); ez_vps = P.add(vs); ez_vpt = P.add(vt); ez_fc1 = P.add(fc1);
         ez_s2 = P.add(s2); ez_t2 = P.add(t2); ez_fc2 = P.add(fc2); ez_b2 = P.add(*B3);
     }
@@ -1016,6 +1026,9 @@ int lz_model_finalize(lz_model *m)
         e.fc1 = base + ez_fc1; e.s2 = base + ez_s2; e.t2 = base + ez_t2; e.fc2 = base + ez_fc2; e.b2 = base + ez_b2;
         e.nin = c.reward_head_channels * kP; e.H = c.lstm_hidden_size; e.hid = c.reward_hidden; e.K = m->K;
         e.support_min = c.support_min; e.support_step = c.support_step;
+        e.wtc = m->d_ez_wtc; e.wtc_inv_scale = 1.0f / ez_scale;
+        int rc3 = ez_prepare_launch();
+        if (rc3 != LZ_OK) return rc3;
     }
 
     // DownSample geometry: conv s2 p1: h -> (h-1)/2+1

@@ -80,6 +80,7 @@ struct lz_model {
     lz::EzNet ez;                     // EfficientZero value-prefix head tables (device pointers into d_weights)
     float *ez_feat, *ez_htmp;         // [ws_B][hc*36], [ws_B][H] scratch between the conv kernel and the LSTM kernels
     int ez_B;
+    unsigned char *d_ez_wtc;          // LSTM weights in the tcgen05 layout (ez.cu)
     int latent_floats;                // floats per root latent (64*36 or latent_dim)
     lz_mlp_config mcfg;
     lz::MlpNet mlp;
