@@ -380,8 +380,8 @@ def ours(args, rank, local_rank, world):
             "gpu_launches": args.steps * (13 + 2 + num_kernels_search + 1),
             "search_graph_kernels": num_kernels_search,
             "roofline": {"bound": "tensor",
-                         "kernel": ("search graph = 1 + num_simulations x [k_net_tc conv trunk + prediction heads (tcgen05), k_ez_lstm (fp32 GEMM over "
-                                    "all roots + cell update), k_ez_head, tree back-up + descent]" if EZ else
+                         "kernel": ("search graph = 1 + num_simulations x [k_net_tc conv trunk + prediction heads (tcgen05), k_ez_lstm_tc (tcgen05 3xFP16 GEMM "
+                                    "over all roots + cell update), k_ez_head, tree back-up + descent]" if EZ else
                                     "k_net_tc, persistent launch = num_simulations x [tree back-up/descent + fused recurrent_inference] (tcgen05)"),
                          "achieved": B * S * FLOP_RECURRENT / (graph_avg_ms * 1e-3) / 1e12,
                          "peak": peak_tf, "unit": "TFLOP/s",
@@ -395,7 +395,7 @@ def ours(args, rank, local_rank, world):
                          "single_simulation_launch_ms": k_avg_ms if not EZ else None,
                          "note": ("achieved = algorithmic FLOPs (18,381,312 per root per simulation: the MuZero count at A=6 with the reward FC1 replaced "
                                   "by the LSTM step and Linear(512,32)) x roots x simulations / CUDA-event duration of the whole search graph, against the "
-                                  "measured bf16 peak; the LSTM GEMM is fp32 FFMA in this round (24% of the algorithmic FLOPs, CUDA cores)") if EZ else "achieved = algorithmic FLOPs (SURVEY 8d, 14,427,392 per root per simulation, counted ONCE) x roots x "
+                                  "measured bf16 peak") if EZ else "achieved = algorithmic FLOPs (SURVEY 8d, 14,427,392 per root per simulation, counted ONCE) x roots x "
                                  "simulations / CUDA-event duration of the persistent launch (which also contains the tree phases), against "
                                  "the measured bf16 peak.  The kernel issues 3 fp16 MMAs per product (fp32-accurate hi/lo split) on 384 padded "
                                  "rows per 252 real ones = 4.57x the algorithmic FLOPs: the ceiling of this formulation is 21.9% of the tensor peak"},
