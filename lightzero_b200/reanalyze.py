@@ -2,7 +2,9 @@
 (lzero/mcts/buffer/game_buffer_muzero.py:578-730): the replay buffer re-searches
 ``batch_size * (num_unroll_steps + 1)`` stored observations with the latest model and turns the root
 visit counts into policy targets.  This is the second caller of ``MuZeroMCTSCtree.search`` in the
-reference and its largest natural batch (1536 roots by default).
+reference and its largest natural batch (1536 roots by default).  With an ``EfficientZeroMCTSCtree`` it follows
+``EfficientZeroGameBuffer._compute_target_policy_reanalyzed`` (game_buffer_efficientzero.py:325-440): the same flow with
+the (zero) reward hidden state of ``initial_inference`` handed to the value-prefix search.
 
 Everything between the observation batch and the visit counts stays on the GPU: ``initial_inference``
 in ``mini_infer_size`` slices (:612-633), root preparation with/without Dirichlet noise (:644-652), one
@@ -14,7 +16,7 @@ from typing import List, Optional, Sequence
 import numpy as np
 import torch
 
-from .mcts_ctree import MuZeroMCTSCtree
+from .mcts_ctree import EfficientZeroMCTSCtree, MuZeroMCTSCtree
 
 
 def compute_target_policy_reanalyzed(
@@ -33,11 +35,15 @@ def compute_target_policy_reanalyzed(
     A = action_space_size or action_mask.shape[1]
     legal_actions = [np.nonzero(action_mask[j])[0].tolist() for j in range(T)]          # :610
     dev = model.device
-    lat, logits = [], []
+    lat, logits, hid0, hid1 = [], [], [], []
+    ez = isinstance(mcts, EfficientZeroMCTSCtree)      # EfficientZeroGameBuffer._compute_target_policy_reanalyzed, game_buffer_efficientzero.py:325-440
     for beg in range(0, T, mini_infer_size):                                              # :612-633
         out = model.initial_inference(policy_obs[beg:beg + mini_infer_size].to(dev, non_blocking=True))
         lat.append(out.latent_state)
         logits.append(out.policy_logits)
+        if ez:                                                                            # game_buffer_efficientzero.py:365-372
+            hid0.append(out.reward_hidden_state[0])
+            hid1.append(out.reward_hidden_state[1])
     latent_state_roots = torch.cat(lat) if len(lat) > 1 else lat[0]
     policy_logits_pool = torch.cat(logits) if len(logits) > 1 else logits[0]
     if noises is None:                                                                    # :638-641 (A entries per root)
@@ -48,7 +54,11 @@ def compute_target_policy_reanalyzed(
         roots.prepare(cfg.root_noise_weight, noises, reward_pool, policy_logits_pool, list(to_play))   # :646
     else:
         roots.prepare_no_noise(reward_pool, policy_logits_pool, list(to_play))            # :648
-    mcts.search(roots, model, latent_state_roots, list(to_play))                          # :654-658
+    if ez:
+        hidden_roots = (torch.cat(hid0, dim=1), torch.cat(hid1, dim=1))                   # game_buffer_efficientzero.py:375-376
+        mcts.search(roots, model, latent_state_roots, hidden_roots, list(to_play))        # :398-400
+    else:
+        mcts.search(roots, model, latent_state_roots, list(to_play))                      # :654-658
     roots_distributions = roots.get_distributions()                                       # :674
     roots_values = roots.get_values()
 

@@ -93,3 +93,39 @@ def test_reanalyze_default_batch_size_runs():
     out = compute_target_policy_reanalyzed(cu, mcts, obs, np.ones((T, A), np.int8), [-1] * T, [1] * T, [0] * segs, None,
                                            unroll, A, mini_infer_size=1024)
     assert out.shape == (segs, unroll + 1, A) and np.allclose(out.sum(-1), 1.0)
+
+
+def test_reanalyze_efficientzero_targets_match_reference_pipeline():
+    """EfficientZeroGameBuffer._compute_target_policy_reanalyzed (game_buffer_efficientzero.py:325-440): the same caller with
+    the value-prefix search and the zero reward hidden state of initial_inference."""
+    import lightzero_b200 as lzb
+    from lightzero_b200.reanalyze import compute_target_policy_reanalyzed
+    from oracle.model_ref import EfficientZeroModelRef, emulate_trained_
+    from oracle.search_ref import SearchRefEZ, load_tree_module
+    torch.manual_seed(4)
+    A, S, unroll, segs, H = 6, 20, 5, 6, 3
+    T = segs * (unroll + 1)
+    ref = emulate_trained_(EfficientZeroModelRef((4, 96, 96), A), 4)
+    cu = lzb.EfficientZeroModel(observation_shape=(4, 96, 96), action_space_size=A).load_state_dict(ref.state_dict())
+    rng = np.random.default_rng(5)
+    obs = torch.rand(T, 4, 96, 96)
+    mask = np.ones((T, A), np.int8)
+    to_play = [-1] * T
+    policy_mask = (rng.random(T) < 0.9).astype(int).tolist()
+    pos_list = rng.integers(0, 50, segs).tolist()
+    noises = np.stack([rng.dirichlet([0.3] * A).astype(np.float32) for _ in range(T)])
+    mcts = lzb.EfficientZeroMCTSCtree(dict(num_simulations=S, discount_factor=0.997, lstm_horizon_len=H))
+    got = compute_target_policy_reanalyzed(cu, mcts, obs, mask, to_play, policy_mask, pos_list, None, unroll, A,
+                                           "fixed_action_space", True, 16, noises)
+    tree, _ = load_tree_module(name="ez_tree")
+    s = SearchRefEZ(tree, lstm_horizon_len=H, num_simulations=S)
+    with torch.no_grad():
+        out = ref.initial_inference(obs)
+    roots = s.roots(T, [list(range(A))] * T, action_space_size=A)
+    roots.prepare(0.25, [n.tolist() for n in noises], [0.] * T, out.policy_logits.numpy().tolist(), to_play)
+    s.search(roots, ref, out.latent_state.numpy(), (out.reward_hidden_state[0].numpy(), out.reward_hidden_state[1].numpy()), to_play)
+    exp = np.array([[v / sum(d) for v in d] if policy_mask[j] else [0] * A for j, d in enumerate(roots.get_distributions())])
+    flat = got.reshape(T, A)
+    same = sum(np.array_equal(a, b) for a, b in zip(flat, exp))
+    assert same >= int(0.85 * T), same
+    assert got.shape == (segs, unroll + 1, A)
