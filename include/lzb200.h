@@ -107,6 +107,14 @@ int lz_tree_backpropagate_ez(lz_tree *t, int latent_index, const float *d_value_
 int lz_tree_results(lz_tree *t, int32_t *d_visits, float *d_values, int32_t *d_nlegal,
                     int32_t *d_traj, lz_stream s);
 
+/* select_action (lzero/policy/utils.py:637-661) on the device, from the root visit counts of the finished search:
+ * p = visit ** (1 / temperature) / sum (fp64), d_entropy = -sum p ln p, d_action_pos = arg-max (deterministic != 0; the
+ * eval path, policy/muzero.py:935) or one draw from p (inverse CDF of a counter-based uniform keyed by seed and tree index;
+ * the reference draws with np.random.choice), d_action = the action id at that legal position (policy/muzero.py:800).
+ * Outputs int32 [B] / f32 [B], any may be NULL.  SURVEY 8(f) row f-3: keeps the collector's action choice on the GPU. */
+int lz_tree_select_action(lz_tree *t, float temperature, int deterministic, uint64_t seed, int32_t *d_action,
+                          int32_t *d_action_pos, float *d_entropy, lz_stream s);
+
 /* ------------------------------------------------------------------ model (muzero_model.py, efficientzero_model.py) */
 
 typedef struct lz_model_config {

@@ -54,14 +54,18 @@ class MuZeroCollectPolicy:
                 to_play=torch.empty(B, dtype=torch.int32, device=d),
                 h_visits=torch.empty(B, A, dtype=torch.int32).pin_memory(),
                 h_values=torch.empty(B).pin_memory(), h_pred=torch.empty(B).pin_memory(),
-                h_logits=torch.empty(B, A).pin_memory(), h_nlegal=torch.empty(B, dtype=torch.int32).pin_memory())
+                h_logits=torch.empty(B, A).pin_memory(), h_nlegal=torch.empty(B, dtype=torch.int32).pin_memory(),
+                action=torch.empty(B, dtype=torch.int32, device=d), action_pos=torch.empty(B, dtype=torch.int32, device=d),
+                entropy=torch.empty(B, device=d), h_action=torch.empty(B, dtype=torch.int32).pin_memory(),
+                h_entropy=torch.empty(B).pin_memory())
         return self._buf[key]
 
     def search_batch(self, obs: torch.Tensor, action_mask, noises, to_play=None, deterministic=None,
-                     read_back: bool = True):
+                     read_back: bool = True, select=None):
         """obs [B,C,H,W] (host or device), action_mask [B,A] 0/1, noises [B,A] rows in legal order or None
         (eval).  Returns dict of tensors; with read_back=True they are pinned host tensors and the call
-        ends with the single stream synchronisation of the step."""
+        ends with the single stream synchronisation of the step.  select=(temperature, deterministic_action, seed) also
+        runs select_action (policy/utils.py:637-661) on the device and returns 'action' / 'entropy'."""
         B = obs.shape[0]
         A = self.model.action_space_size
         S = int(self.cfg.num_simulations)
@@ -114,6 +118,10 @@ class MuZeroCollectPolicy:
                 cabi.check(tree.lib.lz_tree_results(tree.h, tree.visits.data_ptr(), tree.values.data_ptr(),
                                                     tree.nlegal.data_ptr(), None, s), "lz_tree_results")
                 self.last_num_kernels = tree.lib.lz_search_num_kernels(q)
+                if select is not None:
+                    cabi.check(tree.lib.lz_tree_select_action(tree.h, float(select[0]), int(bool(select[1])), int(select[2]) & (2 ** 64 - 1),
+                                                              bufs["action"].data_ptr(), bufs["action_pos"].data_ptr(),
+                                                              bufs["entropy"].data_ptr(), s), "lz_tree_select_action")
                 if not read_back:
                     return dict(visits=tree.visits.clone(), values=tree.values.clone(), nlegal=tree.nlegal.clone(),
                                 pred_value=bufs["pred_value"], policy_logits=bufs["logits"])
@@ -122,16 +130,24 @@ class MuZeroCollectPolicy:
                 bufs["h_nlegal"].copy_(tree.nlegal, non_blocking=True)
                 bufs["h_pred"].copy_(bufs["pred_value"], non_blocking=True)
                 bufs["h_logits"].copy_(bufs["logits"], non_blocking=True)
+                if select is not None:
+                    bufs["h_action"].copy_(bufs["action"], non_blocking=True)
+                    bufs["h_entropy"].copy_(bufs["entropy"], non_blocking=True)
                 torch.cuda.current_stream().synchronize()
             finally:
                 tree.busy = False
-        return dict(visits=bufs["h_visits"], values=bufs["h_values"], nlegal=bufs["h_nlegal"],
-                    pred_value=bufs["h_pred"], policy_logits=bufs["h_logits"])
+        out = dict(visits=bufs["h_visits"], values=bufs["h_values"], nlegal=bufs["h_nlegal"],
+                   pred_value=bufs["h_pred"], policy_logits=bufs["h_logits"])
+        if select is not None:
+            out.update(action=bufs["h_action"], entropy=bufs["h_entropy"])
+        return out
 
     # ---- reference-shaped API --------------------------------------------------------------------
     def forward_collect(self, data: torch.Tensor, action_mask, temperature: float = 1, to_play=(-1,),
-                        epsilon: float = 0.25, ready_env_id=None, **kwargs) -> Dict[int, dict]:
-        """policy/muzero.py:705-829 (collect_with_pure_policy=False, no eps-greedy)."""
+                        epsilon: float = 0.25, ready_env_id=None, device_select_action: bool = False, seed: int = 0,
+                        **kwargs) -> Dict[int, dict]:
+        """policy/muzero.py:705-829 (collect_with_pure_policy=False, no eps-greedy).  device_select_action=True draws the
+        actions on the GPU (lz_tree_select_action, keyed by `seed`) instead of np.random.choice on the host."""
         B = data.shape[0]
         if ready_env_id is None:
             ready_env_id = np.arange(B)
@@ -143,7 +159,8 @@ class MuZeroCollectPolicy:
             n = int(action_mask[j].sum())
             noises[j, :n] = np.random.dirichlet([alpha] * n).astype(np.float32)
         tp = np.broadcast_to(np.asarray(to_play, np.int32).reshape(-1), (B,)) if np.size(to_play) in (1, B) else to_play
-        r = self.search_batch(data, action_mask, noises, tp, deterministic=self.mcts.deterministic)
+        r = self.search_batch(data, action_mask, noises, tp, deterministic=self.mcts.deterministic,
+                              select=(temperature, False, seed) if device_select_action else None)
         return self._format(r, action_mask, ready_env_id, temperature, deterministic_action=False)
 
     def forward_eval(self, data: torch.Tensor, action_mask, to_play=(-1,), ready_env_id=None, **kwargs):
@@ -162,8 +179,11 @@ class MuZeroCollectPolicy:
         output = {}
         for i, env_id in enumerate(ready_env_id):
             distributions = visits[i, :nl[i]].tolist()
-            pos, ent = select_action(distributions, temperature=temperature, deterministic=deterministic_action)
-            action = np.where(action_mask[i] == 1.0)[0][pos]            # policy/muzero.py:800
+            if "action" in r:                                              # chosen on the device
+                action, ent = int(r["action"][i]), float(r["entropy"][i])
+            else:
+                pos, ent = select_action(distributions, temperature=temperature, deterministic=deterministic_action)
+                action = np.where(action_mask[i] == 1.0)[0][pos]            # policy/muzero.py:800
             output[env_id] = {
                 'action': action,
                 'visit_count_distributions': distributions,

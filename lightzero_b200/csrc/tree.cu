@@ -175,6 +175,50 @@ k_tree_results(TreeParams p, int32_t *visits, float *values, int32_t *nlegal, in
     }
 }
 
+// select_action (lzero/policy/utils.py:637-661) on the root visit counts of every tree: probabilities
+// visit ** (1 / temperature) / sum in fp64 like the reference's Python floats, entropy = -sum p ln p (scipy.stats.entropy),
+// action = arg-max (deterministic, first maximum like np.argmax) or an inverse-CDF draw from a counter-based uniform.
+__global__ void __launch_bounds__(kTreeBlock)
+k_tree_select_action(TreeParams p, double inv_temperature, int deterministic, unsigned long long seed,
+                     int32_t *action, int32_t *action_pos, float *entropy)
+{
+    const int b = blockIdx.x * (kTreeBlock / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (b >= p.B) return;
+    const int A = p.A, n = p.nlegal[b];
+    const uint32_t *nb = p.edges + (size_t)b * p.N * kEdgeFields * A;      // root block
+    const int *lg = p.legal + (size_t)b * A;
+    double total = 0.0;
+    for (int k = lane; k < n; k += 32) total += pow((double)(int)nb[F_VISIT * A + lg[k]], inv_temperature);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+    double ent = 0.0;
+    for (int k = lane; k < n; k += 32) {
+        const double pr = pow((double)(int)nb[F_VISIT * A + lg[k]], inv_temperature) / total;
+        if (pr > 0.0) ent -= pr * log(pr);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ent += __shfl_xor_sync(0xffffffffu, ent, o);
+    if (lane == 0) {
+        int pos = 0;
+        if (deterministic) {
+            int best = -1;
+            for (int k = 0; k < n; ++k) { int v = (int)nb[F_VISIT * A + lg[k]]; if (v > best) { best = v; pos = k; } }
+        } else {
+            const unsigned long long h = mix64(seed ^ mix64((unsigned long long)b + 0x1234567ull));
+            const double u = (double)(h >> 11) * (1.0 / 9007199254740992.0);       // uniform [0, 1)
+            double cum = 0.0;
+            pos = n - 1;
+            for (int k = 0; k < n; ++k) {
+                cum += pow((double)(int)nb[F_VISIT * A + lg[k]], inv_temperature) / total;
+                if (u < cum) { pos = k; break; }
+            }
+        }
+        if (action_pos) action_pos[b] = pos;
+        if (action) action[b] = lg[pos];            // np.where(action_mask == 1)[0][pos], policy/muzero.py:800
+        if (entropy) entropy[b] = (float)ent;
+    }
+}
+
 static inline dim3 tree_grid(int B) { return dim3(ceil_div(B, kTreeBlock / 32)); }
 
 template <typename... KArgs, typename... Args>
@@ -388,6 +432,16 @@ int lz_tree_backpropagate_ez(lz_tree *t, int latent_index, const float *d_value_
     LZ_REQUIRE(latent_index >= 1 && latent_index <= t->max_sims, LZ_EINVAL,
                "lz_tree_backpropagate_ez: latent_index %d outside [1, %d]", latent_index, t->max_sims);
     return tree_launch_backprop(t, latent_index, d_value_prefix, d_value, d_logits, d_to_play, (cudaStream_t)s, d_is_reset);
+}
+
+int lz_tree_select_action(lz_tree *t, float temperature, int deterministic, uint64_t seed, int32_t *d_action,
+                          int32_t *d_action_pos, float *d_entropy, lz_stream s)
+{
+    LZ_REQUIRE(t && temperature > 0.0f, LZ_EINVAL, "lz_tree_select_action: bad argument (temperature must be > 0)");
+    k_tree_select_action<<<tree_grid(t->p.B), kTreeBlock, 0, (cudaStream_t)s>>>(t->p, 1.0 / (double)temperature, deterministic,
+                                                                               (unsigned long long)seed, d_action, d_action_pos, d_entropy);
+    LZ_KERNEL_CHECK();
+    return LZ_OK;
 }
 
 int lz_tree_results(lz_tree *t, int32_t *d_visits, float *d_values, int32_t *d_nlegal, int32_t *d_traj, lz_stream s)

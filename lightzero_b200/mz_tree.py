@@ -184,6 +184,18 @@ class Roots:
                                              cabi.stream_ptr()), "lz_tree_results")
         return t.visits, t.nlegal
 
+    def select_action_tensor(self, temperature: float = 1.0, deterministic: bool = False, seed: int = 0):
+        """lzero/policy/utils.py:637-661 for every root on the device -> (action id, position in the legal list, entropy)."""
+        t = self._need_tree()
+        act = torch.empty(self.root_num, dtype=torch.int32, device=self.device)
+        pos = torch.empty(self.root_num, dtype=torch.int32, device=self.device)
+        ent = torch.empty(self.root_num, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            cabi.check(t.lib.lz_tree_select_action(t.h, float(temperature), int(bool(deterministic)), int(seed) & (2 ** 64 - 1),
+                                                   act.data_ptr(), pos.data_ptr(), ent.data_ptr(), cabi.stream_ptr()),
+                       "lz_tree_select_action")
+        return act, pos, ent
+
     def get_values_tensor(self):
         t = self._need_tree()
         with torch.cuda.device(self.device):

@@ -216,3 +216,22 @@ def test_config3_shard_200_simulations():
         roots.clear()
     assert res[0] == res[1]
     assert all(sum(d) == S for d in res[0][0])
+
+
+def test_forward_collect_with_device_side_action_selection():
+    """the collector's select_action on the GPU.  Same visit counts as the host path; every chosen action is a
+    legal, visited one; the entropy equals the host formula."""
+    from lightzero_b200.collect import MuZeroCollectPolicy, select_action
+    B, A, S = 24, 18, 20
+    ref, cu, obs, mask, legal, noises, mcts = _setup(B, A, S, seed=13, masks=True)
+    pol = MuZeroCollectPolicy(cu, dict(num_simulations=S, deterministic=True, discount_factor=0.997))
+    np.random.seed(0)
+    host = pol.forward_collect(obs, mask, temperature=0.5, to_play=[-1])
+    np.random.seed(0)
+    dev = pol.forward_collect(obs, mask, temperature=0.5, to_play=[-1], device_select_action=True, seed=7)
+    for i in range(B):
+        assert dev[i]["visit_count_distributions"] == host[i]["visit_count_distributions"]
+        a = dev[i]["action"]
+        assert mask[i, a] == 1 and dev[i]["visit_count_distributions"][legal[i].index(a)] > 0
+        _, e = select_action(np.asarray(dev[i]["visit_count_distributions"]), temperature=0.5, deterministic=True)
+        assert abs(dev[i]["visit_count_distribution_entropy"] - e) < 1e-5
