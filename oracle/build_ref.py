@@ -33,7 +33,23 @@ CTREE = os.path.join(REF, "lzero", "mcts", "ctree")
 
 def ref_module_path(name: str = "mz_tree"):
     suffix = sysconfig.get_config_var("EXT_SUFFIX")
+    if name == "mz_tree_rand0":
+        return os.path.join(OUT, "rand0", "mz_tree" + suffix)
     return os.path.join(OUT, name + suffix)
+
+
+def load_rand0():
+    """The shimmed MuZero tree as a separate module object (it shares the init symbol PyInit_mz_tree with the plain build)."""
+    import importlib.machinery
+    import importlib.util
+    path = ref_module_path("mz_tree_rand0")
+    if not os.path.exists(path):
+        return None
+    loader = importlib.machinery.ExtensionFileLoader("mz_tree", path)
+    spec = importlib.util.spec_from_file_location("mz_tree", path, loader=loader)
+    mod = importlib.util.module_from_spec(spec)
+    loader.exec_module(mod)
+    return mod
 
 
 # module name -> reference sub-directory.  ez_tree (EfficientZero) has no `deterministic` flag: cselect_child always
@@ -41,7 +57,10 @@ def ref_module_path(name: str = "mz_tree"):
 # (common_lib/utils.cpp:12-26).  To make the UNMODIFIED sources reproducible the module is linked with
 # oracle/rand_shim.c, whose hidden-visibility `rand()` returns 0: index 0 of the tie list is the first position
 # attaining the exact maximum (cnode.cpp:676-688), i.e. exactly the `deterministic=True` rule of the MuZero tree.
-MODULES = {"mz_tree": ("ctree_muzero", False), "ez_tree": ("ctree_efficientzero", True)}
+# "mz_tree_rand0": the MuZero tree again, with the shim, in oracle/_ref/rand0/ (the module itself is still called mz_tree):
+# its *_with_reuse entry points break ties with rand() only (cselect_root_child, cnode.cpp:637-641; cselect_child(..., false),
+# :879), so pinning them needs the same trick.
+MODULES = {"mz_tree": ("ctree_muzero", False), "ez_tree": ("ctree_efficientzero", True), "mz_tree_rand0": ("ctree_muzero", True)}
 
 
 def build(force: bool = False, name: str = "mz_tree") -> str:
@@ -54,13 +73,14 @@ def build(force: bool = False, name: str = "mz_tree") -> str:
     if not os.path.isdir(src_dir):
         return ""
     import numpy
-    os.makedirs(OUT, exist_ok=True)
+    os.makedirs(os.path.dirname(target), exist_ok=True)
+    pyx = "mz_tree" if name == "mz_tree_rand0" else name
     with tempfile.TemporaryDirectory() as tmp:
-        gen_cpp = os.path.join(tmp, name + ".cpp")
+        gen_cpp = os.path.join(tmp, pyx + ".cpp")
         # cython reads the .pyx/.pxd in place; only the generated C++ goes to tmp
         subprocess.check_call(
             [sys.executable, "-m", "cython", "--cplus", "-3", "-I", src_dir,
-             os.path.join(src_dir, name + ".pyx"), "-o", gen_cpp])
+             os.path.join(src_dir, pyx + ".pyx"), "-o", gen_cpp])
         inc = sysconfig.get_paths()["include"]
         extra = []
         if shim:

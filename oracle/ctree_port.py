@@ -44,6 +44,8 @@ def lib():
         L.lzo_tree_values.argtypes = [P, P]
         L.lzo_tree_trajectories.argtypes = [P, P, P]
         L.lzo_tree_seed.argtypes = [P, ctypes.c_uint]
+        L.lzo_tree_traverse_with_reuse.argtypes = [P, I, F, F, P, P, P, P, P, P, P]
+        L.lzo_tree_backpropagate_with_reuse.argtypes = [P, I, F, P, P, P, P, P, P, P]
         _lib = L
     return _lib
 
@@ -182,3 +184,37 @@ def batch_backpropagate(current_latent_state_index, discount_factor, value_prefi
     tp = np.ascontiguousarray(np.asarray(to_play_batch, np.int32))
     lib().lzo_tree_backpropagate(roots._h, int(current_latent_state_index), ctypes.c_float(discount_factor),
                                  _p(rew), _p(val), _p(pol), _p(tp))
+
+
+def batch_traverse_with_reuse(roots, pb_c_base, pb_c_init, discount_factor, min_max_stats_lst, results,
+                              virtual_to_play_batch, true_action, reuse_value):
+    """mz_tree.pyx batch_traverse_with_reuse (cnode.cpp:828-932); ties as with rand() == 0"""
+    min_max_stats_lst._bind(roots)
+    B = roots.root_num
+    vtp = np.ascontiguousarray(np.asarray(virtual_to_play_batch, np.int32))
+    ta = np.ascontiguousarray(np.asarray(true_action, np.int32))
+    rv = np.ascontiguousarray(np.asarray(reuse_value, np.float32))
+    ix = np.empty(B, np.int32); iy = np.empty(B, np.int32)
+    la = np.empty(B, np.int32); sl = np.empty(B, np.int32)
+    lib().lzo_tree_traverse_with_reuse(roots._h, int(pb_c_base), ctypes.c_float(pb_c_init), ctypes.c_float(discount_factor),
+                                       _p(vtp), _p(ta), _p(rv), _p(ix), _p(iy), _p(la), _p(sl))
+    results.search_lens = sl
+    results._roots = roots
+    return ix.tolist(), iy.tolist(), la.tolist(), vtp.tolist()
+
+
+def batch_backpropagate_with_reuse(current_latent_state_index, discount_factor, value_prefixs, values, policies,
+                                   min_max_stats_lst, results, to_play_batch, no_inference_lst, reuse_lst, reuse_value_lst):
+    """mz_tree.pyx batch_backpropagate_with_reuse (cnode.cpp:502-549): compacted network outputs + the driver's index lists"""
+    roots = results._roots
+    B, A = roots.root_num, roots.A
+    n = len(value_prefixs)
+    rew = np.ascontiguousarray(np.asarray(value_prefixs, np.float32).reshape(n))
+    val = np.ascontiguousarray(np.asarray(values, np.float32).reshape(n))
+    pol = np.ascontiguousarray(np.asarray(policies, np.float32).reshape(n, A)) if n else np.zeros((1, A), np.float32)
+    tp = np.ascontiguousarray(np.asarray(to_play_batch, np.int32))
+    ni = np.ascontiguousarray(np.asarray(no_inference_lst, np.int32))
+    ru = np.ascontiguousarray(np.asarray(reuse_lst, np.int32))
+    rv = np.ascontiguousarray(np.asarray(reuse_value_lst, np.float32))
+    lib().lzo_tree_backpropagate_with_reuse(roots._h, int(current_latent_state_index), ctypes.c_float(discount_factor),
+                                            _p(rew), _p(val), _p(pol), _p(tp), _p(ni), _p(ru), _p(rv))
