@@ -107,6 +107,20 @@ int lz_tree_backpropagate_ez(lz_tree *t, int latent_index, const float *d_value_
 int lz_tree_results(lz_tree *t, int32_t *d_visits, float *d_values, int32_t *d_nlegal,
                     int32_t *d_traj, lz_stream s);
 
+/* ---- ReZero search_with_reuse on the MuZero trees (cnode.cpp:502-549, 597-652, 701-752, 828-932) ----
+ * d_true_action int32 [B] / d_reuse_value f32 [B]: the action taken in the stored trajectory and the value to reuse for it.
+ * The root scores that child with carm_score and the descent stops right after the root when it is selected.  d_ix reports -1
+ * for trees that stopped on an already expanded child ("no inference"); d_iy is the batch_index recorded when the parent was
+ * expanded (the compact inference row under reuse).  Ties: first maximum (= the reference's rand() % len(ties) with rand()
+ * == 0; these reference routines have no deterministic switch). */
+int lz_tree_traverse_with_reuse(lz_tree *t, const int32_t *d_true_action, const float *d_reuse_value, int32_t *d_ix, int32_t *d_iy,
+                                int32_t *d_last_action, int32_t *d_search_len, int32_t *d_virtual_to_play, lz_stream s);
+/* cbatch_backpropagate_with_reuse: rows are indexed BY TREE (not compacted; rows of "no inference" trees are ignored).
+ * d_batch_rank int32 [B] or NULL: compact row of each tree in the caller's inference batch, stored as the batch_index of the
+ * node it expands.  Which trees skip the expansion / back up the reuse value is the state the last traverse left. */
+int lz_tree_backpropagate_with_reuse(lz_tree *t, int latent_index, const float *d_reward, const float *d_value, const float *d_logits,
+                                     const float *d_reuse_value, const int32_t *d_batch_rank, const int32_t *d_to_play, lz_stream s);
+
 /* select_action (lzero/policy/utils.py:637-661) on the device, from the root visit counts of the finished search:
  * p = visit ** (1 / temperature) / sum (fp64), d_entropy = -sum p ln p, d_action_pos = arg-max (deterministic != 0; the
  * eval path, policy/muzero.py:935) or one draw from p (inverse CDF of a counter-based uniform keyed by seed and tree index;
@@ -198,6 +212,12 @@ int lz_search_destroy(lz_search *q);
 /* MuZeroMCTSCtree.search (mcts_ctree.py:267-368) on roots already prepared with lz_tree_prepare.
  * d_latent_roots f32 [B,C,h,w].  One graph launch, zero host syncs. */
 int lz_search_run(lz_search *q, const float *d_latent_roots, int deterministic, lz_stream s);
+/* MuZeroMCTSCtree.search_with_reuse (mcts_ctree.py:370-468; ReZero).  d_true_action int32 [B], d_reuse_value f32 [B] as for
+ * lz_tree_traverse_with_reuse; d_infer_count int32 [num_simulations] or NULL receives, per simulation, how many trees needed
+ * the network (the reference returns the last count and the mean).  One CUDA graph; "no inference" rows are computed and
+ * ignored instead of compacted on the host. */
+int lz_search_run_with_reuse(lz_search *q, const float *d_latent_roots, const int32_t *d_true_action, const float *d_reuse_value,
+                             int32_t *d_infer_count, lz_stream s);
 /* EfficientZeroMCTSCtree.search (mcts_ctree.py:671-876) for a search created from an EfficientZero model and a tree in
  * EfficientZero mode.  d_hidden{0,1}_roots: f32 [B, lstm_hidden_size] = reward_hidden_state_roots[0] / [1] (NULL = zeros,
  * what initial_inference returns).  The LSTM state of a leaf is zeroed every lstm_horizon_len steps of depth (:856-861). */

@@ -28,6 +28,10 @@ struct lz_search {
     float *hpool, *cpool;
     size_t hslot_stride;
     int32_t *d_is_reset;
+    // ReZero search_with_reuse: library-owned copies of the caller's per-root true action / reuse value (graph-stable addresses)
+    int32_t *d_true_action;
+    float *d_reuse_value;
+    cudaGraphExec_t exec_reuse;
     cudaGraphExec_t exec[2];     // [deterministic]
     cudaStream_t capture_stream; // library-owned: the caller's stream may be the legacy default stream,
                                  // which cannot be captured; the instantiated graph launches on the caller's
@@ -110,6 +114,32 @@ static int enqueue_search(lz_search *q, int deterministic, cudaStream_t s)
     return LZ_OK;
 }
 
+// MuZeroMCTSCtree.search_with_reuse (mcts_ctree.py:370-468): every tree goes through the network every simulation (the
+// reference compacts the batch on the host; here the rows of "no inference" trees are computed and ignored, which keeps the
+// loop one static CUDA graph): [traverse_with_reuse] + S x [recurrent_inference, backpropagate_with_reuse (+ next traverse)].
+static int enqueue_search_reuse(lz_search *q, cudaStream_t s)
+{
+    int rc;
+    lz_tree *t = q->tree;
+    t->step_counter = 0;
+    if ((rc = tree_launch_traverse_reuse(t, q->d_true_action, q->d_reuse_value, nullptr, q->d_ix, nullptr, q->d_action, nullptr, nullptr, s))) return rc;
+    for (int sim = 0; sim < q->S; ++sim) {
+        RecIO io;
+        memset(&io, 0, sizeof(io));
+        io.B = q->B; io.latent_base = q->pool; io.ix = q->d_ix; io.slot_stride = q->slot_stride; io.action = q->d_action;
+        io.next_latent = q->pool + (size_t)(sim + 1) * q->slot_stride;
+        io.reward = q->d_reward; io.value = q->d_value; io.policy_logits = q->d_policy;
+        if ((rc = model_recurrent(q->model, io, s))) return rc;
+        if (sim + 1 < q->S)
+            rc = tree_launch_backprop_traverse_reuse(t, sim + 1, q->d_reward, q->d_value, q->d_policy, q->d_true_action, q->d_reuse_value,
+                                                     q->d_ix, q->d_action, s);
+        else
+            rc = tree_launch_backprop_reuse(t, sim + 1, q->d_reward, q->d_value, q->d_policy, q->d_reuse_value, nullptr, nullptr, s);
+        if (rc) return rc;
+    }
+    return LZ_OK;
+}
+
 static int run_graph(lz_search *q, int deterministic, cudaStream_t s)
 {
     const int d = deterministic ? 1 : 0;
@@ -182,6 +212,8 @@ int lz_search_destroy(lz_search *q)
     cudaFree(q->pool); cudaFree(q->d_ix); cudaFree(q->d_action); cudaFree(q->d_reward); cudaFree(q->d_value);
     cudaFree(q->d_policy); cudaFree(q->d_root_logits); cudaFree(q->d_root_value);
     cudaFree(q->hpool); cudaFree(q->cpool); cudaFree(q->d_is_reset);
+    cudaFree(q->d_true_action); cudaFree(q->d_reuse_value);
+    if (q->exec_reuse) cudaGraphExecDestroy(q->exec_reuse);
     delete q;
     return LZ_OK;
 }
@@ -205,6 +237,41 @@ int lz_search_run_ez(lz_search *q, const float *d_latent_roots, const float *d_h
     int rc = ez_root_hidden(q, d_hidden0_roots, d_hidden1_roots, (cudaStream_t)s);
     if (rc) return rc;
     return run_graph(q, 1, (cudaStream_t)s);
+}
+
+int lz_search_run_with_reuse(lz_search *q, const float *d_latent_roots, const int32_t *d_true_action, const float *d_reuse_value,
+                             int32_t *d_infer_count, lz_stream s_)
+{
+    LZ_REQUIRE(q && d_true_action && d_reuse_value, LZ_EINVAL, "lz_search_run_with_reuse: null argument");
+    LZ_REQUIRE(!q->hpool, LZ_ESTATE, "lz_search_run_with_reuse: MuZero searches only");
+    LZ_REQUIRE(q->tree->prepared, LZ_ESTATE, "lz_search_run_with_reuse: roots not prepared (call lz_tree_prepare first)");
+    cudaStream_t s = (cudaStream_t)s_;
+    if (!q->d_true_action) {
+        int rc = dev_alloc(&q->d_true_action, (size_t)q->B);
+        if (rc == LZ_OK) rc = dev_alloc(&q->d_reuse_value, (size_t)q->B);
+        if (rc != LZ_OK) return rc;
+    }
+    if (d_latent_roots && d_latent_roots != q->pool)
+        LZ_CUDA_CHECK(cudaMemcpyAsync(q->pool, d_latent_roots, q->slot_stride * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    LZ_CUDA_CHECK(cudaMemcpyAsync(q->d_true_action, d_true_action, (size_t)q->B * sizeof(int32_t), cudaMemcpyDeviceToDevice, s));
+    LZ_CUDA_CHECK(cudaMemcpyAsync(q->d_reuse_value, d_reuse_value, (size_t)q->B * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    LZ_CUDA_CHECK(cudaMemsetAsync(q->tree->p.infer_count, 0, (size_t)q->tree->p.N * sizeof(int), s));
+    if (!q->exec_reuse) {
+        cudaGraph_t graph = nullptr;
+        if (!q->capture_stream) LZ_CUDA_CHECK(cudaStreamCreateWithFlags(&q->capture_stream, cudaStreamNonBlocking));
+        LZ_CUDA_CHECK(cudaStreamBeginCapture(q->capture_stream, cudaStreamCaptureModeThreadLocal));
+        int rc = enqueue_search_reuse(q, q->capture_stream);
+        cudaError_t e = cudaStreamEndCapture(q->capture_stream, &graph);
+        if (rc != LZ_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+        if (e != cudaSuccess) { set_error("cudaStreamEndCapture failed: %s", cudaGetErrorString(e)); return LZ_ECUDA; }
+        e = cudaGraphInstantiate(&q->exec_reuse, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) { set_error("cudaGraphInstantiate failed: %s", cudaGetErrorString(e)); return LZ_ECUDA; }
+    }
+    LZ_CUDA_CHECK(cudaGraphLaunch(q->exec_reuse, s));
+    if (d_infer_count)      // per simulation: how many trees needed the network (mcts_ctree.py:433,466-467)
+        LZ_CUDA_CHECK(cudaMemcpyAsync(d_infer_count, q->tree->p.infer_count, (size_t)q->S * sizeof(int32_t), cudaMemcpyDeviceToDevice, s));
+    return LZ_OK;
 }
 
 int lz_search_run(lz_search *q, const float *d_latent_roots, int deterministic, lz_stream s)

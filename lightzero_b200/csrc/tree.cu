@@ -61,6 +61,8 @@ k_tree_reset(TreeParams p, const int32_t *legal, const int32_t *nlegal, const ui
         p.path_len[b] = 0;
         p.search_len[b] = 0;
         p.n_reset[(size_t)b * p.N] = 0;      // the root is never reset (ctree_efficientzero cnode.cpp:54,75)
+        p.n_batch[(size_t)b * p.N] = b;      // root.expand(to_play, 0, i, ...)
+        p.reuse_state[b] = 0;
     }
 }
 
@@ -138,6 +140,36 @@ k_tree_backprop_traverse(TreeParams p, int latent_index, const float *reward, co
                       (EZ && is_reset) ? is_reset[b] : 0);
     tree_traverse<EZ>(p, b, lane, deterministic, step, ix, nullptr, act, nullptr, nullptr);
     if (EZ && is_reset && lane == 0) is_reset[b] = (p.search_len[b] % p.lstm_horizon == 0) ? 1 : 0;
+}
+
+// ---- ReZero search_with_reuse (MuZero trees) ----
+__global__ void __launch_bounds__(kTreeBlock)
+k_tree_traverse_reuse(TreeParams p, unsigned step, const int32_t *true_action, const float *reuse_value, int32_t *ix, int32_t *ix_net,
+                      int32_t *iy, int32_t *act, int32_t *len, int32_t *vtp)
+{
+    const int b = blockIdx.x * (kTreeBlock / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (b >= p.B) return;
+    tree_traverse<false, true>(p, b, lane, 1, step, ix, iy, act, len, vtp, true_action, reuse_value, ix_net);
+}
+
+__global__ void __launch_bounds__(kTreeBlock)
+k_tree_backprop_reuse(TreeParams p, int latent_index, const float *reward, const float *value, const float *logits,
+                      const float *reuse_value, const int32_t *batch_rank, const int32_t *to_play)
+{
+    const int b = blockIdx.x * (kTreeBlock / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (b >= p.B) return;
+    tree_backprop<false, true>(p, b, lane, latent_index, reward[b], value[b], logits + (size_t)b * p.A, to_play, 0, reuse_value[b],
+                               batch_rank ? batch_rank[b] : -1);
+}
+
+__global__ void __launch_bounds__(kTreeBlock)
+k_tree_backprop_traverse_reuse(TreeParams p, int latent_index, const float *reward, const float *value, const float *logits,
+                               unsigned step, const int32_t *true_action, const float *reuse_value, int32_t *ix_net, int32_t *act)
+{
+    const int b = blockIdx.x * (kTreeBlock / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (b >= p.B) return;
+    tree_backprop<false, true>(p, b, lane, latent_index, reward[b], value[b], logits + (size_t)b * p.A, nullptr, 0, reuse_value[b], -1);
+    tree_traverse<false, true>(p, b, lane, 1, step, nullptr, nullptr, act, nullptr, nullptr, true_action, reuse_value, ix_net);
 }
 
 // get_distributions / get_values / get_trajectories (cnode.cpp:237-277,369-417)
@@ -271,6 +303,34 @@ int tree_launch_backprop_traverse(lz_tree *t, int latent_index, const float *d_r
     return LZ_OK;
 }
 
+int tree_launch_traverse_reuse(lz_tree *t, const int32_t *d_true_action, const float *d_reuse_value, int32_t *d_ix, int32_t *d_ix_net,
+                               int32_t *d_iy, int32_t *d_action, int32_t *d_len, int32_t *d_vtp, cudaStream_t s)
+{
+    k_tree_traverse_reuse<<<tree_grid(t->p.B), kTreeBlock, 0, s>>>(t->p, t->step_counter++, d_true_action, d_reuse_value, d_ix, d_ix_net,
+                                                                  d_iy, d_action, d_len, d_vtp);
+    LZ_KERNEL_CHECK();
+    return LZ_OK;
+}
+
+int tree_launch_backprop_reuse(lz_tree *t, int latent_index, const float *d_reward, const float *d_value, const float *d_logits,
+                               const float *d_reuse_value, const int32_t *d_batch_rank, const int32_t *d_to_play, cudaStream_t s)
+{
+    k_tree_backprop_reuse<<<tree_grid(t->p.B), kTreeBlock, 0, s>>>(t->p, latent_index, d_reward, d_value, d_logits, d_reuse_value,
+                                                                  d_batch_rank, d_to_play);
+    LZ_KERNEL_CHECK();
+    return LZ_OK;
+}
+
+int tree_launch_backprop_traverse_reuse(lz_tree *t, int latent_index, const float *d_reward, const float *d_value, const float *d_logits,
+                                        const int32_t *d_true_action, const float *d_reuse_value, int32_t *d_ix_net, int32_t *d_action,
+                                        cudaStream_t s)
+{
+    k_tree_backprop_traverse_reuse<<<tree_grid(t->p.B), kTreeBlock, 0, s>>>(t->p, latent_index, d_reward, d_value, d_logits,
+                                                                           t->step_counter++, d_true_action, d_reuse_value, d_ix_net, d_action);
+    LZ_KERNEL_CHECK();
+    return LZ_OK;
+}
+
 }  // namespace lz
 
 using namespace lz;
@@ -296,7 +356,8 @@ int lz_tree_create(int B, int A, int max_sims, lz_tree **out)
     size_t words = 0;
     auto take = [&](size_t n) { size_t o = words; words += (n + 31) & ~(size_t)31; return o; };
     size_t o_edges = take((size_t)B * N * kEdgeFields * A);
-    size_t o_ntp = take((size_t)B * N), o_nbest = take((size_t)B * N), o_nreset = take((size_t)B * N);
+    size_t o_ntp = take((size_t)B * N), o_nbest = take((size_t)B * N), o_nreset = take((size_t)B * N), o_nbatch = take((size_t)B * N);
+    size_t o_rstate = take(B), o_infer = take(N);
     size_t o_legal = take((size_t)B * A), o_nlegal = take(B);
     size_t o_rvis = take(B), o_rvsum = take(B), o_rrew = take(B), o_mmax = take(B), o_mmin = take(B);
     size_t o_tp = take(B), o_players = take(1), o_pslot = take((size_t)B * N), o_pact = take((size_t)B * N);
@@ -309,6 +370,7 @@ int lz_tree_create(int B, int A, int max_sims, lz_tree **out)
     t->alloc_base = base;
     p.edges = base + o_edges;
     p.n_to_play = (int *)(base + o_ntp); p.n_best = (int *)(base + o_nbest); p.n_reset = (int *)(base + o_nreset);
+    p.n_batch = (int *)(base + o_nbatch); p.reuse_state = (int *)(base + o_rstate); p.infer_count = (int *)(base + o_infer);
     p.ez = 0; p.lstm_horizon = 5;
     p.legal = (int *)(base + o_legal); p.nlegal = (int *)(base + o_nlegal);
     p.root_visit = (int *)(base + o_rvis); p.root_vsum = (float *)(base + o_rvsum); p.root_reward = (float *)(base + o_rrew);
@@ -432,6 +494,25 @@ int lz_tree_backpropagate_ez(lz_tree *t, int latent_index, const float *d_value_
     LZ_REQUIRE(latent_index >= 1 && latent_index <= t->max_sims, LZ_EINVAL,
                "lz_tree_backpropagate_ez: latent_index %d outside [1, %d]", latent_index, t->max_sims);
     return tree_launch_backprop(t, latent_index, d_value_prefix, d_value, d_logits, d_to_play, (cudaStream_t)s, d_is_reset);
+}
+
+int lz_tree_traverse_with_reuse(lz_tree *t, const int32_t *d_true_action, const float *d_reuse_value, int32_t *d_ix, int32_t *d_iy,
+                                int32_t *d_last_action, int32_t *d_search_len, int32_t *d_virtual_to_play, lz_stream s)
+{
+    LZ_REQUIRE(t && d_true_action && d_reuse_value, LZ_EINVAL, "lz_tree_traverse_with_reuse: null argument");
+    LZ_REQUIRE(t->prepared && !t->p.ez, LZ_ESTATE, "lz_tree_traverse_with_reuse: needs prepared MuZero trees");
+    return tree_launch_traverse_reuse(t, d_true_action, d_reuse_value, d_ix, nullptr, d_iy, d_last_action, d_search_len, d_virtual_to_play,
+                                      (cudaStream_t)s);
+}
+
+int lz_tree_backpropagate_with_reuse(lz_tree *t, int latent_index, const float *d_reward, const float *d_value, const float *d_logits,
+                                     const float *d_reuse_value, const int32_t *d_batch_rank, const int32_t *d_to_play, lz_stream s)
+{
+    LZ_REQUIRE(t && d_reward && d_value && d_logits && d_reuse_value, LZ_EINVAL, "lz_tree_backpropagate_with_reuse: null argument");
+    LZ_REQUIRE(t->prepared && !t->p.ez, LZ_ESTATE, "lz_tree_backpropagate_with_reuse: needs prepared MuZero trees");
+    LZ_REQUIRE(latent_index >= 1 && latent_index <= t->max_sims, LZ_EINVAL,
+               "lz_tree_backpropagate_with_reuse: latent_index %d outside [1, %d]", latent_index, t->max_sims);
+    return tree_launch_backprop_reuse(t, latent_index, d_reward, d_value, d_logits, d_reuse_value, d_batch_rank, d_to_play, (cudaStream_t)s);
 }
 
 int lz_tree_select_action(lz_tree *t, float temperature, int deterministic, uint64_t seed, int32_t *d_action,

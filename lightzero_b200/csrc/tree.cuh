@@ -47,6 +47,12 @@ struct TreeParams {
     // carries is_reset, and a step's reward is the prefix difference unless the parent was reset
     int ez, lstm_horizon;
     int *n_reset;                // [B][N]
+    // ReZero search_with_reuse (cnode.cpp:502-549, 597-652, 701-752, 828-932)
+    int *n_batch;                // [B][N] batch_index recorded at expansion (the compacted inference row under reuse)
+    int *reuse_state;            // [B] result of the last traverse_with_reuse: 0 normal leaf, 1 stopped at the root's true_action
+                                 //     on an unexpanded child (expand, back up the reuse value), 2 stopped on an expanded child
+                                 //     (no inference, no expansion, back up the reuse value)
+    int *infer_count;            // [N] per-simulation number of trees that needed the network (search_with_reuse statistics)
 };
 
 __device__ __forceinline__ float u2f(uint32_t u) { return __uint_as_float(u); }
@@ -80,10 +86,13 @@ __device__ __forceinline__ float mm_normalize(float value, float mmax, float mmi
 }
 
 // cucb_score (cnode.cpp:654-698; EZ: ctree_efficientzero/lib/cnode.cpp:756-814) for the child held by this lane.
+// arm = true: carm_score (cnode.cpp:701-752) -- the stored reuse value replaces the child's mean value and a visited child
+// scores without the prior term.
 template <bool EZ = false>
 __device__ __forceinline__ float ucb_score(const uint32_t *nb, int A, int a, bool active, float pbc, float sq,
                                            float mean_q, float discount, int players, float mmax,
-                                           float mmin, float delta_max, float parent_vp = 0.0f, int parent_reset = 0)
+                                           float mmin, float delta_max, float parent_vp = 0.0f, int parent_reset = 0,
+                                           bool arm = false, float reuse_value = 0.0f)
 {
     if (!active) return -INFINITY;
     int vis = (int)nb[F_VISIT * A + a];
@@ -96,22 +105,26 @@ __device__ __forceinline__ float ucb_score(const uint32_t *nb, int A, int a, boo
     } else {
         float rw = u2f(nb[F_REWARD * A + a]);
         if (EZ && parent_reset != 1) rw = __fsub_rn(rw, parent_vp);   // true_reward = child prefix - parent prefix
-        float v = __fdiv_rn(u2f(nb[F_VSUM * A + a]), (float)vis);
+        float v = arm ? reuse_value : __fdiv_rn(u2f(nb[F_VSUM * A + a]), (float)vis);
         value_score = __fadd_rn(rw, __fmul_rn(discount, players == 1 ? v : -v));
     }
     value_score = mm_normalize(value_score, mmax, mmin, delta_max);
     if (value_score < 0.0f) value_score = 0.0f;
     if (value_score > 1.0f) value_score = 1.0f;
+    if (arm && vis != 0) return value_score;
     return __fadd_rn(prior_score, value_score);
 }
 
 // One PUCT descent of tree b by the calling warp: cbatch_traverse body (cnode.cpp:783-824) with
 // compute_mean_q (169-203) and cselect_child (551-595).  Records the path for the backup.
 // EZ = true: ctree_efficientzero/lib/cnode.cpp:876-958, 173-210, 651-697 (its rand() tie-break == deterministic for rand() == 0).
-template <bool EZ = false>
+// REUSE = true: cbatch_traverse_with_reuse (cnode.cpp:828-932); out_ix gets -1 for "no inference", out_ix_net the same
+// slot clamped to >= 0 (what a batched network launch may safely gather).
+template <bool EZ = false, bool REUSE = false>
 __device__ __forceinline__ void tree_traverse(const TreeParams &p, int b, int lane, int deterministic,
                                               unsigned step, int *out_ix, int *out_iy, int *out_action,
-                                              int *out_len, int *out_vtp)
+                                              int *out_len, int *out_vtp, const int *true_action = nullptr,
+                                              const float *reuse_value = nullptr, int *out_ix_net = nullptr)
 {
     const int A = p.A, N = p.N;
     uint32_t *tree_edges = p.edges + (size_t)b * N * kEdgeFields * A;
@@ -128,6 +141,9 @@ __device__ __forceinline__ void tree_traverse(const TreeParams &p, int b, int la
     float parent_q = 0.0f;
     float cur_vp = EZ ? p.root_reward[b] : 0.0f;      // value prefix / is_reset of the node being scanned
     int cur_reset = EZ ? p.n_reset[(size_t)b * N] : 0;
+    const int ta = REUSE ? true_action[b] : -1;
+    const float rv = REUSE ? reuse_value[b] : 0.0f;
+    int rstate = 0;
 
     while (true) {
         const uint32_t *nb = tree_edges + (size_t)slot * kEdgeFields * A;
@@ -169,7 +185,8 @@ __device__ __forceinline__ void tree_traverse(const TreeParams &p, int b, int la
             int k = c0 + lane;
             bool act = k < n;
             int a = act ? (is_root ? lg[k] : k) : 0;
-            float sc = ucb_score<EZ>(nb, A, a, act, pbc, sq, mean_q, discount, players, mmax, mmin, delta_max, cur_vp, cur_reset);
+            float sc = ucb_score<EZ>(nb, A, a, act, pbc, sq, mean_q, discount, players, mmax, mmin, delta_max, cur_vp, cur_reset,
+                                     REUSE && is_root && a == ta, rv);
             float cmax = warp_max_exact(sc);
             if (best < cmax) {
                 best = cmax;
@@ -185,7 +202,8 @@ __device__ __forceinline__ void tree_traverse(const TreeParams &p, int b, int la
                 int k = c0 + lane;
                 bool act = k < n;
                 int a = act ? (is_root ? lg[k] : k) : 0;
-                float sc = ucb_score<EZ>(nb, A, a, act, pbc, sq, mean_q, discount, players, mmax, mmin, delta_max, cur_vp, cur_reset);
+                float sc = ucb_score<EZ>(nb, A, a, act, pbc, sq, mean_q, discount, players, mmax, mmin, delta_max, cur_vp, cur_reset,
+                                     REUSE && is_root && a == ta, rv);
                 count += __popc(__ballot_sync(0xffffffffu, act && k > best_k && sc >= thr));
             }
             if (count > 1) {
@@ -197,7 +215,8 @@ __device__ __forceinline__ void tree_traverse(const TreeParams &p, int b, int la
                         int k = c0 + lane;
                         bool act = k < n;
                         int a = act ? (is_root ? lg[k] : k) : 0;
-                        float sc = ucb_score<EZ>(nb, A, a, act, pbc, sq, mean_q, discount, players, mmax, mmin, delta_max, cur_vp, cur_reset);
+                        float sc = ucb_score<EZ>(nb, A, a, act, pbc, sq, mean_q, discount, players, mmax, mmin, delta_max, cur_vp, cur_reset,
+                                     REUSE && is_root && a == ta, rv);
                         unsigned m = __ballot_sync(0xffffffffu, act && k > best_k && sc >= thr);
                         int c = __popc(m);
                         if (seen < r && r <= seen + c) {
@@ -225,6 +244,10 @@ __device__ __forceinline__ void tree_traverse(const TreeParams &p, int b, int la
         last_action = action;
         node_visit = (int)nb[F_VISIT * A + action];
         int cs = (int)nb[F_CSLOT * A + action];
+        if (REUSE && is_root && action == ta) {      // cnode.cpp:899-902: stop right after the root
+            rstate = cs >= 0 ? 2 : 1;
+            break;
+        }
         is_root = false;
         parent_q = mean_q;
         if (cs < 0 || plen >= N) break;
@@ -235,8 +258,13 @@ __device__ __forceinline__ void tree_traverse(const TreeParams &p, int b, int la
         p.path_len[b] = plen;
         p.vtp[b] = vtp;
         p.search_len[b] = plen;
-        if (out_ix) out_ix[b] = slot;          // parent of the leaf: its slot == current_latent_state_index
-        if (out_iy) out_iy[b] = b;             // batch_index
+        if (out_ix) out_ix[b] = (REUSE && rstate == 2) ? -1 : slot;     // parent of the leaf: its slot == current_latent_state_index
+        if (out_ix_net) out_ix_net[b] = slot;
+        if (out_iy) out_iy[b] = (REUSE && rstate != 2) ? p.n_batch[(size_t)b * N + slot] : b;      // batch_index (cnode.cpp:907-923)
+        if (REUSE) {
+            p.reuse_state[b] = rstate;
+            if (rstate != 2 && p.infer_count) atomicAdd(p.infer_count + step % (unsigned)N, 1);
+        }
         if (out_action) out_action[b] = last_action;
         if (out_len) out_len[b] = plen;
         if (out_vtp) out_vtp[b] = vtp;
@@ -284,10 +312,14 @@ __device__ __forceinline__ void expand_block(uint32_t *nb, int A, const float *l
 // cbatch_backpropagate body for tree b (cnode.cpp:495-499): expand the leaf reached by the last
 // traverse into slot `latent_index`, then cbackpropagate (cnode.cpp:419-478) along the recorded path.
 // EZ = true: ctree_efficientzero/lib/cnode.cpp:577-601 + 482-575; `reward` is the value prefix, `leaf_reset` the leaf's is_reset.
-template <bool EZ = false>
+// REUSE = true: cbatch_backpropagate_with_reuse (cnode.cpp:502-549) driven by the state the last traverse left: state 2 backs
+// up `reuse_value` without expanding anything, state 1 expands but backs up `reuse_value`; batch_rank = the compact row of
+// this tree in the inference batch (recorded as the new node's batch_index).
+template <bool EZ = false, bool REUSE = false>
 __device__ __forceinline__ void tree_backprop(const TreeParams &p, int b, int lane, int latent_index,
                                               float reward, float value, const float *logits,
-                                              const int *to_play_override, int leaf_reset = 0)
+                                              const int *to_play_override, int leaf_reset = 0, float reuse_value = 0.0f,
+                                              int batch_rank = -1)
 {
     const int A = p.A, N = p.N;
     const int plen = p.path_len[b];
@@ -297,10 +329,14 @@ __device__ __forceinline__ void tree_backprop(const TreeParams &p, int b, int la
     const int tp = to_play_override ? to_play_override[b] : p.vtp[b];
     const float discount = p.discount;
 
-    expand_block(tree_edges + (size_t)latent_index * kEdgeFields * A, A, logits, nullptr, A, lane);
+    const int rstate = REUSE ? p.reuse_state[b] : 0;
+    const bool no_expand = REUSE && rstate == 2;
+    if (REUSE && rstate != 0) value = reuse_value;
+    if (!no_expand) expand_block(tree_edges + (size_t)latent_index * kEdgeFields * A, A, logits, nullptr, A, lane);
     const int leaf_ps = pslot[plen - 1], leaf_pa = pact[plen - 1];
     uint32_t *leaf_nb = tree_edges + (size_t)leaf_ps * kEdgeFields * A;
-    if (lane == 0) {
+    if (lane == 0 && !no_expand) {
+        p.n_batch[(size_t)b * N + latent_index] = (REUSE && batch_rank >= 0) ? batch_rank : b;
         p.n_to_play[(size_t)b * N + latent_index] = tp;
         p.n_best[(size_t)b * N + latent_index] = -1;
         if (EZ) p.n_reset[(size_t)b * N + latent_index] = leaf_reset;
@@ -323,7 +359,7 @@ __device__ __forceinline__ void tree_backprop(const TreeParams &p, int b, int la
             prs = p.n_reset[(size_t)b * N + pslot[i - 1]];
         }
         if (act) {
-            if (i == plen) {               // the leaf: unvisited edge, reward just predicted
+            if (i == plen && !no_expand) { // the leaf: unvisited edge, reward just predicted
                 rw = reward; ntp = tp;
                 enb = leaf_nb; ea = leaf_pa;
             } else if (i == 0) {
@@ -335,7 +371,8 @@ __device__ __forceinline__ void tree_backprop(const TreeParams &p, int b, int la
                 vs = u2f(enb[F_VSUM * A + ea]);
                 vc = (int)enb[F_VISIT * A + ea];
                 rw = u2f(enb[F_REWARD * A + ea]);
-                ntp = p.n_to_play[(size_t)b * N + pslot[i]];
+                // node i's own slot: recorded on the path, or (reuse stop on an expanded child) the child slot of the last edge
+                ntp = p.n_to_play[(size_t)b * N + (i == plen ? (int)enb[F_CSLOT * A + ea] : pslot[i])];
             }
         }
         const int cnt = min(32, hi + 1);
@@ -413,4 +450,12 @@ int tree_launch_backprop(lz_tree *t, int latent_index, const float *d_reward, co
 int tree_launch_backprop_traverse(lz_tree *t, int latent_index, const float *d_reward, const float *d_value,
                                   const float *d_logits, int deterministic, int32_t *d_ix, int32_t *d_action,
                                   cudaStream_t s, int32_t *d_is_reset = nullptr);
+// ReZero reuse variants (MuZero trees): d_ix reports -1 for "no inference", d_ix_net is clamped for the network gather
+int tree_launch_traverse_reuse(lz_tree *t, const int32_t *d_true_action, const float *d_reuse_value, int32_t *d_ix, int32_t *d_ix_net,
+                               int32_t *d_iy, int32_t *d_action, int32_t *d_len, int32_t *d_vtp, cudaStream_t s);
+int tree_launch_backprop_reuse(lz_tree *t, int latent_index, const float *d_reward, const float *d_value, const float *d_logits,
+                               const float *d_reuse_value, const int32_t *d_batch_rank, const int32_t *d_to_play, cudaStream_t s);
+int tree_launch_backprop_traverse_reuse(lz_tree *t, int latent_index, const float *d_reward, const float *d_value, const float *d_logits,
+                                        const int32_t *d_true_action, const float *d_reuse_value, int32_t *d_ix_net, int32_t *d_action,
+                                        cudaStream_t s);
 }  // namespace lz

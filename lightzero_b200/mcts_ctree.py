@@ -114,6 +114,33 @@ class MuZeroMCTSCtree(object):
             return
         self._search_stepwise(roots, model, lat, S)
 
+    def search_with_reuse(self, roots: "mz_tree.Roots", model, latent_state_roots, to_play_batch: Union[int, List[Any]],
+                          true_action_list=None, reuse_value_list=None):
+        """mcts_ctree.py:370-468 (ReZero): the root child of ``true_action`` is scored with the stored ``reuse_value`` and the
+        descent stops there.  Returns ``(length, average_infer)`` like the reference: how many trees needed the network in
+        the last simulation and on average.  One CUDA graph with a ``lightzero_b200`` model."""
+        S = int(self._cfg.num_simulations)
+        roots._materialize(S, self._params())
+        t = roots._tree
+        dev = roots.device
+        if not isinstance(model, (MuZeroModel, MuZeroModelMLP)) or isinstance(model, EfficientZeroModel):
+            raise NotImplementedError("search_with_reuse is fused only: pass a lightzero_b200 MuZeroModel / MuZeroModelMLP "
+                                      "(or drive mz_tree.batch_traverse_with_reuse / batch_backpropagate_with_reuse yourself)")
+        if isinstance(latent_state_roots, torch.Tensor):
+            lat = latent_state_roots.to(dev, torch.float32, non_blocking=True).contiguous()
+        else:
+            lat = torch.from_numpy(np.ascontiguousarray(latent_state_roots, dtype=np.float32)).to(dev, non_blocking=True)
+        B = roots.num
+        ta = mz_tree._to_dev(true_action_list, torch.int32, dev, (B,))
+        rv = mz_tree._to_dev(reuse_value_list, torch.float32, dev, (B,))
+        counts = torch.empty(S, dtype=torch.int32, device=dev)
+        q = t.search_for(model, S)
+        with torch.cuda.device(dev):
+            cabi.check(t.lib.lz_search_run_with_reuse(q, lat.data_ptr(), ta.data_ptr(), rv.data_ptr(), counts.data_ptr(),
+                                                      cabi.stream_ptr()), "lz_search_run_with_reuse")
+        c = counts.cpu().numpy()
+        return int(c[-1]), float(c.sum()) / S
+
     def _search_stepwise(self, roots, model, lat, S):
         t = roots._tree
         dev = roots.device

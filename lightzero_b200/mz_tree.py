@@ -303,3 +303,60 @@ def batch_backpropagate(current_latent_state_index: int, discount_factor: float,
                                                pol.data_ptr(), cabi.ptr(tp), cabi.stream_ptr()),
                    "lz_tree_backpropagate")
     t._keep = (rew, val, pol, tp)
+
+
+def batch_traverse_with_reuse(roots: Roots, pb_c_base: int, pb_c_init: float, discount_factor: float,
+                              min_max_stats_lst: MinMaxStatsList, results: ResultsWrapper, virtual_to_play_batch,
+                              true_action, reuse_value, return_tensors: bool = False):
+    """mz_tree.pyx batch_traverse_with_reuse (cnode.cpp:828-932): ``latent_state_index_in_search_path`` is -1 for trees
+    that stopped on an already expanded child of the root (no inference needed)."""
+    if roots._tree is None:
+        roots._materialize(DEFAULT_MAX_SIMS)
+    t = roots._tree
+    t.set_params(pb_c_base, pb_c_init, discount_factor, min_max_stats_lst.value_delta_max)
+    dev = roots.device
+    ta = _to_dev(true_action, torch.int32, dev, (roots.root_num,))
+    rv = _to_dev(reuse_value, torch.float32, dev, (roots.root_num,))
+    with torch.cuda.device(dev):
+        cabi.check(t.lib.lz_tree_traverse_with_reuse(t.h, ta.data_ptr(), rv.data_ptr(), t.ix.data_ptr(), t.iy.data_ptr(),
+                                                     t.action.data_ptr(), t.search_len.data_ptr(), t.vtp.data_ptr(),
+                                                     cabi.stream_ptr()), "lz_tree_traverse_with_reuse")
+    results._roots = roots
+    t._keep = (ta, rv)
+    if return_tensors:
+        return t.ix, t.iy, t.action, t.vtp
+    packed = torch.stack((t.ix, t.iy, t.action, t.vtp)).cpu().numpy()
+    return packed[0].tolist(), packed[1].tolist(), packed[2].tolist(), packed[3].tolist()
+
+
+def batch_backpropagate_with_reuse(current_latent_state_index: int, discount_factor: float, value_prefixs, values, policies,
+                                   min_max_stats_lst: MinMaxStatsList, results: ResultsWrapper, to_play_batch,
+                                   no_inference_lst, reuse_lst, reuse_value_lst):
+    """mz_tree.pyx batch_backpropagate_with_reuse (cnode.cpp:502-549).  ``value_prefixs`` / ``values`` / ``policies`` are the
+    COMPACTED network outputs of the trees that were inferred (the driver skips the others, mcts_ctree.py:424-432);
+    they are scattered back to per-tree rows here, using ``no_inference_lst`` exactly as the C++ loop consumes it."""
+    roots = results._roots
+    t = roots._tree
+    B, A = roots.root_num, t.A
+    dev = roots.device
+    skip = np.zeros(B, bool)
+    skip[[i for i in no_inference_lst if i >= 0]] = True
+    rank = np.cumsum(~skip) - 1                     # compact row of every inferred tree
+    rank[skip] = -1
+    n = int((~skip).sum())
+    idx = torch.from_numpy(np.nonzero(~skip)[0]).to(dev)
+
+    def scatter(x, shape):
+        full = torch.zeros((B,) + shape, device=dev, dtype=torch.float32)
+        if n:
+            full[idx] = _to_dev(x, torch.float32, dev, (n,) + shape)
+        return full
+    rew, val, pol = scatter(value_prefixs, ()), scatter(values, ()), scatter(policies, (A,))
+    rv = _to_dev(reuse_value_lst, torch.float32, dev, (B,))
+    rk = torch.from_numpy(rank.astype(np.int32)).to(dev)
+    tp = _to_dev(to_play_batch, torch.int32, dev, (B,)) if to_play_batch is not None else None
+    with torch.cuda.device(dev):
+        cabi.check(t.lib.lz_tree_backpropagate_with_reuse(t.h, int(current_latent_state_index), rew.data_ptr(), val.data_ptr(),
+                                                          pol.data_ptr(), rv.data_ptr(), rk.data_ptr(), cabi.ptr(tp),
+                                                          cabi.stream_ptr()), "lz_tree_backpropagate_with_reuse")
+    t._keep = (rew, val, pol, rv, rk, tp)

@@ -235,3 +235,52 @@ def test_forward_collect_with_device_side_action_selection():
         assert mask[i, a] == 1 and dev[i]["visit_count_distributions"][legal[i].index(a)] > 0
         _, e = select_action(np.asarray(dev[i]["visit_count_distributions"]), temperature=0.5, deterministic=True)
         assert abs(dev[i]["visit_count_distribution_entropy"] - e) < 1e-5
+
+
+def test_fused_search_with_reuse_equals_stepwise_drive():
+    """MuZeroMCTSCtree.search_with_reuse (mcts_ctree.py:370-468) as one CUDA graph vs the reference's driver loop restated over
+    the mirror's batch_traverse_with_reuse / batch_backpropagate_with_reuse and the same CUDA model (compacted inference
+    batch, no_inference_lst / reuse_lst built as the driver does): identical visit counts, value bits and inference counts."""
+    from lightzero_b200 import mz_tree
+    B, A, S = 96, 6, 30
+    ref, cu, obs, mask, legal, noises, mcts = _setup(B, A, S, seed=21, masks=True)
+    out = cu.initial_inference(obs.cuda())
+    rng = np.random.default_rng(3)
+    true_action = [int(l[rng.integers(len(l))]) for l in legal]
+    reuse_value = (rng.standard_normal(B) * 0.5).astype(np.float32).tolist()
+    roots = mcts.roots(B, legal)
+    roots.prepare(0.25, noises, [0.] * B, out.policy_logits, [-1] * B)
+    length, avg = mcts.search_with_reuse(roots, cu, out.latent_state, [-1] * B, true_action, reuse_value)
+    fused = (roots.get_distributions(), np.asarray(roots.get_values(), np.float32).view(np.uint32).tolist())
+    roots.clear()
+    # step-wise: the reference loop
+    mz_tree.DEFAULT_MAX_SIMS = max(mz_tree.DEFAULT_MAX_SIMS, S)
+    roots = mz_tree.Roots(B, legal)
+    roots.prepare(0.25, noises, [0.] * B, out.policy_logits, [-1] * B)
+    mm = mz_tree.MinMaxStatsList(B)
+    mm.set_delta(0.01)
+    pool, counts = [out.latent_state], []
+    for s in range(S):
+        res = mz_tree.ResultsWrapper(B)
+        ix, iy, la, vtp = mz_tree.batch_traverse_with_reuse(roots, 19652, 1.25, 0.997, mm, res, [-1] * B, true_action, reuse_value)
+        lat, acts, no_inf, reuse = [], [], [], []
+        for count, (x, y) in enumerate(zip(ix, iy)):
+            if x != -1:
+                lat.append(pool[x][y]); acts.append(la[count])
+            else:
+                no_inf.append(y)
+            if x == 0 and la[count] == true_action[count]:
+                reuse.append(count)
+        counts.append(len(acts))
+        if acts:
+            o = cu.recurrent_inference(torch.stack(lat), torch.tensor(acts), return_scalars=True)
+            pool.append(o.latent_state)
+            r, v, p = o.reward_scalar, o.value_scalar, o.policy_logits
+        else:
+            pool.append([]); r, v, p = [], [], []
+        no_inf.append(-1); reuse.append(-1)
+        mz_tree.batch_backpropagate_with_reuse(s + 1, 0.997, r, v, p, mm, res, vtp, no_inf, reuse, reuse_value)
+    step = (roots.get_distributions(), np.asarray(roots.get_values(), np.float32).view(np.uint32).tolist())
+    assert fused == step
+    assert length == counts[-1] and abs(avg - sum(counts) / S) < 1e-9
+    assert min(counts) < B       # some trees reused a value instead of calling the network
