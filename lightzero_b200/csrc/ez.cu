@@ -172,60 +172,55 @@ __global__ void __launch_bounds__(256) k_ez_head(EzNet net, EzIO io)
 constexpr int kTM = 128, kTN = 64, kTK = 64, kTStages = 3;
 constexpr int kTAPart = 8 * kTM * 16;            // one hi or lo part of an A stage: [8 k-groups][128 rows][16 B] = 16 KB
 constexpr int kTWPart = 8 * kTN * 16;            // one hi or lo part of a W stage: 8 KB
-constexpr int kTWStages = 6;                     // the weight ring runs deeper than the A ring: its chunks only wait on L2 latency
-constexpr int kTABytes = kTStages * 2 * kTAPart;            // 96 KB
-constexpr int kTSmem = kTABytes + kTWStages * 2 * kTWPart + 256;   // + 96 KB
-constexpr int kTGroups = 3;                      // A-producer groups; group g converts chunks g, g+3, ... (3 chunks of L2 latency in flight)
-constexpr int kTGroupThreads = 256;              // two threads per root row (32 of the chunk's 64 inputs each): the conversion is latency-bound
-constexpr int kTThreads = kTGroups * kTGroupThreads + 64;     // + weight-copy warp + MMA warp
+constexpr int kTStageBytes = 2 * kTAPart + 2 * kTWPart;     // 48 KB
+constexpr int kTSmem = kTStages * kTStageBytes + 256;
+constexpr int kTGroups = 3;                      // A-producer groups of 128 threads; group g converts chunks g, g+3, ... (3 chunks of L2 latency in flight)
+constexpr int kTThreads = 192 + (kTGroups - 1) * 128;
 
 struct EzTcBars {
-    uint64_t full_a[kTStages], empty_a[kTStages], full_w[kTWStages], empty_w[kTWStages];
+    uint64_t full_a[kTStages], full_w[kTStages], empty[kTStages];
     uint64_t acc_ready;
     uint32_t tmem_base, pad;
 };
 
-// warps 0-7: producer group 0 (its first four warps are also the epilogue), warp 8: weight copy, warp 9: MMA, warps 10-17 / 18-25: groups 1 / 2
 __global__ void __launch_bounds__(kTThreads, 1) k_ez_lstm_tc(EzNet net, EzIO io)
 {
     extern __shared__ __align__(1024) unsigned char smem[];
-    EzTcBars *bars = reinterpret_cast<EzTcBars *>(smem + kTABytes + kTWStages * 2 * kTWPart);
-    unsigned char *wring = smem + kTABytes;
+    EzTcBars *bars = reinterpret_cast<EzTcBars *>(smem + kTStages * kTStageBytes);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nt = blockIdx.x, m0 = blockIdx.y * kTM;
     const int H = net.H, nin = net.nin, KT = nin + H, nchunks = KT / kTK;
 
     if (tid == 0) {
-        for (int i = 0; i < kTStages; ++i) { mbar_init(&bars->full_a[i], kTGroupThreads); mbar_init(&bars->empty_a[i], 1); }
-        for (int i = 0; i < kTWStages; ++i) { mbar_init(&bars->full_w[i], 1); mbar_init(&bars->empty_w[i], 1); }
+        for (int i = 0; i < kTStages; ++i) { mbar_init(&bars->full_a[i], 128); mbar_init(&bars->full_w[i], 1); mbar_init(&bars->empty[i], 1); }
         mbar_init(&bars->acc_ready, 1);
         fence_mbar_init();
     }
-    if (warp == 9) tmem_alloc(&bars->tmem_base, 64);
+    if (warp == 5) tmem_alloc(&bars->tmem_base, 64);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = bars->tmem_base;
 
-    if (warp == 8) {
+    if (warp == 4) {
         if (lane == 0) {
             const unsigned char *src = net.wtc + (size_t)nt * nchunks * (2 * kTWPart);
             for (int c = 0; c < nchunks; ++c) {
-                const int st = c % kTWStages;
-                if (c >= kTWStages) mbar_wait(&bars->empty_w[st], ((c / kTWStages) - 1) & 1);
+                const int st = c % kTStages;
+                if (c >= kTStages) mbar_wait(&bars->empty[st], ((c / kTStages) - 1) & 1);
                 mbar_expect_tx(&bars->full_w[st], 2 * kTWPart);
-                bulk_g2s(wring + st * 2 * kTWPart, src + (size_t)c * (2 * kTWPart), 2 * kTWPart, &bars->full_w[st]);
+                bulk_g2s(smem + st * kTStageBytes + 2 * kTAPart, src + (size_t)c * (2 * kTWPart), 2 * kTWPart, &bars->full_w[st]);
             }
         }
-    } else if (warp == 9) {
+    } else if (warp == 5) {
         if (lane == 0) {
             const uint32_t idesc = make_idesc_f16(kTM, kTN);
             for (int c = 0; c < nchunks; ++c) {
-                const int st = c % kTStages, sw = c % kTWStages;
+                const int st = c % kTStages;
                 mbar_wait(&bars->full_a[st], (c / kTStages) & 1);
-                mbar_wait(&bars->full_w[sw], (c / kTWStages) & 1);
+                mbar_wait(&bars->full_w[st], (c / kTStages) & 1);
                 tc_fence_after();
-                const uint32_t a_s = smem_u32(smem + st * 2 * kTAPart), w_s = smem_u32(wring + sw * 2 * kTWPart);
+                const uint32_t a_s = smem_u32(smem + st * kTStageBytes), w_s = a_s + 2 * kTAPart;
                 const uint64_t a_hi = make_desc(a_s, (kTM * 16) >> 4, 8), a_lo = make_desc(a_s + kTAPart, (kTM * 16) >> 4, 8);
                 const uint64_t w_hi = make_desc(w_s, (kTN * 16) >> 4, 8), w_lo = make_desc(w_s + kTWPart, (kTN * 16) >> 4, 8);
 #pragma unroll
@@ -235,38 +230,36 @@ __global__ void __launch_bounds__(kTThreads, 1) k_ez_lstm_tc(EzNet net, EzIO io)
                     umma_f16(tmem, a_hi + ao, w_lo + wo, idesc, 1);
                     umma_f16(tmem, a_lo + ao, w_hi + wo, idesc, 1);
                 }
-                umma_commit(&bars->empty_a[st]);
-                umma_commit(&bars->empty_w[sw]);
+                umma_commit(&bars->empty[st]);
             }
             umma_commit(&bars->acc_ready);
         }
     } else {
-        // ---- A producers: two threads per root row of the tile
-        const int grp = warp < 8 ? 0 : (warp - 10) / 8 + 1;
-        const int tg = warp < 8 ? tid : (tid - 320) % kTGroupThreads;
-        const int row = tg & 127, hf = tg >> 7, b = m0 + row;
+        // ---- A producers: thread = one root row of the tile; warps 0-3 are group 0, warps 6-9 group 1, warps 10-13 group 2
+        const int grp = warp < 4 ? 0 : (warp - 6) / 4 + 1;
+        const int row = warp < 4 ? tid : (tid - 192) & 127, b = m0 + row;
         const bool on = b < io.B;
         const float *fsrc = io.feat + (size_t)(on ? b : 0) * nin;
         const size_t hoff = (on && io.ix ? (size_t)io.ix[b] * io.slot_stride : 0) + (size_t)(on ? b : 0) * H;
         const float *hsrc = io.h_base + hoff;
         for (int c = grp; c < nchunks; c += kTGroups) {
             const int st = c % kTStages;
-            const int k0 = c * kTK + hf * 32;
+            const int k0 = c * kTK;
             const float *src = k0 < nin ? fsrc + k0 : hsrc + (k0 - nin);      // nin is a multiple of 64: a chunk never straddles
-            float4 v[8];
+            float4 v[16];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) v[u] = on ? *reinterpret_cast<const float4 *>(src + 4 * u) : make_float4(0, 0, 0, 0);
-            if (c >= kTStages) mbar_wait_warp(&bars->empty_a[st], ((c / kTStages) - 1) & 1);    // one polling lane per warp
-            unsigned char *a_hi = smem + st * 2 * kTAPart + (hf * 4) * (kTM * 16) + row * 16;
+            for (int u = 0; u < 16; ++u) v[u] = on ? *reinterpret_cast<const float4 *>(src + 4 * u) : make_float4(0, 0, 0, 0);
+            if (c >= kTStages) mbar_wait(&bars->empty[st], ((c / kTStages) - 1) & 1);
+            unsigned char *a_hi = smem + st * kTStageBytes + row * 16;
 #pragma unroll
-            for (int kg = 0; kg < 4; ++kg) {
+            for (int kg = 0; kg < 8; ++kg) {
                 const float f[8] = {v[2 * kg].x, v[2 * kg].y, v[2 * kg].z, v[2 * kg].w, v[2 * kg + 1].x, v[2 * kg + 1].y, v[2 * kg + 1].z, v[2 * kg + 1].w};
                 store_split8(a_hi + kg * (kTM * 16), a_hi + kTAPart + kg * (kTM * 16), f);
             }
             fence_proxy_async();
             mbar_arrive(&bars->full_a[st]);
         }
-        if (grp != 0 || hf != 0) goto done;
+        if (grp != 0) goto done;
         // ---- epilogue (group 0): 64 accumulator columns of this thread's row = 16 hidden units x (i, f, g, o)
         mbar_wait_warp(&bars->acc_ready, 0);
         tc_fence_after();
@@ -297,7 +290,7 @@ __global__ void __launch_bounds__(kTThreads, 1) k_ez_lstm_tc(EzNet net, EzIO io)
 done:
     tc_fence_before();
     __syncthreads();
-    if (warp == 9) {
+    if (warp == 5) {
         __syncwarp();
         tmem_dealloc(tmem, 64);
     }
