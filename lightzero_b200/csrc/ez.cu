@@ -208,6 +208,7 @@ __global__ void __launch_bounds__(kTThreads, 1) k_ez_lstm_tc(EzNet net, EzIO io)
             for (int c = 0; c < nchunks; ++c) {
                 const int st = c % kTStages;
                 if (c >= kTStages) mbar_wait(&bars->empty[st], ((c / kTStages) - 1) & 1);
+                if ((io.dbg & 2) && c >= kTStages) { mbar_arrive(&bars->full_w[st]); continue; }
                 mbar_expect_tx(&bars->full_w[st], 2 * kTWPart);
                 bulk_g2s(smem + st * kTStageBytes + 2 * kTAPart, src + (size_t)c * (2 * kTWPart), 2 * kTWPart, &bars->full_w[st]);
             }
@@ -235,55 +236,83 @@ __global__ void __launch_bounds__(kTThreads, 1) k_ez_lstm_tc(EzNet net, EzIO io)
             umma_commit(&bars->acc_ready);
         }
     } else {
-        // ---- A producers: thread = one root row of the tile; warps 0-3 are group 0, warps 6-9 group 1, warps 10-13 group 2
+        // ---- A producers (warps 0-3 group 0, warps 6-9 group 1, warps 10-13 group 2).  Per pass a warp covers 8 rows x 8
+        // k-groups: lane -> (row = lane % 8, k-groups lane / 8 and lane / 8 + 4), so one load instruction touches 8 lines (one
+        // per row) instead of 32 and each quarter-warp stores 8 consecutive rows of one k-group plane (conflict-free).
         const int grp = warp < 4 ? 0 : (warp - 6) / 4 + 1;
-        const int row = warp < 4 ? tid : (tid - 192) & 127, b = m0 + row;
-        const bool on = b < io.B;
-        const float *fsrc = io.feat + (size_t)(on ? b : 0) * nin;
-        const size_t hoff = (on && io.ix ? (size_t)io.ix[b] * io.slot_stride : 0) + (size_t)(on ? b : 0) * H;
-        const float *hsrc = io.h_base + hoff;
+        const int tg = warp < 4 ? tid : (tid - 192) & 127;
+        const int pw = tg >> 5, pl = tg & 31, prow0 = pw * 8 + (pl & 7), pkg = pl >> 3;
+        const float *fsrc[4], *hsrc[4];
+        bool pon[4];
+#pragma unroll
+        for (int ps = 0; ps < 4; ++ps) {
+            const int bb = m0 + ps * 32 + prow0;
+            pon[ps] = bb < io.B;
+            fsrc[ps] = io.feat + (size_t)(pon[ps] ? bb : 0) * nin;
+            hsrc[ps] = io.h_base + (pon[ps] && io.ix ? (size_t)io.ix[bb] * io.slot_stride : 0) + (size_t)(pon[ps] ? bb : 0) * H;
+        }
         for (int c = grp; c < nchunks; c += kTGroups) {
             const int st = c % kTStages;
-            const int k0 = c * kTK;
-            const float *src = k0 < nin ? fsrc + k0 : hsrc + (k0 - nin);      // nin is a multiple of 64: a chunk never straddles
+            const int k0 = c * kTK;                                             // nin is a multiple of 64: a chunk never straddles feat | h
             float4 v[16];
 #pragma unroll
-            for (int u = 0; u < 16; ++u) v[u] = on ? *reinterpret_cast<const float4 *>(src + 4 * u) : make_float4(0, 0, 0, 0);
-            if (c >= kTStages) mbar_wait(&bars->empty[st], ((c / kTStages) - 1) & 1);
-            unsigned char *a_hi = smem + st * kTStageBytes + row * 16;
+            for (int ps = 0; ps < 4; ++ps) {
+                const float *src = (k0 < nin ? fsrc[ps] + k0 : hsrc[ps] + (k0 - nin)) + pkg * 8;
 #pragma unroll
-            for (int kg = 0; kg < 8; ++kg) {
-                const float f[8] = {v[2 * kg].x, v[2 * kg].y, v[2 * kg].z, v[2 * kg].w, v[2 * kg + 1].x, v[2 * kg + 1].y, v[2 * kg + 1].z, v[2 * kg + 1].w};
-                store_split8(a_hi + kg * (kTM * 16), a_hi + kTAPart + kg * (kTM * 16), f);
+                for (int u = 0; u < 4; ++u)      // u: 0,1 = k-group pkg, 2,3 = k-group pkg + 4
+                    v[ps * 4 + u] = (pon[ps] && !(io.dbg & 1)) ? *reinterpret_cast<const float4 *>(src + (u >> 1) * 32 + (u & 1) * 4) : make_float4(0, 0, 0, 0);
+            }
+            if (c >= kTStages) mbar_wait(&bars->empty[st], ((c / kTStages) - 1) & 1);
+#pragma unroll
+            for (int ps = 0; ps < 4; ++ps) {
+                unsigned char *a_hi = smem + st * kTStageBytes + (ps * 32 + prow0) * 16;
+#pragma unroll
+                for (int h2 = 0; h2 < 2; ++h2) {
+                    const float4 x = v[ps * 4 + 2 * h2], y = v[ps * 4 + 2 * h2 + 1];
+                    const float f[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
+                    const int kg = pkg + 4 * h2;
+                    store_split8(a_hi + kg * (kTM * 16), a_hi + kTAPart + kg * (kTM * 16), f);
+                }
             }
             fence_proxy_async();
             mbar_arrive(&bars->full_a[st]);
         }
-        if (grp != 0) goto done;
-        // ---- epilogue (group 0): 64 accumulator columns of this thread's row = 16 hidden units x (i, f, g, o)
-        mbar_wait_warp(&bars->acc_ready, 0);
-        tc_fence_after();
-        const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
-        const float inv = net.wtc_inv_scale;
-        const float *c_in = io.c_base + hoff;
-        const bool reset = on && io.is_reset && io.is_reset[b] != 0;
+        // ---- epilogue, all three groups: warp w may read TMEM lanes 32 * (w % 4) .. +31 = rows of the tile; the 64 accumulator
+        // columns (16 hidden units x (i, f, g, o)) are dealt out in chunks of 16: group 0 takes chunks 0 and 3, groups 1 / 2
+        // chunks 1 / 2.  (A single group doing all 16 units per thread cost 10 us: one warp per scheduler, five
+        // transcendentals per unit.)  sigmoid / tanh through __expf + __fdividef: abs error ~1e-6 on values in (-1, 1).
+        {
+            const int row = (warp & 3) * 32 + lane, b = m0 + row;
+            const bool on = b < io.B;
+            const size_t hoff = (on && io.ix ? (size_t)io.ix[b] * io.slot_stride : 0) + (size_t)(on ? b : 0) * H;
+            mbar_wait_warp(&bars->acc_ready, 0);
+            tc_fence_after();
+            const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+            const float inv = net.wtc_inv_scale;
+            const float *c_in = io.c_base + hoff;
+            const bool reset = on && io.is_reset && io.is_reset[b] != 0;
+            for (int chunk = grp; chunk < 4; chunk += 3) {
+                float g[16];
+                tmem_ld16(lane_base + chunk * 16, g);
+                if (!on || (io.dbg & 4)) continue;
+                const int u0 = nt * 16 + chunk * 4;
+                const float4 cin4 = *reinterpret_cast<const float4 *>(c_in + u0);
+                const float cin[4] = {cin4.x, cin4.y, cin4.z, cin4.w};
+                float hn[4], cn[4];
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            float g[32];
-            tmem_ld32(lane_base + half * 32, g);
-            if (!on) continue;
-            const int u0 = nt * 16 + half * 8;
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const float4 bias = *reinterpret_cast<const float4 *>(net.bias + (size_t)(u0 + u) * 4);
-                const float gi = fmaf(g[4 * u], inv, bias.x), gf = fmaf(g[4 * u + 1], inv, bias.y);
-                const float gg = fmaf(g[4 * u + 2], inv, bias.z), go = fmaf(g[4 * u + 3], inv, bias.w);
-                const float si = 1.0f / (1.0f + expf(-gi)), sf = 1.0f / (1.0f + expf(-gf)), so = 1.0f / (1.0f + expf(-go));
-                const float c_new = sf * c_in[u0 + u] + si * tanhf(gg);
-                const float h_new = so * tanhf(c_new);
-                io.h_tmp[(size_t)b * H + u0 + u] = h_new;
-                if (io.h_out) io.h_out[(size_t)b * H + u0 + u] = reset ? 0.0f : h_new;
-                if (io.c_out) io.c_out[(size_t)b * H + u0 + u] = reset ? 0.0f : c_new;
+                for (int u = 0; u < 4; ++u) {
+                    const float4 bias = *reinterpret_cast<const float4 *>(net.bias + (size_t)(u0 + u) * 4);
+                    const float gi = fmaf(g[4 * u], inv, bias.x), gf = fmaf(g[4 * u + 1], inv, bias.y);
+                    const float gg = fmaf(g[4 * u + 2], inv, bias.z), go = fmaf(g[4 * u + 3], inv, bias.w);
+                    const float si = __fdividef(1.0f, 1.0f + __expf(-gi)), sf = __fdividef(1.0f, 1.0f + __expf(-gf));
+                    const float so = __fdividef(1.0f, 1.0f + __expf(-go));
+                    const float tg_ = 1.0f - __fdividef(2.0f, __expf(2.0f * gg) + 1.0f);
+                    cn[u] = sf * cin[u] + si * tg_;
+                    hn[u] = so * (1.0f - __fdividef(2.0f, __expf(2.0f * cn[u]) + 1.0f));
+                }
+                *reinterpret_cast<float4 *>(io.h_tmp + (size_t)b * H + u0) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+                if (io.h_out) *reinterpret_cast<float4 *>(io.h_out + (size_t)b * H + u0) = reset ? make_float4(0, 0, 0, 0) : make_float4(hn[0], hn[1], hn[2], hn[3]);
+                if (io.c_out) *reinterpret_cast<float4 *>(io.c_out + (size_t)b * H + u0) = reset ? make_float4(0, 0, 0, 0) : make_float4(cn[0], cn[1], cn[2], cn[3]);
             }
         }
     }
@@ -331,8 +360,10 @@ int ez_prepare_launch()
     return LZ_OK;
 }
 
-int ez_launch(const EzNet &net, const EzIO &io, cudaStream_t s, int math)
+int ez_launch(const EzNet &net, const EzIO &io_in, cudaStream_t s, int math)
 {
+    EzIO io = io_in;
+    if (const char *e = getenv("LZ_EZ_DBG")) io.dbg = atoi(e);
     LZ_REQUIRE(net.H <= kHMaxH && net.hid <= kHMaxHid && net.K <= kHLd && (net.H % 8) == 0, LZ_EINVAL,
                "ez_launch: unsupported LSTM / head size (H=%d hid=%d K=%d)", net.H, net.hid, net.K);
     const bool tc_ok = net.wtc && (net.nin % kTK) == 0 && (net.H % kTK) == 0 && !getenv("LZ_EZ_FP32");
