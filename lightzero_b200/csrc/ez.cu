@@ -316,7 +316,6 @@ __global__ void __launch_bounds__(kTThreads, 1) k_ez_lstm_tc(EzNet net, EzIO io)
             }
         }
     }
-done:
     tc_fence_before();
     __syncthreads();
     if (warp == 5) {
