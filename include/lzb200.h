@@ -107,7 +107,8 @@ int lz_tree_backpropagate_ez(lz_tree *t, int latent_index, const float *d_value_
 int lz_tree_results(lz_tree *t, int32_t *d_visits, float *d_values, int32_t *d_nlegal,
                     int32_t *d_traj, lz_stream s);
 
-/* ---- ReZero search_with_reuse on the MuZero trees (cnode.cpp:502-549, 597-652, 701-752, 828-932) ----
+/* ---- ReZero search_with_reuse (cnode.cpp:502-549, 597-652, 701-752, 828-932); works on MuZero trees and,
+ * with value-prefix semantics, on EfficientZero trees (ctree_efficientzero/lib/cnode.cpp:603-650, 699-754, 816-874, 960-1072) ----
  * d_true_action int32 [B] / d_reuse_value f32 [B]: the action taken in the stored trajectory and the value to reuse for it.
  * The root scores that child with carm_score and the descent stops right after the root when it is selected.  d_ix reports -1
  * for trees that stopped on an already expanded child ("no inference"); d_iy is the batch_index recorded when the parent was
@@ -117,9 +118,11 @@ int lz_tree_traverse_with_reuse(lz_tree *t, const int32_t *d_true_action, const 
                                 int32_t *d_last_action, int32_t *d_search_len, int32_t *d_virtual_to_play, lz_stream s);
 /* cbatch_backpropagate_with_reuse: rows are indexed BY TREE (not compacted; rows of "no inference" trees are ignored).
  * d_batch_rank int32 [B] or NULL: compact row of each tree in the caller's inference batch, stored as the batch_index of the
- * node it expands.  Which trees skip the expansion / back up the reuse value is the state the last traverse left. */
+ * node it expands.  d_is_reset int32 [B]: EfficientZero trees only (NULL otherwise).  Which trees skip the expansion / back up
+ * the reuse value is the state the last traverse left. */
 int lz_tree_backpropagate_with_reuse(lz_tree *t, int latent_index, const float *d_reward, const float *d_value, const float *d_logits,
-                                     const float *d_reuse_value, const int32_t *d_batch_rank, const int32_t *d_to_play, lz_stream s);
+                                     const float *d_reuse_value, const int32_t *d_batch_rank, const int32_t *d_is_reset,
+                                     const int32_t *d_to_play, lz_stream s);
 
 /* select_action (lzero/policy/utils.py:637-661) on the device, from the root visit counts of the finished search:
  * p = visit ** (1 / temperature) / sum (fp64), d_entropy = -sum p ln p, d_action_pos = arg-max (deterministic != 0; the

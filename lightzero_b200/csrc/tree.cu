@@ -143,23 +143,25 @@ k_tree_backprop_traverse(TreeParams p, int latent_index, const float *reward, co
 }
 
 // ---- ReZero search_with_reuse (MuZero trees) ----
+template <bool EZ>
 __global__ void __launch_bounds__(kTreeBlock)
 k_tree_traverse_reuse(TreeParams p, unsigned step, const int32_t *true_action, const float *reuse_value, int32_t *ix, int32_t *ix_net,
                       int32_t *iy, int32_t *act, int32_t *len, int32_t *vtp)
 {
     const int b = blockIdx.x * (kTreeBlock / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (b >= p.B) return;
-    tree_traverse<false, true>(p, b, lane, 1, step, ix, iy, act, len, vtp, true_action, reuse_value, ix_net);
+    tree_traverse<EZ, true>(p, b, lane, 1, step, ix, iy, act, len, vtp, true_action, reuse_value, ix_net);
 }
 
+template <bool EZ>
 __global__ void __launch_bounds__(kTreeBlock)
 k_tree_backprop_reuse(TreeParams p, int latent_index, const float *reward, const float *value, const float *logits,
-                      const float *reuse_value, const int32_t *batch_rank, const int32_t *to_play)
+                      const float *reuse_value, const int32_t *batch_rank, const int32_t *to_play, const int32_t *is_reset)
 {
     const int b = blockIdx.x * (kTreeBlock / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (b >= p.B) return;
-    tree_backprop<false, true>(p, b, lane, latent_index, reward[b], value[b], logits + (size_t)b * p.A, to_play, 0, reuse_value[b],
-                               batch_rank ? batch_rank[b] : -1);
+    tree_backprop<EZ, true>(p, b, lane, latent_index, reward[b], value[b], logits + (size_t)b * p.A, to_play,
+                            (EZ && is_reset) ? is_reset[b] : 0, reuse_value[b], batch_rank ? batch_rank[b] : -1);
 }
 
 __global__ void __launch_bounds__(kTreeBlock)
@@ -306,17 +308,26 @@ int tree_launch_backprop_traverse(lz_tree *t, int latent_index, const float *d_r
 int tree_launch_traverse_reuse(lz_tree *t, const int32_t *d_true_action, const float *d_reuse_value, int32_t *d_ix, int32_t *d_ix_net,
                                int32_t *d_iy, int32_t *d_action, int32_t *d_len, int32_t *d_vtp, cudaStream_t s)
 {
-    k_tree_traverse_reuse<<<tree_grid(t->p.B), kTreeBlock, 0, s>>>(t->p, t->step_counter++, d_true_action, d_reuse_value, d_ix, d_ix_net,
-                                                                  d_iy, d_action, d_len, d_vtp);
+    if (t->p.ez)
+        k_tree_traverse_reuse<true><<<tree_grid(t->p.B), kTreeBlock, 0, s>>>(t->p, t->step_counter++, d_true_action, d_reuse_value, d_ix, d_ix_net,
+                                                                            d_iy, d_action, d_len, d_vtp);
+    else
+        k_tree_traverse_reuse<false><<<tree_grid(t->p.B), kTreeBlock, 0, s>>>(t->p, t->step_counter++, d_true_action, d_reuse_value, d_ix, d_ix_net,
+                                                                             d_iy, d_action, d_len, d_vtp);
     LZ_KERNEL_CHECK();
     return LZ_OK;
 }
 
 int tree_launch_backprop_reuse(lz_tree *t, int latent_index, const float *d_reward, const float *d_value, const float *d_logits,
-                               const float *d_reuse_value, const int32_t *d_batch_rank, const int32_t *d_to_play, cudaStream_t s)
+                               const float *d_reuse_value, const int32_t *d_batch_rank, const int32_t *d_to_play, cudaStream_t s,
+                               const int32_t *d_is_reset)
 {
-    k_tree_backprop_reuse<<<tree_grid(t->p.B), kTreeBlock, 0, s>>>(t->p, latent_index, d_reward, d_value, d_logits, d_reuse_value,
-                                                                  d_batch_rank, d_to_play);
+    if (t->p.ez)
+        k_tree_backprop_reuse<true><<<tree_grid(t->p.B), kTreeBlock, 0, s>>>(t->p, latent_index, d_reward, d_value, d_logits, d_reuse_value,
+                                                                            d_batch_rank, d_to_play, d_is_reset);
+    else
+        k_tree_backprop_reuse<false><<<tree_grid(t->p.B), kTreeBlock, 0, s>>>(t->p, latent_index, d_reward, d_value, d_logits, d_reuse_value,
+                                                                             d_batch_rank, d_to_play, d_is_reset);
     LZ_KERNEL_CHECK();
     return LZ_OK;
 }
@@ -500,19 +511,22 @@ int lz_tree_traverse_with_reuse(lz_tree *t, const int32_t *d_true_action, const 
                                 int32_t *d_last_action, int32_t *d_search_len, int32_t *d_virtual_to_play, lz_stream s)
 {
     LZ_REQUIRE(t && d_true_action && d_reuse_value, LZ_EINVAL, "lz_tree_traverse_with_reuse: null argument");
-    LZ_REQUIRE(t->prepared && !t->p.ez, LZ_ESTATE, "lz_tree_traverse_with_reuse: needs prepared MuZero trees");
+    LZ_REQUIRE(t->prepared, LZ_ESTATE, "lz_tree_traverse_with_reuse: roots not prepared");
     return tree_launch_traverse_reuse(t, d_true_action, d_reuse_value, d_ix, nullptr, d_iy, d_last_action, d_search_len, d_virtual_to_play,
                                       (cudaStream_t)s);
 }
 
 int lz_tree_backpropagate_with_reuse(lz_tree *t, int latent_index, const float *d_reward, const float *d_value, const float *d_logits,
-                                     const float *d_reuse_value, const int32_t *d_batch_rank, const int32_t *d_to_play, lz_stream s)
+                                     const float *d_reuse_value, const int32_t *d_batch_rank, const int32_t *d_is_reset,
+                                     const int32_t *d_to_play, lz_stream s)
 {
     LZ_REQUIRE(t && d_reward && d_value && d_logits && d_reuse_value, LZ_EINVAL, "lz_tree_backpropagate_with_reuse: null argument");
-    LZ_REQUIRE(t->prepared && !t->p.ez, LZ_ESTATE, "lz_tree_backpropagate_with_reuse: needs prepared MuZero trees");
+    LZ_REQUIRE(t->prepared, LZ_ESTATE, "lz_tree_backpropagate_with_reuse: roots not prepared");
+    LZ_REQUIRE(!t->p.ez || d_is_reset, LZ_EINVAL, "lz_tree_backpropagate_with_reuse: EfficientZero trees need d_is_reset");
     LZ_REQUIRE(latent_index >= 1 && latent_index <= t->max_sims, LZ_EINVAL,
                "lz_tree_backpropagate_with_reuse: latent_index %d outside [1, %d]", latent_index, t->max_sims);
-    return tree_launch_backprop_reuse(t, latent_index, d_reward, d_value, d_logits, d_reuse_value, d_batch_rank, d_to_play, (cudaStream_t)s);
+    return tree_launch_backprop_reuse(t, latent_index, d_reward, d_value, d_logits, d_reuse_value, d_batch_rank, d_to_play, (cudaStream_t)s,
+                                      d_is_reset);
 }
 
 int lz_tree_select_action(lz_tree *t, float temperature, int deterministic, uint64_t seed, int32_t *d_action,

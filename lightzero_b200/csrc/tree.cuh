@@ -335,6 +335,8 @@ __device__ __forceinline__ void tree_backprop(const TreeParams &p, int b, int la
     if (!no_expand) expand_block(tree_edges + (size_t)latent_index * kEdgeFields * A, A, logits, nullptr, A, lane);
     const int leaf_ps = pslot[plen - 1], leaf_pa = pact[plen - 1];
     uint32_t *leaf_nb = tree_edges + (size_t)leaf_ps * kEdgeFields * A;
+    if (EZ && no_expand && lane == 0)      // ctree_efficientzero cnode.cpp:646: is_reset lands on the reached node even without expansion
+        p.n_reset[(size_t)b * N + (int)leaf_nb[F_CSLOT * A + leaf_pa]] = leaf_reset;
     if (lane == 0 && !no_expand) {
         p.n_batch[(size_t)b * N + latent_index] = (REUSE && batch_rank >= 0) ? batch_rank : b;
         p.n_to_play[(size_t)b * N + latent_index] = tp;
@@ -454,7 +456,8 @@ int tree_launch_backprop_traverse(lz_tree *t, int latent_index, const float *d_r
 int tree_launch_traverse_reuse(lz_tree *t, const int32_t *d_true_action, const float *d_reuse_value, int32_t *d_ix, int32_t *d_ix_net,
                                int32_t *d_iy, int32_t *d_action, int32_t *d_len, int32_t *d_vtp, cudaStream_t s);
 int tree_launch_backprop_reuse(lz_tree *t, int latent_index, const float *d_reward, const float *d_value, const float *d_logits,
-                               const float *d_reuse_value, const int32_t *d_batch_rank, const int32_t *d_to_play, cudaStream_t s);
+                               const float *d_reuse_value, const int32_t *d_batch_rank, const int32_t *d_to_play, cudaStream_t s,
+                               const int32_t *d_is_reset = nullptr);
 int tree_launch_backprop_traverse_reuse(lz_tree *t, int latent_index, const float *d_reward, const float *d_value, const float *d_logits,
                                         const int32_t *d_true_action, const float *d_reuse_value, int32_t *d_ix_net, int32_t *d_action,
                                         cudaStream_t s);

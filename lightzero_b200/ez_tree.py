@@ -63,3 +63,20 @@ def batch_backpropagate(current_latent_state_index: int, discount_factor: float,
                                                   pol.data_ptr(), rs.data_ptr(), cabi.ptr(tp), cabi.stream_ptr()),
                    "lz_tree_backpropagate_ez")
     t._keep = (vp, val, pol, rs, tp)
+
+
+def batch_traverse_with_reuse(roots: Roots, pb_c_base: int, pb_c_init: float, discount_factor: float,
+                              min_max_stats_lst: MinMaxStatsList, results: ResultsWrapper, virtual_to_play_batch,
+                              true_action, reuse_value, return_tensors: bool = False):
+    """ez_tree.pyx batch_traverse_with_reuse (ctree_efficientzero/lib/cnode.cpp:960-1072)"""
+    return _mz.batch_traverse_with_reuse(roots, pb_c_base, pb_c_init, discount_factor, min_max_stats_lst, results,
+                                         virtual_to_play_batch, true_action, reuse_value, return_tensors)
+
+
+def batch_backpropagate_with_reuse(current_latent_state_index: int, discount_factor: float, value_prefixs, values, policies,
+                                   min_max_stats_lst: MinMaxStatsList, results: ResultsWrapper, is_reset_list, to_play_batch,
+                                   no_inference_lst, reuse_lst, reuse_value_lst):
+    """ez_tree.pyx batch_backpropagate_with_reuse (ctree_efficientzero/lib/cnode.cpp:603-650)"""
+    return _mz.batch_backpropagate_with_reuse(current_latent_state_index, discount_factor, value_prefixs, values, policies,
+                                              min_max_stats_lst, results, to_play_batch, no_inference_lst, reuse_lst,
+                                              reuse_value_lst, _is_reset_list=is_reset_list)

@@ -331,7 +331,7 @@ def batch_traverse_with_reuse(roots: Roots, pb_c_base: int, pb_c_init: float, di
 
 def batch_backpropagate_with_reuse(current_latent_state_index: int, discount_factor: float, value_prefixs, values, policies,
                                    min_max_stats_lst: MinMaxStatsList, results: ResultsWrapper, to_play_batch,
-                                   no_inference_lst, reuse_lst, reuse_value_lst):
+                                   no_inference_lst, reuse_lst, reuse_value_lst, _is_reset_list=None):
     """mz_tree.pyx batch_backpropagate_with_reuse (cnode.cpp:502-549).  ``value_prefixs`` / ``values`` / ``policies`` are the
     COMPACTED network outputs of the trees that were inferred (the driver skips the others, mcts_ctree.py:424-432);
     they are scattered back to per-tree rows here, using ``no_inference_lst`` exactly as the C++ loop consumes it."""
@@ -355,8 +355,9 @@ def batch_backpropagate_with_reuse(current_latent_state_index: int, discount_fac
     rv = _to_dev(reuse_value_lst, torch.float32, dev, (B,))
     rk = torch.from_numpy(rank.astype(np.int32)).to(dev)
     tp = _to_dev(to_play_batch, torch.int32, dev, (B,)) if to_play_batch is not None else None
+    rs = _to_dev(_is_reset_list, torch.int32, dev, (B,)) if _is_reset_list is not None else None
     with torch.cuda.device(dev):
         cabi.check(t.lib.lz_tree_backpropagate_with_reuse(t.h, int(current_latent_state_index), rew.data_ptr(), val.data_ptr(),
-                                                          pol.data_ptr(), rv.data_ptr(), rk.data_ptr(), cabi.ptr(tp),
+                                                          pol.data_ptr(), rv.data_ptr(), rk.data_ptr(), cabi.ptr(rs), cabi.ptr(tp),
                                                           cabi.stream_ptr()), "lz_tree_backpropagate_with_reuse")
-    t._keep = (rew, val, pol, rv, rk, tp)
+    t._keep = (rew, val, pol, rv, rk, rs, tp)

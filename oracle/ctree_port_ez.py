@@ -21,6 +21,7 @@ def _lib():
         P, I, F = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
         L.lzo_tree_set_ez.argtypes = [P, I]
         L.lzo_tree_backpropagate_ez.argtypes = [P, I, F, P, P, P, P, P]
+        L.lzo_tree_backpropagate_with_reuse_ez.argtypes = [P, I, F, P, P, P, P, P, P, P, P]
         L._ez_ready = True
     return L
 
@@ -51,3 +52,28 @@ def batch_backpropagate(current_latent_state_index, discount_factor, value_prefi
     tp = np.ascontiguousarray(np.asarray(to_play_batch, np.int32))
     _lib().lzo_tree_backpropagate_ez(roots._h, int(current_latent_state_index), ctypes.c_float(discount_factor),
                                      _p(vp), _p(val), _p(pol), _p(rs), _p(tp))
+
+
+def batch_traverse_with_reuse(roots, pb_c_base, pb_c_init, discount_factor, min_max_stats_lst, results, virtual_to_play_batch,
+                              true_action, reuse_value):
+    """ez_tree.pyx batch_traverse_with_reuse (ctree_efficientzero/lib/cnode.cpp:960-1072)"""
+    return _mz.batch_traverse_with_reuse(roots, pb_c_base, pb_c_init, discount_factor, min_max_stats_lst, results,
+                                         virtual_to_play_batch, true_action, reuse_value)
+
+
+def batch_backpropagate_with_reuse(current_latent_state_index, discount_factor, value_prefixs, values, policies, min_max_stats_lst,
+                                   results, is_reset_list, to_play_batch, no_inference_lst, reuse_lst, reuse_value_lst):
+    """ez_tree.pyx batch_backpropagate_with_reuse (ctree_efficientzero/lib/cnode.cpp:603-650)"""
+    roots = results._roots
+    B, A = roots.root_num, roots.A
+    n = len(value_prefixs)
+    vp = np.ascontiguousarray(np.asarray(value_prefixs, np.float32).reshape(n))
+    val = np.ascontiguousarray(np.asarray(values, np.float32).reshape(n))
+    pol = np.ascontiguousarray(np.asarray(policies, np.float32).reshape(n, A)) if n else np.zeros((1, A), np.float32)
+    rs = np.ascontiguousarray(np.asarray(is_reset_list, np.int32))
+    tp = np.ascontiguousarray(np.asarray(to_play_batch, np.int32))
+    ni = np.ascontiguousarray(np.asarray(no_inference_lst, np.int32))
+    ru = np.ascontiguousarray(np.asarray(reuse_lst, np.int32))
+    rv = np.ascontiguousarray(np.asarray(reuse_value_lst, np.float32))
+    _lib().lzo_tree_backpropagate_with_reuse_ez(roots._h, int(current_latent_state_index), ctypes.c_float(discount_factor),
+                                                _p(vp), _p(val), _p(pol), _p(rs), _p(tp), _p(ni), _p(ru), _p(rv))
