@@ -169,6 +169,90 @@ def make_case_ez(ez, B, A, S, masks, noise, two_player, scale, seed, horizon):
                 delta=np.float32(DELTA), noise_w=np.float32(NOISE_W), lstm_horizon_len=horizon)
 
 
+REUSE_CASES = [
+    # name,               tree,      B,  A,  S, masks, noise, two_player, scale, seed, lstm_horizon_len (EZ only)
+    ("reuse_mz_a6",       "mz",     32,  6, 40, 0, 1, 0, 1.0, 21, 0),
+    ("reuse_mz_a18_mask", "mz",     24, 18, 40, 1, 1, 0, 2.0, 22, 0),
+    ("reuse_mz_2p_a9",    "mz",     16,  9, 30, 1, 1, 1, 1.0, 23, 0),
+    ("reuse_ez_a6",       "ez",     32,  6, 40, 0, 1, 0, 1.0, 24, 3),
+]
+
+
+def make_case_reuse(mod, B, A, S, masks, noise, two_player, scale, seed, horizon):
+    """ReZero *_with_reuse (mcts_ctree.py:370-468 / :878-1000 protocol) on the rand() == 0 builds: besides the usual trace the
+    fixture stores true_action / reuse_value, the compacted network outputs of every simulation (padded to B rows, n_inferred says
+    how many are real) and the -1 terminated no_inference / reuse lists the driver builds."""
+    rng = np.random.default_rng(seed)
+    legal = []
+    for _ in range(B):
+        m = rng.random(A) < 0.6 if masks else np.ones(A, bool)
+        if not m.any():
+            m[rng.integers(A)] = True
+        legal.append(np.nonzero(m)[0].tolist())
+    pol = (rng.standard_normal((B, A)) * scale).astype(np.float32)
+    to_play = rng.integers(1, 3, size=B).astype(np.int32) if two_player else np.full(B, -1, np.int32)
+    true_action = np.asarray([int(l[rng.integers(len(l))]) for l in legal], np.int32)
+    reuse_value = (rng.standard_normal(B) * scale).astype(np.float32)
+    roots = mod.Roots(B, legal)
+    noises = np.zeros((B, A), np.float32)
+    if noise:
+        nz = []
+        for b, l in enumerate(legal):
+            d = rng.dirichlet([0.3] * len(l)).astype(np.float32)
+            noises[b, :len(l)] = d
+            nz.append(d.tolist())
+        roots.prepare(NOISE_W, nz, [0.] * B, pol.tolist(), to_play.tolist())
+    else:
+        roots.prepare_no_noise([0.] * B, pol.tolist(), to_play.tolist())
+    mm = mod.MinMaxStatsList(B)
+    mm.set_delta(DELTA)
+    rew = np.zeros((S, B), np.float32); val = np.zeros((S, B), np.float32); pols = np.zeros((S, B, A), np.float32)
+    ix = np.zeros((S, B), np.int32); iy = np.zeros((S, B), np.int32); la = np.zeros((S, B), np.int32)
+    sl = np.zeros((S, B), np.int32); vtp = np.zeros((S, B), np.int32); rs = np.zeros((S, B), np.int32)
+    n_inf = np.zeros(S, np.int32)
+    no_inf = np.full((S, B + 1), -1, np.int32); reuse = np.full((S, B + 1), -1, np.int32)
+    for s in range(S):
+        res = mod.ResultsWrapper(B)
+        a, b_, c, d = mod.batch_traverse_with_reuse(roots, PB_C_BASE, PB_C_INIT, DISCOUNT, mm, res, copy.deepcopy(to_play.tolist()),
+                                                    true_action.tolist(), reuse_value.tolist())
+        ix[s], iy[s], la[s], vtp[s] = a, b_, c, d
+        sl[s] = res.get_search_len()
+        ni, ru, n = [], [], 0
+        for count, (x, y) in enumerate(zip(a, b_)):
+            if x != -1:
+                n += 1
+            else:
+                ni.append(y)
+            if x == 0 and c[count] == true_action[count]:
+                ru.append(count)
+        n_inf[s] = n
+        no_inf[s, :len(ni)] = ni
+        reuse[s, :len(ru)] = ru
+        rew[s] = (rng.standard_normal(B) * scale).astype(np.float32)
+        val[s] = (rng.standard_normal(B) * scale).astype(np.float32)
+        pols[s] = (rng.standard_normal((B, A)) * scale).astype(np.float32)
+        args = (s + 1, DISCOUNT, rew[s, :n].tolist(), val[s, :n].tolist(), pols[s, :n].tolist(), mm, res)
+        if horizon:
+            rs[s] = (sl[s] % horizon == 0).astype(np.int32)
+            mod.batch_backpropagate_with_reuse(*args, rs[s].tolist(), d, ni + [-1], ru + [-1], reuse_value.tolist())
+        else:
+            mod.batch_backpropagate_with_reuse(*args, d, ni + [-1], ru + [-1], reuse_value.tolist())
+    dist = np.full((B, A), -1, np.int32)
+    for b, dd in enumerate(roots.get_distributions()):
+        dist[b, :len(dd)] = dd
+    values = np.asarray(roots.get_values(), np.float32)
+    legal_arr = np.full((B, A), -1, np.int32)
+    nlegal = np.zeros(B, np.int32)
+    for b, l in enumerate(legal):
+        legal_arr[b, :len(l)] = l
+        nlegal[b] = len(l)
+    return dict(B=B, A=A, S=S, use_noise=noise, legal=legal_arr, nlegal=nlegal, root_logits=pol, noises=noises, to_play=to_play,
+                true_action=true_action, reuse_value=reuse_value, rewards=rew, values_in=val, policies=pols, n_inferred=n_inf,
+                no_inference=no_inf, reuse_list=reuse, is_reset=rs, ix=ix, iy=iy, last_action=la, search_len=sl, virtual_to_play=vtp,
+                distributions=dist, root_values_bits=values.view(np.uint32), pb_c_base=PB_C_BASE, pb_c_init=np.float32(PB_C_INIT),
+                discount=np.float32(DISCOUNT), delta=np.float32(DELTA), noise_w=np.float32(NOISE_W), lstm_horizon_len=horizon)
+
+
 def main():
     import mz_tree
     for name, *args in CASES:
@@ -194,6 +278,17 @@ def main():
         np.savez_compressed(os.path.join(HERE, f"tree_{name}.npz"), **case)
         print(name, "sum visits ok:", bool((np.where(case["distributions"] < 0, 0, case["distributions"]).sum(1) == case["S"]).all()),
               "resets:", int(case["is_reset"].sum()))
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import build_ref
+    mz_rand0 = build_ref.load_rand0()
+    for name, tree, *args in REUSE_CASES:
+        mod = mz_rand0 if tree == "mz" else ez_tree
+        case = make_case_reuse(mod, *args)
+        again = make_case_reuse(mod, *args)
+        assert all(np.array_equal(case[k], again[k]) for k in case), name
+        np.savez_compressed(os.path.join(HERE, f"{name}.npz"), **case)
+        print(name, "sum visits ok:", bool((np.where(case["distributions"] < 0, 0, case["distributions"]).sum(1) == case["S"]).all()),
+              "no-inference marks:", int((case["ix"] == -1).sum()))
 
 
 if __name__ == "__main__":
