@@ -36,6 +36,8 @@ extern "C" __global__ void __launch_bounds__(128, 1) k_mma_probe(const ProbeCfg 
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ uint64_t bar;
     __shared__ uint32_t tmem_base;
+    __shared__ uint64_t t_ad[512], t_bd[512];      // descriptors precomputed per configuration: the timed loop only issues
+    __shared__ uint32_t t_d[512];
     const int tid = threadIdx.x, warp = tid >> 5;
     for (int i = tid; i < 200 * 1024 / 16; i += blockDim.x) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);
     if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
@@ -51,17 +53,18 @@ extern "C" __global__ void __launch_bounds__(128, 1) k_mma_probe(const ProbeCfg 
         for (int c = 0; c < ncfg; ++c) {
             const ProbeCfg g = cfgs[c];
             const uint32_t idesc = make_idesc_f16(128, g.N);
+            for (int i = 0; i < g.n_mma; ++i) {
+                const int ks = i % g.n_ksteps, acc = (i / g.switch_every) % g.n_acc;
+                if (g.swz_a) t_ad[i] = desc_swz128(a_s + (uint32_t)g.a_shift_rows * 128u + (uint32_t)ks * 32u);
+                else t_ad[i] = make_desc(a_s + (uint32_t)g.a_shift_rows * 16u + (uint32_t)ks * 2u * (uint32_t)g.a_lbo16 * 16u, g.a_lbo16, 8);
+                if (g.swz_b) t_bd[i] = desc_swz128(b_s + (uint32_t)ks * 32u);
+                else t_bd[i] = make_desc(b_s + (uint32_t)ks * 2u * (uint32_t)g.N * 16u, g.N, 8);
+                t_d[i] = tmem + acc * g.N;
+            }
             for (int rep = 0; rep < 3; ++rep) {      // the last repetition is reported
                 const long long t0 = clock64();
-                for (int i = 0; i < g.n_mma; ++i) {
-                    const int ks = i % g.n_ksteps, acc = (i / g.switch_every) % g.n_acc;
-                    uint64_t ad, bd;
-                    if (g.swz_a) ad = desc_swz128(a_s + (uint32_t)g.a_shift_rows * 128u + (uint32_t)ks * 32u);
-                    else ad = make_desc(a_s + (uint32_t)g.a_shift_rows * 16u + (uint32_t)ks * 2u * (uint32_t)g.a_lbo16 * 16u, g.a_lbo16, 8);
-                    if (g.swz_b) bd = desc_swz128(b_s + (uint32_t)ks * 32u);
-                    else bd = make_desc(b_s + (uint32_t)ks * 2u * (uint32_t)g.N * 16u, g.N, 8);
-                    umma_f16(tmem + acc * g.N, ad, bd, idesc, 1);
-                }
+#pragma unroll 4
+                for (int i = 0; i < g.n_mma; ++i) umma_f16(t_d[i], t_ad[i], t_bd[i], idesc, 1);
                 umma_commit(&bar);
                 mbar_wait(&bar, parity);
                 parity ^= 1;
