@@ -21,6 +21,8 @@ struct ProbeCfg {
     int a_lbo16;        // no-swizzle: k-group stride of A in 16-byte units (128 = 128-row tile, 400 = net_tc.cu's activation buffer)
     int swz_a, swz_b;   // 1: SWIZZLE_128B K-major (rows of 128 B, 8-row groups of 1024 B)
     int n_ksteps;       // distinct K-steps cycled through (operand addresses change every MMA like in the real kernels)
+    int warp_issue;     // 1: the whole warp runs the issue loop and the MMA is predicated on elect.sync (uniform control flow,
+                        //    the CUTLASS pattern); 0: `if (lane == 0)` divergent branch (what net_tc.cu / conv_tc.cu / ez.cu do)
 };
 
 __device__ __forceinline__ uint64_t desc_swz128(uint32_t saddr)
@@ -29,6 +31,18 @@ __device__ __forceinline__ uint64_t desc_swz128(uint32_t saddr)
     // start address is not 1024-byte aligned
     const uint64_t base_off = (uint64_t)((saddr >> 7) & 7u);
     return (uint64_t)((saddr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (base_off << 49) | (2ull << 61);
+}
+
+__device__ __forceinline__ void umma_f16_elect(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc)
+{
+    asm volatile("{\n\t.reg .pred pe;\n\t.reg .pred pa;\n\telect.sync _|pe, 0xffffffff;\n\tsetp.ne.b32 pa, 1, 0;\n\t"
+                 "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, pa;\n\t}\n"
+                 ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc) : "memory");
+}
+__device__ __forceinline__ void umma_commit_elect(uint64_t *bar)
+{
+    asm volatile("{\n\t.reg .pred pe;\n\telect.sync _|pe, 0xffffffff;\n\t"
+                 "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}\n" ::"r"(smem_u32(bar)) : "memory");
 }
 
 extern "C" __global__ void __launch_bounds__(128, 1) k_mma_probe(const ProbeCfg *cfgs, int ncfg, unsigned long long *out)
@@ -47,13 +61,14 @@ extern "C" __global__ void __launch_bounds__(128, 1) k_mma_probe(const ProbeCfg 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_base;
-    if (tid == 0) {
+    if (warp == 0 && (cfgs[0].warp_issue || tid == 0)) {
+        const bool wi = cfgs[0].warp_issue != 0;
         const uint32_t a_s = smem_u32(smem) + 16 * 1024, b_s = smem_u32(smem) + 120 * 1024;     // room for negative shifts
         uint32_t parity = 0;
         for (int c = 0; c < ncfg; ++c) {
             const ProbeCfg g = cfgs[c];
             const uint32_t idesc = make_idesc_f16(128, g.N);
-            for (int i = 0; i < g.n_mma; ++i) {
+            for (int i = (wi ? (tid & 31) : 0); i < g.n_mma; i += (wi ? 32 : 1)) {
                 const int ks = i % g.n_ksteps, acc = (i / g.switch_every) % g.n_acc;
                 if (g.swz_a) t_ad[i] = desc_swz128(a_s + (uint32_t)g.a_shift_rows * 128u + (uint32_t)ks * 32u);
                 else t_ad[i] = make_desc(a_s + (uint32_t)g.a_shift_rows * 16u + (uint32_t)ks * 2u * (uint32_t)g.a_lbo16 * 16u, g.a_lbo16, 8);
@@ -61,15 +76,22 @@ extern "C" __global__ void __launch_bounds__(128, 1) k_mma_probe(const ProbeCfg 
                 else t_bd[i] = make_desc(b_s + (uint32_t)ks * 2u * (uint32_t)g.N * 16u, g.N, 8);
                 t_d[i] = tmem + acc * g.N;
             }
+            if (wi) __syncwarp();
             for (int rep = 0; rep < 3; ++rep) {      // the last repetition is reported
                 const long long t0 = clock64();
+                if (wi) {
 #pragma unroll 4
-                for (int i = 0; i < g.n_mma; ++i) umma_f16(t_d[i], t_ad[i], t_bd[i], idesc, 1);
-                umma_commit(&bar);
+                    for (int i = 0; i < g.n_mma; ++i) umma_f16_elect(t_d[i], t_ad[i], t_bd[i], idesc);
+                    umma_commit_elect(&bar);
+                } else {
+#pragma unroll 4
+                    for (int i = 0; i < g.n_mma; ++i) umma_f16(t_d[i], t_ad[i], t_bd[i], idesc, 1);
+                    umma_commit(&bar);
+                }
                 mbar_wait(&bar, parity);
                 parity ^= 1;
                 const long long t1 = clock64();
-                out[c] = (unsigned long long)(t1 - t0);
+                if (tid == 0) out[c] = (unsigned long long)(t1 - t0);
             }
         }
     }

@@ -9,31 +9,23 @@ lib = ctypes.CDLL(so)
 
 
 class Cfg(ctypes.Structure):
-    _fields_ = [(n, ctypes.c_int) for n in ("N", "n_mma", "n_acc", "switch_every", "a_shift_rows", "a_lbo16", "swz_a", "swz_b", "n_ksteps")]
+    _fields_ = [(n, ctypes.c_int) for n in ("N", "n_mma", "n_acc", "switch_every", "a_shift_rows", "a_lbo16", "swz_a", "swz_b", "n_ksteps", "warp_issue")]
 
 
 NM = 384
-cases = [
-    ("N=64  one accumulator, aligned A (tile stride 128 rows)", Cfg(64, NM, 1, NM, 0, 128, 0, 0, 4)),
-    ("N=64  one accumulator, A shifted by 1 row", Cfg(64, NM, 1, NM, 1, 128, 0, 0, 4)),
-    ("N=64  one accumulator, A shifted by 7 rows", Cfg(64, NM, 1, NM, 7, 128, 0, 0, 4)),
-    ("N=64  one accumulator, A shifted by 8 rows", Cfg(64, NM, 1, NM, 8, 128, 0, 0, 4)),
-    ("N=64  one accumulator, aligned, plane stride 400 rows (net_tc)", Cfg(64, NM, 1, NM, 0, 400, 0, 0, 4)),
-    ("N=64  plane stride 400 rows, shift 7", Cfg(64, NM, 1, NM, 7, 400, 0, 0, 4)),
-    ("N=64  3 accumulators, switch every MMA", Cfg(64, NM, 3, 1, 0, 128, 0, 0, 4)),
-    ("N=64  3 accumulators, switch every 4", Cfg(64, NM, 3, 4, 0, 128, 0, 0, 4)),
-    ("N=64  3 accumulators, switch every 12 (net_tc order)", Cfg(64, NM, 3, 12, 0, 128, 0, 0, 4)),
-    ("N=64  3 accumulators, switch every 36", Cfg(64, NM, 3, 36, 0, 128, 0, 0, 4)),
-    ("N=32  one accumulator", Cfg(32, NM, 1, NM, 0, 128, 0, 0, 4)),
-    ("N=128 one accumulator", Cfg(128, NM, 1, NM, 0, 128, 0, 0, 4)),
-    ("N=256 one accumulator", Cfg(256, NM, 1, NM, 0, 128, 0, 0, 2)),
-    ("N=64  A SWIZZLE_128B, aligned", Cfg(64, NM, 1, NM, 0, 128, 1, 0, 4)),
-    ("N=64  A SWIZZLE_128B, shifted 1 row", Cfg(64, NM, 1, NM, 1, 128, 1, 0, 4)),
-    ("N=64  A SWIZZLE_128B, shifted 7 rows", Cfg(64, NM, 1, NM, 7, 128, 1, 0, 4)),
-    ("N=64  A and B SWIZZLE_128B, aligned", Cfg(64, NM, 1, NM, 0, 128, 1, 1, 4)),
-    ("N=64  A and B SWIZZLE_128B, A shifted 7 rows", Cfg(64, NM, 1, NM, 7, 128, 1, 1, 4)),
-    ("N=128 A and B SWIZZLE_128B", Cfg(128, NM, 1, NM, 0, 128, 1, 1, 4)),
-]
+cases = []
+for wi, tag in ((0, "lane0 "), (1, "elect ")):
+    cases += [
+        (tag + "N=64  one accumulator, aligned A", Cfg(64, NM, 1, NM, 0, 128, 0, 0, 4, wi)),
+        (tag + "N=64  A shifted by 7 rows, plane stride 400 rows (net_tc)", Cfg(64, NM, 1, NM, 7, 400, 0, 0, 4, wi)),
+        (tag + "N=64  3 accumulators, switch every MMA", Cfg(64, NM, 3, 1, 0, 128, 0, 0, 4, wi)),
+        (tag + "N=64  3 accumulators, switch every 12 (net_tc order)", Cfg(64, NM, 3, 12, 0, 128, 0, 0, 4, wi)),
+        (tag + "N=32  one accumulator", Cfg(32, NM, 1, NM, 0, 128, 0, 0, 4, wi)),
+        (tag + "N=128 one accumulator", Cfg(128, NM, 1, NM, 0, 128, 0, 0, 4, wi)),
+        (tag + "N=256 one accumulator", Cfg(256, NM, 1, NM, 0, 128, 0, 0, 2, wi)),
+        (tag + "N=64  A SWIZZLE_128B, shifted 7 rows", Cfg(64, NM, 1, NM, 7, 128, 1, 0, 4, wi)),
+        (tag + "N=64  A and B SWIZZLE_128B", Cfg(64, NM, 1, NM, 0, 128, 1, 1, 4, wi)),
+    ]
 arr = (Cfg * len(cases))(*[c for _, c in cases])
 out = (ctypes.c_ulonglong * len(cases))()
 rc = lib.mma_probe_run(arr, len(cases), out)
