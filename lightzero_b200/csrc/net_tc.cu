@@ -39,6 +39,19 @@
 
 namespace lz {
 
+// Build with -DLZ_UNIFORM_ISSUE (env LZ_UNIFORM_ISSUE=1 for lightzero_b200/_build.py) to issue the MMAs from uniform control
+// flow (all 32 lanes of the issuing warp run the loop, elect.sync picks the issuer).  NOT the default in round 1: the
+// measurement that motivates it (profiles/r01e_mma_probe.md) arrived when no GPU time was left to validate the kernel.
+#ifdef LZ_UNIFORM_ISSUE
+#define LZ_MMA_ISSUER_ON true
+#define LZ_UMMA umma_f16_elect
+#define LZ_UCOMMIT umma_commit_elect
+#else
+#define LZ_MMA_ISSUER_ON (lane == 0)
+#define LZ_UMMA umma_f16
+#define LZ_UCOMMIT umma_commit
+#endif
+
 // ---------------------------------------------------------------------------------------------- geometry
 constexpr int kEpiWarps = 8, kEpiThreads = kEpiWarps * 32;   // two warps per TMEM lane quarter, one 32-column half each
 constexpr int kTcThreads = kEpiThreads + 64;
@@ -273,7 +286,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_net_tc(TcNet net, TcIO io, Tr
         }
     } else if (warp == kEpiWarps + 1) {
         // ================= MMA issuer =================
-        if (lane == 0) {
+        if (LZ_MMA_ISSUER_ON) {
             const uint32_t act_s = smem_u32(act), ring_s = smem_u32(ring), headw_s = smem_u32(headw);
             const uint32_t idesc64 = make_idesc_f16(128, 64), idesc16 = make_idesc_f16(128, 16), idesc32 = make_idesc_f16(128, 32);
             const bool sw = false;
@@ -300,19 +313,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_net_tc(TcNet net, TcIO io, Tr
                         const uint32_t d = tmem + kColAcc + t * 64;
 #pragma unroll
                         for (int ks = 0; ks < 4; ++ks)
-                            umma_f16(d, a0 + ks * (2 * kPlaneBytes >> 4), b0 + ks * (2048 >> 4), idesc64, (tap | ks) != 0);
+                            LZ_UMMA(d, a0 + ks * (2 * kPlaneBytes >> 4), b0 + ks * (2048 >> 4), idesc64, (tap | ks) != 0);
                         if (npass == 3) {
 #pragma unroll
                             for (int ks = 0; ks < 4; ++ks)      // A_hi * B_lo
-                                umma_f16(d, a0 + ks * (2 * kPlaneBytes >> 4), b0 + ((kTapBytes / 2) >> 4) + ks * (2048 >> 4), idesc64, 1);
+                                LZ_UMMA(d, a0 + ks * (2 * kPlaneBytes >> 4), b0 + ((kTapBytes / 2) >> 4) + ks * (2048 >> 4), idesc64, 1);
 #pragma unroll
                             for (int ks = 0; ks < 4; ++ks)      // A_lo * B_hi
-                                umma_f16(d, a0 + (kPartBytes >> 4) + ks * (2 * kPlaneBytes >> 4), b0 + ks * (2048 >> 4), idesc64, 1);
+                                LZ_UMMA(d, a0 + (kPartBytes >> 4) + ks * (2 * kPlaneBytes >> 4), b0 + ks * (2048 >> 4), idesc64, 1);
                         }
                     }
-                    umma_commit(&bars->empty[st]);               // frees this ring slot when the MMAs have read it
+                    LZ_UCOMMIT(&bars->empty[st]);               // frees this ring slot when the MMAs have read it
                 }
-                umma_commit(&bars->acc_ready);
+                LZ_UCOMMIT(&bars->acc_ready);
                 if (dbg && sim == 0) dbg[33 + 2 * L] = clock64();
                 const int flags = net.layer_flags[L];
                 if (flags & (LF_HOOK_REWARD | LF_HOOK_VALPOL)) {
@@ -333,15 +346,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_net_tc(TcNet net, TcIO io, Tr
                                     const uint64_t ad = make_desc(arow + apart + ks * 2 * kPlaneBytes, a_lbo, a_sbo);
                                     if (hook == 0) {   // reward head: N = 16, [kg][16 co][8]
                                         const uint32_t wb = headw_s + ((ps == 1) ? 2048 : 0);
-                                        umma_f16(tmem + kColRew + t * 16, ad, make_desc(wb + ks * 512, sw ? 8 : 16, sw ? 16 : 8), idesc16, (ps | ks) != 0);
+                                        LZ_UMMA(tmem + kColRew + t * 16, ad, make_desc(wb + ks * 512, sw ? 8 : 16, sw ? 16 : 8), idesc16, (ps | ks) != 0);
                                     } else {           // value + policy heads as one N = 32 matrix, [kg][32 co][8]
                                         const uint32_t wb = headw_s + 4096 + ((ps == 1) ? 4096 : 0);
-                                        umma_f16(tmem + kColAcc + t * 32, ad, make_desc(wb + ks * 1024, sw ? 8 : 32, sw ? 32 : 8), idesc32, (ps | ks) != 0);
+                                        LZ_UMMA(tmem + kColAcc + t * 32, ad, make_desc(wb + ks * 1024, sw ? 8 : 32, sw ? 32 : 8), idesc32, (ps | ks) != 0);
                                     }
                                 }
                             }
                         }
-                        umma_commit(hook == 0 ? &bars->rew_ready : &bars->vp_ready);
+                        LZ_UCOMMIT(hook == 0 ? &bars->rew_ready : &bars->vp_ready);
                     }
                 }
             }

@@ -85,6 +85,20 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64
                  "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
                  ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// The same, to be executed by ALL lanes of the issuing warp in uniform control flow: one elected lane issues.  Measured
+// (profiles/r01e_mma_probe.md): 48.6 cycles per N = 64 MMA (the shared-memory operand floor) against 60-78 when the
+// instruction sits in an `if (lane == 0)` branch, where ptxas wraps it in an ELECT / BRA.U.ANY loop.
+__device__ __forceinline__ void umma_f16_elect(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile("{\n\t.reg .pred pe;\n\t.reg .pred pa;\n\telect.sync _|pe, 0xffffffff;\n\tsetp.ne.b32 pa, %4, 0;\n\t"
+                 "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, pa;\n\t}\n"
+                 ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit_elect(uint64_t *bar)
+{
+    asm volatile("{\n\t.reg .pred pe;\n\telect.sync _|pe, 0xffffffff;\n\t"
+                 "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}\n" ::"r"(smem_u32(bar)) : "memory");
+}
 // arrives on the mbarrier once every MMA issued so far by this thread has completed
 __device__ __forceinline__ void umma_commit(uint64_t *bar)
 {
