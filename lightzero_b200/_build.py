@@ -14,7 +14,7 @@ LIBDIR = os.path.join(HERE, "_lib")
 LIB = os.path.join(LIBDIR, "liblzb200.so")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fno-fast-math"]
-if os.environ.get("LZ_UNIFORM_ISSUE"):      # experimental (round 2): elect.sync MMA issue in net_tc.cu, see profiles/r01e_mma_probe.md
+if os.environ.get("LZ_UNIFORM_ISSUE"):      # experimental (round 2): elect.sync MMA issue in net_tc.cu / conv_tc.cu / ez.cu, see profiles/r01e_mma_probe.md
     COMMON.append("-DLZ_UNIFORM_ISSUE")
 UNITS = [("tree.cu", ["-fmad=false"]), ("model.cu", []), ("net_tc.cu", []), ("conv_tc.cu", []), ("mlp.cu", []), ("ez.cu", []), ("search.cu", [])]
 

@@ -12,6 +12,17 @@
 #include "conv_tc.cuh"
 #include "tc_ptx.cuh"
 
+// -DLZ_UNIFORM_ISSUE (see net_tc.cu / profiles/r01e_mma_probe.md): issue the MMAs from uniform control flow with elect.sync.
+#ifdef LZ_UNIFORM_ISSUE
+#define LZ_MMA_ISSUER_ON true
+#define LZ_UMMA umma_f16_elect
+#define LZ_UCOMMIT umma_commit_elect
+#else
+#define LZ_MMA_ISSUER_ON (lane == 0)
+#define LZ_UMMA umma_f16
+#define LZ_UCOMMIT umma_commit
+#endif
+
 namespace lz {
 
 constexpr int kCvEpiWarps = 4, kCvEpiThreads = kCvEpiWarps * 32, kCvThreads = kCvEpiThreads + 64;   // 192 threads: 2 CTAs / SM
@@ -104,7 +115,7 @@ __global__ void __launch_bounds__(kCvThreads, 2) k_conv_tc(ConvTc p)
         }
     } else if (warp == kCvEpiWarps + 1) {
         // ================= MMA issuer =================
-        if (lane == 0) {
+        if (LZ_MMA_ISSUER_ON) {
             const uint32_t idesc = make_idesc_f16(128, N);
             const uint32_t plane16 = (uint32_t)(g.plane >> 4);
             const uint64_t a_desc0 = make_desc(smem_u32(in_s), plane16, 8);
@@ -124,17 +135,17 @@ __global__ void __launch_bounds__(kCvThreads, 2) k_conv_tc(ConvTc p)
                     const uint64_t a0 = a_tap + (uint64_t)(t * 128);
                     const uint32_t d = tmem + t * N;
                     for (int ks = 0; ks < nks; ++ks)
-                        umma_f16(d, a0 + ks * 2 * plane16, b0 + ks * 2 * N, idesc, (tap | ks) != 0);
+                        LZ_UMMA(d, a0 + ks * 2 * plane16, b0 + ks * 2 * N, idesc, (tap | ks) != 0);
                     if (npass == 3) {
                         for (int ks = 0; ks < nks; ++ks)
-                            umma_f16(d, a0 + ks * 2 * plane16, b0 + b_lo16 + ks * 2 * N, idesc, 1);
+                            LZ_UMMA(d, a0 + ks * 2 * plane16, b0 + b_lo16 + ks * 2 * N, idesc, 1);
                         for (int ks = 0; ks < nks; ++ks)
-                            umma_f16(d, a0 + a_lo16 + ks * 2 * plane16, b0 + ks * 2 * N, idesc, 1);
+                            LZ_UMMA(d, a0 + a_lo16 + ks * 2 * plane16, b0 + ks * 2 * N, idesc, 1);
                     }
                 }
-                umma_commit(&bars->empty[st]);
+                LZ_UCOMMIT(&bars->empty[st]);
             }
-            umma_commit(&bars->acc_ready);
+            LZ_UCOMMIT(&bars->acc_ready);
         }
     } else {
         // ================= epilogue: TMEM -> BN (+residual) (+ReLU) -> fp16 hi/lo -> next layer's TCL =================

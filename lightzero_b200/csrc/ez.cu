@@ -16,6 +16,17 @@
 #include "lz_common.cuh"
 #include "tc_ptx.cuh"
 
+// -DLZ_UNIFORM_ISSUE (see net_tc.cu / profiles/r01e_mma_probe.md): issue the MMAs from uniform control flow with elect.sync.
+#ifdef LZ_UNIFORM_ISSUE
+#define LZ_MMA_ISSUER_ON true
+#define LZ_UMMA umma_f16_elect
+#define LZ_UCOMMIT umma_commit_elect
+#else
+#define LZ_MMA_ISSUER_ON (lane == 0)
+#define LZ_UMMA umma_f16
+#define LZ_UCOMMIT umma_commit
+#endif
+
 namespace lz {
 
 constexpr int kGM = 64, kGN = 32, kGK = 16;      // 64 roots x 32 gate columns (= 8 hidden units) per CTA: 64 x ceil(B/64) CTAs
@@ -214,7 +225,7 @@ __global__ void __launch_bounds__(kTThreads, 1) k_ez_lstm_tc(EzNet net, EzIO io)
             }
         }
     } else if (warp == 5) {
-        if (lane == 0) {
+        if (LZ_MMA_ISSUER_ON) {
             const uint32_t idesc = make_idesc_f16(kTM, kTN);
             for (int c = 0; c < nchunks; ++c) {
                 const int st = c % kTStages;
@@ -227,13 +238,13 @@ __global__ void __launch_bounds__(kTThreads, 1) k_ez_lstm_tc(EzNet net, EzIO io)
 #pragma unroll
                 for (int ks = 0; ks < kTK / 16; ++ks) {
                     const uint64_t ao = (uint64_t)(ks * 2 * kTM * 16 >> 4), wo = (uint64_t)(ks * 2 * kTN * 16 >> 4);
-                    umma_f16(tmem, a_hi + ao, w_hi + wo, idesc, (c | ks) != 0);
-                    umma_f16(tmem, a_hi + ao, w_lo + wo, idesc, 1);
-                    umma_f16(tmem, a_lo + ao, w_hi + wo, idesc, 1);
+                    LZ_UMMA(tmem, a_hi + ao, w_hi + wo, idesc, (c | ks) != 0);
+                    LZ_UMMA(tmem, a_hi + ao, w_lo + wo, idesc, 1);
+                    LZ_UMMA(tmem, a_lo + ao, w_hi + wo, idesc, 1);
                 }
-                umma_commit(&bars->empty[st]);
+                LZ_UCOMMIT(&bars->empty[st]);
             }
-            umma_commit(&bars->acc_ready);
+            LZ_UCOMMIT(&bars->acc_ready);
         }
     } else {
         // ---- A producers (warps 0-3 group 0, warps 6-9 group 1, warps 10-13 group 2).  Per pass a warp covers 8 rows x 8
