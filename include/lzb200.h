@@ -240,6 +240,16 @@ int lz_search_collect(lz_search *q, const float *d_obs, const uint8_t *d_mask, c
 int lz_search_collect_host(lz_search *q, const float *h_obs, const uint8_t *h_mask, const float *h_noise,
                            float noise_weight, const int32_t *h_to_play, int deterministic, int nchunks,
                            float *d_pred_value, float *d_policy_logits, lz_stream s);
+/* The same two entry points for uint8 frames [B,obs_c,H,W] (Atari frames as the emulator delivers them; a quarter of the
+ * bytes on the wire).  The [0, 1] scaling of the reference's env wrapper (ScaledFloatFrameWrapper: obs / 255 -> float32,
+ * zoo/atari/envs/atari_wrappers.py:219-220, atari_lightzero_env.py:87-88) is applied inside the first conv kernel, bit-identical
+ * to that host arithmetic.  tcgen05 conv model with 84x84 / 96x96 frames only. */
+int lz_search_collect_u8(lz_search *q, const uint8_t *d_obs_u8, const uint8_t *d_mask, const float *d_noise,
+                         float noise_weight, const int32_t *d_to_play, int deterministic,
+                         float *d_pred_value, float *d_policy_logits, lz_stream s);
+int lz_search_collect_host_u8(lz_search *q, const uint8_t *h_obs_u8, const uint8_t *h_mask, const float *h_noise,
+                              float noise_weight, const int32_t *h_to_play, int deterministic, int nchunks,
+                              float *d_pred_value, float *d_policy_logits, lz_stream s);
 /* Number of kernel nodes one lz_search_run enqueues (for launch accounting). */
 int lz_search_num_kernels(const lz_search *q);
 /* Device pointer of the latent pool (NCHW per slot) for inspection in tests. */

@@ -7,7 +7,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_lib", "liblzb200.so")
+# LZ_LIB_TAG=NAME selects an experiment build (_lib/NAME/liblzb200.so, see _build.py); still the CUDA library, never a fallback
+LIB_PATH = os.path.join(_HERE, "_lib", os.environ.get("LZ_LIB_TAG", ""), "liblzb200.so")
 _lib = None
 
 c_int, c_float, c_void_p, c_char_p, c_int64 = (ctypes.c_int, ctypes.c_float, ctypes.c_void_p,
@@ -72,6 +73,10 @@ SIGNATURES = {
                                   c_void_p, c_void_p]),
     "lz_search_collect_host": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_int, c_int, c_void_p,
                                        c_void_p, c_void_p]),
+    "lz_search_collect_u8": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_int, c_void_p,
+                                     c_void_p, c_void_p]),
+    "lz_search_collect_host_u8": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_int, c_int, c_void_p,
+                                          c_void_p, c_void_p]),
     "lz_search_num_kernels": (c_int, [c_void_p]),
     "lz_search_latent_pool": (c_void_p, [c_void_p]),
     "lz_search_run_with_reuse": (c_int, [c_void_p] * 6),

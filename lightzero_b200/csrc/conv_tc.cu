@@ -12,8 +12,11 @@
 #include "conv_tc.cuh"
 #include "tc_ptx.cuh"
 
-// -DLZ_UNIFORM_ISSUE (see net_tc.cu / profiles/r01e_mma_probe.md): issue the MMAs from uniform control flow with elect.sync.
-#ifdef LZ_UNIFORM_ISSUE
+// The MMAs are issued from uniform control flow: the whole issuing warp runs the loop and elect.sync picks the lane
+// (48.6 cycles per N = 64 MMA, the shared-memory operand floor, against 60-78 from an `if (lane == 0)` branch, where ptxas
+// wraps every UTCHMMA in an ELECT / BRA.U.ANY loop: profiles/r01e_mma_probe.md; validated on hardware in round 2).
+// -DLZ_LANE0_ISSUE restores the round-1 single-lane branch for A/B measurements.
+#ifndef LZ_LANE0_ISSUE
 #define LZ_MMA_ISSUER_ON true
 #define LZ_UMMA umma_f16_elect
 #define LZ_UCOMMIT umma_commit_elect
@@ -68,7 +71,7 @@ __global__ void __launch_bounds__(kCvThreads, 2) k_conv_tc(ConvTc p)
     unsigned char *ring = smem + g.in_bytes;
     CvBars *bars = reinterpret_cast<CvBars *>(ring + p.stages * g.tap_bytes);
     const int nstages = p.stages;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;   // warp-uniform value: uniform role branches (see net_tc.cu)
     const int pitch = p.in.pitch, H = p.in.H, W = p.in.W, kg_in = p.in.C / 8;
     const int group = blockIdx.x / g.nbands, band = blockIdx.x - group * g.nbands;
     const int img0 = group * p.G, nimg = min(p.G, p.B - img0);
@@ -88,7 +91,7 @@ __global__ void __launch_bounds__(kCvThreads, 2) k_conv_tc(ConvTc p)
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = bars->tmem_base;
+    const uint32_t tmem = __shfl_sync(0xffffffffu, bars->tmem_base, 0);
 
     if (warp == kCvEpiWarps) {
         // ================= producer: input band, then the 9 weight taps =================

@@ -16,8 +16,11 @@
 #include "lz_common.cuh"
 #include "tc_ptx.cuh"
 
-// -DLZ_UNIFORM_ISSUE (see net_tc.cu / profiles/r01e_mma_probe.md): issue the MMAs from uniform control flow with elect.sync.
-#ifdef LZ_UNIFORM_ISSUE
+// The MMAs are issued from uniform control flow: the whole issuing warp runs the loop and elect.sync picks the lane
+// (48.6 cycles per N = 64 MMA, the shared-memory operand floor, against 60-78 from an `if (lane == 0)` branch, where ptxas
+// wraps every UTCHMMA in an ELECT / BRA.U.ANY loop: profiles/r01e_mma_probe.md; validated on hardware in round 2).
+// -DLZ_LANE0_ISSUE restores the round-1 single-lane branch for A/B measurements.
+#ifndef LZ_LANE0_ISSUE
 #define LZ_MMA_ISSUER_ON true
 #define LZ_UMMA umma_f16_elect
 #define LZ_UCOMMIT umma_commit_elect
@@ -111,7 +114,7 @@ __global__ void __launch_bounds__(256) k_ez_head(EzNet net, EzIO io)
     __shared__ float part[8][kHR][kHMaxHid];
     __shared__ float hidden[kHR][kHMaxHid];
     __shared__ float logits[kHR][kHLd];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;   // warp-uniform value: uniform role branches (see net_tc.cu)
     const int r0 = blockIdx.x * kHR, nr = min(kHR, io.B - r0);
     const int H = net.H, hid = net.hid, K = net.K;
     for (int i = tid; i < kHR * H; i += 256) {                       // norm_value_prefix + ReLU (efficientzero_model.py:565-566)
@@ -198,7 +201,7 @@ __global__ void __launch_bounds__(kTThreads, 1) k_ez_lstm_tc(EzNet net, EzIO io)
 {
     extern __shared__ __align__(1024) unsigned char smem[];
     EzTcBars *bars = reinterpret_cast<EzTcBars *>(smem + kTStages * kTStageBytes);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;   // warp-uniform value: uniform role branches (see net_tc.cu)
     const int nt = blockIdx.x, m0 = blockIdx.y * kTM;
     const int H = net.H, nin = net.nin, KT = nin + H, nchunks = KT / kTK;
 
@@ -211,7 +214,7 @@ __global__ void __launch_bounds__(kTThreads, 1) k_ez_lstm_tc(EzNet net, EzIO io)
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = bars->tmem_base;
+    const uint32_t tmem = __shfl_sync(0xffffffffu, bars->tmem_base, 0);
 
     if (warp == 4) {
         if (lane == 0) {

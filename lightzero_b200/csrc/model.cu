@@ -181,7 +181,7 @@ static inline size_t fused_smem_bytes(int W)
 template <int S>
 __global__ void __launch_bounds__(128)
 k_conv3x3_generic(ConvG L, const float *__restrict__ in, float *__restrict__ out, const float *__restrict__ res,
-                  int relu, int cic, int nrows_max, Tcl tcl)
+                  int relu, int cic, int nrows_max, Tcl tcl, const uint8_t *__restrict__ in_u8 = nullptr)
 {
     extern __shared__ __align__(16) float sm[];
     const int pitch = L.win + 2;
@@ -204,8 +204,13 @@ k_conv3x3_generic(ConvG L, const float *__restrict__ in, float *__restrict__ out
             int cl = i / per_c, rem = i - cl * per_c, rr = rem / pitch, cc = rem - rr * pitch;
             int gy = r0 + rr, gx = cc - 1, c = c0 + cl;
             float v = 0.0f;
-            if (c < L.cin && gy >= 0 && gy < L.hin && gx >= 0 && gx < L.win)
-                v = in[(((size_t)b * L.cin + c) * L.hin + gy) * L.win + gx];
+            if (c < L.cin && gy >= 0 && gy < L.hin && gx >= 0 && gx < L.win) {
+                const size_t gi = (((size_t)b * L.cin + c) * L.hin + gy) * L.win + gx;
+                // uint8 frames: the [0, 1] scaling of the reference's env wrapper (ScaledFloatFrameWrapper: (obs - 0) / 255 ->
+                // float32, zoo/atari/envs/atari_wrappers.py:219-220) happens here; a correctly rounded fp32 division
+                // reproduces that float64-divide-then-cast bit for bit for all 256 inputs (tests/test_host_logic_cpu.py)
+                v = in_u8 ? __fdiv_rn((float)in_u8[gi], 255.0f) : in[gi];
+            }
             in_t[((size_t)cl * nrows_max + rr) * pitch + cc] = v;
         }
         for (int i = tid; i < cic * 288; i += 128) {
@@ -355,6 +360,11 @@ int model_recurrent(lz_model *m, const RecIO &io, cudaStream_t s)
         t.latent_out = io.next_latent; t.reward = io.reward; t.value = io.value; t.policy_logits = io.policy_logits;
         t.reward_logits = io.reward_logits; t.value_logits = io.value_logits;
         t.pdl = io.pdl;
+        t.skip_scratch = io.skip_scratch;
+        if (!t.skip_scratch) {
+            LZ_REQUIRE(io.B <= m->tc_skip_B, LZ_ESTATE, "model_recurrent: scratch sized for %d roots, got %d (model_reserve)", m->tc_skip_B, io.B);
+            t.skip_scratch = m->tc_skip;
+        }
         if (m->cfg.efficientzero) {
             // conv trunk + prediction heads on the tensor cores; the reward features go through the LSTM head (ez.cu)
             LZ_REQUIRE(io.B <= m->ez_B, LZ_ESTATE, "model_recurrent: EfficientZero scratch sized for %d roots, got %d (model_reserve)", m->ez_B, io.B);
@@ -380,7 +390,7 @@ int model_recurrent(lz_model *m, const RecIO &io, cudaStream_t s)
 }
 
 static int launch_convg(const ConvG &L, const float *in, float *out, const float *res, int relu, int B, cudaStream_t s,
-                        const Tcl *tcl = nullptr)
+                        const Tcl *tcl = nullptr, const uint8_t *in_u8 = nullptr)
 {
     Tcl t;
     memset(&t, 0, sizeof(t));
@@ -392,8 +402,8 @@ static int launch_convg(const ConvG &L, const float *in, float *out, const float
     const size_t smem = ((((size_t)cic * nrows_max * pitch + 3) & ~(size_t)3) + (size_t)cic * 288) * sizeof(float);
     dim3 grid(ceil_div(L.hout * L.wout, 128), L.cout / 32, B);
     LZ_REQUIRE(smem <= 200 * 1024, LZ_EINVAL, "conv tower stage needs %zu B shared memory", smem);
-    if (L.stride == 1) k_conv3x3_generic<1><<<grid, 128, smem, s>>>(L, in, out, res, relu, cic, nrows_max, t);
-    else k_conv3x3_generic<2><<<grid, 128, smem, s>>>(L, in, out, res, relu, cic, nrows_max, t);
+    if (L.stride == 1) k_conv3x3_generic<1><<<grid, 128, smem, s>>>(L, in, out, res, relu, cic, nrows_max, t, in_u8);
+    else k_conv3x3_generic<2><<<grid, 128, smem, s>>>(L, in, out, res, relu, cic, nrows_max, t, in_u8);
     LZ_KERNEL_CHECK();
     return LZ_OK;
 }
@@ -407,9 +417,27 @@ static int launch_pool(const float *in, float *out, int planes, int hin, int hou
     return LZ_OK;
 }
 
+// skip scratch of the tcgen05 latent-grid kernel (grown outside stream capture: API entry points and lz_search_create)
+static int reserve_tc_skip(lz_model *m, int B)
+{
+    if (m->kind != 0 || B <= m->tc_skip_B) return LZ_OK;
+    ++m->generation;
+    cudaFree(m->tc_skip);
+    m->tc_skip = nullptr; m->tc_skip_B = 0;
+    int rc = dev_alloc(&m->tc_skip, (size_t)kActFloats * B);
+    if (rc != LZ_OK) return rc;
+    m->tc_skip_B = B;
+    return LZ_OK;
+}
+
 int model_reserve(lz_model *m, int B)
 {
+    {
+        int rc = reserve_tc_skip(m, B);
+        if (rc != LZ_OK) return rc;
+    }
     if (m->kind == 0 && m->cfg.efficientzero && B > m->ez_B) {
+        ++m->generation;
         cudaFree(m->ez_feat); cudaFree(m->ez_htmp);
         m->ez_feat = m->ez_htmp = nullptr;
         int rc = dev_alloc(&m->ez_feat, (size_t)B * m->cfg.reward_head_channels * kP);
@@ -418,6 +446,7 @@ int model_reserve(lz_model *m, int B)
         m->ez_B = B;
     }
     if (m->kind == 1 || B <= m->ws_B) return LZ_OK;
+    ++m->generation;
     size_t per_root = 0;
     for (const ConvG &L : m->tower) per_root = std::max(per_root, (size_t)L.cout * L.hout * L.wout);
     per_root = std::max(per_root, (size_t)kActFloats);
@@ -483,12 +512,12 @@ static void pick_band(ConvTc &p)
     p.stages = best_st;
 }
 
-static int tower_tc_run(lz_model *m, int B, const float *d_obs, float *pre_latent, cudaStream_t s)
+static int tower_tc_run(lz_model *m, int B, const float *d_obs, float *pre_latent, cudaStream_t s, const uint8_t *d_obs_u8 = nullptr)
 {
     int rc;
     const int npass = (m->math == 1) ? 3 : 1;
-    // stem: conv1 (Cin = 4/12, stride 2) on the CUDA cores, written straight into TCL
-    if ((rc = launch_convg(m->tower[0], d_obs, nullptr, nullptr, 1, B, s, &m->T0))) return rc;
+    // stem: conv1 (Cin = 4/12, stride 2) on the CUDA cores, written straight into TCL (uint8 frames are scaled to [0, 1] here)
+    if ((rc = launch_convg(m->tower[0], d_obs, nullptr, nullptr, 1, B, s, &m->T0, d_obs_u8))) return rc;
     auto run = [&](ConvTc p, const Tcl &in, const Tcl &o0, const Tcl *o1, const Tcl *res) {
         p.in = in; p.out[0] = o0;
         if (o1) p.out[1] = *o1;
@@ -509,11 +538,11 @@ static int tower_tc_run(lz_model *m, int B, const float *d_obs, float *pre_laten
 }
 
 // tcgen05 path only: the DownSample tower alone (obs -> pre-latent [B][64][36]) ...
-int model_initial_tower(lz_model *m, int B, const float *d_obs, float *pre_latent, cudaStream_t s)
+int model_initial_tower(lz_model *m, int B, const float *d_obs, float *pre_latent, cudaStream_t s, const uint8_t *d_obs_u8)
 {
     LZ_REQUIRE(m->kind == 0 && m->math != 0 && m->cfg.obs_h != 64, LZ_ESTATE, "model_initial_tower: tensor-core conv model only");
     LZ_REQUIRE(B <= m->ws_B, LZ_ESTATE, "model_initial_tower: workspace sized for %d roots, got %d", m->ws_B, B);
-    return tower_tc_run(m, B, d_obs, pre_latent, s);
+    return tower_tc_run(m, B, d_obs, pre_latent, s, d_obs_u8);
 }
 
 // ... and the latent-grid tail (representation ResBlocks -> latent -> prediction network)
@@ -524,6 +553,8 @@ int model_initial_tail(lz_model *m, int B, const float *pre_latent, const TailIO
     t.B = B; t.npass = (m->math == 1) ? 3 : 1;
     t.latent_base = pre_latent; t.latent_out = io_in.latent; t.latent_out2 = io_in.latent2;
     t.value = io_in.value; t.policy_logits = io_in.policy_logits; t.value_logits = io_in.value_logits;
+    LZ_REQUIRE(B <= m->tc_skip_B, LZ_ESTATE, "model_initial_tail: scratch sized for %d roots, got %d (model_reserve)", m->tc_skip_B, B);
+    t.skip_scratch = m->tc_skip;
     return tc_launch(m->tc_tail, t, s);
 }
 
@@ -566,6 +597,7 @@ int model_initial(lz_model *m, int B, const float *d_obs, const TailIO &io_in, c
         t.B = B; t.npass = (m->math == 1) ? 3 : 1;
         t.latent_base = pre; t.latent_out = io.latent; t.latent_out2 = io.latent2;
         t.value = io.value; t.policy_logits = io.policy_logits; t.value_logits = io.value_logits;
+        t.skip_scratch = m->tc_skip;
         return tc_launch(m->tc_tail, t, s);
     }
     switch (pick_W(B)) {
@@ -759,7 +791,23 @@ static int pack_tc(lz_model *m, const NetDev &net)
     const size_t off_bn = off_headw + tc_head_layout_bytes();
     const size_t off_headbn = off_bn + (size_t)nconv * 128 * 4;
     const size_t off_abias = off_headbn + 96 * 4;
-    const size_t total = off_abias + (size_t)A * kC * kP * 4;
+    // FC weight stream of the heads (16 KB blocks for the shared-memory ring of k_net_tc): FC1 as [nin][32] fp32 rows (hidden
+    // units zero padded to 32), FC2 as [ceil(K/128)][32][128] fp32 blocks
+    const std::string fc_names[3] = {"dynamics_network.fc_reward_head", "prediction_network.fc_value", "prediction_network.fc_policy"};
+    const Head *fc_heads[3] = {&net.reward, &net.value, &net.policy};
+    size_t fc_off1[3], fc_off2[3];
+    size_t off_fc = (off_abias + (size_t)A * kC * kP * 4 + 127) & ~(size_t)127;
+    const size_t off_fc0 = off_fc;
+    for (int h = 0; h < 3; ++h) {
+        const Head &H = *fc_heads[h];
+        const bool on = H.hid > 0;      // EfficientZero: the reward head's FC part lives in ez.cu
+        fc_off1[h] = off_fc - off_fc0;
+        if (on) off_fc += (size_t)H.hc * kP * 32 * 4;
+        off_fc = (off_fc + 127) & ~(size_t)127;
+        fc_off2[h] = off_fc - off_fc0;
+        if (on) off_fc += (size_t)((H.K + 127) / 128) * 32 * 128 * 4;
+    }
+    const size_t total = off_fc;
     std::vector<unsigned char> host(total, 0);
     float *bn = reinterpret_cast<float *>(host.data() + off_bn);
     float *head_bn = reinterpret_cast<float *>(host.data() + off_headbn);
@@ -793,7 +841,7 @@ static int pack_tc(lz_model *m, const NetDev &net)
                                     if (yy < 0 || yy >= kHW || xx < 0 || xx >= kHW) continue;
                                     acc += (*w)[((size_t)co * cin_total + kC + a) * 9 + ky * 3 + kx];
                                 }
-                            abias[((size_t)a * kC + co) * kP + y * kHW + x] = acc * scale[co];
+                            abias[((size_t)a * kP + y * kHW + x) * kC + co] = acc * scale[co];   // pixel-major: 32 consecutive channels per epilogue thread
                         }
         }
     }
@@ -814,6 +862,20 @@ static int pack_tc(lz_model *m, const NetDev &net)
             head_bn[h.bn_off + 16 + i] = t1[i] + s1[i] * (*b1)[i];
         }
     }
+    for (int h = 0; h < 3; ++h) {
+        const Head &H = *fc_heads[h];
+        if (H.hid <= 0) continue;
+        const int nin = H.hc * kP;
+        LZ_REQUIRE(H.hid <= 32 && H.K <= 608, LZ_EINVAL, "lz_model_finalize: tcgen05 path needs head hidden <= 32 and support <= 608");
+        auto W0 = find(m, fc_names[h] + ".0.weight", (size_t)H.hid * nin), W3 = find(m, fc_names[h] + ".3.weight", (size_t)H.K * H.hid);
+        if (!W0 || !W3) return LZ_EINVAL;
+        float *f1 = reinterpret_cast<float *>(host.data() + off_fc0 + fc_off1[h]);
+        float *f2 = reinterpret_cast<float *>(host.data() + off_fc0 + fc_off2[h]);
+        for (int i = 0; i < nin; ++i)
+            for (int j = 0; j < H.hid; ++j) f1[(size_t)i * 32 + j] = (*W0)[(size_t)j * nin + i];
+        for (int k = 0; k < H.K; ++k)
+            for (int j = 0; j < H.hid; ++j) f2[((size_t)(k / 128) * 32 + j) * 128 + (k % 128)] = (*W3)[(size_t)k * H.hid + j];
+    }
     if (m->d_tc) cudaFree(m->d_tc);
     m->d_tc = nullptr;
     int rc = dev_alloc(&m->d_tc, total);
@@ -826,6 +888,12 @@ static int pack_tc(lz_model *m, const NetDev &net)
     base.head_bn = reinterpret_cast<const float *>(m->d_tc + off_headbn);
     base.abias = reinterpret_cast<const float *>(m->d_tc + off_abias);
     base.reward = net.reward; base.value = net.value; base.policy = net.policy;
+    base.fcw = m->d_tc + off_fc0;
+    for (int h = 0; h < 3; ++h) {
+        base.fc[h].fc1_off = (uint32_t)fc_off1[h]; base.fc[h].fc2_off = (uint32_t)fc_off2[h];
+        base.fc[h].nin = fc_heads[h]->hid > 0 ? fc_heads[h]->hc * kP : 0;
+        base.fc[h].K = fc_heads[h]->hid > 0 ? fc_heads[h]->K : 0;
+    }
     base.hc[0] = c.reward_head_channels; base.hc[1] = c.value_head_channels; base.hc[2] = c.policy_head_channels;
     base.A = A; base.support_min = c.support_min; base.support_step = c.support_step;
     // conv indices: 0 dyn conv | 1..2n dyn blocks | 2n+1..4n pred blocks | 4n+1..6n rep blocks
@@ -841,7 +909,6 @@ static int pack_tc(lz_model *m, const NetDev &net)
         rec.layer_w[L] = 2 * n + 2 + 2 * i; rec.layer_flags[L++] = LF_RES | LF_STORE_RES | (i == n - 1 ? LF_HOOK_VALPOL : 0);
     }
     rec.nlayers = L; rec.has_reward = 1;
-    rec.has_reward_early = (A <= 608 && !getenv("LZ_TC_LATE_REWARD")) ? 1 : 0;   // scratch sized for ldl = 608
     L = 0;
     for (int i = 0; i < n; ++i) {
         tail.layer_w[L] = 4 * n + 1 + 2 * i; tail.layer_flags[L++] = 0;
@@ -891,7 +958,7 @@ int lz_model_create(const lz_model_config *cfg, lz_model **out)
     m->ws[0] = m->ws[1] = m->ws[2] = nullptr;
     m->ws_floats = 0; m->ws_B = 0;
     m->math = 1; m->d_tc = nullptr;   // default: tcgen05 3xFP16 (fp32-accurate)
-    m->d_tower = nullptr; m->tws = nullptr; m->tws_bytes = 0;
+    m->d_tower = nullptr; m->tws = nullptr; m->tws_bytes = 0; m->tc_skip = nullptr; m->tc_skip_B = 0;
     *out = m;
     return LZ_OK;
 }
@@ -903,6 +970,7 @@ int lz_model_destroy(lz_model *m)
     cudaFree(m->d_tc);
     cudaFree(m->d_tower);
     cudaFree(m->tws);
+    cudaFree(m->tc_skip);
     cudaFree(m->ez_feat); cudaFree(m->ez_htmp); cudaFree(m->d_ez_wtc);
     for (int i = 0; i < 3; ++i) cudaFree(m->ws[i]);
     delete m;
@@ -925,6 +993,7 @@ int lz_model_set_tensor(lz_model *m, const char *name, const float *h_data, int6
 int lz_model_finalize(lz_model *m)
 {
     LZ_REQUIRE(m, LZ_EINVAL, "lz_model_finalize: null model");
+    ++m->generation;          // every device table is re-allocated below: graphs captured against the old ones are stale
     if (m->kind == 1) return mlp_finalize(m);
     const lz_model_config &c = m->cfg;
     const int A = c.action_space_size, n = c.num_res_blocks;
@@ -1064,6 +1133,7 @@ int lz_model_set_math(lz_model *m, int mode)
     LZ_REQUIRE(m && mode >= 0 && mode <= 2, LZ_EINVAL, "lz_model_set_math: mode must be 0 (fp32 FFMA), 1 (tcgen05 3xFP16) or 2 (tcgen05 fp16)");
     LZ_REQUIRE(m->kind == 0 || mode == 0, LZ_EINVAL, "lz_model_set_math: the MLP model only has the fp32 path");
     LZ_REQUIRE(!(m->kind == 0 && m->cfg.efficientzero && mode == 0), LZ_EINVAL, "lz_model_set_math: the EfficientZero model runs its conv stack on the tcgen05 path only (mode 1 or 2)");
+    if (m->math != mode) ++m->generation;      // captured search graphs bake the path (and pass count) in
     m->math = mode;
     return LZ_OK;
 }
@@ -1072,11 +1142,11 @@ int lz_model_set_math(lz_model *m, int mode)
 int lz_model_debug_tc_program(lz_model *m, int which, int nlayers, const int *layer_w, const int *layer_flags, int has_reward)
 {
     LZ_REQUIRE(m && m->finalized && nlayers >= 1 && nlayers <= kTcMaxLayers, LZ_EINVAL, "lz_model_debug_tc_program: bad argument");
+    ++m->generation;
     TcNet &n = which ? m->tc_tail : m->tc_rec;
     n.nlayers = nlayers;
     for (int i = 0; i < nlayers; ++i) { n.layer_w[i] = layer_w[i]; n.layer_flags[i] = layer_flags[i]; }
     n.has_reward = has_reward;
-    n.has_reward_early = 0;
     return LZ_OK;
 }
 
@@ -1112,6 +1182,10 @@ int lz_model_recurrent_inference(lz_model *m, int B, const float *d_latent, cons
 {
     LZ_REQUIRE(m && d_latent && d_action && B > 0, LZ_EINVAL, "lz_model_recurrent_inference: bad argument");
     LZ_REQUIRE(m->finalized, LZ_ESTATE, "lz_model_recurrent_inference: model not finalized");
+    {
+        int rc = reserve_tc_skip(m, B);
+        if (rc != LZ_OK) return rc;
+    }
     RecIO io;
     memset(&io, 0, sizeof(io));
     io.B = B; io.latent_base = d_latent; io.ix = nullptr; io.slot_stride = 0; io.action = d_action;
@@ -1127,7 +1201,7 @@ int lz_model_recurrent_inference_ez(lz_model *m, int B, const float *d_latent, c
 {
     LZ_REQUIRE(m && d_latent && d_hidden0 && d_hidden1 && d_action && d_next_latent && B > 0, LZ_EINVAL, "lz_model_recurrent_inference_ez: bad argument");
     LZ_REQUIRE(m->finalized && m->kind == 0 && m->cfg.efficientzero, LZ_ESTATE, "lz_model_recurrent_inference_ez: not a finalized EfficientZero model");
-    if (B > m->ez_B) {
+    if (B > m->ez_B || B > m->tc_skip_B) {
         int rc = model_reserve(m, B);
         if (rc != LZ_OK) return rc;
     }

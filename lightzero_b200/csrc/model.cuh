@@ -56,6 +56,7 @@ struct RecIO {
     float *policy_logits;             // [B][A] or nullptr
     float *reward_logits, *value_logits;   // [B][K] or nullptr
     int pdl;                          // programmatic dependent launch (search graph)
+    float *skip_scratch;              // [B][2304] scratch of the tcgen05 path (nullptr: the model's own, lz_model::tc_skip)
     // EfficientZero (reward == value prefix): LSTM state in / out, see ez.cuh
     const float *h_base, *c_base;     // base + ix[b]*hslot_stride + b*H
     size_t hslot_stride;
@@ -95,6 +96,8 @@ struct lz_model {
     int math;                         // 0 = fp32 FFMA (net6.cuh), 1 = tcgen05 3xFP16 (fp32-accurate), 2 = tcgen05 fp16 single pass
     unsigned char *d_tc;              // packed fp16 hi/lo weights + tables of the tcgen05 path
     lz::TcNet tc_rec, tc_tail;
+    float *tc_skip;                   // [tc_skip_B][2304] ResBlock skip scratch of k_net_tc for launches outside a search (model_reserve)
+    int tc_skip_B;
     // tcgen05 DownSample tower: packed weights / folded BN per layer, TCL activation workspace
     unsigned char *d_tower;           // weights + scale/shift tables
     lz::ConvTc tower_tc[7];           // rb1.c1, rb1.c2, ds(c1+c3), ds.c2, rb2.c1, rb2.c2, rb3.c1 / rb3.c2 share [6]: see model.cu
@@ -106,12 +109,14 @@ struct lz_model {
     float *ws[3];
     size_t ws_floats;
     int ws_B;
+    unsigned long long generation;    // bumped when device tables / workspaces that captured search graphs point into are re-allocated
+                                      // or the math mode changes (finalize, set_math, model_reserve): lz_search re-captures
 };
 
 namespace lz {
 int model_recurrent(lz_model *m, const RecIO &io, cudaStream_t s);
 int model_initial(lz_model *m, int B, const float *d_obs, const TailIO &io, cudaStream_t s);
-int model_initial_tower(lz_model *m, int B, const float *d_obs, float *pre_latent, cudaStream_t s);
+int model_initial_tower(lz_model *m, int B, const float *d_obs, float *pre_latent, cudaStream_t s, const uint8_t *d_obs_u8 = nullptr);   // exactly one of d_obs / d_obs_u8
 int model_initial_tail(lz_model *m, int B, const float *pre_latent, const TailIO &io, cudaStream_t s);
 int model_reserve(lz_model *m, int B);   // sizes the initial-inference workspace (synchronous)
 int mlp_recurrent(lz_model *m, const RecIO &io, cudaStream_t s);

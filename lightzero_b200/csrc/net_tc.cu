@@ -36,20 +36,12 @@
 #include "net_tc.cuh"
 #include "tc_ptx.cuh"
 #include "tree.cuh"
+#include "tree_persist.cuh"
 
 namespace lz {
 
-// Build with -DLZ_UNIFORM_ISSUE (env LZ_UNIFORM_ISSUE=1 for lightzero_b200/_build.py) to issue the MMAs from uniform control
-// flow (all 32 lanes of the issuing warp run the loop, elect.sync picks the issuer).  NOT the default in round 1: the
-// measurement that motivates it (profiles/r01e_mma_probe.md) arrived when no GPU time was left to validate the kernel.
-#ifdef LZ_UNIFORM_ISSUE
-#define LZ_MMA_ISSUER_ON true
-#define LZ_UMMA umma_f16_elect
-#define LZ_UCOMMIT umma_commit_elect
-#else
-#define LZ_MMA_ISSUER_ON (lane == 0)
-#define LZ_UMMA umma_f16
-#define LZ_UCOMMIT umma_commit
+#ifndef LZ_FOLD
+#define LZ_FOLD 1      // see the MMA issuer (measured variants; the default is the fastest one on hardware)
 #endif
 
 // ---------------------------------------------------------------------------------------------- geometry
@@ -62,16 +54,19 @@ constexpr int kRowsAlloc = kMargin + kMaxTiles * 128 + kMargin;   // 400
 constexpr int kPlaneBytes = kRowsAlloc * 16;     // one k-group (8 fp16 channels) of all rows: 6400 B
 constexpr int kPartBytes = 8 * kPlaneBytes;      // 64 channels: 51200 B
 constexpr int kActBytes = 2 * kPartBytes;        // hi + lo: 102400 B
-constexpr int kTapBytes = 2 * 64 * 64 * 2;       // one 3x3 tap, hi + lo: 16384 B
+constexpr int kTapKgBytes = 128 * 16;            // one k-group (8 input channels) of a tap: 64 hi rows then 64 lo rows of 16 B
+constexpr int kTapBytes = 8 * kTapKgBytes;       // one 3x3 tap, [kg 8][co: 64 hi | 64 lo][ci % 8]: 16384 B
 constexpr int kStages = 4;
 constexpr int kHeadWBytes = 3 * 2 * 16 * 64 * 2; // three 1x1 heads (hc <= 16), hi + lo: 12288 B
-constexpr int kSmemMain = kActBytes + kStages * kTapBytes + kHeadWBytes + 1024;
-constexpr int kHeadScratch = (kMaxRoots * (576 + 32 + 608) + 8 * kMaxRoots * 32) * 4;   // one head: features, hidden, logits, partials
+constexpr int kBnSmemBytes = kTcMaxLayers * 128 * 4;   // folded BatchNorm tables of the program's layers
+constexpr int kSmemMain = kActBytes + kStages * kTapBytes + kHeadWBytes + 1024 + kBnSmemBytes;
+constexpr int kHeadScratch = (kMaxRoots * 577 + kMaxRoots * 608) * 4;   // reward head: features (parked from its hook to the end of the simulation) + logits
 constexpr int kSmemBytes = kSmemMain + kHeadScratch;
 
 // TMEM columns
-constexpr int kColAcc = 0;        // 3 tiles x 64
-constexpr int kColRes = 192;      // 3 tiles x 64  (ResBlock skip tensor, fp32)
+constexpr int kColAcc = 0;        // 3 tiles x 128: [0,64) = A_hi*B_hi + A_lo*B_hi, [64,128) = A_hi*B_lo (one N = 128 MMA)
+constexpr int kAccCols = 128;
+constexpr int kColVp = 0;         // 3 tiles x 32  (value + policy 1x1: reuses the drained accumulator columns of tile 0)
 constexpr int kColRew = 384;      // 3 tiles x 16  (reward 1x1)
 constexpr int kTmemCols = 512;
 
@@ -82,31 +77,26 @@ struct TcBars {
     uint64_t rew_ready;     // MMA -> heads: reward 1x1 accumulators complete (single phase)
     uint64_t vp_ready;      // MMA -> heads: value/policy 1x1 accumulators complete (single phase)
     uint32_t tmem_base;
-    uint32_t pad;
+    uint32_t fc_cnt[kStages];   // epilogue warps done with an FC weight block (the last one releases the ring stage)
 };
 
 // ---------------------------------------------------------------------------------------------- heads
-// 1x1-conv accumulators (TMEM) -> BN/ReLU features -> FC1 -> BN/ReLU -> FC2 -> softmax expectation -> h^-1 for the
-// heads in `hmask` (bit 0 reward, 1 value, 2 policy).  Executed by the kEpiThreads epilogue threads together
-// (named barrier 1).  scr: [nh][7][576] features | [nh][7][32] hidden | [nh][7][ldl] logits | [8][nh][7][32] partials.
-__device__ __forceinline__ void head_stage(const TcNet &net, const TcIO &io, int hmask, float *scr, uint32_t tmem, int NT,
-                                           int rows_used, int nvalid, int root0)
+// The fully connected parts of the heads (reward / value / policy: Linear(hc*36 -> hid) + BN + ReLU, Linear(hid -> K),
+// muzero_model.py:465-502, common.py:1130-1187) run on the CUDA cores at the END of a simulation, with their fp32 weights
+// STREAMED through the same shared-memory ring as the conv taps (16 KB blocks, cp.async.bulk by the producer warp): 375 KB of
+// weights per simulation arrive bandwidth-bound and prefetched instead of as latency-bound global loads from 256 threads.
+//   FC1 block = 128 input rows x 32 hidden units; lane = (root, 8-unit group), warp = 16 of the block's rows.
+//   FC2 block = 32 hidden units x 128 outputs;    thread = output k (tid % 128) x root group (tid / 128).
+constexpr int kHfStride = 577;                    // feature row stride (odd: the 7 roots of one input fall in 7 banks)
+constexpr int kLdK = 608;                         // categorical logits row stride (support size <= 608)
+
+// 1x1-conv accumulators (TMEM) -> BatchNorm + ReLU -> flattened features [root][c*36 + p] (stride kHfStride) for the heads in
+// hmask (bit 0 reward -> f_rew, bit 1 value / bit 2 policy -> f_vp[0 / 1]).  No barrier inside.
+__device__ __forceinline__ void head_scatter(const TcNet &net, int hmask, float *f_rew, float *f_vp, uint32_t tmem, int NT, int rows_used, int nvalid)
 {
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q4 = warp & 3, half = warp >> 2, rowid = q4 * 32 + lane;
     const uint32_t lane_base = tmem + ((uint32_t)(q4 * 32) << 16);
-    const int A = net.A, ldl = max(608, (A + 31) & ~31);
-    const int nh = __popc(hmask);
-    int slot[3];
-    slot[0] = 0; slot[1] = hmask & 1; slot[2] = (hmask & 1) + ((hmask >> 1) & 1);
-    float *hflat = scr, *hidden = hflat + nh * kMaxRoots * 576, *logits = hidden + nh * kMaxRoots * 32;
-    float *part = logits + nh * kMaxRoots * ldl;
-    // The scratch may overlay the activation buffer the epilogue has just written (value/policy stage).  Those writes are
-    // already ordered before this point through act_ready -> MMA issuer -> vp_ready, but an explicit barrier among the
-    // epilogue threads costs nothing and keeps compute-sanitizer's racecheck (which does not follow mbarriers) quiet.
-    asm volatile("bar.sync 1, %0;\n" ::"n"(kEpiThreads) : "memory");
-    for (int i = tid; i < nh * kMaxRoots * 576; i += kEpiThreads) hflat[i] = 0.0f;
-    asm volatile("bar.sync 1, %0;\n" ::"n"(kEpiThreads) : "memory");
     for (int t = 0; t < NT; ++t) {
         const int m = t * 128 + rowid;
         const int r = m / kRowsPerRoot, q = m - r * kRowsPerRoot, y = q / kPitch, x = q - y * kPitch;
@@ -118,111 +108,154 @@ __device__ __forceinline__ void head_stage(const TcNet &net, const TcIO &io, int
             tmem_ld16(lane_base + kColRew + t * 16, v);
             if (valid)
                 for (int c = 0; c < net.hc[0]; ++c)
-                    hflat[(slot[0] * kMaxRoots + r) * 576 + c * kP + p] = fmaxf(fmaf(v[c], __ldg(net.head_bn + c), __ldg(net.head_bn + 16 + c)), 0.0f);
+                    f_rew[r * kHfStride + c * kP + p] = fmaxf(fmaf(v[c], __ldg(net.head_bn + c), __ldg(net.head_bn + 16 + c)), 0.0f);
         }
         if (half == 0 && (hmask & 2)) {
-            tmem_ld16(lane_base + kColAcc + t * 32, v);
+            tmem_ld16(lane_base + kColVp + t * 32, v);
             if (valid)
                 for (int c = 0; c < net.hc[1]; ++c)
-                    hflat[(slot[1] * kMaxRoots + r) * 576 + c * kP + p] = fmaxf(fmaf(v[c], __ldg(net.head_bn + 32 + c), __ldg(net.head_bn + 48 + c)), 0.0f);
+                    f_vp[r * kHfStride + c * kP + p] = fmaxf(fmaf(v[c], __ldg(net.head_bn + 32 + c), __ldg(net.head_bn + 48 + c)), 0.0f);
         }
         if (half == 1 && (hmask & 4)) {
-            tmem_ld16(lane_base + kColAcc + t * 32 + 16, v);
+            tmem_ld16(lane_base + kColVp + t * 32 + 16, v);
             if (valid)
                 for (int c = 0; c < net.hc[2]; ++c)
-                    hflat[(slot[2] * kMaxRoots + r) * 576 + c * kP + p] = fmaxf(fmaf(v[c], __ldg(net.head_bn + 64 + c), __ldg(net.head_bn + 80 + c)), 0.0f);
+                    f_vp[(kMaxRoots + r) * kHfStride + c * kP + p] = fmaxf(fmaf(v[c], __ldg(net.head_bn + 64 + c), __ldg(net.head_bn + 80 + c)), 0.0f);
         }
     }
     tc_fence_before();
-    asm volatile("bar.sync 1, %0;\n" ::"n"(kEpiThreads) : "memory");
-    if (hmask == 1 && io.ez_feat) {
-        // EfficientZero (efficientzero_model.py:556-562): the flattened reward features feed an LSTM that is evaluated as
-        // one batched GEMM over all roots by the next kernel (ez.cu)
-        const int nin = net.hc[0] * kP;
-        for (int i = tid; i < nvalid * nin; i += kEpiThreads) {
-            const int r = i / nin, j = i - r * nin;
-            io.ez_feat[(size_t)(root0 + r) * nin + j] = hflat[r * 576 + j];
+}
+
+// the last of the 8 epilogue warps to finish with ring stage `st` hands it back to the producer
+__device__ __forceinline__ void fc_release_stage(TcBars *bars, int st)
+{
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) {
+        __threadfence_block();
+        if (atomicAdd(&bars->fc_cnt[st], 1u) == (unsigned)(kEpiWarps - 1)) {
+            bars->fc_cnt[st] = 0u;
+            mbar_arrive(&bars->empty[st]);
         }
-        return;
     }
-    // ---- FC1 (hc*36 -> hid): warp w takes an eighth of the inputs, lane = hidden unit; 24 coalesced weight rows in flight
-    for (int h = 0; h < 3; ++h) {
-        if (!((hmask >> h) & 1)) continue;
-        const Head &H = h == 0 ? net.reward : (h == 1 ? net.value : net.policy);
-        const int nin = H.hc * kP, qn = (nin + kEpiWarps - 1) / kEpiWarps, i0 = warp * qn, i1 = min(nin, i0 + qn);
-        float a[kMaxRoots];
+}
+
+// FC1 -> BN/ReLU -> FC2 -> softmax expectation -> h^-1 for the heads in hmask, weights from the ring (hn: this simulation's
+// position in the ring sequence, advanced per block).  f_rew / f_vp: features from head_scatter; wk: >= kFcWorkFloats floats of
+// scratch; lg_rew: [7][kLdK] (outside wk: it may live next to f_rew).  Executed by the kEpiThreads epilogue threads together.
+constexpr int kFcPart = kEpiWarps * 3 * kMaxRoots * 32;        // FC1 partial sums [warp][head][root][32]
+constexpr int kFcHidT = 3 * 32 * 8;                             // hidden activations, transposed [head][unit][8 roots]
+__device__ __forceinline__ void heads_fc(const TcNet &net, const TcIO &io, int hmask, unsigned char *ring, TcBars *bars, uint32_t &hn,
+                                         const float *f_rew, const float *f_vp, float *wk, float *lg_rew, int nvalid, int root0,
+                                         unsigned long long *dbg)
+{
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int A = net.A, ldp = (A + 31) & ~31;
+    float *part = wk, *hidT = part + kFcPart, *lg_val = hidT + kFcHidT, *lg_pol = lg_val + kMaxRoots * kLdK;
+    // ---- FC1: lane = (root, group of 8 hidden units); warp w takes rows [16 w, 16 w + 16) of every 128-row block
+    {
+        const int r_l = min(lane >> 2, kMaxRoots - 1), jq = lane & 3;
+        for (int h = 0; h < 3; ++h) {
+            if (!((hmask >> h) & 1)) continue;
+            const int nin = net.fc[h].nin, nblk = (nin + 127) >> 7;
+            const float *hf = (h == 0 ? f_rew : f_vp + (h - 1) * kMaxRoots * kHfStride) + r_l * kHfStride;
+            float a[8];
 #pragma unroll
-        for (int r = 0; r < kMaxRoots; ++r) a[r] = 0.0f;
-        const float *hf = hflat + slot[h] * kMaxRoots * 576;
-        const float *wp = H.fc1 + lane;
-        const bool lane_on = lane < H.hid;
-        for (int i = i0; i < i1; i += 24) {
-            float w[24];
+            for (int k = 0; k < 8; ++k) a[k] = 0.0f;
+            for (int blk = 0; blk < nblk; ++blk, ++hn) {
+                const int st = hn % kStages;
+                const long long tw0 = dbg ? clock64() : 0;
+                mbar_wait_converged(&bars->full[st], (hn / kStages) & 1);
+                if (dbg) dbg[54] += (unsigned long long)(clock64() - tw0);      // FC1 ring waits of warp 0
+                const float *w = reinterpret_cast<const float *>(ring + st * kTapBytes) + (warp * 16) * 32 + jq * 8;
+                const int ii0 = blk * 128 + warp * 16;
 #pragma unroll
-            for (int u = 0; u < 24; ++u) w[u] = (lane_on && i + u < i1) ? __ldg(wp + (size_t)(i + u) * H.hid) : 0.0f;
-#pragma unroll
-            for (int u = 0; u < 24; ++u) {
-                const int ii = min(i + u, nin - 1);
-#pragma unroll
-                for (int r = 0; r < kMaxRoots; ++r) a[r] = fmaf(hf[r * 576 + ii], w[u], a[r]);
+                for (int i = 0; i < 16; ++i) {
+                    if (ii0 + i < nin) {
+                        const float f = hf[ii0 + i];
+                        const float4 w0 = *reinterpret_cast<const float4 *>(w + i * 32);
+                        const float4 w1 = *reinterpret_cast<const float4 *>(w + i * 32 + 4);
+                        a[0] = fmaf(f, w0.x, a[0]); a[1] = fmaf(f, w0.y, a[1]); a[2] = fmaf(f, w0.z, a[2]); a[3] = fmaf(f, w0.w, a[3]);
+                        a[4] = fmaf(f, w1.x, a[4]); a[5] = fmaf(f, w1.y, a[5]); a[6] = fmaf(f, w1.z, a[6]); a[7] = fmaf(f, w1.w, a[7]);
+                    }
+                }
+                fc_release_stage(bars, st);
+            }
+            if ((lane >> 2) < kMaxRoots) {
+                float *dst = part + ((warp * 3 + h) * kMaxRoots + r_l) * 32 + jq * 8;
+                *reinterpret_cast<float4 *>(dst) = make_float4(a[0], a[1], a[2], a[3]);
+                *reinterpret_cast<float4 *>(dst + 4) = make_float4(a[4], a[5], a[6], a[7]);
             }
         }
-#pragma unroll
-        for (int r = 0; r < kMaxRoots; ++r) part[((warp * nh + slot[h]) * kMaxRoots + r) * 32 + lane] = a[r];
     }
     asm volatile("bar.sync 1, %0;\n" ::"n"(kEpiThreads) : "memory");
-    for (int o = tid; o < nh * kMaxRoots * 32; o += kEpiThreads) {
-        const int sl = o / (kMaxRoots * 32), j = o & 31;
-        const int h = (sl == slot[0] && (hmask & 1)) ? 0 : ((sl == slot[1] && (hmask & 2)) ? 1 : 2);
+    if (dbg) dbg[45] = clock64();
+    // ---- hidden = ReLU(BN(sum of the 8 warps' partials)), stored transposed for FC2
+    for (int o = tid; o < 3 * kMaxRoots * 32; o += kEpiThreads) {
+        const int h = o / (kMaxRoots * 32), r = (o >> 5) % kMaxRoots, j = o & 31;
+        if (!((hmask >> h) & 1)) continue;
         const Head &H = h == 0 ? net.reward : (h == 1 ? net.value : net.policy);
         float v = 0.0f;
 #pragma unroll
-        for (int w8 = 0; w8 < kEpiWarps; ++w8) v += part[o + w8 * nh * kMaxRoots * 32];
-        hidden[o] = (j < H.hid) ? fmaxf(fmaf(v, __ldg(H.s2 + j), __ldg(H.t2 + j)), 0.0f) : 0.0f;
+        for (int w8 = 0; w8 < kEpiWarps; ++w8) v += part[((w8 * 3 + h) * kMaxRoots + r) * 32 + j];
+        hidT[(h * 32 + j) * 8 + r] = (j < H.hid) ? fmaxf(fmaf(v, __ldg(H.s2 + j), __ldg(H.t2 + j)), 0.0f) : 0.0f;
     }
     asm volatile("bar.sync 1, %0;\n" ::"n"(kEpiThreads) : "memory");
-    // ---- FC2 (hid -> K): thread = output k, weights [j][K] coalesced over k, all 32 rows in flight
-    for (int h = 0; h < 3; ++h) {
-        if (!((hmask >> h) & 1)) continue;
-        const Head &H = h == 0 ? net.reward : (h == 1 ? net.value : net.policy);
-        float *lg = logits + slot[h] * kMaxRoots * ldl;
-        const float *hid = hidden + slot[h] * kMaxRoots * 32;
-        for (int k = tid; k < H.K; k += kEpiThreads) {
-            float o[kMaxRoots];
-            const float bias = __ldg(H.b2 + k);
+    if (dbg) dbg[46] = clock64();
+    // ---- FC2: thread = (output k of the 128-output block, root group g)
+    {
+        const int kl = tid & 127, g = tid >> 7;
+        for (int h = 0; h < 3; ++h) {
+            if (!((hmask >> h) & 1)) continue;
+            const Head &H = h == 0 ? net.reward : (h == 1 ? net.value : net.policy);
+            const int K = H.K, nblk = (K + 127) >> 7;
+            float *lg = h == 0 ? lg_rew : (h == 1 ? lg_val : lg_pol);
+            const int ld = h == 2 ? ldp : kLdK;
+            for (int blk = 0; blk < nblk; ++blk, ++hn) {
+                const int st = hn % kStages;
+                const int k = blk * 128 + kl;
+                const float bias = (k < K) ? __ldg(H.b2 + k) : 0.0f;
+                const long long tw0 = dbg ? clock64() : 0;
+                mbar_wait_converged(&bars->full[st], (hn / kStages) & 1);
+                if (dbg) dbg[55] += (unsigned long long)(clock64() - tw0);      // FC2 ring waits of warp 0
+                const float *w = reinterpret_cast<const float *>(ring + st * kTapBytes) + kl;
+                const float *hq = hidT + h * 32 * 8 + g * 4;
+                float o0 = bias, o1 = bias, o2 = bias, o3 = bias;
 #pragma unroll
-            for (int r = 0; r < kMaxRoots; ++r) o[r] = bias;
-            float w[32];
-#pragma unroll
-            for (int u = 0; u < 32; ++u) w[u] = (u < H.hid) ? __ldg(H.fc2 + (size_t)u * H.K + k) : 0.0f;
-#pragma unroll
-            for (int u = 0; u < 32; ++u) {
-#pragma unroll
-                for (int r = 0; r < kMaxRoots; ++r) o[r] = fmaf(hid[r * 32 + u], w[u], o[r]);
+                for (int u = 0; u < 32; ++u) {
+                    const float wv = w[u * 128];
+                    const float4 hv = *reinterpret_cast<const float4 *>(hq + u * 8);
+                    o0 = fmaf(hv.x, wv, o0); o1 = fmaf(hv.y, wv, o1); o2 = fmaf(hv.z, wv, o2); o3 = fmaf(hv.w, wv, o3);
+                }
+                if (k < K) {
+                    float *d = lg + (g * 4) * ld + k;
+                    d[0] = o0; d[ld] = o1; d[2 * ld] = o2;
+                    if (g == 0) d[3 * ld] = o3;
+                }
+                fc_release_stage(bars, st);
             }
-#pragma unroll
-            for (int r = 0; r < kMaxRoots; ++r) lg[r * ldl + k] = o[r];
         }
     }
     asm volatile("bar.sync 1, %0;\n" ::"n"(kEpiThreads) : "memory");
+    if (dbg) dbg[47] = clock64();
     // ---- softmax expectation + inverse transform: one warp per (categorical head, root)
     for (int task = warp; task < 2 * kMaxRoots; task += kEpiWarps) {
         const int h = task / kMaxRoots, r = task - h * kMaxRoots;       // h: 0 reward, 1 value (+ policy copy)
         if (r >= nvalid || !((hmask >> h) & 1)) continue;
         const int b = root0 + r;
-        const float *lg = logits + (slot[h] * kMaxRoots + r) * ldl;
         if (h == 0) {
+            const float *lg = lg_rew + r * kLdK;
             const float rv = categorical_to_scalar(lg, net.reward.K, net.support_min, net.support_step, lane);
             if (lane == 0 && io.reward) io.reward[b] = rv;
             if (io.reward_logits)
                 for (int k = lane; k < net.reward.K; k += 32) io.reward_logits[(size_t)b * net.reward.K + k] = lg[k];
         } else {
+            const float *lg = lg_val + r * kLdK;
             const float vv = categorical_to_scalar(lg, net.value.K, net.support_min, net.support_step, lane);
             if (lane == 0 && io.value) io.value[b] = vv;
             if (io.value_logits)
                 for (int k = lane; k < net.value.K; k += 32) io.value_logits[(size_t)b * net.value.K + k] = lg[k];
             if (io.policy_logits && (hmask & 4)) {
-                const float *lp = logits + (slot[2] * kMaxRoots + r) * ldl;
+                const float *lp = lg_pol + r * ldp;
                 for (int a = lane; a < A; a += 32) io.policy_logits[(size_t)b * A + a] = lp[a];
             }
         }
@@ -230,15 +263,48 @@ __device__ __forceinline__ void head_stage(const TcNet &net, const TcIO &io, int
 }
 
 // ---------------------------------------------------------------------------------------------- kernel
+// 32 consecutive channels [32*half, 32*half+32) of pixel p of one root latent.  cl: channels-last [36][64] (the pool slots this
+// kernel writes in persistent mode, and the skip scratch); else NCHW [64][36] (every tensor that crosses the API).
+__device__ __forceinline__ void load_row32(const float *root, bool cl, int p, int half, float (&v)[32])
+{
+    if (cl) {
+        const float4 *src = reinterpret_cast<const float4 *>(root + p * kC + half * 32);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float4 q = src[j];      // plain loads: the pool / scratch are written by this launch
+            v[4 * j] = q.x; v[4 * j + 1] = q.y; v[4 * j + 2] = q.z; v[4 * j + 3] = q.w;
+        }
+    } else {
+        const float *src = root + (size_t)(half * 32) * kP + p;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) v[c] = src[(size_t)c * kP];
+    }
+}
+__device__ __forceinline__ void store_row32(float *root, bool cl, int p, int half, const float (&v)[32])
+{
+    if (cl) {
+        float4 *dst = reinterpret_cast<float4 *>(root + p * kC + half * 32);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    } else {
+        float *dst = root + (size_t)(half * 32) * kP + p;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) dst[(size_t)c * kP] = v[c];
+    }
+}
+
 __global__ void __launch_bounds__(kTcThreads, 1) k_net_tc(TcNet net, TcIO io, TreeParams tp)
 {
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char *act = smem;                                   // [2 parts][8 planes][400 rows][16 B]
-    unsigned char *ring = smem + kActBytes;                      // [kStages][hi 8 KB | lo 8 KB]
+    unsigned char *ring = smem + kActBytes;                      // [kStages][8 k-groups][128 rows: 64 hi | 64 lo][16 B]
     unsigned char *headw = ring + kStages * kTapBytes;           // [3 heads][hi 2 KB | lo 2 KB]
     TcBars *bars = reinterpret_cast<TcBars *>(headw + kHeadWBytes);
+    float *bn_s = reinterpret_cast<float *>(headw + kHeadWBytes + 1024);   // [nlayers][scale 64 | shift 64]
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // warp index as a warp-UNIFORM value (shuffle broadcast): the role branches below become uniform branches, so ptxas keeps the
+    // MMA issuer's descriptors in uniform registers instead of moving every operand through R2UR per tcgen05.mma
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
     const int R = io.roots_per_cta;
     const int root0 = blockIdx.x * R;
     const int nvalid = min(R, io.B - root0);                     // roots of this CTA that exist
@@ -257,24 +323,41 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_net_tc(TcNet net, TcIO io, Tr
         mbar_init(&bars->act_ready, kEpiThreads);
         mbar_init(&bars->rew_ready, 1);
         mbar_init(&bars->vp_ready, 1);
+        for (int i = 0; i < kStages; ++i) bars->fc_cnt[i] = 0u;
         fence_mbar_init();
     }
+    // heads whose fully connected parts run in this kernel (EfficientZero: the reward features go to the LSTM kernels instead),
+    // and the number of 16 KB weight blocks they stream through the ring per simulation, after the conv taps
+    const int hmask_fc = ((net.has_reward && !io.ez_feat) ? 1 : 0) | 6;
+    int nfc = 0;
+    for (int h = 0; h < 3; ++h)
+        if ((hmask_fc >> h) & 1) nfc += ((net.fc[h].nin + 127) >> 7) + ((net.fc[h].K + 127) >> 7);
     if (warp == kEpiWarps + 1) tmem_alloc(&bars->tmem_base, kTmemCols);
-    // 1x1 head weights: plain copy (12 KB)
+    // 1x1 head weights (12 KB) and the folded BatchNorm tables of this program's layers: plain copies
     for (int i = tid; i < kHeadWBytes / 16; i += kTcThreads)
         reinterpret_cast<uint4 *>(headw)[i] = __ldg(reinterpret_cast<const uint4 *>(net.headw) + i);
+    for (int i = tid; i < nlayers * 128; i += kTcThreads)
+        bn_s[i] = __ldg(net.bn + (size_t)net.layer_w[i >> 7] * 128 + (i & 127));
+    // persistent search: the exploration-rate table of the PUCT rule next to them when it fits (else it is read from global)
+    const bool fast_tree = persistent && tp.A <= 32 && !io.generic_tree;
+    const float *pbc_tab = tp.pbc;
+    if (fast_tree && (nlayers * 128 + tp.N + 1) * 4 <= kBnSmemBytes) {
+        float *pbc_s = bn_s + nlayers * 128;
+        for (int i = tid; i <= tp.N; i += kTcThreads) pbc_s[i] = tp.pbc[i];
+        pbc_tab = pbc_s;
+    }
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = bars->tmem_base;
+    const uint32_t tmem = __shfl_sync(0xffffffffu, bars->tmem_base, 0);      // uniform as well
 
     if (warp == kEpiWarps) {
         // ================= weight producer =================
         if (lane == 0) {
             uint32_t n = 0;
-            for (int sim = 0; sim < nsims; ++sim)       // runs ahead of the MMAs: the next simulation's first taps are
-                for (int L = 0; L < nlayers; ++L) {     // already in the ring while heads / tree work is going on
+            for (int sim = 0; sim < nsims; ++sim) {     // runs ahead of the consumers: the next simulation's first taps are
+                for (int L = 0; L < nlayers; ++L) {     // already in the ring while the tree work is going on
                     const unsigned char *src = net.convw + (size_t)net.layer_w[L] * (9 * kTapBytes);
                     for (int tap = 0; tap < 9; ++tap, ++n) {
                         const int st = n % kStages;
@@ -283,79 +366,130 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_net_tc(TcNet net, TcIO io, Tr
                         bulk_g2s(ring + st * kTapBytes, src + (size_t)tap * kTapBytes, kTapBytes, &bars->full[st]);
                     }
                 }
-        }
-    } else if (warp == kEpiWarps + 1) {
-        // ================= MMA issuer =================
-        if (LZ_MMA_ISSUER_ON) {
-            const uint32_t act_s = smem_u32(act), ring_s = smem_u32(ring), headw_s = smem_u32(headw);
-            const uint32_t idesc64 = make_idesc_f16(128, 64), idesc16 = make_idesc_f16(128, 16), idesc32 = make_idesc_f16(128, 32);
-            const bool sw = false;
-            const uint32_t a_lbo = kPlaneBytes >> 4, a_sbo = 8;
-            const uint64_t a_desc0 = make_desc(act_s + kMargin * 16, a_lbo, a_sbo);   // row 0, hi part, k-step 0
-            const uint64_t b_desc0 = make_desc(ring_s, 64, 8);                        // stage 0, hi part, k-step 0
-            unsigned long long *dbg = (io.dbg && blockIdx.x == 0) ? io.dbg : nullptr;
-            uint32_t n = 0;
-            for (int sim = 0; sim < nsims; ++sim)
-            for (int L = 0; L < nlayers; ++L) {
-                const uint32_t ev = (uint32_t)sim * (nlayers + 1) + L;   // act_ready event index: 1 load + nlayers epilogues per simulation
-                mbar_wait(&bars->act_ready, ev & 1);             // inputs written, TMEM accumulators drained
-                tc_fence_after();
-                if (dbg && sim == 0) dbg[32 + 2 * L] = clock64();
-                for (int tap = 0; tap < 9; ++tap, ++n) {
-                    const int st = n % kStages;
-                    mbar_wait(&bars->full[st], (n / kStages) & 1);
-                    tc_fence_after();
-                    const int shift = (tap / 3 - 1) * kPitch + (tap % 3 - 1);
-                    // descriptors differ only in the 14-bit start-address field: add 16-byte-unit offsets to a base
-                    const uint64_t b0 = b_desc0 + (uint64_t)((st * kTapBytes) >> 4);
-                    for (int t = 0; t < NT; ++t) {
-                        const uint64_t a0 = a_desc0 + (uint64_t)(t * 128 + shift);
-                        const uint32_t d = tmem + kColAcc + t * 64;
-#pragma unroll
-                        for (int ks = 0; ks < 4; ++ks)
-                            LZ_UMMA(d, a0 + ks * (2 * kPlaneBytes >> 4), b0 + ks * (2048 >> 4), idesc64, (tap | ks) != 0);
-                        if (npass == 3) {
-#pragma unroll
-                            for (int ks = 0; ks < 4; ++ks)      // A_hi * B_lo
-                                LZ_UMMA(d, a0 + ks * (2 * kPlaneBytes >> 4), b0 + ((kTapBytes / 2) >> 4) + ks * (2048 >> 4), idesc64, 1);
-#pragma unroll
-                            for (int ks = 0; ks < 4; ++ks)      // A_lo * B_hi
-                                LZ_UMMA(d, a0 + (kPartBytes >> 4) + ks * (2 * kPlaneBytes >> 4), b0 + ks * (2048 >> 4), idesc64, 1);
+                // the heads' FC1 blocks ([128 inputs][32 units] fp32), then their FC2 blocks ([32 units][128 outputs]), in the
+                // order heads_fc consumes them
+                for (int pass = 0; pass < 2; ++pass)
+                    for (int h = 0; h < 3; ++h) {
+                        if (!((hmask_fc >> h) & 1)) continue;
+                        const int nblk = pass == 0 ? ((net.fc[h].nin + 127) >> 7) : ((net.fc[h].K + 127) >> 7);
+                        const unsigned char *src = net.fcw + (pass == 0 ? net.fc[h].fc1_off : net.fc[h].fc2_off);
+                        for (int blk = 0; blk < nblk; ++blk, ++n) {
+                            const int st = n % kStages;
+                            const uint32_t bytes = pass == 0 ? (uint32_t)min(kTapBytes, net.fc[h].nin * 128 - blk * kTapBytes) : (uint32_t)kTapBytes;
+                            if (n >= kStages) mbar_wait(&bars->empty[st], ((n / kStages) - 1) & 1);
+                            mbar_expect_tx(&bars->full[st], bytes);
+                            bulk_g2s(ring + st * kTapBytes, src + (size_t)blk * kTapBytes, bytes, &bars->full[st]);
                         }
                     }
-                    LZ_UCOMMIT(&bars->empty[st]);               // frees this ring slot when the MMAs have read it
-                }
-                LZ_UCOMMIT(&bars->acc_ready);
-                if (dbg && sim == 0) dbg[33 + 2 * L] = clock64();
-                const int flags = net.layer_flags[L];
-                if (flags & (LF_HOOK_REWARD | LF_HOOK_VALPOL)) {
-                    // 1x1 head convolutions on this layer's OUTPUT: wait for the epilogue to have written it (the same
-                    // phase the next layer waits for; waiting twice on a completed phase is immediate).  The
-                    // value/policy result reuses the drained conv accumulator columns, so that hook is only legal on
-                    // the LAST layer; the reward result has its own columns.
-                    mbar_wait(&bars->act_ready, (ev + 1) & 1);
-                    tc_fence_after();
-                    for (int hook = 0; hook < 2; ++hook) {
-                        if (!(flags & (hook == 0 ? LF_HOOK_REWARD : LF_HOOK_VALPOL))) continue;
-                        for (int t = 0; t < NT; ++t) {
-                            const uint32_t arow = act_s + (uint32_t)(kMargin + t * 128) * 16u;
-                            for (int ps = 0; ps < npass; ++ps) {
-                                const uint32_t apart = (ps == 2) ? kPartBytes : 0;
+            }
+        }
+    } else if (warp == kEpiWarps + 1) {
+        // ================= MMA issuer: the whole warp runs the loops (uniform control flow), one elected lane issues =================
+        const uint32_t act_s = smem_u32(act), ring_s = smem_u32(ring), headw_s = smem_u32(headw);
+        const uint32_t idesc128 = make_idesc_f16(128, 128), idesc64 = make_idesc_f16(128, 64);
+        const uint32_t idesc16 = make_idesc_f16(128, 16), idesc32 = make_idesc_f16(128, 32);
+        const uint32_t a_lbo = kPlaneBytes >> 4, a_sbo = 8;
+        const uint64_t a_desc0 = make_desc(act_s + kMargin * 16, a_lbo, a_sbo);   // row 0, hi part, k-step 0
+        const uint64_t b_desc0 = make_desc(ring_s, kTapKgBytes >> 4, 8);          // stage 0, k-group 0: rows 0-63 hi, 64-127 lo
+        unsigned long long *dbg = (io.dbg && blockIdx.x == 0) ? io.dbg : nullptr;
+        uint32_t n = 0;
+        for (int sim = 0; sim < nsims; ++sim, n += nfc)     // the ring stages after the conv taps carry the heads' FC weights
+        for (int L = 0; L < nlayers; ++L) {
+            const uint32_t ev = (uint32_t)sim * (nlayers + 1) + L;   // act_ready event index: 1 load + nlayers epilogues per simulation
+            mbar_wait_converged(&bars->act_ready, ev & 1);       // inputs written, TMEM accumulators drained
+            tc_fence_after();
+            if (dbg) dbg[32 + 2 * L] = clock64();
+            for (int tap = 0; tap < 9; ++tap, ++n) {
+                const int st = n % kStages;
+                const long long tw0 = dbg ? clock64() : 0;
+                mbar_wait_converged(&bars->full[st], (n / kStages) & 1);
+                if (dbg) dbg[52 + (L == 0 && tap == 0 ? 1 : 0)] += (unsigned long long)(clock64() - tw0);   // [52] ring waits, [53] first tap of a simulation
+                tc_fence_after();
+                const int shift = (tap / 3 - 1) * kPitch + (tap % 3 - 1);
+                // descriptors differ only in the 14-bit start-address field: add 16-byte-unit offsets to a base
+                const uint64_t b0 = b_desc0 + (uint64_t)((st * kTapBytes) >> 4);
+                // fp32-accurate mode, per (tile, tap, k-step): A_hi x B_hi + A_hi x B_lo + A_lo x B_hi.  LZ_FOLD selects how they are
+                // issued (the tap block holds [B_hi | B_lo] as 128 operand rows, so A_hi x [B_hi | B_lo] can be ONE N = 128 MMA):
+                //   0  three N = 64 MMAs into the same 64 columns
+                //   1  N = 128 (A_hi) then N = 64 (A_lo x B_hi into columns 0-63), tile by tile
+                //   2  N = 128 (A_hi) then N = 128 (A_lo x [B_hi | B_lo]; the extra lo x lo term is harmless), tile by tile
+                //   3  as 1, but all tiles' N = 128 MMAs of the tap first, then all tiles' N = 64 MMAs
+                const uint32_t kA = (2 * kPlaneBytes) >> 4, kB = (2 * kTapKgBytes) >> 4, kLo = kPartBytes >> 4, kBlo = (64 * 16) >> 4;
+                if (npass != 3) {
+                    for (int t = 0; t < NT; ++t) {
+                        const uint64_t a0 = a_desc0 + (uint64_t)(t * 128 + shift);
+                        const uint32_t d = tmem + kColAcc + t * kAccCols;
 #pragma unroll
-                                for (int ks = 0; ks < 4; ++ks) {
-                                    const uint64_t ad = make_desc(arow + apart + ks * 2 * kPlaneBytes, a_lbo, a_sbo);
-                                    if (hook == 0) {   // reward head: N = 16, [kg][16 co][8]
-                                        const uint32_t wb = headw_s + ((ps == 1) ? 2048 : 0);
-                                        LZ_UMMA(tmem + kColRew + t * 16, ad, make_desc(wb + ks * 512, sw ? 8 : 16, sw ? 16 : 8), idesc16, (ps | ks) != 0);
-                                    } else {           // value + policy heads as one N = 32 matrix, [kg][32 co][8]
-                                        const uint32_t wb = headw_s + 4096 + ((ps == 1) ? 4096 : 0);
-                                        LZ_UMMA(tmem + kColAcc + t * 32, ad, make_desc(wb + ks * 1024, sw ? 8 : 32, sw ? 32 : 8), idesc32, (ps | ks) != 0);
-                                    }
+                        for (int ks = 0; ks < 4; ++ks) umma_f16_elect(d, a0 + ks * kA, b0 + ks * kB, idesc64, (tap | ks) != 0);
+                    }
+                } else {
+#if LZ_FOLD == 0
+                    for (int t = 0; t < NT; ++t) {
+                        const uint64_t a0 = a_desc0 + (uint64_t)(t * 128 + shift);
+                        const uint32_t d = tmem + kColAcc + t * kAccCols;
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks) umma_f16_elect(d, a0 + ks * kA, b0 + ks * kB, idesc64, (tap | ks) != 0);
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks) umma_f16_elect(d, a0 + ks * kA, b0 + kBlo + ks * kB, idesc64, 1);
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks) umma_f16_elect(d, a0 + kLo + ks * kA, b0 + ks * kB, idesc64, 1);
+                    }
+#elif LZ_FOLD == 3
+                    for (int t = 0; t < NT; ++t) {
+                        const uint64_t a0 = a_desc0 + (uint64_t)(t * 128 + shift);
+                        const uint32_t d = tmem + kColAcc + t * kAccCols;
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks) umma_f16_elect(d, a0 + ks * kA, b0 + ks * kB, idesc128, (tap | ks) != 0);
+                    }
+                    for (int t = 0; t < NT; ++t) {
+                        const uint64_t a0 = a_desc0 + (uint64_t)(t * 128 + shift);
+                        const uint32_t d = tmem + kColAcc + t * kAccCols;
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks) umma_f16_elect(d, a0 + kLo + ks * kA, b0 + ks * kB, idesc64, 1);
+                    }
+#else
+                    for (int t = 0; t < NT; ++t) {
+                        const uint64_t a0 = a_desc0 + (uint64_t)(t * 128 + shift);
+                        const uint32_t d = tmem + kColAcc + t * kAccCols;
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks) umma_f16_elect(d, a0 + ks * kA, b0 + ks * kB, idesc128, (tap | ks) != 0);
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks) umma_f16_elect(d, a0 + kLo + ks * kA, b0 + ks * kB, LZ_FOLD == 2 ? idesc128 : idesc64, 1);
+                    }
+#endif
+                }
+                umma_commit_elect(&bars->empty[st]);               // frees this ring slot when the MMAs have read it
+            }
+            umma_commit_elect(&bars->acc_ready);
+            if (dbg) dbg[33 + 2 * L] = clock64();
+            const int flags = net.layer_flags[L];
+            if (flags & (LF_HOOK_REWARD | LF_HOOK_VALPOL)) {
+                // 1x1 head convolutions on this layer's OUTPUT: wait for the epilogue to have written it (the same
+                // phase the next layer waits for; waiting twice on a completed phase is immediate).  The
+                // value/policy result reuses the drained conv accumulator columns, so that hook is only legal on
+                // the LAST layer; the reward result has its own columns.
+                mbar_wait_converged(&bars->act_ready, (ev + 1) & 1);
+                tc_fence_after();
+                for (int hook = 0; hook < 2; ++hook) {
+                    if (!(flags & (hook == 0 ? LF_HOOK_REWARD : LF_HOOK_VALPOL))) continue;
+                    for (int t = 0; t < NT; ++t) {
+                        const uint32_t arow = act_s + (uint32_t)(kMargin + t * 128) * 16u;
+                        for (int ps = 0; ps < npass; ++ps) {
+                            const uint32_t apart = (ps == 2) ? kPartBytes : 0;
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks) {
+                                const uint64_t ad = make_desc(arow + apart + ks * 2 * kPlaneBytes, a_lbo, a_sbo);
+                                if (hook == 0) {   // reward head: N = 16, [kg][16 co][8]
+                                    const uint32_t wb = headw_s + ((ps == 1) ? 2048 : 0);
+                                    umma_f16_elect(tmem + kColRew + t * 16, ad, make_desc(wb + ks * 512, 16, 8), idesc16, (ps | ks) != 0);
+                                } else {           // value + policy heads as one N = 32 matrix, [kg][32 co][8]
+                                    const uint32_t wb = headw_s + 4096 + ((ps == 1) ? 4096 : 0);
+                                    umma_f16_elect(tmem + kColVp + t * 32, ad, make_desc(wb + ks * 1024, 32, 8), idesc32, (ps | ks) != 0);
                                 }
                             }
                         }
-                        LZ_UCOMMIT(hook == 0 ? &bars->rew_ready : &bars->vp_ready);
                     }
+                    umma_commit_elect(hook == 0 ? &bars->rew_ready : &bars->vp_ready);
                 }
             }
         }
@@ -363,23 +497,34 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_net_tc(TcNet net, TcIO io, Tr
         // ================= epilogue warps: warp w owns TMEM lanes 32*(w%4).. and the 32-column half w/4 =================
         const int q4 = warp & 3, half = warp >> 2, rowid = q4 * 32 + lane;
         const uint32_t lane_base = tmem + ((uint32_t)(q4 * 32) << 16);
+        float *f_rew = reinterpret_cast<float *>(smem + kSmemMain);      // reward features [7][kHfStride], then reward logits [7][kLdK]
         unsigned long long *dbg = (io.dbg && blockIdx.x == 0 && tid == 0) ? io.dbg : nullptr;
         if (dbg) dbg[0] = clock64();
         pdl_wait();                   // ix / action / the latent pool come from the preceding kernels
         int acc_par = 0;
+        PTree T;                      // this warp's tree (tree_persist.cuh): per-tree scalars stay in registers across simulations
+        if (fast_tree && warp < nvalid) ptree_init(tp, T, root0 + warp, lane);
         for (int sim = 0; sim < nsims; ++sim) {
+            if (dbg) dbg[50] = clock64();
             if (persistent) {
                 // ---- tree phase: one warp per root of this CTA (roots never interact, so the whole search of these roots
                 // lives in this CTA): back up the previous simulation, then descend to the next leaf.  cnode.cpp:480-500,754-825
                 if (warp < nvalid) {
                     const int b = root0 + warp;
-                    if (sim > 0)
-                        tree_backprop(tp, b, lane, io.sim0 + sim, io.reward[b], io.value[b], io.policy_logits + (size_t)b * net.A, nullptr);
-                    tree_traverse(tp, b, lane, io.deterministic, (unsigned)(io.sim0 + sim), io.ix_rw, nullptr, io.action_rw, nullptr, nullptr);
+                    if (fast_tree) {
+                        if (sim > 0)
+                            ptree_backprop(tp, T, b, lane, io.sim0 + sim, io.reward[b], io.value[b], io.policy_logits + (size_t)b * net.A);
+                        ptree_traverse(tp, T, b, lane, io.deterministic, (unsigned)(io.sim0 + sim), pbc_tab, io.ix_rw, io.action_rw);
+                    } else {
+                        if (sim > 0)
+                            tree_backprop(tp, b, lane, io.sim0 + sim, io.reward[b], io.value[b], io.policy_logits + (size_t)b * net.A, nullptr);
+                        tree_traverse(tp, b, lane, io.deterministic, (unsigned)(io.sim0 + sim), io.ix_rw, nullptr, io.action_rw, nullptr, nullptr);
+                    }
                 }
                 __threadfence_block();
                 asm volatile("bar.sync 1, %0;\n" ::"n"(kEpiThreads) : "memory");
             }
+            if (dbg) dbg[51] = clock64();
             float *latent_out = persistent ? (io.latent_pool_rw + (size_t)(io.sim0 + sim + 1) * io.slot_stride) : io.latent_out;
             // zero the margins (the head scratch of the previous simulation overlays them; pad rows inside the tiles are
             // rewritten as zeros by every load / epilogue)
@@ -388,115 +533,168 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_net_tc(TcNet net, TcIO io, Tr
                 int row = r < kMargin ? r : kMargin + kMaxTiles * 128 + (r - kMargin);
                 *reinterpret_cast<uint4 *>(act + part * kPartBytes + plane * kPlaneBytes + row * 16) = make_uint4(0, 0, 0, 0);
             }
-            // ---- load the input activation: gather NCHW latents, split to fp16 hi/lo, park fp32 copy in TMEM ----
-            for (int t = 0; t < NT; ++t) {
+            // per-tile row bookkeeping of this thread: root, pixel, validity; the input latent of the row's root
+            const float *in_root[kMaxTiles];
+            bool in_cl[kMaxTiles];
+            int rowp[kMaxTiles], rowb[kMaxTiles];       // pixel (or -1: pad / unused row), global root index
+#pragma unroll
+            for (int t = 0; t < kMaxTiles; ++t) {
                 const int m = t * 128 + rowid;
                 const int r = m / kRowsPerRoot, q = m - r * kRowsPerRoot, y = q / kPitch, x = q - y * kPitch;
-                const bool valid = (m < rows_used) && (r < nvalid) && (y < 6) && (x < 6);
-                const float *src = nullptr;
+                const bool valid = (t < NT) && (m < rows_used) && (r < nvalid) && (y < 6) && (x < 6);
+                rowp[t] = valid ? y * 6 + x : -1;
+                rowb[t] = root0 + r;
+                in_root[t] = nullptr; in_cl[t] = false;
                 if (valid) {
-                    const int b = root0 + r;
-                    const size_t slot = io.ix ? (size_t)io.ix[b] : 0;
-                    src = io.latent_base + slot * io.slot_stride + (size_t)b * (kC * kP) + (y * 6 + x);
+                    const size_t slot = io.ix ? (size_t)io.ix[rowb[t]] : 0;
+                    in_root[t] = io.latent_base + slot * io.slot_stride + (size_t)rowb[t] * (kC * kP);
+                    in_cl[t] = io.pool_cl && slot > 0;      // slot 0 holds the root latents as the API delivered them (NCHW)
                 }
+            }
+            // ---- load the input activation: gather the latents, split to fp16 hi/lo ----
+#pragma unroll
+            for (int t = 0; t < kMaxTiles; ++t) {
+                if (t >= NT) continue;
+                const int m = t * 128 + rowid;
                 float v[32];
-    #pragma unroll
-                for (int c = 0; c < 32; ++c) v[c] = valid ? src[(size_t)(half * 32 + c) * kP] : 0.0f   /* plain load: the pool is written by this launch in persistent mode */;
-    #pragma unroll
+                if (rowp[t] >= 0) load_row32(in_root[t], in_cl[t], rowp[t], half, v);
+                else {
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) v[c] = 0.0f;
+                }
+#pragma unroll
                 for (int g = 0; g < 4; ++g) {
                     unsigned char *p = act + (half * 4 + g) * kPlaneBytes + (kMargin + m) * 16;
                     store_split8(p, p + kPartBytes, v + 8 * g);
                 }
-                tmem_st32(lane_base + kColRes + t * 64 + half * 32, v);
             }
             fence_proxy_async();
             tc_fence_before();
             mbar_arrive(&bars->act_ready);                          // phase 0: layer 0 may start
             if (dbg) dbg[1] = clock64();
 
-
+            bool skip_in_scratch = false;      // the residual operand: the input latent until a layer has parked its output
             for (int L = 0; L < nlayers; ++L) {
                 const int flags = net.layer_flags[L];
-                const float *bn = net.bn + (size_t)net.layer_w[L] * 128;      // [scale 64 | shift 64]
-                mbar_wait_warp(&bars->acc_ready, acc_par);
-                acc_par ^= 1;                                       // one commit per layer, across simulations
-                tc_fence_after();
-                if (dbg) dbg[2 + 2 * L] = clock64();
-                float bs[32], bt[32];                               // folded BatchNorm of this thread's 32 channels
-    #pragma unroll
-                for (int c = 0; c < 32; ++c) { bs[c] = __ldg(bn + half * 32 + c); bt[c] = __ldg(bn + 64 + half * 32 + c); }
-                for (int t = 0; t < NT; ++t) {
+                const float4 *bn4 = reinterpret_cast<const float4 *>(bn_s + L * 128 + half * 32);   // scale; shift 16 float4 further
+                const bool park = (flags & LF_STORE_RES) && (L + 1 < nlayers);
+#pragma unroll
+                for (int t = 0; t < kMaxTiles; ++t) {
+                    if (t >= NT) continue;
                     const int m = t * 128 + rowid;
-                    const int r = m / kRowsPerRoot, q = m - r * kRowsPerRoot, y = q / kPitch, x = q - y * kPitch;
-                    const bool valid = (m < rows_used) && (r < nvalid) && (y < 6) && (x < 6);
-                    const int b = root0 + r, p = y * 6 + x;
+                    const int p = rowp[t], b = rowb[t];
+                    const bool valid = p >= 0;
+                    float *scr_root = io.skip_scratch + (size_t)b * (kC * kP);
+                    // residual operand of this row (L2-resident, thread-private addresses): issued before the accumulator wait
+                    float rs[32];
+                    if ((flags & LF_RES) && valid) {
+                        if (skip_in_scratch) load_row32(scr_root, true, p, half, rs);
+                        else load_row32(in_root[t], in_cl[t], p, half, rs);
+                    }
+                    if (t == 0) {
+                        mbar_wait_warp(&bars->acc_ready, acc_par);
+                        acc_par ^= 1;                               // one commit per layer, across simulations
+                        tc_fence_after();
+                        if (dbg) dbg[2 + 2 * L] = clock64();
+                    }
+                    uint32_t ua[32];
                     float v[32];
-                    tmem_ld32(lane_base + kColAcc + t * 64 + half * 32, v);
-                    if (flags & LF_RES) {
-                        float rs[32];
-                        tmem_ld32(lane_base + kColRes + t * 64 + half * 32, rs);
-    #pragma unroll
-                        for (int c = 0; c < 32; ++c) v[c] = fmaf(v[c], bs[c], bt[c]) + rs[c];
+                    tmem_ld32_issue(lane_base + kColAcc + t * kAccCols + half * 32, ua);
+                    if (npass == 3 && LZ_FOLD != 0) {
+                        uint32_t ub[32];
+                        tmem_ld32_issue(lane_base + kColAcc + t * kAccCols + 64 + half * 32, ub);
+                        tmem_ld_wait();
+                        tmem_pin(ua); tmem_pin(ub);
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) v[c] = __uint_as_float(ua[c]) + __uint_as_float(ub[c]);
                     } else {
-    #pragma unroll
-                        for (int c = 0; c < 32; ++c) v[c] = fmaf(v[c], bs[c], bt[c]);
+                        tmem_ld_wait();
+                        tmem_pin(ua);
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) v[c] = __uint_as_float(ua[c]);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 sc = bn4[j], sh = bn4[16 + j];
+                        v[4 * j] = fmaf(v[4 * j], sc.x, sh.x); v[4 * j + 1] = fmaf(v[4 * j + 1], sc.y, sh.y);
+                        v[4 * j + 2] = fmaf(v[4 * j + 2], sc.z, sh.z); v[4 * j + 3] = fmaf(v[4 * j + 3], sc.w, sh.w);
+                    }
+                    if ((flags & LF_RES) && valid) {
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) v[c] += rs[c];
                     }
                     if ((flags & LF_ACT_BIAS) && valid) {
                         const int action = min(max(io.action[b], 0), net.A - 1);
-                        const float *ab = net.abias + ((size_t)action * kC + half * 32) * kP + p;
-    #pragma unroll
-                        for (int c = 0; c < 32; ++c) v[c] += __ldg(ab + (size_t)c * kP);
+                        const float4 *ab = reinterpret_cast<const float4 *>(net.abias + ((size_t)action * kP + p) * kC + half * 32);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 q = __ldg(ab + j);
+                            v[4 * j] += q.x; v[4 * j + 1] += q.y; v[4 * j + 2] += q.z; v[4 * j + 3] += q.w;
+                        }
                     }
-    #pragma unroll
+#pragma unroll
                     for (int c = 0; c < 32; ++c) v[c] = valid ? fmaxf(v[c], 0.0f) : 0.0f;
-                    if (flags & LF_STORE_RES) tmem_st32(lane_base + kColRes + t * 64 + half * 32, v);
+                    if (park && valid) store_row32(scr_root, true, p, half, v);
                     if ((flags & LF_WRITE_LATENT) && valid) {
-                        if (latent_out) {
-                            float *dst = latent_out + (size_t)b * (kC * kP) + (size_t)(half * 32) * kP + p;
-    #pragma unroll
-                            for (int c = 0; c < 32; ++c) dst[(size_t)c * kP] = v[c];
-                        }
-                        if (io.latent_out2) {
-                            float *dst = io.latent_out2 + (size_t)b * (kC * kP) + (size_t)(half * 32) * kP + p;
-    #pragma unroll
-                            for (int c = 0; c < 32; ++c) dst[(size_t)c * kP] = v[c];
-                        }
+                        if (latent_out) store_row32(latent_out + (size_t)b * (kC * kP), io.pool_cl != 0, p, half, v);
+                        if (io.latent_out2) store_row32(io.latent_out2 + (size_t)b * (kC * kP), false, p, half, v);
                     }
-    #pragma unroll
+#pragma unroll
                     for (int g = 0; g < 4; ++g) {
                         unsigned char *pp = act + (half * 4 + g) * kPlaneBytes + (kMargin + m) * 16;
                         store_split8(pp, pp + kPartBytes, v + 8 * g);
                     }
                 }
+                if (park) skip_in_scratch = true;
                 fence_proxy_async();
                 tc_fence_before();
                 mbar_arrive(&bars->act_ready);                      // phase L+1: next layer / this layer's hook may start
                 if (dbg) dbg[3 + 2 * L] = clock64();
-                if ((flags & LF_HOOK_REWARD) && net.has_reward_early) {
-                    // the reward head (FC1, FC2, softmax, h^-1) runs here, underneath the NEXT layer's MMAs
+                if ((flags & LF_HOOK_REWARD) && net.has_reward) {
+                    // reward 1x1 accumulators -> BN/ReLU features, parked in their own scratch until the heads' FC pass at the
+                    // end of the simulation (underneath the NEXT layer's MMAs)
                     mbar_wait_warp(&bars->rew_ready, sim & 1);
                     tc_fence_after();
-                    head_stage(net, io, 1, reinterpret_cast<float *>(smem + kSmemMain), tmem, NT, rows_used, nvalid, root0);
+                    head_scatter(net, 1, f_rew, nullptr, tmem, NT, rows_used, nvalid);
+                    if (io.ez_feat) {
+                        // EfficientZero (efficientzero_model.py:556-562): the flattened reward features feed an LSTM that is
+                        // evaluated as one batched GEMM over all roots by the next kernel (ez.cu)
+                        asm volatile("bar.sync 1, %0;\n" ::"n"(kEpiThreads) : "memory");
+                        const int nin = net.hc[0] * kP;
+                        for (int i = tid; i < nvalid * nin; i += kEpiThreads) {
+                            const int r = i / nin, j = i - r * nin;
+                            io.ez_feat[(size_t)(root0 + r) * nin + j] = f_rew[r * kHfStride + j];
+                        }
+                    }
                     if (dbg) dbg[28] = clock64();
                 }
             }
 
-            // all 1x1 head accumulators must be complete before the head stage reads them / reuses the buffer
-            if (net.has_reward && !net.has_reward_early) mbar_wait_warp(&bars->rew_ready, sim & 1);
+            // the value / policy 1x1 accumulators must be complete before the head stage reads them / reuses the buffer
             mbar_wait_warp(&bars->vp_ready, sim & 1);
             tc_fence_after();
             if (dbg) dbg[24] = clock64();
-            // ---- heads: 1x1 accumulators -> BN/ReLU -> FC1 -> FC2 -> softmax expectation -> h^-1 (scratch overlays the
-            // activation buffer: every conv MMA of this simulation has completed)
-            head_stage(net, io, net.has_reward_early ? 6 : (net.has_reward ? 7 : 6), reinterpret_cast<float *>(act), tmem, NT, rows_used, nvalid, root0);
+            // ---- heads: 1x1 accumulators -> BN/ReLU features, then FC1 -> FC2 -> softmax expectation -> h^-1 for all heads with the
+            // weights streamed through the ring.  The scratch overlays the activation buffer: every conv MMA of this simulation
+            // has completed (ordered through act_ready -> MMA issuer -> vp_ready; the explicit barrier keeps racecheck, which
+            // does not follow mbarriers, quiet)
+            {
+                float *f_vp = reinterpret_cast<float *>(act), *wk = f_vp + ((2 * kMaxRoots * kHfStride + 3) & ~3);   // 16-byte aligned work area
+                asm volatile("bar.sync 1, %0;\n" ::"n"(kEpiThreads) : "memory");
+                head_scatter(net, 6, nullptr, f_vp, tmem, NT, rows_used, nvalid);
+                asm volatile("bar.sync 1, %0;\n" ::"n"(kEpiThreads) : "memory");
+                if (dbg) dbg[44] = clock64();
+                uint32_t hn = (uint32_t)sim * (9 * nlayers + nfc) + 9 * nlayers;
+                heads_fc(net, io, hmask_fc, ring, bars, hn, f_rew, f_vp, wk, f_rew + kMaxRoots * kHfStride, nvalid, root0, dbg);
+            }
             if (dbg) dbg[27] = clock64();
-            dbg = nullptr;
             __threadfence_block();
             asm volatile("bar.sync 1, %0;\n" ::"n"(kEpiThreads) : "memory");
         }
         if (persistent && warp < nvalid) {        // back up the last simulation (mcts_ctree.py:365-368)
             const int b = root0 + warp;
-            tree_backprop(tp, b, lane, io.sim0 + nsims, io.reward[b], io.value[b], io.policy_logits + (size_t)b * net.A, nullptr);
+            if (fast_tree) ptree_backprop(tp, T, b, lane, io.sim0 + nsims, io.reward[b], io.value[b], io.policy_logits + (size_t)b * net.A);
+            else tree_backprop(tp, b, lane, io.sim0 + nsims, io.reward[b], io.value[b], io.policy_logits + (size_t)b * net.A, nullptr);
         }
     }
 
@@ -516,7 +714,7 @@ static void split_half(float v, float scale, __half &hi, __half &lo)
     lo = __float2half_rn(s - __half2float(hi));
 }
 
-// One 3x3 conv -> 9 tap blocks of [hi | lo], each [kg = ci/8][co 64][ci % 8] fp16.  Returns the power-of-two
+// One 3x3 conv -> 9 tap blocks, each [kg = ci/8][co: 64 hi rows | 64 lo rows][ci % 8] fp16.  Returns the power-of-two
 // scale applied to the weights (exact), which the caller folds into the BatchNorm scale.
 float tc_pack_conv3(const float *w_torch /*[64][cin][3][3]*/, int cin_total, int cin_used, unsigned char *dst)
 {
@@ -533,9 +731,9 @@ float tc_pack_conv3(const float *w_torch /*[64][cin][3][3]*/, int cin_total, int
             for (int ci = 0; ci < 64; ++ci) {
                 __half hi, lo;
                 split_half(w_torch[((size_t)co * cin_total + ci) * 9 + t], scale, hi, lo);
-                const size_t off = (size_t)t * (kTapBytes / 2) + ((size_t)(ci / 8) * 64 + co) * 8 + (ci % 8);
+                const size_t off = (size_t)t * (kTapBytes / 2) + ((size_t)(ci / 8) * 128 + co) * 8 + (ci % 8);
                 h[off] = hi;
-                h[off + kTapBytes / 4] = lo;      // lo block follows the 8 KB hi block (4096 halves)
+                h[off + 64 * 8] = lo;             // rows 64-127 of the k-group: the lo parts ([B_hi | B_lo] is one N = 128 operand)
             }
     return scale;
 }
@@ -563,9 +761,16 @@ float tc_pack_conv1(const float *w /*[hc][64]*/, int hc, int nco, int co_offset,
 int tc_head_layout_bytes() { return kHeadWBytes; }
 int tc_conv_layout_bytes() { return 9 * kTapBytes; }
 
+static unsigned long long *g_dbg = nullptr;     // bring-up instrumentation only (env LZ_TC_DEBUG at model finalize time)
+unsigned long long *tc_debug_buffer() { return g_dbg; }
+
 int tc_prepare_launch()
 {
     LZ_CUDA_CHECK(cudaFuncSetAttribute(k_net_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    if (getenv("LZ_TC_DEBUG") && !g_dbg) {      // allocated here (model finalize), never inside a stream capture
+        LZ_CUDA_CHECK(cudaMalloc(&g_dbg, 64 * 8));
+        LZ_CUDA_CHECK(cudaMemset(g_dbg, 0, 64 * 8));
+    }
     return LZ_OK;
 }
 
@@ -575,22 +780,18 @@ int tc_pick_roots(int B)
     return std::min(std::max(r, 1), kMaxRoots);
 }
 
-static unsigned long long *g_dbg = nullptr;
-unsigned long long *tc_debug_buffer() { return g_dbg; }
-
 int tc_launch(const TcNet &net, const TcIO &io_in, cudaStream_t s, const TreeParams *tp_in)
 {
     TcIO io = io_in;
     TreeParams tp;
     memset(&tp, 0, sizeof(tp));
     if (tp_in) tp = *tp_in;
-    LZ_REQUIRE(!io.persistent || (tp_in && net.has_reward_early), LZ_EINVAL, "tc_launch: persistent search needs tree parameters and the early reward head");
-    if (getenv("LZ_TC_DEBUG")) {
-        if (!g_dbg) { cudaMalloc(&g_dbg, 64 * 8); cudaMemset(g_dbg, 0, 64 * 8); }
-        io.dbg = g_dbg;
-    }
+    LZ_REQUIRE(!io.persistent || tp_in, LZ_EINVAL, "tc_launch: persistent search needs tree parameters");
+    LZ_REQUIRE(net.A <= 1000, LZ_EINVAL, "tc_launch: action space %d too large for the head scratch of the tcgen05 path", net.A);
+    LZ_REQUIRE(io.skip_scratch, LZ_EINVAL, "tc_launch: no skip scratch");
+    io.dbg = g_dbg;
     io.roots_per_cta = tc_pick_roots(io.B);
-    if (const char *e = getenv("LZ_TC_VARIANT")) io.variant = atoi(e);
+    if (getenv("LZ_TC_GENERIC_TREE")) io.generic_tree = 1;    // A/B switch: tree.cuh's routines inside the persistent kernel
     if (const char *e = getenv("LZ_TC_ROOTS")) io.roots_per_cta = std::min(std::max(atoi(e), 1), kMaxRoots);
     const int grid = (io.B + io.roots_per_cta - 1) / io.roots_per_cta;
     cudaLaunchConfig_t cfg;

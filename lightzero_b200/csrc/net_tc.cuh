@@ -9,19 +9,25 @@ namespace lz {
 constexpr int kMaxResBlocksTc = 4;
 constexpr int kTcMaxLayers = 1 + 4 * kMaxResBlocksTc;
 
+struct TcFc {                      // fully connected part of one head, streamed through the weight ring as 16 KB blocks
+    uint32_t fc1_off, fc2_off;     // byte offsets into TcNet::fcw: FC1 [nin][32] fp32; FC2 [ceil(K/128)][32][128] fp32 (zero padded)
+    int nin, K;                    // FC1 inputs (hc*36), FC2 outputs
+};
+
 struct TcNet {
-    const unsigned char *convw;    // [nconv][9 taps][hi 8 KB | lo 8 KB] fp16, K-major core-matrix layout
+    const unsigned char *convw;    // [nconv][9 taps][8 k-groups][64 hi rows | 64 lo rows][8] fp16, K-major core-matrix layout
     const float *bn;               // [nconv][scale 64 | shift 64] (weight power-of-two scale folded in)
     const unsigned char *headw;    // [reward hi 2K | lo 2K][value+policy hi 4K | lo 4K]
     const float *head_bn;          // [reward s16 t16 | value s16 t16 | policy s16 t16]
-    const float *abias;            // [A][64][36] action-plane contribution of the dynamics conv, x BN scale
-    Head reward, value, policy;    // FC parts (fp32, same tables as the SIMT path)
+    const float *abias;            // [A][36][64] (pixel-major) action-plane contribution of the dynamics conv, x BN scale
+    const unsigned char *fcw;      // FC weight stream of the three heads (TcFc offsets)
+    TcFc fc[3];                    // reward, value, policy
+    Head reward, value, policy;    // folded BN / bias tables of the FC parts (fp32, same tables as the SIMT path)
     int hc[3];
     int nlayers;
     int layer_w[kTcMaxLayers];     // conv index into convw / bn
     int layer_flags[kTcMaxLayers];
     int has_reward;
-    int has_reward_early;          // reward head evaluated right after its hook, under the next layer's MMAs
     int A;
     float support_min, support_step;
 };
@@ -31,7 +37,7 @@ struct TcIO {
     int roots_per_cta;             // filled by tc_launch
     int npass;                     // 3 = fp32-accurate (hi*hi + hi*lo + lo*hi), 1 = fast (hi*hi)
     int pdl;                       // launch with programmatic stream serialization (inside the search graph)
-    int variant;                   // debug (env LZ_TC_VARIANT): 1 swaps the LBO / SBO descriptor fields
+    int generic_tree;              // debug (env LZ_TC_GENERIC_TREE): persistent search with tree.cuh's routines instead of tree_persist.cuh
     const float *latent_base;      // input latents: base + ix[b]*slot_stride + b*2304 (NCHW [64][36])
     const int *ix;                 // or nullptr
     size_t slot_stride;
@@ -44,6 +50,8 @@ struct TcIO {
     int persistent, nsims, sim0, deterministic;
     int *ix_rw, *action_rw;        // [B] tree -> network hand-off (same arrays as ix / action)
     float *latent_pool_rw;         // == latent_base; slot s+1 receives the latents of simulation s
+    float *skip_scratch;           // [B][36][64] fp32: ResBlock skip tensors parked between layers (thread-private rows, L2-resident)
+    int pool_cl;                   // latent pool slots >= 1 and latent_out are channels-last [36][64] (persistent search); else NCHW
     float *ez_feat;                // EfficientZero: the reward head stops after conv1x1+BN+ReLU and writes [B][hc*36] here
     unsigned long long *dbg;       // optional [64] clock64 stamps of CTA 0 (bring-up instrumentation)
 };

@@ -23,6 +23,7 @@ struct lz_search {
     float *d_policy;             // [B][A]
     float *d_root_logits;        // [B][A]
     float *d_root_value;         // [B]
+    float *d_skip;               // [B][C*P] ResBlock skip scratch of the tcgen05 network kernel (per search: searches may overlap on streams)
     // EfficientZero: LSTM state pools [(S+1)][B][H] (tuple element 0 / 1 of reward_hidden_state, mcts_ctree.py:775-776)
     // and the per-leaf is_reset flags handed from the traverse to the LSTM kernel and the back-up (:856-861)
     float *hpool, *cpool;
@@ -33,6 +34,7 @@ struct lz_search {
     float *d_reuse_value;
     cudaGraphExec_t exec_reuse;
     cudaGraphExec_t exec[2];     // [deterministic]
+    unsigned long long gen_model[3], gen_tree[3];   // model / tree generation each graph (exec[0], exec[1], exec_reuse) was captured at
     cudaStream_t capture_stream; // library-owned: the caller's stream may be the legacy default stream,
                                  // which cannot be captured; the instantiated graph launches on the caller's
     int num_kernels;
@@ -68,6 +70,7 @@ static int enqueue_search(lz_search *q, int deterministic, cudaStream_t s)
             io.h_base = q->hpool; io.c_base = q->cpool; io.hslot_stride = q->hslot_stride;
             io.h_out = q->hpool + (size_t)(sim + 1) * q->hslot_stride; io.c_out = q->cpool + (size_t)(sim + 1) * q->hslot_stride;
             io.is_reset = q->d_is_reset;
+            io.skip_scratch = q->d_skip;
             if ((rc = model_recurrent(q->model, io, s))) return rc;
             if (sim + 1 < q->S)
                 rc = tree_launch_backprop_traverse(t, sim + 1, q->d_reward, q->d_value, q->d_policy, 1, q->d_ix, q->d_action, s, q->d_is_reset);
@@ -77,7 +80,7 @@ static int enqueue_search(lz_search *q, int deterministic, cudaStream_t s)
         }
         return LZ_OK;
     }
-    if (q->model->kind == 0 && q->model->math != 0 && q->model->tc_rec.has_reward_early && !getenv("LZ_NO_PERSIST")) {
+    if (q->model->kind == 0 && q->model->math != 0 && !getenv("LZ_NO_PERSIST")) {
         TcIO io;
         memset(&io, 0, sizeof(io));
         io.B = q->B; io.npass = (q->model->math == 1) ? 3 : 1;
@@ -85,6 +88,8 @@ static int enqueue_search(lz_search *q, int deterministic, cudaStream_t s)
         io.ix = q->d_ix; io.ix_rw = q->d_ix; io.action = q->d_action; io.action_rw = q->d_action;
         io.reward = q->d_reward; io.value = q->d_value; io.policy_logits = q->d_policy;
         io.persistent = 1; io.nsims = q->S; io.sim0 = 0; io.deterministic = deterministic;
+        io.skip_scratch = q->d_skip;
+        io.pool_cl = 1;      // slots >= 1 are written and read only by this kernel: channels-last (vector loads / stores); slot 0 stays NCHW
         return tc_launch(q->model->tc_rec, io, s, &t->p);
     }
     const bool pdl = q->model->kind == 0 && q->model->math != 0 && getenv("LZ_PDL");   // opt-in: measured slower (6.26 vs 5.90 ms per 50-sim search)
@@ -103,6 +108,7 @@ static int enqueue_search(lz_search *q, int deterministic, cudaStream_t s)
         io.value = q->d_value;
         io.policy_logits = q->d_policy;
         io.pdl = pdl ? 1 : 0;
+        io.skip_scratch = q->d_skip;
         if ((rc = model_recurrent(q->model, io, s))) { t->pdl = false; return rc; }
         if (sim + 1 < q->S)
             rc = tree_launch_backprop_traverse(t, sim + 1, q->d_reward, q->d_value, q->d_policy, deterministic, q->d_ix, q->d_action, s);
@@ -129,6 +135,7 @@ static int enqueue_search_reuse(lz_search *q, cudaStream_t s)
         io.B = q->B; io.latent_base = q->pool; io.ix = q->d_ix; io.slot_stride = q->slot_stride; io.action = q->d_action;
         io.next_latent = q->pool + (size_t)(sim + 1) * q->slot_stride;
         io.reward = q->d_reward; io.value = q->d_value; io.policy_logits = q->d_policy;
+        io.skip_scratch = q->d_skip;
         if ((rc = model_recurrent(q->model, io, s))) return rc;
         if (sim + 1 < q->S)
             rc = tree_launch_backprop_traverse_reuse(t, sim + 1, q->d_reward, q->d_value, q->d_policy, q->d_true_action, q->d_reuse_value,
@@ -143,7 +150,16 @@ static int enqueue_search_reuse(lz_search *q, cudaStream_t s)
 static int run_graph(lz_search *q, int deterministic, cudaStream_t s)
 {
     const int d = deterministic ? 1 : 0;
+    // a captured graph bakes in device pointers of the model's tables (passed by value in TcNet / NetDev / EzNet), the math mode
+    // and the tree parameters (TreeParams by value): re-capture when any of them changed since (weight reload, set_math,
+    // model_reserve growth, lz_tree_set_params / lz_tree_set_ez)
+    if (q->exec[d] && (q->gen_model[d] != q->model->generation || q->gen_tree[d] != q->tree->generation)) {
+        cudaGraphExecDestroy(q->exec[d]);
+        q->exec[d] = nullptr;
+    }
     if (!q->exec[d]) {
+        q->gen_model[d] = q->model->generation;
+        q->gen_tree[d] = q->tree->generation;
         cudaGraph_t graph = nullptr;
         if (!q->capture_stream) LZ_CUDA_CHECK(cudaStreamCreateWithFlags(&q->capture_stream, cudaStreamNonBlocking));
         LZ_CUDA_CHECK(cudaStreamBeginCapture(q->capture_stream, cudaStreamCaptureModeThreadLocal));
@@ -185,6 +201,7 @@ int lz_search_create(lz_tree *t, lz_model *m, int num_simulations, lz_search **o
     if (rc == LZ_OK) rc = dev_alloc(&q->d_policy, (size_t)q->B * q->A);
     if (rc == LZ_OK) rc = dev_alloc(&q->d_root_logits, (size_t)q->B * q->A);
     if (rc == LZ_OK) rc = dev_alloc(&q->d_root_value, (size_t)q->B);
+    if (rc == LZ_OK) rc = dev_alloc(&q->d_skip, q->slot_stride);
     if (rc == LZ_OK && ez) {
         q->hslot_stride = (size_t)q->B * m->cfg.lstm_hidden_size;
         rc = dev_alloc(&q->hpool, q->hslot_stride * (size_t)(q->S + 1));
@@ -210,7 +227,7 @@ int lz_search_destroy(lz_search *q)
     }
     cudaFree(q->d_obs_stage); cudaFree(q->d_noise_stage); cudaFree(q->d_pre_stage); cudaFree(q->d_mask_stage); cudaFree(q->d_tp_stage);
     cudaFree(q->pool); cudaFree(q->d_ix); cudaFree(q->d_action); cudaFree(q->d_reward); cudaFree(q->d_value);
-    cudaFree(q->d_policy); cudaFree(q->d_root_logits); cudaFree(q->d_root_value);
+    cudaFree(q->d_policy); cudaFree(q->d_root_logits); cudaFree(q->d_root_value); cudaFree(q->d_skip);
     cudaFree(q->hpool); cudaFree(q->cpool); cudaFree(q->d_is_reset);
     cudaFree(q->d_true_action); cudaFree(q->d_reuse_value);
     if (q->exec_reuse) cudaGraphExecDestroy(q->exec_reuse);
@@ -256,7 +273,13 @@ int lz_search_run_with_reuse(lz_search *q, const float *d_latent_roots, const in
     LZ_CUDA_CHECK(cudaMemcpyAsync(q->d_true_action, d_true_action, (size_t)q->B * sizeof(int32_t), cudaMemcpyDeviceToDevice, s));
     LZ_CUDA_CHECK(cudaMemcpyAsync(q->d_reuse_value, d_reuse_value, (size_t)q->B * sizeof(float), cudaMemcpyDeviceToDevice, s));
     LZ_CUDA_CHECK(cudaMemsetAsync(q->tree->p.infer_count, 0, (size_t)q->tree->p.N * sizeof(int), s));
+    if (q->exec_reuse && (q->gen_model[2] != q->model->generation || q->gen_tree[2] != q->tree->generation)) {
+        cudaGraphExecDestroy(q->exec_reuse);
+        q->exec_reuse = nullptr;
+    }
     if (!q->exec_reuse) {
+        q->gen_model[2] = q->model->generation;
+        q->gen_tree[2] = q->tree->generation;
         cudaGraph_t graph = nullptr;
         if (!q->capture_stream) LZ_CUDA_CHECK(cudaStreamCreateWithFlags(&q->capture_stream, cudaStreamNonBlocking));
         LZ_CUDA_CHECK(cudaStreamBeginCapture(q->capture_stream, cudaStreamCaptureModeThreadLocal));
@@ -284,17 +307,26 @@ int lz_search_run(lz_search *q, const float *d_latent_roots, int deterministic, 
     return run_graph(q, deterministic, (cudaStream_t)s);
 }
 
-int lz_search_collect(lz_search *q, const float *d_obs, const uint8_t *d_mask, const float *d_noise, float noise_weight,
-                      const int32_t *d_to_play, int deterministic, float *d_pred_value, float *d_policy_logits,
-                      lz_stream s)
+static int collect_device(lz_search *q, const float *d_obs, const uint8_t *d_obs_u8, const uint8_t *d_mask, const float *d_noise,
+                          float noise_weight, const int32_t *d_to_play, int deterministic, float *d_pred_value,
+                          float *d_policy_logits, lz_stream s)
 {
-    LZ_REQUIRE(q && d_obs, LZ_EINVAL, "lz_search_collect: bad argument");
+    LZ_REQUIRE(q && (d_obs || d_obs_u8), LZ_EINVAL, "lz_search_collect: bad argument");
     TailIO io;
     memset(&io, 0, sizeof(io));
     io.latent2 = q->pool;                                   // latent roots go straight into pool slot 0
     io.policy_logits = d_policy_logits ? d_policy_logits : q->d_root_logits;
     io.value = d_pred_value ? d_pred_value : q->d_root_value;
-    int rc = model_initial(q->model, q->B, d_obs, io, (cudaStream_t)s);          // policy/muzero.py:749
+    int rc;
+    if (d_obs_u8) {
+        LZ_REQUIRE(q->model->kind == 0 && q->model->math != 0 && q->model->cfg.obs_h != 64, LZ_EINVAL,
+                   "lz_search_collect_u8: uint8 frames need the tcgen05 conv model (84x84 / 96x96)");
+        if (!q->d_pre_stage && (rc = dev_alloc(&q->d_pre_stage, (size_t)q->B * q->model->latent_floats))) return rc;
+        rc = model_initial_tower(q->model, q->B, nullptr, q->d_pre_stage, (cudaStream_t)s, d_obs_u8);
+        if (rc == LZ_OK) rc = model_initial_tail(q->model, q->B, q->d_pre_stage, io, (cudaStream_t)s);
+    } else {
+        rc = model_initial(q->model, q->B, d_obs, io, (cudaStream_t)s);          // policy/muzero.py:749
+    }
     if (rc) return rc;
     if ((rc = lz_tree_reset_mask(q->tree, d_mask, s))) return rc;                // :760,769
     if ((rc = lz_tree_prepare(q->tree, io.policy_logits, d_noise, noise_weight, nullptr, d_to_play, s))) return rc;   // :774
@@ -302,11 +334,26 @@ int lz_search_collect(lz_search *q, const float *d_obs, const uint8_t *d_mask, c
     return run_graph(q, deterministic, (cudaStream_t)s);                         // :775
 }
 
-int lz_search_collect_host(lz_search *q, const float *h_obs, const uint8_t *h_mask, const float *h_noise, float noise_weight,
-                           const int32_t *h_to_play, int deterministic, int nchunks, float *d_pred_value,
-                           float *d_policy_logits, lz_stream s_)
+int lz_search_collect(lz_search *q, const float *d_obs, const uint8_t *d_mask, const float *d_noise, float noise_weight,
+                      const int32_t *d_to_play, int deterministic, float *d_pred_value, float *d_policy_logits, lz_stream s)
+{
+    return collect_device(q, d_obs, nullptr, d_mask, d_noise, noise_weight, d_to_play, deterministic, d_pred_value, d_policy_logits, s);
+}
+
+int lz_search_collect_u8(lz_search *q, const uint8_t *d_obs_u8, const uint8_t *d_mask, const float *d_noise, float noise_weight,
+                         const int32_t *d_to_play, int deterministic, float *d_pred_value, float *d_policy_logits, lz_stream s)
+{
+    return collect_device(q, nullptr, d_obs_u8, d_mask, d_noise, noise_weight, d_to_play, deterministic, d_pred_value, d_policy_logits, s);
+}
+
+static int collect_host(lz_search *q, const void *h_obs, int obs_u8, const uint8_t *h_mask, const float *h_noise, float noise_weight,
+                        const int32_t *h_to_play, int deterministic, int nchunks, float *d_pred_value,
+                        float *d_policy_logits, lz_stream s_)
 {
     LZ_REQUIRE(q && h_obs, LZ_EINVAL, "lz_search_collect_host: bad argument");
+    LZ_REQUIRE(!obs_u8 || (q->model->kind == 0 && q->model->math != 0 && q->model->cfg.obs_h != 64), LZ_EINVAL,
+               "lz_search_collect_host_u8: uint8 frames need the tcgen05 conv model (84x84 / 96x96)");
+    const size_t esz = obs_u8 ? 1 : sizeof(float);         // bytes per observation element on the wire and in the staging buffer
     cudaStream_t s = (cudaStream_t)s_;
     const lz_model_config &c = q->model->cfg;
     const int B = q->B, A = q->A;
@@ -320,7 +367,7 @@ int lz_search_collect_host(lz_search *q, const float *h_obs, const uint8_t *h_ma
         LZ_CUDA_CHECK(cudaEventCreateWithFlags(&q->ev_start, cudaEventDisableTiming));
         int rc = dev_alloc(&q->d_obs_stage, q->obs_elems * B);
         if (rc == LZ_OK) rc = dev_alloc(&q->d_noise_stage, (size_t)B * A);
-        if (rc == LZ_OK) rc = dev_alloc(&q->d_pre_stage, (size_t)B * q->model->latent_floats);
+        if (rc == LZ_OK && !q->d_pre_stage) rc = dev_alloc(&q->d_pre_stage, (size_t)B * q->model->latent_floats);
         if (rc == LZ_OK) rc = dev_alloc(&q->d_mask_stage, (size_t)B * A);
         if (rc == LZ_OK) rc = dev_alloc(&q->d_tp_stage, (size_t)B);
         if (rc != LZ_OK) return rc;
@@ -335,8 +382,9 @@ int lz_search_collect_host(lz_search *q, const float *h_obs, const uint8_t *h_ma
         const int b0 = i * per, bc = std::min(per, B - b0);
         if (bc <= 0) { nchunks = i; break; }
         cudaStream_t cs = (two && (i & 1)) ? q->copy_stream2 : q->copy_stream;
-        LZ_CUDA_CHECK(cudaMemcpyAsync(q->d_obs_stage + (size_t)b0 * q->obs_elems, h_obs + (size_t)b0 * q->obs_elems,
-                                      (size_t)bc * q->obs_elems * sizeof(float), cudaMemcpyHostToDevice, cs));
+        LZ_CUDA_CHECK(cudaMemcpyAsync(reinterpret_cast<unsigned char *>(q->d_obs_stage) + (size_t)b0 * q->obs_elems * esz,
+                                      static_cast<const unsigned char *>(h_obs) + (size_t)b0 * q->obs_elems * esz,
+                                      (size_t)bc * q->obs_elems * esz, cudaMemcpyHostToDevice, cs));
         LZ_CUDA_CHECK(cudaEventRecord(q->ev_chunk[i], cs));
     }
     if (h_mask) LZ_CUDA_CHECK(cudaMemcpyAsync(q->d_mask_stage, h_mask, (size_t)B * A, cudaMemcpyHostToDevice, s));
@@ -350,8 +398,9 @@ int lz_search_collect_host(lz_search *q, const float *h_obs, const uint8_t *h_ma
         LZ_CUDA_CHECK(cudaStreamWaitEvent(s, q->ev_chunk[i], 0));
         int rc;
         if (split) {
-            rc = model_initial_tower(q->model, bc, q->d_obs_stage + (size_t)b0 * q->obs_elems,
-                                     q->d_pre_stage + (size_t)b0 * q->model->latent_floats, s);
+            const unsigned char *stage = reinterpret_cast<const unsigned char *>(q->d_obs_stage) + (size_t)b0 * q->obs_elems * esz;
+            rc = model_initial_tower(q->model, bc, obs_u8 ? nullptr : reinterpret_cast<const float *>(stage),
+                                     q->d_pre_stage + (size_t)b0 * q->model->latent_floats, s, obs_u8 ? stage : nullptr);
         } else {
             TailIO io;
             memset(&io, 0, sizeof(io));
@@ -377,6 +426,20 @@ int lz_search_collect_host(lz_search *q, const float *h_obs, const uint8_t *h_ma
                               h_to_play ? q->d_tp_stage : nullptr, s))) return rc;
     if (q->hpool && (rc = ez_root_hidden(q, nullptr, nullptr, s))) return rc;
     return run_graph(q, deterministic, s);
+}
+
+int lz_search_collect_host(lz_search *q, const float *h_obs, const uint8_t *h_mask, const float *h_noise, float noise_weight,
+                           const int32_t *h_to_play, int deterministic, int nchunks, float *d_pred_value,
+                           float *d_policy_logits, lz_stream s)
+{
+    return collect_host(q, h_obs, 0, h_mask, h_noise, noise_weight, h_to_play, deterministic, nchunks, d_pred_value, d_policy_logits, s);
+}
+
+int lz_search_collect_host_u8(lz_search *q, const uint8_t *h_obs_u8, const uint8_t *h_mask, const float *h_noise, float noise_weight,
+                              const int32_t *h_to_play, int deterministic, int nchunks, float *d_pred_value,
+                              float *d_policy_logits, lz_stream s)
+{
+    return collect_host(q, h_obs_u8, 1, h_mask, h_noise, noise_weight, h_to_play, deterministic, nchunks, d_pred_value, d_policy_logits, s);
 }
 
 int lz_search_num_kernels(const lz_search *q) { return q ? q->num_kernels : 0; }

@@ -422,6 +422,7 @@ int lz_tree_set_params(lz_tree *t, int pb_c_base, float pb_c_init, float discoun
         tab[i] = lg + pb_c_init;
     }
     LZ_CUDA_CHECK(cudaMemcpy(t->d_pbc, tab.data(), n * sizeof(float), cudaMemcpyHostToDevice));
+    if (t->p.discount != discount || t->p.delta != value_delta_max) ++t->generation;   // passed BY VALUE into captured search graphs
     t->p.discount = discount;
     t->p.delta = value_delta_max;
     t->params_set = true;
@@ -483,8 +484,10 @@ int lz_tree_set_ez(lz_tree *t, int efficientzero, int lstm_horizon_len)
 {
     LZ_REQUIRE(t, LZ_EINVAL, "lz_tree_set_ez: null tree");
     LZ_REQUIRE(!efficientzero || lstm_horizon_len > 0, LZ_EINVAL, "lz_tree_set_ez: lstm_horizon_len must be > 0 (mcts_ctree.py:857)");
-    t->p.ez = efficientzero ? 1 : 0;
-    if (efficientzero) t->p.lstm_horizon = lstm_horizon_len;
+    const int ez = efficientzero ? 1 : 0, hor = efficientzero ? lstm_horizon_len : t->p.lstm_horizon;
+    if (t->p.ez != ez || t->p.lstm_horizon != hor) ++t->generation;
+    t->p.ez = ez;
+    t->p.lstm_horizon = hor;
     return LZ_OK;
 }
 

@@ -439,6 +439,7 @@ struct lz_tree {
     int max_sims;
     unsigned step_counter;
     bool params_set, prepared;
+    unsigned long long generation;   // bumped whenever TreeParams values that captured graphs bake in change (set_params / set_ez)
     bool pdl;                    // launch tree kernels with programmatic stream serialization (set by the search graph)
     void *alloc_base;
 };

@@ -21,6 +21,9 @@ struct ProbeCfg {
     int a_lbo16;        // no-swizzle: k-group stride of A in 16-byte units (128 = 128-row tile, 400 = net_tc.cu's activation buffer)
     int swz_a, swz_b;   // 1: SWIZZLE_128B K-major (rows of 128 B, 8-row groups of 1024 B)
     int n_ksteps;       // distinct K-steps cycled through (operand addresses change every MMA like in the real kernels)
+    int mix_n2;         // > 0: groups of `mix_group` MMAs alternate between N and this second N (net_tc.cu's [B_hi | B_lo] fold: N = 128 then N = 64)
+    int mix_group;
+    int mix_d2_off;     // TMEM column offset of the second shape's accumulator relative to the first (0: same columns)
     int warp_issue;     // 1: the whole warp runs the issue loop and the MMA is predicated on elect.sync (uniform control flow,
                         //    the CUTLASS pattern); 0: `if (lane == 0)` divergent branch (what net_tc.cu / conv_tc.cu / ez.cu do)
 };
@@ -35,14 +38,7 @@ __device__ __forceinline__ uint64_t desc_swz128(uint32_t saddr)
 
 __device__ __forceinline__ void umma_f16_elect(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc)
 {
-    asm volatile("{\n\t.reg .pred pe;\n\t.reg .pred pa;\n\telect.sync _|pe, 0xffffffff;\n\tsetp.ne.b32 pa, 1, 0;\n\t"
-                 "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, pa;\n\t}\n"
-                 ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc) : "memory");
-}
-__device__ __forceinline__ void umma_commit_elect(uint64_t *bar)
-{
-    asm volatile("{\n\t.reg .pred pe;\n\telect.sync _|pe, 0xffffffff;\n\t"
-                 "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}\n" ::"r"(smem_u32(bar)) : "memory");
+    lz::umma_f16_elect(d_tmem, adesc, bdesc, idesc, 1u);
 }
 
 extern "C" __global__ void __launch_bounds__(128, 1) k_mma_probe(const ProbeCfg *cfgs, int ncfg, unsigned long long *out)
@@ -51,7 +47,7 @@ extern "C" __global__ void __launch_bounds__(128, 1) k_mma_probe(const ProbeCfg 
     __shared__ uint64_t bar;
     __shared__ uint32_t tmem_base;
     __shared__ uint64_t t_ad[512], t_bd[512];      // descriptors precomputed per configuration: the timed loop only issues
-    __shared__ uint32_t t_d[512];
+    __shared__ uint32_t t_d[512], t_id[512];
     const int tid = threadIdx.x, warp = tid >> 5;
     for (int i = tid; i < 200 * 1024 / 16; i += blockDim.x) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);
     if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
@@ -75,17 +71,22 @@ extern "C" __global__ void __launch_bounds__(128, 1) k_mma_probe(const ProbeCfg 
                 if (g.swz_b) t_bd[i] = desc_swz128(b_s + (uint32_t)ks * 32u);
                 else t_bd[i] = make_desc(b_s + (uint32_t)ks * 2u * (uint32_t)g.N * 16u, g.N, 8);
                 t_d[i] = tmem + acc * g.N;
+                t_id[i] = idesc;
+                if (g.mix_n2 > 0 && ((i / g.mix_group) & 1)) {
+                    t_id[i] = make_idesc_f16(128, g.mix_n2);
+                    t_d[i] += g.mix_d2_off;
+                }
             }
             if (wi) __syncwarp();
             for (int rep = 0; rep < 3; ++rep) {      // the last repetition is reported
                 const long long t0 = clock64();
                 if (wi) {
 #pragma unroll 4
-                    for (int i = 0; i < g.n_mma; ++i) umma_f16_elect(t_d[i], t_ad[i], t_bd[i], idesc);
+                    for (int i = 0; i < g.n_mma; ++i) umma_f16_elect(t_d[i], t_ad[i], t_bd[i], t_id[i]);
                     umma_commit_elect(&bar);
                 } else {
 #pragma unroll 4
-                    for (int i = 0; i < g.n_mma; ++i) umma_f16(t_d[i], t_ad[i], t_bd[i], idesc, 1);
+                    for (int i = 0; i < g.n_mma; ++i) umma_f16(t_d[i], t_ad[i], t_bd[i], t_id[i], 1);
                     umma_commit(&bar);
                 }
                 mbar_wait(&bar, parity);
