@@ -199,22 +199,50 @@ __device__ __forceinline__ float warp_max(float v)
     return v;
 }
 
-// softmax(logits) . support  ->  inverse transform  (scaling_transform.py:82-92) by one warp.
+// softmax(logits) . support  ->  inverse transform  (scaling_transform.py:82-92).
+//
+// ONE canonical evaluation order for every kernel of the library (so that the fused search, the step-wise drive and the stand-alone
+// lz_inverse_scalar_transform agree bit for bit): the K logits are dealt to 128 virtual threads (k mod 128), each folds its logits
+// in increasing k into a running (max m, sum s of exp(x - m), sum w of exp(x - m) * support_k); the 128 triples are combined as
+// 4 groups of 32 (xor-shuffle max, maximum of the 4 group maxima in group order, rescale by exp(m - M), xor-shuffle sums, the 4
+// group sums added in group order).  k_net_tc's FC2 stage runs it natively (thread = output k, heads_fc in net_tc.cu); a single
+// warp emulates it here with 4 virtual threads per lane.
+__device__ __forceinline__ void softmax_push(float &m, float &s, float &w, float x, float sup)
+{
+    // one exponential per logit, no divergent branch: t = exp(-|x - m|) is the rescale factor of the old sums when x is the new
+    // maximum and the new term otherwise (exp(-inf) = 0 for the first logit)
+    const float t = expf(-fabsf(x - m));
+    const bool gt = x > m;
+    s = gt ? fmaf(s, t, 1.0f) : s + t;
+    w = gt ? fmaf(w, t, sup) : fmaf(t, sup, w);
+    m = gt ? x : m;
+}
+__device__ __forceinline__ float support_at(float support_min, float support_step, int k) { return fmaf(support_step, (float)k, support_min); }
+
 __device__ __forceinline__ float categorical_to_scalar(const float *logits /*shared or global*/, int K,
                                                        float support_min, float support_step, int lane)
 {
-    float m = -INFINITY;
-    for (int k = lane; k < K; k += 32) m = fmaxf(m, logits[k]);
-    m = warp_max(m);
-    float s = 0.0f, ws = 0.0f;
-    for (int k = lane; k < K; k += 32) {
-        float e = expf(logits[k] - m);
-        s += e;
-        ws = fmaf(e, support_min + support_step * (float)k, ws);
+    float m[4], s[4], w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { m[j] = -INFINITY; s[j] = 0.0f; w[j] = 0.0f; }
+    for (int k0 = 0; k0 < K; k0 += 128) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int k = k0 + j * 32 + lane;
+            if (k < K) softmax_push(m[j], s[j], w[j], logits[k], support_at(support_min, support_step, k));
+        }
     }
-    s = warp_sum(s);
-    ws = warp_sum(ws);
-    return inverse_scalar_transform(ws / s);
+    float M = warp_max(m[0]);
+#pragma unroll
+    for (int j = 1; j < 4; ++j) M = fmaxf(M, warp_max(m[j]));
+    float S = 0.0f, W = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float sc = (m[j] == -INFINITY) ? 0.0f : expf(m[j] - M);
+        S += warp_sum(s[j] * sc);
+        W += warp_sum(w[j] * sc);
+    }
+    return inverse_scalar_transform(W / S);
 }
 
 // Fully connected part of one head for NR roots at once by the calling warp (weights are read once

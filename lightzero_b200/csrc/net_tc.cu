@@ -56,11 +56,11 @@ constexpr int kPartBytes = 8 * kPlaneBytes;      // 64 channels: 51200 B
 constexpr int kActBytes = 2 * kPartBytes;        // hi + lo: 102400 B
 constexpr int kTapKgBytes = 128 * 16;            // one k-group (8 input channels) of a tap: 64 hi rows then 64 lo rows of 16 B
 constexpr int kTapBytes = 8 * kTapKgBytes;       // one 3x3 tap, [kg 8][co: 64 hi | 64 lo][ci % 8]: 16384 B
-constexpr int kStages = 4;
+constexpr int kStages = 5;                       // 16 KB ring stages: conv taps, then the heads' FC weight blocks
 constexpr int kHeadWBytes = 3 * 2 * 16 * 64 * 2; // three 1x1 heads (hc <= 16), hi + lo: 12288 B
 constexpr int kBnSmemBytes = kTcMaxLayers * 128 * 4;   // folded BatchNorm tables of the program's layers
 constexpr int kSmemMain = kActBytes + kStages * kTapBytes + kHeadWBytes + 1024 + kBnSmemBytes;
-constexpr int kHeadScratch = (kMaxRoots * 577 + kMaxRoots * 608) * 4;   // reward head: features (parked from its hook to the end of the simulation) + logits
+constexpr int kHeadScratch = kMaxRoots * 577 * 4 + kEpiWarps * (16 + 3 * 32) * 4;   // + the parked trees (kTreeParkWords per warp)   // reward head features, parked from their hook to the heads' FC pass at the end of the simulation
 constexpr int kSmemBytes = kSmemMain + kHeadScratch;
 
 // TMEM columns
@@ -76,8 +76,9 @@ struct TcBars {
     uint64_t act_ready;     // epilogue -> MMA: activations (and TMEM) are ready for the next layer
     uint64_t rew_ready;     // MMA -> heads: reward 1x1 accumulators complete (single phase)
     uint64_t vp_ready;      // MMA -> heads: value/policy 1x1 accumulators complete (single phase)
+    uint64_t fc_empty[kStages];   // heads -> producer: all kEpiWarps epilogue warps are done with the FC weight block in this stage
     uint32_t tmem_base;
-    uint32_t fc_cnt[kStages];   // epilogue warps done with an FC weight block (the last one releases the ring stage)
+    uint32_t pad;
 };
 
 // ---------------------------------------------------------------------------------------------- heads
@@ -88,7 +89,6 @@ struct TcBars {
 //   FC1 block = 128 input rows x 32 hidden units; lane = (root, 8-unit group), warp = 16 of the block's rows.
 //   FC2 block = 32 hidden units x 128 outputs;    thread = output k (tid % 128) x root group (tid / 128).
 constexpr int kHfStride = 577;                    // feature row stride (odd: the 7 roots of one input fall in 7 banks)
-constexpr int kLdK = 608;                         // categorical logits row stride (support size <= 608)
 
 // 1x1-conv accumulators (TMEM) -> BatchNorm + ReLU -> flattened features [root][c*36 + p] (stride kHfStride) for the heads in
 // hmask (bit 0 reward -> f_rew, bit 1 value / bit 2 policy -> f_vp[0 / 1]).  No barrier inside.
@@ -126,64 +126,76 @@ __device__ __forceinline__ void head_scatter(const TcNet &net, int hmask, float 
     tc_fence_before();
 }
 
-// the last of the 8 epilogue warps to finish with ring stage `st` hands it back to the producer
+// every epilogue warp arrives on the stage's FC-release barrier (count kEpiWarps) once its lanes are done with the block
 __device__ __forceinline__ void fc_release_stage(TcBars *bars, int st)
 {
     __syncwarp();
-    if ((threadIdx.x & 31) == 0) {
-        __threadfence_block();
-        if (atomicAdd(&bars->fc_cnt[st], 1u) == (unsigned)(kEpiWarps - 1)) {
-            bars->fc_cnt[st] = 0u;
-            mbar_arrive(&bars->empty[st]);
-        }
-    }
+    if ((threadIdx.x & 31) == 0) mbar_arrive(&bars->fc_empty[st]);
 }
 
 // FC1 -> BN/ReLU -> FC2 -> softmax expectation -> h^-1 for the heads in hmask, weights from the ring (hn: this simulation's
-// position in the ring sequence, advanced per block).  f_rew / f_vp: features from head_scatter; wk: >= kFcWorkFloats floats of
-// scratch; lg_rew: [7][kLdK] (outside wk: it may live next to f_rew).  Executed by the kEpiThreads epilogue threads together.
+// position in the ring sequence, advanced per block).  f_rew / f_vp: features from head_scatter; wk: kFcWorkFloats floats of
+// scratch.  Executed by the kEpiThreads epilogue threads together.
+//   FC1 block = 128 input rows x 32 hidden units: warp w takes rows [16 w, 16 w + 16) in 4 groups of 4; lane = (row in group,
+//   4-unit column chunk), so one LDS.128 per lane reads 4 whole weight rows per warp instruction (every weight byte leaves shared
+//   memory exactly once); 7 roots x 4 units = 28 accumulators per lane, reduced over the 4 row lanes at the end of the head.
+//   FC2 block = 32 hidden units x 128 outputs: thread = (output k, root group g of 4).  The categorical heads never store their
+//   601 logits: each thread folds its logits into a running (max, sum exp, sum exp * support) per root, reduced over the block
+//   after the head's last block (softmax expectation of scaling_transform.py:82-92 in one pass).
 constexpr int kFcPart = kEpiWarps * 3 * kMaxRoots * 32;        // FC1 partial sums [warp][head][root][32]
 constexpr int kFcHidT = 3 * 32 * 8;                             // hidden activations, transposed [head][unit][8 roots]
+constexpr int kFcRed = 2 * 4 * 4 * 3 + 8;                       // softmax reduction scratch [root group][warp][root][m, s, ws]
+constexpr int kFcWorkFloats = kFcPart + kFcHidT + kFcRed;
 __device__ __forceinline__ void heads_fc(const TcNet &net, const TcIO &io, int hmask, unsigned char *ring, TcBars *bars, uint32_t &hn,
-                                         const float *f_rew, const float *f_vp, float *wk, float *lg_rew, int nvalid, int root0,
+                                         const float *f_rew, const float *f_vp, float *wk, int nvalid, int root0,
                                          unsigned long long *dbg)
 {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int A = net.A, ldp = (A + 31) & ~31;
-    float *part = wk, *hidT = part + kFcPart, *lg_val = hidT + kFcHidT, *lg_pol = lg_val + kMaxRoots * kLdK;
-    // ---- FC1: lane = (root, group of 8 hidden units); warp w takes rows [16 w, 16 w + 16) of every 128-row block
+    const int A = net.A;
+    float *part = wk, *hidT = part + kFcPart, *red = hidT + kFcHidT;
+    // ---- FC1
     {
-        const int r_l = min(lane >> 2, kMaxRoots - 1), jq = lane & 3;
+        const int rsub = lane >> 3, c8 = lane & 7;
         for (int h = 0; h < 3; ++h) {
             if (!((hmask >> h) & 1)) continue;
             const int nin = net.fc[h].nin, nblk = (nin + 127) >> 7;
-            const float *hf = (h == 0 ? f_rew : f_vp + (h - 1) * kMaxRoots * kHfStride) + r_l * kHfStride;
-            float a[8];
+            const float *hf = (h == 0 ? f_rew : f_vp + (h - 1) * kMaxRoots * kHfStride);
+            float acc[kMaxRoots][4];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) a[k] = 0.0f;
+            for (int r = 0; r < kMaxRoots; ++r) { acc[r][0] = 0.0f; acc[r][1] = 0.0f; acc[r][2] = 0.0f; acc[r][3] = 0.0f; }
             for (int blk = 0; blk < nblk; ++blk, ++hn) {
                 const int st = hn % kStages;
                 const long long tw0 = dbg ? clock64() : 0;
                 mbar_wait_converged(&bars->full[st], (hn / kStages) & 1);
                 if (dbg) dbg[54] += (unsigned long long)(clock64() - tw0);      // FC1 ring waits of warp 0
-                const float *w = reinterpret_cast<const float *>(ring + st * kTapBytes) + (warp * 16) * 32 + jq * 8;
-                const int ii0 = blk * 128 + warp * 16;
+                const float *w = reinterpret_cast<const float *>(ring + st * kTapBytes) + (warp * 16 + rsub) * 32 + c8 * 4;
+                const int ii0 = blk * 128 + warp * 16 + rsub;
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    if (ii0 + i < nin) {
-                        const float f = hf[ii0 + i];
-                        const float4 w0 = *reinterpret_cast<const float4 *>(w + i * 32);
-                        const float4 w1 = *reinterpret_cast<const float4 *>(w + i * 32 + 4);
-                        a[0] = fmaf(f, w0.x, a[0]); a[1] = fmaf(f, w0.y, a[1]); a[2] = fmaf(f, w0.z, a[2]); a[3] = fmaf(f, w0.w, a[3]);
-                        a[4] = fmaf(f, w1.x, a[4]); a[5] = fmaf(f, w1.y, a[5]); a[6] = fmaf(f, w1.z, a[6]); a[7] = fmaf(f, w1.w, a[7]);
+                for (int g4 = 0; g4 < 4; ++g4) {
+                    const int ii = ii0 + g4 * 4;
+                    if (ii < nin) {
+                        const float4 wv = *reinterpret_cast<const float4 *>(w + g4 * 4 * 32);
+#pragma unroll
+                        for (int r = 0; r < kMaxRoots; ++r) {
+                            const float f = hf[r * kHfStride + ii];
+                            acc[r][0] = fmaf(f, wv.x, acc[r][0]); acc[r][1] = fmaf(f, wv.y, acc[r][1]);
+                            acc[r][2] = fmaf(f, wv.z, acc[r][2]); acc[r][3] = fmaf(f, wv.w, acc[r][3]);
+                        }
                     }
                 }
                 fc_release_stage(bars, st);
             }
-            if ((lane >> 2) < kMaxRoots) {
-                float *dst = part + ((warp * 3 + h) * kMaxRoots + r_l) * 32 + jq * 8;
-                *reinterpret_cast<float4 *>(dst) = make_float4(a[0], a[1], a[2], a[3]);
-                *reinterpret_cast<float4 *>(dst + 4) = make_float4(a[4], a[5], a[6], a[7]);
+#pragma unroll
+            for (int r = 0; r < kMaxRoots; ++r) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    float v = acc[r][k];
+                    v += __shfl_xor_sync(0xffffffffu, v, 8);
+                    v += __shfl_xor_sync(0xffffffffu, v, 16);
+                    acc[r][k] = v;
+                }
+                if (rsub == 0)
+                    *reinterpret_cast<float4 *>(part + ((warp * 3 + h) * kMaxRoots + r) * 32 + c8 * 4) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
             }
         }
     }
@@ -201,15 +213,17 @@ __device__ __forceinline__ void heads_fc(const TcNet &net, const TcIO &io, int h
     }
     asm volatile("bar.sync 1, %0;\n" ::"n"(kEpiThreads) : "memory");
     if (dbg) dbg[46] = clock64();
-    // ---- FC2: thread = (output k of the 128-output block, root group g)
+    // ---- FC2 (+ one-pass softmax expectation for the categorical heads)
     {
-        const int kl = tid & 127, g = tid >> 7;
+        const int kl = tid & 127, g = tid >> 7, wg = warp & 3;
         for (int h = 0; h < 3; ++h) {
             if (!((hmask >> h) & 1)) continue;
             const Head &H = h == 0 ? net.reward : (h == 1 ? net.value : net.policy);
             const int K = H.K, nblk = (K + 127) >> 7;
-            float *lg = h == 0 ? lg_rew : (h == 1 ? lg_val : lg_pol);
-            const int ld = h == 2 ? ldp : kLdK;
+            float *glog = h == 0 ? io.reward_logits : (h == 1 ? io.value_logits : io.policy_logits);
+            float m[4], sm[4], ws[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { m[q] = -INFINITY; sm[q] = 0.0f; ws[q] = 0.0f; }
             for (int blk = 0; blk < nblk; ++blk, ++hn) {
                 const int st = hn % kStages;
                 const int k = blk * 128 + kl;
@@ -219,47 +233,65 @@ __device__ __forceinline__ void heads_fc(const TcNet &net, const TcIO &io, int h
                 if (dbg) dbg[55] += (unsigned long long)(clock64() - tw0);      // FC2 ring waits of warp 0
                 const float *w = reinterpret_cast<const float *>(ring + st * kTapBytes) + kl;
                 const float *hq = hidT + h * 32 * 8 + g * 4;
-                float o0 = bias, o1 = bias, o2 = bias, o3 = bias;
+                float o[4] = {bias, bias, bias, bias};
 #pragma unroll
                 for (int u = 0; u < 32; ++u) {
                     const float wv = w[u * 128];
                     const float4 hv = *reinterpret_cast<const float4 *>(hq + u * 8);
-                    o0 = fmaf(hv.x, wv, o0); o1 = fmaf(hv.y, wv, o1); o2 = fmaf(hv.z, wv, o2); o3 = fmaf(hv.w, wv, o3);
-                }
-                if (k < K) {
-                    float *d = lg + (g * 4) * ld + k;
-                    d[0] = o0; d[ld] = o1; d[2 * ld] = o2;
-                    if (g == 0) d[3 * ld] = o3;
+                    o[0] = fmaf(hv.x, wv, o[0]); o[1] = fmaf(hv.y, wv, o[1]); o[2] = fmaf(hv.z, wv, o[2]); o[3] = fmaf(hv.w, wv, o[3]);
                 }
                 fc_release_stage(bars, st);
+                if (k < K) {
+                    const float sup = support_at(net.support_min, net.support_step, k);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int r = g * 4 + q;
+                        if (r >= nvalid) continue;
+                        if (glog) glog[(size_t)(root0 + r) * K + k] = o[q];
+                        if (h < 2) softmax_push(m[q], sm[q], ws[q], o[q], sup);   // running softmax statistics (net6.cuh: the canonical order)
+                    }
+                }
+            }
+            if (h < 2) {
+                // block-wide combine per root: max, then rescaled sums (4 warps per root group)
+                float mg[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) mg[q] = warp_max(m[q]);
+                if (lane == 0) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) red[((g * 4 + wg) * 4 + q) * 3] = mg[q];
+                }
+                asm volatile("bar.sync 1, %0;\n" ::"n"(kEpiThreads) : "memory");
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    float M = red[((g * 4 + 0) * 4 + q) * 3];
+#pragma unroll
+                    for (int w4 = 1; w4 < 4; ++w4) M = fmaxf(M, red[((g * 4 + w4) * 4 + q) * 3]);
+                    const float sc = (m[q] == -INFINITY) ? 0.0f : expf(m[q] - M);
+                    sm[q] = warp_sum(sm[q] * sc);
+                    ws[q] = warp_sum(ws[q] * sc);
+                }
+                if (lane == 0) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) { red[((g * 4 + wg) * 4 + q) * 3 + 1] = sm[q]; red[((g * 4 + wg) * 4 + q) * 3 + 2] = ws[q]; }
+                }
+                asm volatile("bar.sync 1, %0;\n" ::"n"(kEpiThreads) : "memory");
+                if (wg == 0 && lane < 4) {
+                    const int q = lane, r = g * 4 + q;
+                    if (r < nvalid) {
+                        float S = 0.0f, W = 0.0f;
+#pragma unroll
+                        for (int w4 = 0; w4 < 4; ++w4) { S += red[((g * 4 + w4) * 4 + q) * 3 + 1]; W += red[((g * 4 + w4) * 4 + q) * 3 + 2]; }
+                        const float v = inverse_scalar_transform(W / S);
+                        float *dst = h == 0 ? io.reward : io.value;
+                        if (dst) dst[root0 + r] = v;
+                    }
+                }
+                asm volatile("bar.sync 1, %0;\n" ::"n"(kEpiThreads) : "memory");   // red is reused by the next head
             }
         }
     }
-    asm volatile("bar.sync 1, %0;\n" ::"n"(kEpiThreads) : "memory");
     if (dbg) dbg[47] = clock64();
-    // ---- softmax expectation + inverse transform: one warp per (categorical head, root)
-    for (int task = warp; task < 2 * kMaxRoots; task += kEpiWarps) {
-        const int h = task / kMaxRoots, r = task - h * kMaxRoots;       // h: 0 reward, 1 value (+ policy copy)
-        if (r >= nvalid || !((hmask >> h) & 1)) continue;
-        const int b = root0 + r;
-        if (h == 0) {
-            const float *lg = lg_rew + r * kLdK;
-            const float rv = categorical_to_scalar(lg, net.reward.K, net.support_min, net.support_step, lane);
-            if (lane == 0 && io.reward) io.reward[b] = rv;
-            if (io.reward_logits)
-                for (int k = lane; k < net.reward.K; k += 32) io.reward_logits[(size_t)b * net.reward.K + k] = lg[k];
-        } else {
-            const float *lg = lg_val + r * kLdK;
-            const float vv = categorical_to_scalar(lg, net.value.K, net.support_min, net.support_step, lane);
-            if (lane == 0 && io.value) io.value[b] = vv;
-            if (io.value_logits)
-                for (int k = lane; k < net.value.K; k += 32) io.value_logits[(size_t)b * net.value.K + k] = lg[k];
-            if (io.policy_logits && (hmask & 4)) {
-                const float *lp = lg_pol + r * ldp;
-                for (int a = lane; a < A; a += 32) io.policy_logits[(size_t)b * A + a] = lp[a];
-            }
-        }
-    }
 }
 
 // ---------------------------------------------------------------------------------------------- kernel
@@ -293,6 +325,41 @@ __device__ __forceinline__ void store_row32(float *root, bool cl, int p, int hal
     }
 }
 
+// 16 consecutive channels [c0, c0 + 16) of pixel p of one root (same layouts)
+__device__ __forceinline__ void store_row16(float *root, bool cl, int p, int c0, const float (&v)[16])
+{
+    if (cl) {
+        float4 *dst = reinterpret_cast<float4 *>(root + p * kC + c0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    } else {
+        float *dst = root + (size_t)c0 * kP + p;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) dst[(size_t)c * kP] = v[c];
+    }
+}
+
+// the tree of a warp (tree_persist.cuh) parked in shared memory while the warp does network work: 16 uniform words + 3 x 32
+// per-lane words
+constexpr int kTreeParkWords = 16 + 3 * 32;
+__device__ __forceinline__ void ptree_park(const PTree &T, uint32_t *w, int lane)
+{
+    if (lane == 0) {
+        w[0] = (uint32_t)T.nl; w[1] = (uint32_t)T.plen; w[2] = (uint32_t)T.vtp; w[3] = __float_as_uint(T.mmax); w[4] = __float_as_uint(T.mmin);
+        w[5] = (uint32_t)T.root_visit; w[6] = __float_as_uint(T.root_vsum); w[7] = __float_as_uint(T.root_reward);
+        w[8] = (uint32_t)T.root_to_play; w[9] = (uint32_t)T.tp0; w[10] = (uint32_t)T.players;
+    }
+    w[16 + lane] = (uint32_t)T.my_legal; w[48 + lane] = (uint32_t)T.my_pslot; w[80 + lane] = (uint32_t)T.my_pact;
+    __syncwarp();
+}
+__device__ __forceinline__ void ptree_unpark(PTree &T, const uint32_t *w, int lane)
+{
+    T.nl = (int)w[0]; T.plen = (int)w[1]; T.vtp = (int)w[2]; T.mmax = __uint_as_float(w[3]); T.mmin = __uint_as_float(w[4]);
+    T.root_visit = (int)w[5]; T.root_vsum = __uint_as_float(w[6]); T.root_reward = __uint_as_float(w[7]);
+    T.root_to_play = (int)w[8]; T.tp0 = (int)w[9]; T.players = (int)w[10];
+    T.my_legal = (int)w[16 + lane]; T.my_pslot = (int)w[48 + lane]; T.my_pact = (int)w[80 + lane];
+}
+
 __global__ void __launch_bounds__(kTcThreads, 1) k_net_tc(TcNet net, TcIO io, TreeParams tp)
 {
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -323,7 +390,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_net_tc(TcNet net, TcIO io, Tr
         mbar_init(&bars->act_ready, kEpiThreads);
         mbar_init(&bars->rew_ready, 1);
         mbar_init(&bars->vp_ready, 1);
-        for (int i = 0; i < kStages; ++i) bars->fc_cnt[i] = 0u;
+        for (int i = 0; i < kStages; ++i) mbar_init(&bars->fc_empty[i], kEpiWarps);
         fence_mbar_init();
     }
     // heads whose fully connected parts run in this kernel (EfficientZero: the reward features go to the LSTM kernels instead),
@@ -356,12 +423,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_net_tc(TcNet net, TcIO io, Tr
         // ================= weight producer =================
         if (lane == 0) {
             uint32_t n = 0;
+            // a ring stage is handed back either by the MMA issuer (tcgen05.commit on empty[st], conv taps) or by the epilogue
+            // warps (fc_empty[st], FC blocks): per-stage phase parities of both barriers, and who used the stage last
+            uint32_t par_tap = 0, par_fc = 0, last_fc = 0;
+            auto acquire = [&](int st, bool fc_use) {
+                if (n >= (uint32_t)kStages) {
+                    if ((last_fc >> st) & 1u) { mbar_wait(&bars->fc_empty[st], (par_fc >> st) & 1u); par_fc ^= 1u << st; }
+                    else { mbar_wait(&bars->empty[st], (par_tap >> st) & 1u); par_tap ^= 1u << st; }
+                }
+                last_fc = fc_use ? (last_fc | (1u << st)) : (last_fc & ~(1u << st));
+            };
             for (int sim = 0; sim < nsims; ++sim) {     // runs ahead of the consumers: the next simulation's first taps are
                 for (int L = 0; L < nlayers; ++L) {     // already in the ring while the tree work is going on
                     const unsigned char *src = net.convw + (size_t)net.layer_w[L] * (9 * kTapBytes);
                     for (int tap = 0; tap < 9; ++tap, ++n) {
                         const int st = n % kStages;
-                        if (n >= kStages) mbar_wait(&bars->empty[st], ((n / kStages) - 1) & 1);
+                        acquire(st, false);
                         mbar_expect_tx(&bars->full[st], kTapBytes);
                         bulk_g2s(ring + st * kTapBytes, src + (size_t)tap * kTapBytes, kTapBytes, &bars->full[st]);
                     }
@@ -376,7 +453,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_net_tc(TcNet net, TcIO io, Tr
                         for (int blk = 0; blk < nblk; ++blk, ++n) {
                             const int st = n % kStages;
                             const uint32_t bytes = pass == 0 ? (uint32_t)min(kTapBytes, net.fc[h].nin * 128 - blk * kTapBytes) : (uint32_t)kTapBytes;
-                            if (n >= kStages) mbar_wait(&bars->empty[st], ((n / kStages) - 1) & 1);
+                            acquire(st, true);
                             mbar_expect_tx(&bars->full[st], bytes);
                             bulk_g2s(ring + st * kTapBytes, src + (size_t)blk * kTapBytes, bytes, &bars->full[st]);
                         }
@@ -497,13 +574,28 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_net_tc(TcNet net, TcIO io, Tr
         // ================= epilogue warps: warp w owns TMEM lanes 32*(w%4).. and the 32-column half w/4 =================
         const int q4 = warp & 3, half = warp >> 2, rowid = q4 * 32 + lane;
         const uint32_t lane_base = tmem + ((uint32_t)(q4 * 32) << 16);
-        float *f_rew = reinterpret_cast<float *>(smem + kSmemMain);      // reward features [7][kHfStride], then reward logits [7][kLdK]
+        float *f_rew = reinterpret_cast<float *>(smem + kSmemMain);      // reward features [7][kHfStride]
         unsigned long long *dbg = (io.dbg && blockIdx.x == 0 && tid == 0) ? io.dbg : nullptr;
         if (dbg) dbg[0] = clock64();
         pdl_wait();                   // ix / action / the latent pool come from the preceding kernels
         int acc_par = 0;
-        PTree T;                      // this warp's tree (tree_persist.cuh): per-tree scalars stay in registers across simulations
-        if (fast_tree && warp < nvalid) ptree_init(tp, T, root0 + warp, lane);
+        // this warp's tree (tree_persist.cuh): its scalars / first path entries live in registers during the tree phase and are
+        // parked in shared memory while the warp does network work
+        uint32_t *tree_park = reinterpret_cast<uint32_t *>(smem + kSmemMain + kMaxRoots * kHfStride * 4) + warp * kTreeParkWords;
+        if (fast_tree && warp < nvalid) {
+            PTree T;
+            ptree_init(tp, T, root0 + warp, lane);
+            ptree_park(T, tree_park, lane);
+        }
+        // row bookkeeping of this thread (simulation-invariant): per tile (root slot in the CTA) << 8 | pixel, or -1 for pad rows
+        int rowc[kMaxTiles];
+#pragma unroll
+        for (int t = 0; t < kMaxTiles; ++t) {
+            const int m = t * 128 + rowid;
+            const int r = m / kRowsPerRoot, q = m - r * kRowsPerRoot, y = q / kPitch, x = q - y * kPitch;
+            const bool valid = (t < NT) && (m < rows_used) && (r < nvalid) && (y < 6) && (x < 6);
+            rowc[t] = valid ? ((r << 8) | (y * 6 + x)) : -1;
+        }
         for (int sim = 0; sim < nsims; ++sim) {
             if (dbg) dbg[50] = clock64();
             if (persistent) {
@@ -512,9 +604,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_net_tc(TcNet net, TcIO io, Tr
                 if (warp < nvalid) {
                     const int b = root0 + warp;
                     if (fast_tree) {
+                        PTree T;
+                        ptree_unpark(T, tree_park, lane);
                         if (sim > 0)
                             ptree_backprop(tp, T, b, lane, io.sim0 + sim, io.reward[b], io.value[b], io.policy_logits + (size_t)b * net.A);
                         ptree_traverse(tp, T, b, lane, io.deterministic, (unsigned)(io.sim0 + sim), pbc_tab, io.ix_rw, io.action_rw);
+                        ptree_park(T, tree_park, lane);
                     } else {
                         if (sim > 0)
                             tree_backprop(tp, b, lane, io.sim0 + sim, io.reward[b], io.value[b], io.policy_logits + (size_t)b * net.A, nullptr);
@@ -533,40 +628,36 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_net_tc(TcNet net, TcIO io, Tr
                 int row = r < kMargin ? r : kMargin + kMaxTiles * 128 + (r - kMargin);
                 *reinterpret_cast<uint4 *>(act + part * kPartBytes + plane * kPlaneBytes + row * 16) = make_uint4(0, 0, 0, 0);
             }
-            // per-tile row bookkeeping of this thread: root, pixel, validity; the input latent of the row's root
-            const float *in_root[kMaxTiles];
-            bool in_cl[kMaxTiles];
-            int rowp[kMaxTiles], rowb[kMaxTiles];       // pixel (or -1: pad / unused row), global root index
+            // the pool slot holding the input latent of each of this thread's rows (tree -> network hand-off)
+            int slot[kMaxTiles];
 #pragma unroll
-            for (int t = 0; t < kMaxTiles; ++t) {
-                const int m = t * 128 + rowid;
-                const int r = m / kRowsPerRoot, q = m - r * kRowsPerRoot, y = q / kPitch, x = q - y * kPitch;
-                const bool valid = (t < NT) && (m < rows_used) && (r < nvalid) && (y < 6) && (x < 6);
-                rowp[t] = valid ? y * 6 + x : -1;
-                rowb[t] = root0 + r;
-                in_root[t] = nullptr; in_cl[t] = false;
-                if (valid) {
-                    const size_t slot = io.ix ? (size_t)io.ix[rowb[t]] : 0;
-                    in_root[t] = io.latent_base + slot * io.slot_stride + (size_t)rowb[t] * (kC * kP);
-                    in_cl[t] = io.pool_cl && slot > 0;      // slot 0 holds the root latents as the API delivered them (NCHW)
-                }
-            }
-            // ---- load the input activation: gather the latents, split to fp16 hi/lo ----
+            for (int t = 0; t < kMaxTiles; ++t) slot[t] = (rowc[t] >= 0 && io.ix) ? io.ix[root0 + (rowc[t] >> 8)] : 0;
+            auto in_ptr = [&](int t) { return io.latent_base + (size_t)slot[t] * io.slot_stride + (size_t)(root0 + (rowc[t] >> 8)) * (kC * kP); };
+            auto in_is_cl = [&](int t) { return io.pool_cl != 0 && slot[t] > 0; };      // slot 0: root latents as the API delivered them (NCHW)
+            // ---- load the input activation: gather the latents (two tiles' loads in flight), split to fp16 hi/lo ----
+            {
+                float va[32], vb[32];
+                auto fetch_in = [&](int t, float (&dst)[32]) {
+                    if (rowc[t] >= 0) load_row32(in_ptr(t), in_is_cl(t), rowc[t] & 255, half, dst);
+                    else {
 #pragma unroll
-            for (int t = 0; t < kMaxTiles; ++t) {
-                if (t >= NT) continue;
-                const int m = t * 128 + rowid;
-                float v[32];
-                if (rowp[t] >= 0) load_row32(in_root[t], in_cl[t], rowp[t], half, v);
-                else {
+                        for (int c = 0; c < 32; ++c) dst[c] = 0.0f;
+                    }
+                };
+                auto put = [&](int t, const float (&src)[32]) {
+                    const int m = t * 128 + rowid;
 #pragma unroll
-                    for (int c = 0; c < 32; ++c) v[c] = 0.0f;
-                }
-#pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    unsigned char *p = act + (half * 4 + g) * kPlaneBytes + (kMargin + m) * 16;
-                    store_split8(p, p + kPartBytes, v + 8 * g);
-                }
+                    for (int g = 0; g < 4; ++g) {
+                        unsigned char *p = act + (half * 4 + g) * kPlaneBytes + (kMargin + m) * 16;
+                        store_split8(p, p + kPartBytes, src + 8 * g);
+                    }
+                };
+                fetch_in(0, va);
+                if (NT > 1) fetch_in(1, vb);
+                put(0, va);
+                if (NT > 2) fetch_in(2, va);
+                if (NT > 1) put(1, vb);
+                if (NT > 2) put(2, va);
             }
             fence_proxy_async();
             tc_fence_before();
@@ -578,72 +669,103 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_net_tc(TcNet net, TcIO io, Tr
                 const int flags = net.layer_flags[L];
                 const float4 *bn4 = reinterpret_cast<const float4 *>(bn_s + L * 128 + half * 32);   // scale; shift 16 float4 further
                 const bool park = (flags & LF_STORE_RES) && (L + 1 < nlayers);
+                // Residual operands (and, for the dynamics conv, the action-plane bias) are thread-private global rows (L2-resident).
+                // Two row buffers stay in flight so that no load latency is exposed after the accumulators arrive: tiles 0 and 1 are
+                // fetched BEFORE the accumulator wait (this thread idles through the layer's MMAs anyway), tile 2's skip right after
+                // tile 0 is done and its action bias right after tile 1.
+                const bool has_res = (flags & LF_RES) != 0, has_ab = (flags & LF_ACT_BIAS) != 0;
+                float ra[32], rb[32];
+                auto fetch_skip = [&](int t, float (&dst)[32]) {
+                    if (rowc[t] < 0) return;
+                    if (skip_in_scratch) load_row32(io.skip_scratch + (size_t)(root0 + (rowc[t] >> 8)) * (kC * kP), true, rowc[t] & 255, half, dst);
+                    else load_row32(in_ptr(t), in_is_cl(t), rowc[t] & 255, half, dst);
+                };
+                auto fetch_abias = [&](int t, float (&dst)[32], bool add) {
+                    if (rowc[t] < 0) return;
+                    const int action = min(max(io.action[root0 + (rowc[t] >> 8)], 0), net.A - 1);
+                    const float4 *ab = reinterpret_cast<const float4 *>(net.abias + ((size_t)action * kP + (rowc[t] & 255)) * kC + half * 32);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 q = __ldg(ab + j);
+                        if (add) { dst[4 * j] += q.x; dst[4 * j + 1] += q.y; dst[4 * j + 2] += q.z; dst[4 * j + 3] += q.w; }
+                        else { dst[4 * j] = q.x; dst[4 * j + 1] = q.y; dst[4 * j + 2] = q.z; dst[4 * j + 3] = q.w; }
+                    }
+                };
+                if (has_res) {
+                    fetch_skip(0, ra);
+                    if (NT > 1) fetch_skip(1, rb);
+                    if (has_ab) {
+                        fetch_abias(0, ra, true);
+                        if (NT > 1) fetch_abias(1, rb, true);
+                    }
+                }
+                mbar_wait_warp(&bars->acc_ready, acc_par);
+                acc_par ^= 1;                               // one commit per layer, across simulations
+                tc_fence_after();
+                if (dbg) dbg[2 + 2 * L] = clock64();
 #pragma unroll
                 for (int t = 0; t < kMaxTiles; ++t) {
                     if (t >= NT) continue;
                     const int m = t * 128 + rowid;
-                    const int p = rowp[t], b = rowb[t];
-                    const bool valid = p >= 0;
-                    float *scr_root = io.skip_scratch + (size_t)b * (kC * kP);
-                    // residual operand of this row (L2-resident, thread-private addresses): issued before the accumulator wait
-                    float rs[32];
-                    if ((flags & LF_RES) && valid) {
-                        if (skip_in_scratch) load_row32(scr_root, true, p, half, rs);
-                        else load_row32(in_root[t], in_cl[t], p, half, rs);
-                    }
-                    if (t == 0) {
-                        mbar_wait_warp(&bars->acc_ready, acc_par);
-                        acc_par ^= 1;                               // one commit per layer, across simulations
-                        tc_fence_after();
-                        if (dbg) dbg[2 + 2 * L] = clock64();
-                    }
-                    uint32_t ua[32];
-                    float v[32];
-                    tmem_ld32_issue(lane_base + kColAcc + t * kAccCols + half * 32, ua);
-                    if (npass == 3 && LZ_FOLD != 0) {
-                        uint32_t ub[32];
-                        tmem_ld32_issue(lane_base + kColAcc + t * kAccCols + 64 + half * 32, ub);
-                        tmem_ld_wait();
-                        tmem_pin(ua); tmem_pin(ub);
+                    const bool valid = rowc[t] >= 0;
+                    const int p = rowc[t] & 255, b = root0 + (rowc[t] >> 8);
+                    float (&rs)[32] = (t == 1) ? rb : ra;
+                    if (has_res && has_ab && t == 2) {
+                        // tile 2's action bias arrived in the other buffer: the same (skip + bias) association as tiles 0 / 1, so
+                        // that a root's bits do not depend on which tile of the CTA it lands in
 #pragma unroll
-                        for (int c = 0; c < 32; ++c) v[c] = __uint_as_float(ua[c]) + __uint_as_float(ub[c]);
-                    } else {
-                        tmem_ld_wait();
-                        tmem_pin(ua);
-#pragma unroll
-                        for (int c = 0; c < 32; ++c) v[c] = __uint_as_float(ua[c]);
+                        for (int c = 0; c < 32; ++c) ra[c] += rb[c];
                     }
+                    // the thread's 32 channels in two halves of 16 (keeps the live registers of this loop under the budget)
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float4 sc = bn4[j], sh = bn4[16 + j];
-                        v[4 * j] = fmaf(v[4 * j], sc.x, sh.x); v[4 * j + 1] = fmaf(v[4 * j + 1], sc.y, sh.y);
-                        v[4 * j + 2] = fmaf(v[4 * j + 2], sc.z, sh.z); v[4 * j + 3] = fmaf(v[4 * j + 3], sc.w, sh.w);
-                    }
-                    if ((flags & LF_RES) && valid) {
+                    for (int hs = 0; hs < 2; ++hs) {
+                        uint32_t ua[16];
+                        float v[16];
+                        tmem_ld16_issue(lane_base + kColAcc + t * kAccCols + half * 32 + hs * 16, ua);
+                        if (npass == 3 && LZ_FOLD != 0) {
+                            uint32_t ub[16];
+                            tmem_ld16_issue(lane_base + kColAcc + t * kAccCols + 64 + half * 32 + hs * 16, ub);
+                            tmem_ld_wait();
+                            tmem_pin(ua); tmem_pin(ub);
 #pragma unroll
-                        for (int c = 0; c < 32; ++c) v[c] += rs[c];
-                    }
-                    if ((flags & LF_ACT_BIAS) && valid) {
-                        const int action = min(max(io.action[b], 0), net.A - 1);
-                        const float4 *ab = reinterpret_cast<const float4 *>(net.abias + ((size_t)action * kP + p) * kC + half * 32);
+                            for (int c = 0; c < 16; ++c) v[c] = __uint_as_float(ua[c]) + __uint_as_float(ub[c]);
+                        } else {
+                            tmem_ld_wait();
+                            tmem_pin(ua);
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const float4 q = __ldg(ab + j);
-                            v[4 * j] += q.x; v[4 * j + 1] += q.y; v[4 * j + 2] += q.z; v[4 * j + 3] += q.w;
+                            for (int c = 0; c < 16; ++c) v[c] = __uint_as_float(ua[c]);
+                        }
+                        if (valid) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const float4 sc = bn4[hs * 4 + j], sh = bn4[16 + hs * 4 + j];
+                                v[4 * j] = fmaf(v[4 * j], sc.x, sh.x); v[4 * j + 1] = fmaf(v[4 * j + 1], sc.y, sh.y);
+                                v[4 * j + 2] = fmaf(v[4 * j + 2], sc.z, sh.z); v[4 * j + 3] = fmaf(v[4 * j + 3], sc.w, sh.w);
+                            }
+                            if (has_res) {
+#pragma unroll
+                                for (int c = 0; c < 16; ++c) v[c] += rs[hs * 16 + c];
+                            }
+#pragma unroll
+                            for (int c = 0; c < 16; ++c) v[c] = fmaxf(v[c], 0.0f);       // every layer of these programs ends in ReLU
+                            if (park) store_row16(io.skip_scratch + (size_t)b * (kC * kP), true, p, half * 32 + hs * 16, v);
+                            if (flags & LF_WRITE_LATENT) {
+                                if (latent_out) store_row16(latent_out + (size_t)b * (kC * kP), io.pool_cl != 0, p, half * 32 + hs * 16, v);
+                                if (io.latent_out2) store_row16(io.latent_out2 + (size_t)b * (kC * kP), false, p, half * 32 + hs * 16, v);
+                            }
+                        } else {
+#pragma unroll
+                            for (int c = 0; c < 16; ++c) v[c] = 0.0f;          // pad rows / absent roots: the conv padding of the next layer
+                        }
+#pragma unroll
+                        for (int g = 0; g < 2; ++g) {
+                            unsigned char *pp = act + (half * 4 + hs * 2 + g) * kPlaneBytes + (kMargin + m) * 16;
+                            store_split8_pos(pp, pp + kPartBytes, v + 8 * g);
                         }
                     }
-#pragma unroll
-                    for (int c = 0; c < 32; ++c) v[c] = valid ? fmaxf(v[c], 0.0f) : 0.0f;
-                    if (park && valid) store_row32(scr_root, true, p, half, v);
-                    if ((flags & LF_WRITE_LATENT) && valid) {
-                        if (latent_out) store_row32(latent_out + (size_t)b * (kC * kP), io.pool_cl != 0, p, half, v);
-                        if (io.latent_out2) store_row32(io.latent_out2 + (size_t)b * (kC * kP), false, p, half, v);
-                    }
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        unsigned char *pp = act + (half * 4 + g) * kPlaneBytes + (kMargin + m) * 16;
-                        store_split8(pp, pp + kPartBytes, v + 8 * g);
-                    }
+                    // next fetches into the buffer this tile has just released
+                    if (has_res && t == 0 && NT > 2) fetch_skip(2, ra);
+                    if (has_res && has_ab && t == 1 && NT > 2) fetch_abias(2, rb, false);
                 }
                 if (park) skip_in_scratch = true;
                 fence_proxy_async();
@@ -685,7 +807,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_net_tc(TcNet net, TcIO io, Tr
                 asm volatile("bar.sync 1, %0;\n" ::"n"(kEpiThreads) : "memory");
                 if (dbg) dbg[44] = clock64();
                 uint32_t hn = (uint32_t)sim * (9 * nlayers + nfc) + 9 * nlayers;
-                heads_fc(net, io, hmask_fc, ring, bars, hn, f_rew, f_vp, wk, f_rew + kMaxRoots * kHfStride, nvalid, root0, dbg);
+                heads_fc(net, io, hmask_fc, ring, bars, hn, f_rew, f_vp, wk, nvalid, root0, dbg);
             }
             if (dbg) dbg[27] = clock64();
             __threadfence_block();
@@ -693,7 +815,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_net_tc(TcNet net, TcIO io, Tr
         }
         if (persistent && warp < nvalid) {        // back up the last simulation (mcts_ctree.py:365-368)
             const int b = root0 + warp;
-            if (fast_tree) ptree_backprop(tp, T, b, lane, io.sim0 + nsims, io.reward[b], io.value[b], io.policy_logits + (size_t)b * net.A);
+            if (fast_tree) {
+                PTree T;
+                ptree_unpark(T, tree_park, lane);
+                ptree_backprop(tp, T, b, lane, io.sim0 + nsims, io.reward[b], io.value[b], io.policy_logits + (size_t)b * net.A);
+            }
             else tree_backprop(tp, b, lane, io.sim0 + nsims, io.reward[b], io.value[b], io.policy_logits + (size_t)b * net.A, nullptr);
         }
     }

@@ -227,4 +227,19 @@ __device__ __forceinline__ void store_split8(unsigned char *hi_ptr, unsigned cha
 }
 
 
+// the same for values known to be >= 0 (post-ReLU activations): only the upper clamp, packed conversions
+__device__ __forceinline__ void store_split8_pos(unsigned char *hi_ptr, unsigned char *lo_ptr, const float *v)
+{
+    __half2 h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float a = fminf(v[2 * i], 65504.0f), b = fminf(v[2 * i + 1], 65504.0f);
+        h[i] = __floats2half2_rn(a, b);
+        const float2 back = __half22float2(h[i]);
+        l[i] = __floats2half2_rn(a - back.x, b - back.y);
+    }
+    *reinterpret_cast<uint4 *>(hi_ptr) = *reinterpret_cast<uint4 *>(h);
+    *reinterpret_cast<uint4 *>(lo_ptr) = *reinterpret_cast<uint4 *>(l);
+}
+
 }  // namespace lz
