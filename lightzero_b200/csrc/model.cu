@@ -841,7 +841,7 @@ static int pack_tc(lz_model *m, const NetDev &net)
                                     if (yy < 0 || yy >= kHW || xx < 0 || xx >= kHW) continue;
                                     acc += (*w)[((size_t)co * cin_total + kC + a) * 9 + ky * 3 + kx];
                                 }
-                            abias[((size_t)a * kP + y * kHW + x) * kC + co] = acc * scale[co];   // pixel-major: 32 consecutive channels per epilogue thread
+                            abias[(((size_t)a * 16 + co / 4) * kP + y * kHW + x) * 4 + co % 4] = acc * scale[co];   // k_net_tc's internal [c / 4][36][c % 4] layout
                         }
         }
     }

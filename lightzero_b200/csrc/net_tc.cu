@@ -295,15 +295,18 @@ __device__ __forceinline__ void heads_fc(const TcNet &net, const TcIO &io, int h
 }
 
 // ---------------------------------------------------------------------------------------------- kernel
-// 32 consecutive channels [32*half, 32*half+32) of pixel p of one root latent.  cl: channels-last [36][64] (the pool slots this
-// kernel writes in persistent mode, and the skip scratch); else NCHW [64][36] (every tensor that crosses the API).
+// 32 consecutive channels [32*half, 32*half+32) of pixel p of one root latent.  cl: the kernel-internal layout [c / 4][36][c % 4]
+// (the pool slots this kernel writes in persistent mode, the skip scratch, the action-bias table): a thread's float4 j is at
+// ((c0 / 4 + j) * 36 + p) * 4, so the lanes of a warp (consecutive pixels) touch consecutive 16-byte chunks -- coalesced 512-byte
+// warp accesses (a plain channels-last row per lane costs 32 separate sectors per warp instruction).  Else NCHW [64][36]
+// (every tensor that crosses the API).
 __device__ __forceinline__ void load_row32(const float *root, bool cl, int p, int half, float (&v)[32])
 {
     if (cl) {
-        const float4 *src = reinterpret_cast<const float4 *>(root + p * kC + half * 32);
+        const float4 *src = reinterpret_cast<const float4 *>(root) + (half * 8) * kP + p;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const float4 q = src[j];      // plain loads: the pool / scratch are written by this launch
+            const float4 q = src[j * kP];      // plain loads: the pool / scratch are written by this launch
             v[4 * j] = q.x; v[4 * j + 1] = q.y; v[4 * j + 2] = q.z; v[4 * j + 3] = q.w;
         }
     } else {
@@ -312,26 +315,14 @@ __device__ __forceinline__ void load_row32(const float *root, bool cl, int p, in
         for (int c = 0; c < 32; ++c) v[c] = src[(size_t)c * kP];
     }
 }
-__device__ __forceinline__ void store_row32(float *root, bool cl, int p, int half, const float (&v)[32])
-{
-    if (cl) {
-        float4 *dst = reinterpret_cast<float4 *>(root + p * kC + half * 32);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-    } else {
-        float *dst = root + (size_t)(half * 32) * kP + p;
-#pragma unroll
-        for (int c = 0; c < 32; ++c) dst[(size_t)c * kP] = v[c];
-    }
-}
 
 // 16 consecutive channels [c0, c0 + 16) of pixel p of one root (same layouts)
 __device__ __forceinline__ void store_row16(float *root, bool cl, int p, int c0, const float (&v)[16])
 {
     if (cl) {
-        float4 *dst = reinterpret_cast<float4 *>(root + p * kC + c0);
+        float4 *dst = reinterpret_cast<float4 *>(root) + (c0 >> 2) * kP + p;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        for (int j = 0; j < 4; ++j) dst[j * kP] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
     } else {
         float *dst = root + (size_t)c0 * kP + p;
 #pragma unroll
@@ -683,10 +674,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_net_tc(TcNet net, TcIO io, Tr
                 auto fetch_abias = [&](int t, float (&dst)[32], bool add) {
                     if (rowc[t] < 0) return;
                     const int action = min(max(io.action[root0 + (rowc[t] >> 8)], 0), net.A - 1);
-                    const float4 *ab = reinterpret_cast<const float4 *>(net.abias + ((size_t)action * kP + (rowc[t] & 255)) * kC + half * 32);
+                    const float4 *ab = reinterpret_cast<const float4 *>(net.abias) + ((size_t)action * 16 + half * 8) * kP + (rowc[t] & 255);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        const float4 q = __ldg(ab + j);
+                        const float4 q = __ldg(ab + j * kP);
                         if (add) { dst[4 * j] += q.x; dst[4 * j + 1] += q.y; dst[4 * j + 2] += q.z; dst[4 * j + 3] += q.w; }
                         else { dst[4 * j] = q.x; dst[4 * j + 1] = q.y; dst[4 * j + 2] = q.z; dst[4 * j + 3] = q.w; }
                     }

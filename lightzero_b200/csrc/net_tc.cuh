@@ -19,7 +19,7 @@ struct TcNet {
     const float *bn;               // [nconv][scale 64 | shift 64] (weight power-of-two scale folded in)
     const unsigned char *headw;    // [reward hi 2K | lo 2K][value+policy hi 4K | lo 4K]
     const float *head_bn;          // [reward s16 t16 | value s16 t16 | policy s16 t16]
-    const float *abias;            // [A][36][64] (pixel-major) action-plane contribution of the dynamics conv, x BN scale
+    const float *abias;            // [A][16][36][4] ([c / 4][pixel][c % 4]) action-plane contribution of the dynamics conv, x BN scale
     const unsigned char *fcw;      // FC weight stream of the three heads (TcFc offsets)
     TcFc fc[3];                    // reward, value, policy
     Head reward, value, policy;    // folded BN / bias tables of the FC parts (fp32, same tables as the SIMT path)
@@ -50,8 +50,8 @@ struct TcIO {
     int persistent, nsims, sim0, deterministic;
     int *ix_rw, *action_rw;        // [B] tree -> network hand-off (same arrays as ix / action)
     float *latent_pool_rw;         // == latent_base; slot s+1 receives the latents of simulation s
-    float *skip_scratch;           // [B][36][64] fp32: ResBlock skip tensors parked between layers (thread-private rows, L2-resident)
-    int pool_cl;                   // latent pool slots >= 1 and latent_out are channels-last [36][64] (persistent search); else NCHW
+    float *skip_scratch;           // [B][16][36][4] fp32: ResBlock skip tensors parked between layers (thread-private rows, L2-resident)
+    int pool_cl;                   // latent pool slots >= 1 and latent_out use the kernel-internal [c / 4][36][c % 4] layout (persistent search); else NCHW
     float *ez_feat;                // EfficientZero: the reward head stops after conv1x1+BN+ReLU and writes [B][hc*36] here
     unsigned long long *dbg;       // optional [64] clock64 stamps of CTA 0 (bring-up instrumentation)
 };
