@@ -47,6 +47,8 @@ typedef struct lz_search lz_search;
 typedef void *lz_stream;   /* cudaStream_t */
 
 int lz_version(void);
+/* Launch accounting: kernels this library has enqueued since load (kernel nodes of launched graphs included). */
+unsigned long long lz_debug_launch_count(void);
 const char *lz_last_error(void);
 
 /* ------------------------------------------------------------------ tree (mz_tree / cnode.cpp) */
@@ -125,7 +127,7 @@ int lz_tree_backpropagate_with_reuse(lz_tree *t, int latent_index, const float *
                                      const int32_t *d_to_play, lz_stream s);
 
 /* select_action (lzero/policy/utils.py:637-661) on the device, from the root visit counts of the finished search:
- * p = visit ** (1 / temperature) / sum (fp64), d_entropy = -sum p ln p, d_action_pos = arg-max (deterministic != 0; the
+ * p = visit ** (1 / temperature) / sum (fp64), d_entropy = -sum p log2 p (scipy.stats.entropy(p, base=2)), d_action_pos = arg-max (deterministic != 0; the
  * eval path, policy/muzero.py:935) or one draw from p (inverse CDF of a counter-based uniform keyed by seed and tree index;
  * the reference draws with np.random.choice), d_action = the action id at that legal position (policy/muzero.py:800).
  * Outputs int32 [B] / f32 [B], any may be NULL.  SURVEY 8(f) row f-3: keeps the collector's action choice on the GPU. */

@@ -34,6 +34,7 @@ class MlpConfig(ctypes.Structure):
 # name -> (restype, argtypes); every symbol include/lzb200.h declares
 SIGNATURES = {
     "lz_version": (c_int, []),
+    "lz_debug_launch_count": (ctypes.c_uint64, []),
     "lz_last_error": (c_char_p, []),
     "lz_tree_create": (c_int, [c_int, c_int, c_int, ctypes.POINTER(c_void_p)]),
     "lz_tree_destroy": (c_int, [c_void_p]),

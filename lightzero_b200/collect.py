@@ -29,7 +29,7 @@ def select_action(visit_counts: np.ndarray, temperature: float = 1, deterministi
         action_pos = int(np.random.choice(len(visit_counts), p=action_probs))
     p = np.asarray(action_probs, np.float64)
     nz = p[p > 0]
-    entropy = float(-(nz * np.log(nz)).sum())   # scipy.stats.entropy(action_probs, base=None)
+    entropy = float(-(nz * np.log(nz)).sum() / np.log(2.0))   # scipy.stats.entropy(action_probs, base=2): natural-log entropy / ln 2
     return action_pos, entropy
 
 
@@ -74,8 +74,11 @@ class MuZeroCollectPolicy:
         det = self.mcts.deterministic if deterministic is None else bool(deterministic)
         with torch.cuda.device(dev):
             host_path = not obs.is_cuda
+            # uint8 frames (what the Atari emulator delivers) stay uint8 on the wire: a quarter of the bytes; the [0, 1] scaling
+            # of the reference's ScaledFloatFrameWrapper happens inside the first conv kernel (lz_search_collect*_u8)
+            u8 = obs.dtype == torch.uint8
             if host_path:
-                h_obs = obs.to(torch.float32).contiguous()
+                h_obs = obs.contiguous() if u8 else obs.to(torch.float32).contiguous()
                 h_mask = (action_mask if isinstance(action_mask, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(action_mask))).to(torch.uint8).contiguous()
                 h_noise = None
                 if noises is not None:
@@ -86,7 +89,7 @@ class MuZeroCollectPolicy:
                 assert not h_mask.is_cuda and (h_noise is None or not h_noise.is_cuda), "host observation batch needs host mask / noise"
                 self._keep_host = (h_obs, h_mask, h_noise, h_tp)
             else:
-                d_obs = obs.to(torch.float32).contiguous()
+                d_obs = obs.contiguous() if u8 else obs.to(torch.float32).contiguous()
                 mask_t = action_mask if isinstance(action_mask, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(action_mask))
                 bufs["mask"].copy_(mask_t.to(torch.uint8), non_blocking=True)
                 d_noise = None
@@ -106,14 +109,16 @@ class MuZeroCollectPolicy:
                 q = tree.search_for(self.model, S, self._tree_mode if self._tree_mode[0] else ())
                 s = cabi.stream_ptr()
                 if host_path:
-                    cabi.check(tree.lib.lz_search_collect_host(q, h_obs.data_ptr(), h_mask.data_ptr(), cabi.ptr(h_noise),
-                                                               float(self.cfg.root_noise_weight), cabi.ptr(h_tp), int(det),
-                                                               int(self.h2d_chunks), bufs["pred_value"].data_ptr(),
-                                                               bufs["logits"].data_ptr(), s), "lz_search_collect_host")
+                    fn = tree.lib.lz_search_collect_host_u8 if u8 else tree.lib.lz_search_collect_host
+                    cabi.check(fn(q, h_obs.data_ptr(), h_mask.data_ptr(), cabi.ptr(h_noise),
+                                  float(self.cfg.root_noise_weight), cabi.ptr(h_tp), int(det),
+                                  int(self.h2d_chunks), bufs["pred_value"].data_ptr(),
+                                  bufs["logits"].data_ptr(), s), "lz_search_collect_host")
                 else:
-                    cabi.check(tree.lib.lz_search_collect(q, d_obs.data_ptr(), bufs["mask"].data_ptr(), cabi.ptr(d_noise),
-                                                          float(self.cfg.root_noise_weight), cabi.ptr(d_tp), int(det),
-                                                          bufs["pred_value"].data_ptr(), bufs["logits"].data_ptr(), s),
+                    fn = tree.lib.lz_search_collect_u8 if u8 else tree.lib.lz_search_collect
+                    cabi.check(fn(q, d_obs.data_ptr(), bufs["mask"].data_ptr(), cabi.ptr(d_noise),
+                                  float(self.cfg.root_noise_weight), cabi.ptr(d_tp), int(det),
+                                  bufs["pred_value"].data_ptr(), bufs["logits"].data_ptr(), s),
                                "lz_search_collect")
                 cabi.check(tree.lib.lz_tree_results(tree.h, tree.visits.data_ptr(), tree.values.data_ptr(),
                                                     tree.nlegal.data_ptr(), None, s), "lz_tree_results")

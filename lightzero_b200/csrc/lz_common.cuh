@@ -10,6 +10,7 @@
 namespace lz {
 
 void set_error(const char *fmt, ...);
+void count_launch(int n = 1);      // launch accounting (lz_debug_launch_count): kernels enqueued by this library, graph nodes included
 
 #define LZ_CUDA_CHECK(expr)                                                                    \
     do {                                                                                       \
@@ -29,7 +30,11 @@ void set_error(const char *fmt, ...);
         }                                    \
     } while (0)
 
-#define LZ_KERNEL_CHECK() LZ_CUDA_CHECK(cudaGetLastError())
+#define LZ_KERNEL_CHECK()                    \
+    do {                                     \
+        lz::count_launch();                  \
+        LZ_CUDA_CHECK(cudaGetLastError());   \
+    } while (0)
 
 template <typename T>
 inline int dev_alloc(T **p, size_t n)

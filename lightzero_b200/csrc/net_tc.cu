@@ -918,6 +918,7 @@ int tc_launch(const TcNet &net, const TcIO &io_in, cudaStream_t s, const TreePar
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = io_in.pdl ? 1 : 0;
     cfg.attrs = attr; cfg.numAttrs = 1;
+    count_launch();
     LZ_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_net_tc, net, io, tp));
     return LZ_OK;
 }

@@ -175,6 +175,7 @@ static int run_graph(lz_search *q, int deterministic, cudaStream_t s)
         if (e != cudaSuccess) { set_error("cudaGraphInstantiate failed: %s", cudaGetErrorString(e)); return LZ_ECUDA; }
     }
     LZ_CUDA_CHECK(cudaGraphLaunch(q->exec[d], s));
+    count_launch(q->num_kernels);       // the graph's kernel nodes
     return LZ_OK;
 }
 

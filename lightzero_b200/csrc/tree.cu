@@ -2,6 +2,8 @@
 // Compiled with -fmad=false: no fp32 contraction anywhere in this translation unit.
 #include <math.h>
 #include <stdarg.h>
+
+#include <atomic>
 #include <limits.h>
 #include <vector>
 
@@ -12,6 +14,9 @@
 namespace lz {
 
 static thread_local char g_err[512] = "";
+static std::atomic<unsigned long long> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+
 void set_error(const char *fmt, ...)
 {
     va_list ap;
@@ -210,7 +215,7 @@ k_tree_results(TreeParams p, int32_t *visits, float *values, int32_t *nlegal, in
 }
 
 // select_action (lzero/policy/utils.py:637-661) on the root visit counts of every tree: probabilities
-// visit ** (1 / temperature) / sum in fp64 like the reference's Python floats, entropy = -sum p ln p (scipy.stats.entropy),
+// visit ** (1 / temperature) / sum in fp64 like the reference's Python floats, entropy in bits = -sum p ln p / ln 2 (scipy.stats.entropy(p, base=2), policy/utils.py:660),
 // action = arg-max (deterministic, first maximum like np.argmax) or an inverse-CDF draw from a counter-based uniform.
 __global__ void __launch_bounds__(kTreeBlock)
 k_tree_select_action(TreeParams p, double inv_temperature, int deterministic, unsigned long long seed,
@@ -249,7 +254,7 @@ k_tree_select_action(TreeParams p, double inv_temperature, int deterministic, un
         }
         if (action_pos) action_pos[b] = pos;
         if (action) action[b] = lg[pos];            // np.where(action_mask == 1)[0][pos], policy/muzero.py:800
-        if (entropy) entropy[b] = (float)ent;
+        if (entropy) entropy[b] = (float)(ent / 0.69314718055994530942);    // base 2, as scipy divides the natural-log entropy by ln 2
     }
 }
 
@@ -265,6 +270,7 @@ static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, cudaStream_t 
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
     cfg.attrs = attr; cfg.numAttrs = 1;
+    count_launch();
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
@@ -348,7 +354,8 @@ using namespace lz;
 
 extern "C" {
 
-int lz_version(void) { return 100; }
+int lz_version(void) { return 200; }
+unsigned long long lz_debug_launch_count(void) { return lz::g_launches.load(std::memory_order_relaxed); }
 const char *lz_last_error(void) { return lz::g_err; }
 
 int lz_tree_create(int B, int A, int max_sims, lz_tree **out)

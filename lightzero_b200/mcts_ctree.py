@@ -81,7 +81,7 @@ class MuZeroMCTSCtree(object):
         self._cfg.setdefault("discount_factor", 0.997)
         self._cfg.setdefault("device", "cuda")
         self.deterministic = bool(self._cfg.get("deterministic", self.deterministic_default))
-        self._inv = None    # lazily: InverseScalarTransform for the step-wise mode (mcts_ctree.py:250-253)
+        self._inv = self._inv_reward = None    # lazily: InverseScalarTransforms for the step-wise mode (mcts_ctree.py:249-253)
 
     @classmethod
     def roots(cls, active_collect_env_num: int, legal_actions: List[Any]) -> "mz_tree.Roots":
@@ -141,13 +141,25 @@ class MuZeroMCTSCtree(object):
         c = counts.cpu().numpy()
         return int(c[-1]), float(c.sum()) / S
 
+    def _make_inverse_transforms(self, dev):
+        """mcts_ctree.py:249-253: separate value and reward supports, both categorical (the only representation the CUDA
+        transform implements)."""
+        if self._inv is not None:
+            return
+        m = self._cfg.get("model", None)
+
+        def rng(key):
+            return tuple(m[key]) if m is not None and key in m else (-300., 301., 1.)
+        if m is not None and not m.get("categorical_distribution", True):
+            raise NotImplementedError("model.categorical_distribution=False: only the categorical (support) representation is implemented")
+        self._inv = InverseScalarTransform(DiscreteSupport(*rng("value_support_range"), device=dev))
+        vr, rr = rng("value_support_range"), rng("reward_support_range")
+        self._inv_reward = self._inv if vr == rr else InverseScalarTransform(DiscreteSupport(*rr, device=dev))
+
     def _search_stepwise(self, roots, model, lat, S):
         t = roots._tree
         dev = roots.device
-        if self._inv is None:
-            m = self._cfg.get("model", None)
-            rng = tuple(m.value_support_range) if m is not None and "value_support_range" in m else (-300., 301., 1.)
-            self._inv = InverseScalarTransform(DiscreteSupport(*rng, device=dev))
+        self._make_inverse_transforms(dev)
         B = roots.num
         pool = torch.empty((S + 1,) + tuple(lat.shape), device=dev, dtype=torch.float32)
         pool[0] = lat
@@ -162,8 +174,8 @@ class MuZeroMCTSCtree(object):
                 latent_states = pool[t.ix.long(), rows]                       # mcts_ctree.py:323-324 on device
                 out = model.recurrent_inference(latent_states, t.action.long())
                 pool[sim + 1] = out.latent_state
-                value = self._inv(out.value).reshape(-1).contiguous()        # :349
-                reward = self._inv(out.reward).reshape(-1).contiguous()      # :350
+                value = self._inv(out.value).reshape(-1).contiguous()        # :349 (value support)
+                reward = self._inv_reward(out.reward).reshape(-1).contiguous()      # :350 (reward support)
                 pol = out.policy_logits.to(torch.float32).contiguous()
                 cabi.check(t.lib.lz_tree_backpropagate(t.h, sim + 1, reward.data_ptr(), value.data_ptr(),
                                                        pol.data_ptr(), None, cabi.stream_ptr()),
@@ -219,10 +231,7 @@ class EfficientZeroMCTSCtree(MuZeroMCTSCtree):
     def _search_stepwise_ez(self, roots, model, lat, h0, h1, S, H):
         t = roots._tree
         dev = roots.device
-        if self._inv is None:
-            m = self._cfg.get("model", None)
-            rng = tuple(m.value_support_range) if m is not None and "value_support_range" in m else (-300., 301., 1.)
-            self._inv = InverseScalarTransform(DiscreteSupport(*rng, device=dev))
+        self._make_inverse_transforms(dev)
         B = roots.num
         pool = torch.empty((S + 1,) + tuple(lat.shape), device=dev, dtype=torch.float32)
         hp0 = torch.zeros((S + 1, B, h0.shape[1]), device=dev)
@@ -245,7 +254,7 @@ class EfficientZeroMCTSCtree(MuZeroMCTSCtree):
                 hp0[sim + 1] = out.reward_hidden_state[0].reshape(B, -1) * keep
                 hp1[sim + 1] = out.reward_hidden_state[1].reshape(B, -1) * keep
                 value = self._inv(out.value).reshape(-1).contiguous()
-                vprefix = self._inv(out.value_prefix).reshape(-1).contiguous()
+                vprefix = self._inv_reward(out.value_prefix).reshape(-1).contiguous()
                 pol = out.policy_logits.to(torch.float32).contiguous()
                 cabi.check(t.lib.lz_tree_backpropagate_ez(t.h, sim + 1, vprefix.data_ptr(), value.data_ptr(), pol.data_ptr(),
                                                           reset.data_ptr(), None, cabi.stream_ptr()),

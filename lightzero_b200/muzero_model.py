@@ -7,9 +7,13 @@ PyTorch eager path.  Inference (eval mode, BatchNorm running statistics) only.
 from dataclasses import dataclass
 from typing import Dict, Optional, Sequence
 
+import itertools
+
 import torch
 
 from . import cabi
+
+_model_serial = itertools.count(1)      # never reused (unlike id()): keys of the per-tree lz_search caches in mz_tree
 
 
 @dataclass
@@ -60,6 +64,7 @@ class MuZeroModel:
         with torch.cuda.device(self.device):
             cabi.check(self._lib.lz_model_create(cfg, h), "lz_model_create")
         self._h = h
+        self._serial = next(_model_serial)
         self.latent_hw = self._lib.lz_model_latent_hw(self._h)
         self.value_support_size = self.reward_support_size = self._lib.lz_model_support_size(self._h)
         self._loaded = False
@@ -155,6 +160,8 @@ class MuZeroModel:
     def __del__(self):
         try:
             if getattr(self, "_h", None):
+                from . import mz_tree
+                mz_tree.drop_model_searches(self._serial)     # lz_search handles point at this lz_model: destroy them first
                 self._lib.lz_model_destroy(self._h)
         except Exception:
             pass

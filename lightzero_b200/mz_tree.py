@@ -10,6 +10,7 @@ Differences a caller can observe:
   * ``MinMaxStatsList`` is bookkeeping only -- min/max live inside the tree and are reset when the
     Roots are (re)prepared, i.e. once per search like mcts_ctree.py:291-292.
 """
+import threading
 from typing import List, Optional
 
 import numpy as np
@@ -19,6 +20,7 @@ from . import cabi
 
 DEFAULT_MAX_SIMS = 64     # node-pool capacity when a Roots is driven step-wise without a known budget
 _tree_pool = {}           # (device index, B, A, max_sims) -> [TreeHandle]
+_pool_lock = threading.Lock()
 
 
 class TreeHandle:
@@ -40,7 +42,7 @@ class TreeHandle:
         self.nlegal = torch.empty(B, **i32)
         self.values = torch.empty(B, dtype=torch.float32, device=device)
         self.traj = torch.empty(B, max_sims + 1, **i32)
-        self.searches = {}    # id(model) -> lz_search handle
+        self.searches = {}    # (model serial, num_simulations, mode...) -> lz_search handle; dropped when the model dies
 
     def set_params(self, pb_c_base, pb_c_init, discount, delta):
         p = (int(pb_c_base), float(pb_c_init), float(discount), float(delta))
@@ -50,7 +52,10 @@ class TreeHandle:
             self.params = p
 
     def search_for(self, model, num_simulations, mode=()):
-        key = (id(model), num_simulations) + tuple(mode)     # mode: (ez, lstm_horizon_len) -- both are baked into the graph
+        # keyed by the model's serial (unique for the life of the process; id() is recycled after garbage collection).  The
+        # captured graph is re-captured inside the library when the model's weights / math mode or this tree's parameters
+        # change (generation counters, csrc/search.cu), so one lz_search per (model, num_simulations, mode) is enough
+        key = (model._serial, num_simulations) + tuple(mode)     # mode: (ez, lstm_horizon_len)
         if key not in self.searches:
             q = cabi.c_void_p()
             with torch.cuda.device(self.device):
@@ -69,14 +74,29 @@ class TreeHandle:
 
 def acquire_tree(device, B, A, max_sims) -> TreeHandle:
     key = (device.index, B, A, max_sims)
-    for h in _tree_pool.setdefault(key, []):
-        if not h.busy:
-            h.busy = True
-            return h
-    h = TreeHandle(device, B, A, max_sims)
-    h.busy = True
-    _tree_pool[key].append(h)
-    return h
+    with _pool_lock:
+        for h in _tree_pool.setdefault(key, []):
+            if not h.busy:
+                h.busy = True
+                return h
+        h = TreeHandle(device, B, A, max_sims)
+        h.busy = True
+        _tree_pool[key].append(h)
+        return h
+
+
+def drop_model_searches(serial: int):
+    """Called when a model wrapper is destroyed: destroys every lz_search bound to that lz_model (they hold its pointer and
+    graphs captured against its device tables)."""
+    with _pool_lock:
+        handles = [h for hs in _tree_pool.values() for h in hs]
+    for h in handles:
+        for key in [k for k in h.searches if k[0] == serial]:
+            q = h.searches.pop(key)
+            try:
+                h.lib.lz_search_destroy(q)
+            except Exception:
+                pass
 
 
 def _to_dev(x, dtype, device, shape=None):

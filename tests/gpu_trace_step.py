@@ -1,0 +1,88 @@
+"""CUPTI trace (torch.profiler; nsys is not installed in this image) of (1) one initial_inference and (2) one fused
+MuZeroMCTSCtree.search(): the kernel timeline with the idle gaps between kernels, and every CUDA runtime / driver API call made
+inside search() -- the evidence for "one cudaGraphLaunch, no cudaStreamSynchronize / cudaMemcpy inside search()" (SURVEY 8d).
+Run on the GPU box; writes gpurun_out/trace_step.json and prints a summary."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+from torch.profiler import ProfilerActivity, profile
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import lightzero_b200 as lzb
+from lightzero_b200.synthetic_weights import synthetic_state_dict
+
+B, S, A = 1024, 50, 18
+model = lzb.MuZeroModel(observation_shape=(4, 84, 84), action_space_size=A).load_state_dict(synthetic_state_dict((4, 84, 84), A))
+obs = torch.rand(B, 4, 84, 84).cuda()
+mcts = lzb.MuZeroMCTSCtree(dict(num_simulations=S, deterministic=True, discount_factor=0.997))
+noise = torch.from_numpy(np.random.default_rng(0).dirichlet([0.3] * A, size=B).astype(np.float32)).cuda()
+mask = torch.ones(B, A, dtype=torch.uint8)
+
+
+def prep():
+    out0 = model.initial_inference(obs)
+    roots = mcts.roots(B, mask)
+    roots.prepare(0.25, noise, None, out0.policy_logits, None)
+    roots._materialize(S, mcts._params())
+    return out0, roots
+
+
+for _ in range(3):                       # warm-up: graph capture, allocations
+    out0, roots = prep()
+    mcts.search(roots, model, out0.latent_state, None)
+torch.cuda.synchronize()
+
+
+def events(prof):
+    ev = []
+    for e in prof.events():
+        dt = str(getattr(e, "device_type", ""))
+        ev.append(dict(name=e.name, cuda="CUDA" in dt, start_us=e.time_range.start, dur_us=e.time_range.end - e.time_range.start))
+    return ev
+
+
+summary = {}
+# ---- (1) initial_inference: kernel timeline
+with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+    model.initial_inference(obs)
+    torch.cuda.synchronize()
+ev = events(prof)
+kern = sorted([e for e in ev if e["cuda"]], key=lambda e: e["start_us"])
+rows, prev_end = [], None
+for e in kern:
+    gap = (e["start_us"] - prev_end) if prev_end is not None else 0.0
+    rows.append(dict(kernel=e["name"][:60], dur_us=round(e["dur_us"], 1), gap_before_us=round(gap, 1)))
+    prev_end = e["start_us"] + e["dur_us"]
+span = (kern[-1]["start_us"] + kern[-1]["dur_us"] - kern[0]["start_us"]) if kern else 0.0
+summary["initial_inference"] = dict(kernels=rows, busy_us=round(sum(e["dur_us"] for e in kern), 1), span_us=round(span, 1))
+print("initial_inference: %d device activities, busy %.1f us, span %.1f us" % (len(kern), summary["initial_inference"]["busy_us"], span))
+for r in rows:
+    print("   %-60s %9.1f us   gap before %7.1f us" % (r["kernel"], r["dur_us"], r["gap_before_us"]))
+
+# ---- (2) search(): runtime API calls between entering and leaving search()
+out0, roots = prep()
+torch.cuda.synchronize()
+with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+    mcts.search(roots, model, out0.latent_state, None)
+    torch.cuda.synchronize()            # outside search(): closes the trace
+ev = events(prof)
+api = {}
+for e in ev:
+    if not e["cuda"] and (e["name"].startswith("cuda") or e["name"].startswith("cu")):
+        api[e["name"]] = api.get(e["name"], 0) + 1
+dev = sorted([e for e in ev if e["cuda"]], key=lambda e: e["start_us"])
+summary["search"] = dict(runtime_api_calls=api, device_activities=[dict(name=e["name"][:60], dur_us=round(e["dur_us"], 1)) for e in dev])
+print("search(): CUDA API calls:", api)
+print("search(): device activities:", [(e["name"][:40], round(e["dur_us"], 1)) for e in dev])
+n_sync = sum(v for k, v in api.items() if "Synchronize" in k) - 1     # the one after search() that closes the trace
+n_cpy = sum(v for k, v in api.items() if "Memcpy" in k)
+summary["search"]["syncs_inside_search"] = n_sync
+summary["search"]["memcpys_inside_search"] = n_cpy
+print("search(): cudaGraphLaunch x%d, synchronisations inside search(): %d, memcpy calls inside search(): %d"
+      % (api.get("cudaGraphLaunch", 0), n_sync, n_cpy))
+os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+json.dump(summary, open(os.path.join(ROOT, "gpurun_out", "trace_step.json"), "w"), indent=1)

@@ -24,7 +24,7 @@ def _models(A, seed=0, obs=(4, 84, 84), nres=1):
     return ref, cu
 
 
-@pytest.mark.parametrize("B,A", [(5, 6), (130, 18), (300, 6)])
+@pytest.mark.parametrize("B,A", [(5, 6), (130, 18), (300, 6), (1024, 18)])
 def test_initial_inference_matches_oracle(B, A):
     ref, cu = _models(A)
     obs = torch.rand(B, 4, 84, 84)
@@ -133,7 +133,7 @@ def test_tensor_core_3xfp16_recurrent_matches_oracle(B, A):
     assert torch.allclose(out.reward_scalar.cpu(), inv(exp.reward).reshape(-1), rtol=2e-4, atol=2e-4)
 
 
-@pytest.mark.parametrize("B,A,nres", [(5, 6, 1), (300, 18, 1), (9, 6, 2)])
+@pytest.mark.parametrize("B,A,nres", [(5, 6, 1), (300, 18, 1), (9, 6, 2), (1024, 18, 1)])
 def test_tensor_core_3xfp16_initial_matches_oracle(B, A, nres):
     ref, cu = _models(A, seed=5, nres=nres)
     cu.set_math("tc3")

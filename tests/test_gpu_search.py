@@ -284,3 +284,63 @@ def test_fused_search_with_reuse_equals_stepwise_drive():
     assert fused == step
     assert length == counts[-1] and abs(avg - sum(counts) / S) < 1e-9
     assert min(counts) < B       # some trees reused a value instead of calling the network
+
+
+def test_uint8_frames_equal_scaled_float_frames_bit_for_bit():
+    """lz_search_collect*_u8: uint8 frames scaled inside the first conv kernel == the float frames the reference's env wrapper
+    produces ((obs - 0) / 255 in float64, cast to float32: ScaledFloatFrameWrapper, zoo/atari/envs/atari_wrappers.py:219-220),
+    through the host entry point and the device entry point."""
+    from lightzero_b200.collect import MuZeroCollectPolicy
+    B, A, S = 48, 6, 12
+    ref, cu, obs, mask, legal, noises, mcts = _setup(B, A, S, seed=5, math="tc3")
+    g = torch.Generator().manual_seed(3)
+    u8 = torch.randint(0, 256, (B, 4, 84, 84), dtype=torch.uint8, generator=g)
+    f32 = torch.from_numpy((u8.numpy() / 255.).astype(np.float32))
+    pol = MuZeroCollectPolicy(cu, dict(num_simulations=S, deterministic=True, discount_factor=0.997))
+    noise = np.zeros((B, A), np.float32)
+    for b in range(B):
+        noise[b, :len(noises[b])] = noises[b]
+    res = []
+    for o in (f32.pin_memory(), u8.pin_memory(), u8.cuda(), f32.cuda()):
+        r = pol.search_batch(o, torch.from_numpy(mask), torch.from_numpy(noise), None, deterministic=True, read_back=True)
+        res.append({k: v.clone() for k, v in r.items()})
+    for r in res[1:]:
+        for k in ("visits", "values", "pred_value", "policy_logits"):
+            assert torch.equal(res[0][k].view(torch.int32) if res[0][k].dtype == torch.float32 else res[0][k],
+                               r[k].view(torch.int32) if r[k].dtype == torch.float32 else r[k]), k
+
+
+def test_weight_reload_and_parameter_change_recapture_the_search_graph():
+    """A captured search graph bakes in device pointers of the model tables and the tree parameters (by value): reloading the
+    weights (the collector's weight sync) or changing discount / value_delta_max must not replay a stale graph."""
+    import lightzero_b200 as lzb
+    from oracle.model_ref import MuZeroModelRef, emulate_trained_
+    B, A, S = 40, 6, 16
+    ref, cu, obs, mask, legal, noises, mcts = _setup(B, A, S, seed=3, math="tc3")
+    ref2 = emulate_trained_(MuZeroModelRef((4, 84, 84), A), 77)
+
+    def run(model, m):
+        out = model.initial_inference(obs.cuda())
+        roots = m.roots(B, legal)
+        roots.prepare(0.25, noises, [0.] * B, out.policy_logits, [-1] * B)
+        m.search(roots, model, out.latent_state, [-1] * B)
+        r = (roots.get_distributions(), np.asarray(roots.get_values(), np.float32).view(np.uint32).tolist())
+        roots.clear()
+        return r
+
+    first = run(cu, mcts)
+    cu.load_state_dict(ref2.state_dict())                       # same lz_model, new device tables
+    reloaded = run(cu, mcts)
+    fresh = lzb.MuZeroModel(observation_shape=(4, 84, 84), action_space_size=A).load_state_dict(ref2.state_dict())
+    assert reloaded == run(fresh, mcts) and reloaded != first
+    # tree parameters: the fused graph must follow the step-wise drive after a discount change on the same pooled tree
+    mcts2 = lzb.MuZeroMCTSCtree(dict(num_simulations=S, deterministic=True, discount_factor=0.9, value_delta_max=0.05))
+    fused = run(cu, mcts2)
+    step = run_step = None
+    out = cu.initial_inference(obs.cuda())
+    roots = mcts2.roots(B, legal)
+    roots.prepare(0.25, noises, [0.] * B, out.policy_logits, [-1] * B)
+    mcts2.search(roots, _Recorder(cu), out.latent_state, [-1] * B)
+    step = (roots.get_distributions(), np.asarray(roots.get_values(), np.float32).view(np.uint32).tolist())
+    roots.clear()
+    assert fused == step and fused != reloaded

@@ -16,7 +16,7 @@ def test_select_action_follows_the_reference_formula():
             probs = v.astype(np.float64) ** (1 / temp)
             probs /= probs.sum()
             assert pos == int(np.argmax(v))
-            assert abs(ent - entropy(probs, base=None)) < 1e-12
+            assert abs(ent - entropy(probs, base=2)) < 1e-12       # lzero/policy/utils.py:660
     np.random.seed(0)
     draws = [select_action(np.array([1, 0, 3]), temperature=1.0, deterministic=False)[0] for _ in range(400)]
     assert 1 not in draws and 0.15 < draws.count(0) / 400 < 0.35
