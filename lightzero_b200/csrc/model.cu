@@ -791,21 +791,17 @@ static int pack_tc(lz_model *m, const NetDev &net)
     const size_t off_bn = off_headw + tc_head_layout_bytes();
     const size_t off_headbn = off_bn + (size_t)nconv * 128 * 4;
     const size_t off_abias = off_headbn + 96 * 4;
-    // FC weight stream of the heads (16 KB blocks for the shared-memory ring of k_net_tc): FC1 as [nin][32] fp32 rows (hidden
-    // units zero padded to 32), FC2 as [ceil(K/128)][32][128] fp32 blocks
+    // FC weight stream of the heads (16 KB stages for the shared-memory ring of k_net_tc, fp16 hi / lo, the weights are the
+    // tensor cores' M operand): 18 FC1 stages covering all three heads, then one stage per 128-output tile of each head's FC2
     const std::string fc_names[3] = {"dynamics_network.fc_reward_head", "prediction_network.fc_value", "prediction_network.fc_policy"};
     const Head *fc_heads[3] = {&net.reward, &net.value, &net.policy};
-    size_t fc_off1[3], fc_off2[3];
+    size_t fc_off2[3];
     size_t off_fc = (off_abias + (size_t)A * kC * kP * 4 + 127) & ~(size_t)127;
     const size_t off_fc0 = off_fc;
+    off_fc += (size_t)18 * 16384;
     for (int h = 0; h < 3; ++h) {
-        const Head &H = *fc_heads[h];
-        const bool on = H.hid > 0;      // EfficientZero: the reward head's FC part lives in ez.cu
-        fc_off1[h] = off_fc - off_fc0;
-        if (on) off_fc += (size_t)H.hc * kP * 32 * 4;
-        off_fc = (off_fc + 127) & ~(size_t)127;
         fc_off2[h] = off_fc - off_fc0;
-        if (on) off_fc += (size_t)((H.K + 127) / 128) * 32 * 128 * 4;
+        if (fc_heads[h]->hid > 0) off_fc += (size_t)((fc_heads[h]->K + 127) / 128) * 16384;      // EfficientZero: the reward head's FC part lives in ez.cu
     }
     const size_t total = off_fc;
     std::vector<unsigned char> host(total, 0);
@@ -862,19 +858,43 @@ static int pack_tc(lz_model *m, const NetDev &net)
             head_bn[h.bn_off + 16 + i] = t1[i] + s1[i] * (*b1)[i];
         }
     }
+    float fc1_inv[3] = {1.0f, 1.0f, 1.0f}, fc2_inv[3] = {1.0f, 1.0f, 1.0f};
     for (int h = 0; h < 3; ++h) {
         const Head &H = *fc_heads[h];
         if (H.hid <= 0) continue;
         const int nin = H.hc * kP;
-        LZ_REQUIRE(H.hid <= 32 && H.K <= 608, LZ_EINVAL, "lz_model_finalize: tcgen05 path needs head hidden <= 32 and support <= 608");
+        LZ_REQUIRE(H.hid <= 32 && H.K <= 608 && nin <= 576, LZ_EINVAL, "lz_model_finalize: tcgen05 path needs head hidden <= 32, head channels <= 16 and support <= 608");
         auto W0 = find(m, fc_names[h] + ".0.weight", (size_t)H.hid * nin), W3 = find(m, fc_names[h] + ".3.weight", (size_t)H.K * H.hid);
         if (!W0 || !W3) return LZ_EINVAL;
-        float *f1 = reinterpret_cast<float *>(host.data() + off_fc0 + fc_off1[h]);
-        float *f2 = reinterpret_cast<float *>(host.data() + off_fc0 + fc_off2[h]);
+        auto pow2_scale = [](const std::vector<float> &w) {
+            float mx = 0.0f;
+            for (float v : w) mx = std::max(mx, fabsf(v));
+            int e = 0;
+            if (mx > 0.0f) frexpf(mx, &e);
+            return ldexpf(1.0f, 13 - e);            // largest |w| lands in [4096, 8192): the lo parts stay in fp16's normal range
+        };
+        const float s1 = pow2_scale(*W0), s2 = pow2_scale(*W3);
+        fc1_inv[h] = 1.0f / s1; fc2_inv[h] = 1.0f / s2;
+        auto put = [&](unsigned char *hi, unsigned char *lo, size_t off, float v) {
+            const __half a = __float2half_rn(v), b = __float2half_rn(v - __half2float(a));
+            *reinterpret_cast<__half *>(hi + off) = a;
+            *reinterpret_cast<__half *>(lo + off) = b;
+        };
+        // FC1: stage i = inputs [32 i, 32 i + 32): [k-step 2][hi 4 KB | lo 4 KB], each [kg 2][128 rows][8]; row = 32 h + unit
+        unsigned char *f1 = host.data() + off_fc0;
         for (int i = 0; i < nin; ++i)
-            for (int j = 0; j < H.hid; ++j) f1[(size_t)i * 32 + j] = (*W0)[(size_t)j * nin + i];
+            for (int j = 0; j < H.hid; ++j) {
+                const int kstep = i >> 4, kg = (i >> 3) & 1, e = i & 7;
+                unsigned char *base = f1 + (size_t)(kstep >> 1) * 16384 + (size_t)(kstep & 1) * 8192;
+                put(base, base + 4096, ((size_t)kg * 128 + h * 32 + j) * 16 + e * 2, (*W0)[(size_t)j * nin + i] * s1);
+            }
+        // FC2: tile mt = outputs [128 mt, 128 mt + 128): [hi 8 KB | lo 8 KB], each [kg 4][128 rows][8]
+        unsigned char *f2 = host.data() + off_fc0 + fc_off2[h];
         for (int k = 0; k < H.K; ++k)
-            for (int j = 0; j < H.hid; ++j) f2[((size_t)(k / 128) * 32 + j) * 128 + (k % 128)] = (*W3)[(size_t)k * H.hid + j];
+            for (int j = 0; j < H.hid; ++j) {
+                unsigned char *base = f2 + (size_t)(k >> 7) * 16384;
+                put(base, base + 8192, ((size_t)(j >> 3) * 128 + (k & 127)) * 16 + (j & 7) * 2, (*W3)[(size_t)k * H.hid + j] * s2);
+            }
     }
     if (m->d_tc) cudaFree(m->d_tc);
     m->d_tc = nullptr;
@@ -890,9 +910,10 @@ static int pack_tc(lz_model *m, const NetDev &net)
     base.reward = net.reward; base.value = net.value; base.policy = net.policy;
     base.fcw = m->d_tc + off_fc0;
     for (int h = 0; h < 3; ++h) {
-        base.fc[h].fc1_off = (uint32_t)fc_off1[h]; base.fc[h].fc2_off = (uint32_t)fc_off2[h];
+        base.fc[h].fc2_off = (uint32_t)fc_off2[h];
         base.fc[h].nin = fc_heads[h]->hid > 0 ? fc_heads[h]->hc * kP : 0;
         base.fc[h].K = fc_heads[h]->hid > 0 ? fc_heads[h]->K : 0;
+        base.fc[h].fc1_inv = fc1_inv[h]; base.fc[h].fc2_inv = fc2_inv[h];
     }
     base.hc[0] = c.reward_head_channels; base.hc[1] = c.value_head_channels; base.hc[2] = c.policy_head_channels;
     base.A = A; base.support_min = c.support_min; base.support_step = c.support_step;

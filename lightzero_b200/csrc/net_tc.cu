@@ -60,7 +60,7 @@ constexpr int kStages = 5;                       // 16 KB ring stages: conv taps
 constexpr int kHeadWBytes = 3 * 2 * 16 * 64 * 2; // three 1x1 heads (hc <= 16), hi + lo: 12288 B
 constexpr int kBnSmemBytes = kTcMaxLayers * 128 * 4;   // folded BatchNorm tables of the program's layers
 constexpr int kSmemMain = kActBytes + kStages * kTapBytes + kHeadWBytes + 1024 + kBnSmemBytes;
-constexpr int kHeadScratch = kMaxRoots * 577 * 4 + kEpiWarps * (16 + 3 * 32) * 4;   // + the parked trees (kTreeParkWords per warp)   // reward head features, parked from their hook to the heads' FC pass at the end of the simulation
+constexpr int kHeadScratch = 72 * 8 * 16 * 2 + kEpiWarps * (16 + 3 * 32) * 4;   // kFrBytes (parked reward features) + the parked trees   // + the parked trees (kTreeParkWords per warp)   // reward head features, parked from their hook to the heads' FC pass at the end of the simulation
 constexpr int kSmemBytes = kSmemMain + kHeadScratch;
 
 // TMEM columns
@@ -76,23 +76,47 @@ struct TcBars {
     uint64_t act_ready;     // epilogue -> MMA: activations (and TMEM) are ready for the next layer
     uint64_t rew_ready;     // MMA -> heads: reward 1x1 accumulators complete (single phase)
     uint64_t vp_ready;      // MMA -> heads: value/policy 1x1 accumulators complete (single phase)
-    uint64_t fc_empty[kStages];   // heads -> producer: all kEpiWarps epilogue warps are done with the FC weight block in this stage
+    uint64_t fcb_ready;     // heads -> MMA: the head features (FC1's B operand) are in shared memory
+    uint64_t fc1_done;      // MMA -> heads: FC1 accumulators complete
+    uint64_t fc2b_ready;    // heads -> MMA: the hidden activations (FC2's B operand) are in shared memory
+    uint64_t fc2_done;      // MMA -> heads: FC2 accumulators (the heads' logits) complete
     uint32_t tmem_base;
     uint32_t pad;
 };
 
 // ---------------------------------------------------------------------------------------------- heads
 // The fully connected parts of the heads (reward / value / policy: Linear(hc*36 -> hid) + BN + ReLU, Linear(hid -> K),
-// muzero_model.py:465-502, common.py:1130-1187) run on the CUDA cores at the END of a simulation, with their fp32 weights
-// STREAMED through the same shared-memory ring as the conv taps (16 KB blocks, cp.async.bulk by the producer warp): 375 KB of
-// weights per simulation arrive bandwidth-bound and prefetched instead of as latency-bound global loads from 256 threads.
-//   FC1 block = 128 input rows x 32 hidden units; lane = (root, 8-unit group), warp = 16 of the block's rows.
-//   FC2 block = 32 hidden units x 128 outputs;    thread = output k (tid % 128) x root group (tid / 128).
-constexpr int kHfStride = 577;                    // feature row stride (odd: the 7 roots of one input fall in 7 banks)
+// muzero_model.py:465-502, common.py:1130-1187) run on the TENSOR CORES at the end of a simulation with the roles swapped: the
+// weights are the M operand (streamed through the same 16 KB ring as the conv taps, fp16 hi/lo), the 7 roots are N columns:
+//   FC1  D[(head, unit) 96 of 128 rows][(head, root) 32 columns] += W1^T[rows][K = 576 inputs] x F[K][columns]; only the diagonal
+//        (head == head) blocks are read back (one MMA stream for all three heads, A-operand-bound);
+//   FC2  per head and per 128-output tile: D[output k][root] = W2[k][K = 32 units] x H[units][root]: a thread of the read-out owns
+//        output k = tile * 128 + lane for every root -- exactly the distribution of the canonical softmax order (net6.cuh), so the
+//        softmax expectation runs straight out of TMEM, the 601 logits are never stored.
+// Both products keep the fp32-accurate 3xFP16 scheme: A_hi x [B_hi | B_lo] and A_lo x [B_hi | B_lo] (the extra lo x lo term is
+// harmless), the two column halves are added at read-out.
+constexpr int kFbKgBytes = 64 * 16 + 16;                  // FC1 B operand: per k-group 32 hi rows + 32 lo rows of 16 B (+16 B: bank spread)
+constexpr int kFbBytes = 72 * kFbKgBytes;                 // 576 inputs = 72 k-groups: 74,880 B (overlays the activation buffer)
+constexpr int kFrBytes = 72 * 8 * 16 * 2;                 // reward features parked from their hook: [hi | lo][72 k-groups][8 roots][16 B] = 18,432 B
+constexpr int kHbHeadBytes = 4 * 16 * 16;                 // FC2 B operand of one head: [4 k-groups][8 roots hi | 8 roots lo][16 B] = 1 KB
+constexpr int kFc1Stages = 18;                            // 576 inputs / 32 per 16 KB stage (2 k-steps x (A_hi 4 KB + A_lo 4 KB))
+// TMEM columns of the FC phase (the conv accumulators are drained by then; the value/policy 1x1 results in columns 0-95 are
+// consumed by head_scatter before FC1 starts)
+constexpr int kColFc1 = 0;        // 64: [0,32) hi x hi + lo x hi, [32,64) hi x lo (+ lo x lo)
+constexpr int kColFc2 = 64;       // 16 per (head, 128-output tile): [0,8) / [8,16) likewise
 
-// 1x1-conv accumulators (TMEM) -> BatchNorm + ReLU -> flattened features [root][c*36 + p] (stride kHfStride) for the heads in
-// hmask (bit 0 reward -> f_rew, bit 1 value / bit 2 policy -> f_vp[0 / 1]).  No barrier inside.
-__device__ __forceinline__ void head_scatter(const TcNet &net, int hmask, float *f_rew, float *f_vp, uint32_t tmem, int NT, int rows_used, int nvalid)
+__device__ __forceinline__ void put_half(unsigned char *p, float v, float &rem)
+{
+    const __half h = __float2half_rn(fminf(v, 65504.0f));
+    *reinterpret_cast<__half *>(p) = h;
+    rem = v - __half2float(h);
+}
+
+// 1x1-conv accumulators (TMEM) -> BatchNorm + ReLU -> fp16 hi/lo features in FC1's B-operand layout, for the heads in hmask (bit 0
+// reward -> its parking buffer fr, bit 1 value / bit 2 policy -> rows 8-15 / 16-23 of fb).  Feature k = c * 36 + p of root r sits at
+// k-group k / 8, row (head * 8 + r), element k % 8.  No barrier inside.
+__device__ __forceinline__ void head_scatter(const TcNet &net, int hmask, unsigned char *fr, unsigned char *fb, uint32_t tmem, int NT,
+                                             int rows_used, int nvalid)
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q4 = warp & 3, half = warp >> 2, rowid = q4 * 32 + lane;
@@ -107,191 +131,147 @@ __device__ __forceinline__ void head_scatter(const TcNet &net, int hmask, float 
         if (half == 0 && (hmask & 1)) {
             tmem_ld16(lane_base + kColRew + t * 16, v);
             if (valid)
-                for (int c = 0; c < net.hc[0]; ++c)
-                    f_rew[r * kHfStride + c * kP + p] = fmaxf(fmaf(v[c], __ldg(net.head_bn + c), __ldg(net.head_bn + 16 + c)), 0.0f);
+                for (int c = 0; c < net.hc[0]; ++c) {
+                    const int k = c * kP + p;
+                    unsigned char *d = fr + ((k >> 3) * 8 + r) * 16 + (k & 7) * 2;
+                    float rem;
+                    put_half(d, fmaxf(fmaf(v[c], __ldg(net.head_bn + c), __ldg(net.head_bn + 16 + c)), 0.0f), rem);
+                    *reinterpret_cast<__half *>(d + kFrBytes / 2) = __float2half_rn(rem);
+                }
         }
         if (half == 0 && (hmask & 2)) {
             tmem_ld16(lane_base + kColVp + t * 32, v);
             if (valid)
-                for (int c = 0; c < net.hc[1]; ++c)
-                    f_vp[r * kHfStride + c * kP + p] = fmaxf(fmaf(v[c], __ldg(net.head_bn + 32 + c), __ldg(net.head_bn + 48 + c)), 0.0f);
+                for (int c = 0; c < net.hc[1]; ++c) {
+                    const int k = c * kP + p;
+                    unsigned char *d = fb + (k >> 3) * kFbKgBytes + (8 + r) * 16 + (k & 7) * 2;
+                    float rem;
+                    put_half(d, fmaxf(fmaf(v[c], __ldg(net.head_bn + 32 + c), __ldg(net.head_bn + 48 + c)), 0.0f), rem);
+                    *reinterpret_cast<__half *>(d + 32 * 16) = __float2half_rn(rem);
+                }
         }
         if (half == 1 && (hmask & 4)) {
             tmem_ld16(lane_base + kColVp + t * 32 + 16, v);
             if (valid)
-                for (int c = 0; c < net.hc[2]; ++c)
-                    f_vp[(kMaxRoots + r) * kHfStride + c * kP + p] = fmaxf(fmaf(v[c], __ldg(net.head_bn + 64 + c), __ldg(net.head_bn + 80 + c)), 0.0f);
+                for (int c = 0; c < net.hc[2]; ++c) {
+                    const int k = c * kP + p;
+                    unsigned char *d = fb + (k >> 3) * kFbKgBytes + (16 + r) * 16 + (k & 7) * 2;
+                    float rem;
+                    put_half(d, fmaxf(fmaf(v[c], __ldg(net.head_bn + 64 + c), __ldg(net.head_bn + 80 + c)), 0.0f), rem);
+                    *reinterpret_cast<__half *>(d + 32 * 16) = __float2half_rn(rem);
+                }
         }
     }
     tc_fence_before();
 }
 
-// every epilogue warp arrives on the stage's FC-release barrier (count kEpiWarps) once its lanes are done with the block
-__device__ __forceinline__ void fc_release_stage(TcBars *bars, int st)
+// FC1 read-out (warps 0-2: rows 32 h + unit j of head h): BatchNorm + ReLU, then the hidden activations as FC2's B operand
+// hb[head][k-group j / 8][root | 8 + root (lo)][j % 8].
+__device__ __forceinline__ void heads_hidden(const TcNet &net, int hmask, unsigned char *hb, uint32_t tmem)
 {
-    __syncwarp();
-    if ((threadIdx.x & 31) == 0) mbar_arrive(&bars->fc_empty[st]);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp >= 3 || !((hmask >> warp) & 1)) return;
+    const int h = warp, j = lane;
+    const Head &H = h == 0 ? net.reward : (h == 1 ? net.value : net.policy);
+    const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+    uint32_t a[8], b[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+                 : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]), "=r"(a[4]), "=r"(a[5]), "=r"(a[6]), "=r"(a[7]) : "r"(lane_base + kColFc1 + h * 8));
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+                 : "=r"(b[0]), "=r"(b[1]), "=r"(b[2]), "=r"(b[3]), "=r"(b[4]), "=r"(b[5]), "=r"(b[6]), "=r"(b[7]) : "r"(lane_base + kColFc1 + 32 + h * 8));
+    tmem_ld_wait();
+    tmem_pin(a); tmem_pin(b);
+    const float inv = net.fc[h].fc1_inv;
+    const float s2 = (j < H.hid) ? __ldg(H.s2 + j) : 0.0f, t2 = (j < H.hid) ? __ldg(H.t2 + j) : 0.0f;
+    unsigned char *dst = hb + h * kHbHeadBytes + (j >> 3) * 256 + (j & 7) * 2;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const float pre = (__uint_as_float(a[r]) + __uint_as_float(b[r])) * inv;
+        const float hid = (j < H.hid) ? fmaxf(fmaf(pre, s2, t2), 0.0f) : 0.0f;
+        float rem;
+        put_half(dst + r * 16, hid, rem);
+        *reinterpret_cast<__half *>(dst + (8 + r) * 16) = __float2half_rn(rem);
+    }
+    tc_fence_before();
 }
 
-// FC1 -> BN/ReLU -> FC2 -> softmax expectation -> h^-1 for the heads in hmask, weights from the ring (hn: this simulation's
-// position in the ring sequence, advanced per block).  f_rew / f_vp: features from head_scatter; wk: kFcWorkFloats floats of
-// scratch.  Executed by the kEpiThreads epilogue threads together.
-//   FC1 block = 128 input rows x 32 hidden units: warp w takes rows [16 w, 16 w + 16) in 4 groups of 4; lane = (row in group,
-//   4-unit column chunk), so one LDS.128 per lane reads 4 whole weight rows per warp instruction (every weight byte leaves shared
-//   memory exactly once); 7 roots x 4 units = 28 accumulators per lane, reduced over the 4 row lanes at the end of the head.
-//   FC2 block = 32 hidden units x 128 outputs: thread = (output k, root group g of 4).  The categorical heads never store their
-//   601 logits: each thread folds its logits into a running (max, sum exp, sum exp * support) per root, reduced over the block
-//   after the head's last block (softmax expectation of scaling_transform.py:82-92 in one pass).
-constexpr int kFcPart = kEpiWarps * 3 * kMaxRoots * 32;        // FC1 partial sums [warp][head][root][32]
-constexpr int kFcHidT = 3 * 32 * 8;                             // hidden activations, transposed [head][unit][8 roots]
-constexpr int kFcRed = 2 * 4 * 4 * 3 + 8;                       // softmax reduction scratch [root group][warp][root][m, s, ws]
-constexpr int kFcWorkFloats = kFcPart + kFcHidT + kFcRed;
-__device__ __forceinline__ void heads_fc(const TcNet &net, const TcIO &io, int hmask, unsigned char *ring, TcBars *bars, uint32_t &hn,
-                                         const float *f_rew, const float *f_vp, float *wk, int nvalid, int root0,
-                                         unsigned long long *dbg)
+// FC2 read-out: thread (g = root group of 4, wg = TMEM lane quarter, lane) owns output k = tile * 128 + wg * 32 + lane of roots
+// 4 g .. 4 g + 3: logits = D / scale + bias; raw logits to global when asked for; the categorical heads fold them into the
+// canonical one-pass softmax expectation (net6.cuh) and the inverse scalar transform.  red: 2 x 4 x 4 x 3 floats of scratch.
+__device__ __forceinline__ void heads_outputs(const TcNet &net, const TcIO &io, int hmask, uint32_t tmem, float *red, int nvalid, int root0)
 {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int A = net.A;
-    float *part = wk, *hidT = part + kFcPart, *red = hidT + kFcHidT;
-    // ---- FC1
-    {
-        const int rsub = lane >> 3, c8 = lane & 7;
-        for (int h = 0; h < 3; ++h) {
-            if (!((hmask >> h) & 1)) continue;
-            const int nin = net.fc[h].nin, nblk = (nin + 127) >> 7;
-            const float *hf = (h == 0 ? f_rew : f_vp + (h - 1) * kMaxRoots * kHfStride);
-            float acc[kMaxRoots][4];
-#pragma unroll
-            for (int r = 0; r < kMaxRoots; ++r) { acc[r][0] = 0.0f; acc[r][1] = 0.0f; acc[r][2] = 0.0f; acc[r][3] = 0.0f; }
-            for (int blk = 0; blk < nblk; ++blk, ++hn) {
-                const int st = hn % kStages;
-                const long long tw0 = dbg ? clock64() : 0;
-                mbar_wait_converged(&bars->full[st], (hn / kStages) & 1);
-                if (dbg) dbg[54] += (unsigned long long)(clock64() - tw0);      // FC1 ring waits of warp 0
-                const float *w = reinterpret_cast<const float *>(ring + st * kTapBytes) + (warp * 16 + rsub) * 32 + c8 * 4;
-                const int ii0 = blk * 128 + warp * 16 + rsub;
-#pragma unroll
-                for (int g4 = 0; g4 < 4; ++g4) {
-                    const int ii = ii0 + g4 * 4;
-                    if (ii < nin) {
-                        const float4 wv = *reinterpret_cast<const float4 *>(w + g4 * 4 * 32);
-#pragma unroll
-                        for (int r = 0; r < kMaxRoots; ++r) {
-                            const float f = hf[r * kHfStride + ii];
-                            acc[r][0] = fmaf(f, wv.x, acc[r][0]); acc[r][1] = fmaf(f, wv.y, acc[r][1]);
-                            acc[r][2] = fmaf(f, wv.z, acc[r][2]); acc[r][3] = fmaf(f, wv.w, acc[r][3]);
-                        }
-                    }
-                }
-                fc_release_stage(bars, st);
-            }
-#pragma unroll
-            for (int r = 0; r < kMaxRoots; ++r) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    float v = acc[r][k];
-                    v += __shfl_xor_sync(0xffffffffu, v, 8);
-                    v += __shfl_xor_sync(0xffffffffu, v, 16);
-                    acc[r][k] = v;
-                }
-                if (rsub == 0)
-                    *reinterpret_cast<float4 *>(part + ((warp * 3 + h) * kMaxRoots + r) * 32 + c8 * 4) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
-            }
-        }
-    }
-    asm volatile("bar.sync 1, %0;\n" ::"n"(kEpiThreads) : "memory");
-    if (dbg) dbg[45] = clock64();
-    // ---- hidden = ReLU(BN(sum of the 8 warps' partials)), stored transposed for FC2
-    for (int o = tid; o < 3 * kMaxRoots * 32; o += kEpiThreads) {
-        const int h = o / (kMaxRoots * 32), r = (o >> 5) % kMaxRoots, j = o & 31;
+    const int g = warp >> 2, wg = warp & 3;
+    const uint32_t lane_base = tmem + ((uint32_t)(wg * 32) << 16);
+    int tile = 0;
+    for (int h = 0; h < 3; ++h) {
         if (!((hmask >> h) & 1)) continue;
         const Head &H = h == 0 ? net.reward : (h == 1 ? net.value : net.policy);
-        float v = 0.0f;
+        const int K = H.K, nblk = (K + 127) >> 7;
+        const float inv = net.fc[h].fc2_inv;
+        float *glog = h == 0 ? io.reward_logits : (h == 1 ? io.value_logits : io.policy_logits);
+        float m[4], sm[4], ws[4];
 #pragma unroll
-        for (int w8 = 0; w8 < kEpiWarps; ++w8) v += part[((w8 * 3 + h) * kMaxRoots + r) * 32 + j];
-        hidT[(h * 32 + j) * 8 + r] = (j < H.hid) ? fmaxf(fmaf(v, __ldg(H.s2 + j), __ldg(H.t2 + j)), 0.0f) : 0.0f;
-    }
-    asm volatile("bar.sync 1, %0;\n" ::"n"(kEpiThreads) : "memory");
-    if (dbg) dbg[46] = clock64();
-    // ---- FC2 (+ one-pass softmax expectation for the categorical heads)
-    {
-        const int kl = tid & 127, g = tid >> 7, wg = warp & 3;
-        for (int h = 0; h < 3; ++h) {
-            if (!((hmask >> h) & 1)) continue;
-            const Head &H = h == 0 ? net.reward : (h == 1 ? net.value : net.policy);
-            const int K = H.K, nblk = (K + 127) >> 7;
-            float *glog = h == 0 ? io.reward_logits : (h == 1 ? io.value_logits : io.policy_logits);
-            float m[4], sm[4], ws[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) { m[q] = -INFINITY; sm[q] = 0.0f; ws[q] = 0.0f; }
-            for (int blk = 0; blk < nblk; ++blk, ++hn) {
-                const int st = hn % kStages;
-                const int k = blk * 128 + kl;
-                const float bias = (k < K) ? __ldg(H.b2 + k) : 0.0f;
-                const long long tw0 = dbg ? clock64() : 0;
-                mbar_wait_converged(&bars->full[st], (hn / kStages) & 1);
-                if (dbg) dbg[55] += (unsigned long long)(clock64() - tw0);      // FC2 ring waits of warp 0
-                const float *w = reinterpret_cast<const float *>(ring + st * kTapBytes) + kl;
-                const float *hq = hidT + h * 32 * 8 + g * 4;
-                float o[4] = {bias, bias, bias, bias};
-#pragma unroll
-                for (int u = 0; u < 32; ++u) {
-                    const float wv = w[u * 128];
-                    const float4 hv = *reinterpret_cast<const float4 *>(hq + u * 8);
-                    o[0] = fmaf(hv.x, wv, o[0]); o[1] = fmaf(hv.y, wv, o[1]); o[2] = fmaf(hv.z, wv, o[2]); o[3] = fmaf(hv.w, wv, o[3]);
-                }
-                fc_release_stage(bars, st);
-                if (k < K) {
-                    const float sup = support_at(net.support_min, net.support_step, k);
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const int r = g * 4 + q;
-                        if (r >= nvalid) continue;
-                        if (glog) glog[(size_t)(root0 + r) * K + k] = o[q];
-                        if (h < 2) softmax_push(m[q], sm[q], ws[q], o[q], sup);   // running softmax statistics (net6.cuh: the canonical order)
-                    }
-                }
-            }
-            if (h < 2) {
-                // block-wide combine per root: max, then rescaled sums (4 warps per root group)
-                float mg[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) mg[q] = warp_max(m[q]);
-                if (lane == 0) {
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) red[((g * 4 + wg) * 4 + q) * 3] = mg[q];
-                }
-                asm volatile("bar.sync 1, %0;\n" ::"n"(kEpiThreads) : "memory");
+        for (int q = 0; q < 4; ++q) { m[q] = -INFINITY; sm[q] = 0.0f; ws[q] = 0.0f; }
+        for (int blk = 0; blk < nblk; ++blk, ++tile) {
+            const int k = blk * 128 + wg * 32 + lane;
+            const float bias = (k < K) ? __ldg(H.b2 + k) : 0.0f;
+            uint32_t a[4], b[4];
+            const uint32_t col = lane_base + kColFc2 + tile * 16 + g * 4;
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];\n" : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]) : "r"(col));
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];\n" : "=r"(b[0]), "=r"(b[1]), "=r"(b[2]), "=r"(b[3]) : "r"(col + 8));
+            tmem_ld_wait();
+            tmem_pin(a); tmem_pin(b);
+            if (k < K) {
+                const float sup = support_at(net.support_min, net.support_step, k);
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    float M = red[((g * 4 + 0) * 4 + q) * 3];
-#pragma unroll
-                    for (int w4 = 1; w4 < 4; ++w4) M = fmaxf(M, red[((g * 4 + w4) * 4 + q) * 3]);
-                    const float sc = (m[q] == -INFINITY) ? 0.0f : expf(m[q] - M);
-                    sm[q] = warp_sum(sm[q] * sc);
-                    ws[q] = warp_sum(ws[q] * sc);
+                    const int r = g * 4 + q;
+                    if (r >= nvalid) continue;
+                    const float o = fmaf(__uint_as_float(a[q]) + __uint_as_float(b[q]), inv, bias);
+                    if (glog) glog[(size_t)(root0 + r) * K + k] = o;
+                    if (h < 2) softmax_push(m[q], sm[q], ws[q], o, sup);   // running softmax statistics (net6.cuh: the canonical order)
                 }
-                if (lane == 0) {
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) { red[((g * 4 + wg) * 4 + q) * 3 + 1] = sm[q]; red[((g * 4 + wg) * 4 + q) * 3 + 2] = ws[q]; }
-                }
-                asm volatile("bar.sync 1, %0;\n" ::"n"(kEpiThreads) : "memory");
-                if (wg == 0 && lane < 4) {
-                    const int q = lane, r = g * 4 + q;
-                    if (r < nvalid) {
-                        float S = 0.0f, W = 0.0f;
-#pragma unroll
-                        for (int w4 = 0; w4 < 4; ++w4) { S += red[((g * 4 + w4) * 4 + q) * 3 + 1]; W += red[((g * 4 + w4) * 4 + q) * 3 + 2]; }
-                        const float v = inverse_scalar_transform(W / S);
-                        float *dst = h == 0 ? io.reward : io.value;
-                        if (dst) dst[root0 + r] = v;
-                    }
-                }
-                asm volatile("bar.sync 1, %0;\n" ::"n"(kEpiThreads) : "memory");   // red is reused by the next head
             }
         }
+        if (h < 2) {
+            // block-wide combine per root: max, then rescaled sums (4 warps per root group)
+            float mg[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) mg[q] = warp_max(m[q]);
+            if (lane == 0) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) red[((g * 4 + wg) * 4 + q) * 3] = mg[q];
+            }
+            asm volatile("bar.sync 1, %0;\n" ::"n"(kEpiThreads) : "memory");
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float M = red[((g * 4 + 0) * 4 + q) * 3];
+#pragma unroll
+                for (int w4 = 1; w4 < 4; ++w4) M = fmaxf(M, red[((g * 4 + w4) * 4 + q) * 3]);
+                const float sc = (m[q] == -INFINITY) ? 0.0f : expf(m[q] - M);
+                sm[q] = warp_sum(sm[q] * sc);
+                ws[q] = warp_sum(ws[q] * sc);
+            }
+            if (lane == 0) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { red[((g * 4 + wg) * 4 + q) * 3 + 1] = sm[q]; red[((g * 4 + wg) * 4 + q) * 3 + 2] = ws[q]; }
+            }
+            asm volatile("bar.sync 1, %0;\n" ::"n"(kEpiThreads) : "memory");
+            if (wg == 0 && lane < 4) {
+                const int q = lane, r = g * 4 + q;
+                if (r < nvalid) {
+                    float S = 0.0f, W = 0.0f;
+#pragma unroll
+                    for (int w4 = 0; w4 < 4; ++w4) { S += red[((g * 4 + w4) * 4 + q) * 3 + 1]; W += red[((g * 4 + w4) * 4 + q) * 3 + 2]; }
+                    const float v = inverse_scalar_transform(W / S);
+                    float *dst = h == 0 ? io.reward : io.value;
+                    if (dst) dst[root0 + r] = v;
+                }
+            }
+            asm volatile("bar.sync 1, %0;\n" ::"n"(kEpiThreads) : "memory");   // red is reused by the next head
+        }
     }
-    if (dbg) dbg[47] = clock64();
 }
 
 // ---------------------------------------------------------------------------------------------- kernel
@@ -381,15 +361,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_net_tc(TcNet net, TcIO io, Tr
         mbar_init(&bars->act_ready, kEpiThreads);
         mbar_init(&bars->rew_ready, 1);
         mbar_init(&bars->vp_ready, 1);
-        for (int i = 0; i < kStages; ++i) mbar_init(&bars->fc_empty[i], kEpiWarps);
+        mbar_init(&bars->fcb_ready, kEpiThreads);
+        mbar_init(&bars->fc1_done, 1);
+        mbar_init(&bars->fc2b_ready, kEpiThreads);
+        mbar_init(&bars->fc2_done, 1);
         fence_mbar_init();
     }
     // heads whose fully connected parts run in this kernel (EfficientZero: the reward features go to the LSTM kernels instead),
-    // and the number of 16 KB weight blocks they stream through the ring per simulation, after the conv taps
+    // and the number of 16 KB weight stages they stream through the ring per simulation, after the conv taps: FC1 of all heads
+    // as one [128 rows][576] operand (18 stages of 2 k-steps), then one stage per 128-output tile of each head's FC2
     const int hmask_fc = ((net.has_reward && !io.ez_feat) ? 1 : 0) | 6;
-    int nfc = 0;
+    int nfc = kFc1Stages;
     for (int h = 0; h < 3; ++h)
-        if ((hmask_fc >> h) & 1) nfc += ((net.fc[h].nin + 127) >> 7) + ((net.fc[h].K + 127) >> 7);
+        if ((hmask_fc >> h) & 1) nfc += (net.fc[h].K + 127) >> 7;
     if (warp == kEpiWarps + 1) tmem_alloc(&bars->tmem_base, kTmemCols);
     // 1x1 head weights (12 KB) and the folded BatchNorm tables of this program's layers: plain copies
     for (int i = tid; i < kHeadWBytes / 16; i += kTcThreads)
@@ -414,41 +398,25 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_net_tc(TcNet net, TcIO io, Tr
         // ================= weight producer =================
         if (lane == 0) {
             uint32_t n = 0;
-            // a ring stage is handed back either by the MMA issuer (tcgen05.commit on empty[st], conv taps) or by the epilogue
-            // warps (fc_empty[st], FC blocks): per-stage phase parities of both barriers, and who used the stage last
-            uint32_t par_tap = 0, par_fc = 0, last_fc = 0;
-            auto acquire = [&](int st, bool fc_use) {
-                if (n >= (uint32_t)kStages) {
-                    if ((last_fc >> st) & 1u) { mbar_wait(&bars->fc_empty[st], (par_fc >> st) & 1u); par_fc ^= 1u << st; }
-                    else { mbar_wait(&bars->empty[st], (par_tap >> st) & 1u); par_tap ^= 1u << st; }
-                }
-                last_fc = fc_use ? (last_fc | (1u << st)) : (last_fc & ~(1u << st));
+            auto stage_in = [&](const unsigned char *src) {      // every stage is released by a tcgen05.commit of its consumer MMAs
+                const int st = n % kStages;
+                if (n >= (uint32_t)kStages) mbar_wait(&bars->empty[st], ((n / kStages) - 1) & 1);
+                mbar_expect_tx(&bars->full[st], kTapBytes);
+                bulk_g2s(ring + st * kTapBytes, src, kTapBytes, &bars->full[st]);
+                ++n;
             };
             for (int sim = 0; sim < nsims; ++sim) {     // runs ahead of the consumers: the next simulation's first taps are
                 for (int L = 0; L < nlayers; ++L) {     // already in the ring while the tree work is going on
                     const unsigned char *src = net.convw + (size_t)net.layer_w[L] * (9 * kTapBytes);
-                    for (int tap = 0; tap < 9; ++tap, ++n) {
-                        const int st = n % kStages;
-                        acquire(st, false);
-                        mbar_expect_tx(&bars->full[st], kTapBytes);
-                        bulk_g2s(ring + st * kTapBytes, src + (size_t)tap * kTapBytes, kTapBytes, &bars->full[st]);
-                    }
+                    for (int tap = 0; tap < 9; ++tap) stage_in(src + (size_t)tap * kTapBytes);
                 }
-                // the heads' FC1 blocks ([128 inputs][32 units] fp32), then their FC2 blocks ([32 units][128 outputs]), in the
-                // order heads_fc consumes them
-                for (int pass = 0; pass < 2; ++pass)
-                    for (int h = 0; h < 3; ++h) {
-                        if (!((hmask_fc >> h) & 1)) continue;
-                        const int nblk = pass == 0 ? ((net.fc[h].nin + 127) >> 7) : ((net.fc[h].K + 127) >> 7);
-                        const unsigned char *src = net.fcw + (pass == 0 ? net.fc[h].fc1_off : net.fc[h].fc2_off);
-                        for (int blk = 0; blk < nblk; ++blk, ++n) {
-                            const int st = n % kStages;
-                            const uint32_t bytes = pass == 0 ? (uint32_t)min(kTapBytes, net.fc[h].nin * 128 - blk * kTapBytes) : (uint32_t)kTapBytes;
-                            acquire(st, true);
-                            mbar_expect_tx(&bars->full[st], bytes);
-                            bulk_g2s(ring + st * kTapBytes, src + (size_t)blk * kTapBytes, bytes, &bars->full[st]);
-                        }
-                    }
+                // the heads: FC1 weights of all heads (18 stages), then the FC2 tiles of every head this kernel evaluates
+                for (int i = 0; i < kFc1Stages; ++i) stage_in(net.fcw + (size_t)i * kTapBytes);
+                for (int h = 0; h < 3; ++h) {
+                    if (!((hmask_fc >> h) & 1)) continue;
+                    const int nblk = (net.fc[h].K + 127) >> 7;
+                    for (int blk = 0; blk < nblk; ++blk) stage_in(net.fcw + net.fc[h].fc2_off + (size_t)blk * kTapBytes);
+                }
             }
         }
     } else if (warp == kEpiWarps + 1) {
@@ -461,7 +429,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_net_tc(TcNet net, TcIO io, Tr
         const uint64_t b_desc0 = make_desc(ring_s, kTapKgBytes >> 4, 8);          // stage 0, k-group 0: rows 0-63 hi, 64-127 lo
         unsigned long long *dbg = (io.dbg && blockIdx.x == 0) ? io.dbg : nullptr;
         uint32_t n = 0;
-        for (int sim = 0; sim < nsims; ++sim, n += nfc)     // the ring stages after the conv taps carry the heads' FC weights
+        for (int sim = 0; sim < nsims; ++sim) {
         for (int L = 0; L < nlayers; ++L) {
             const uint32_t ev = (uint32_t)sim * (nlayers + 1) + L;   // act_ready event index: 1 load + nlayers epilogues per simulation
             mbar_wait_converged(&bars->act_ready, ev & 1);       // inputs written, TMEM accumulators drained
@@ -561,18 +529,62 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_net_tc(TcNet net, TcIO io, Tr
                 }
             }
         }
+        // ---- the heads' fully connected layers (weights = M operand from the ring, roots = N columns; see the heads section)
+        {
+            const uint32_t fb_s = act_s, hb_s = act_s + kFbBytes;
+            const uint32_t idesc_fc1 = make_idesc_f16(128, 64), idesc_fc2 = make_idesc_f16(128, 16);
+            mbar_wait_converged(&bars->fcb_ready, sim & 1);          // features of all heads are in shared memory
+            tc_fence_after();
+            for (int i = 0; i < kFc1Stages; ++i, ++n) {
+                const int st = n % kStages;
+                mbar_wait_converged(&bars->full[st], (n / kStages) & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int ksi = 0; ksi < 2; ++ksi) {
+                    const int kstep = 2 * i + ksi;
+                    const uint64_t a_hi = make_desc(ring_s + st * kTapBytes + ksi * 8192, 2048 >> 4, 8), a_lo = a_hi + (4096 >> 4);
+                    const uint64_t b = make_desc(fb_s + kstep * 2 * kFbKgBytes, kFbKgBytes >> 4, 8);
+                    umma_f16_elect(tmem + kColFc1, a_hi, b, idesc_fc1, kstep != 0);
+                    umma_f16_elect(tmem + kColFc1, a_lo, b, idesc_fc1, 1);
+                }
+                umma_commit_elect(&bars->empty[st]);
+            }
+            umma_commit_elect(&bars->fc1_done);
+            mbar_wait_converged(&bars->fc2b_ready, sim & 1);         // hidden activations (FC2's B operand) written
+            tc_fence_after();
+            int tile = 0;
+            for (int h = 0; h < 3; ++h) {
+                if (!((hmask_fc >> h) & 1)) continue;
+                const int nblk = (net.fc[h].K + 127) >> 7;
+                for (int blk = 0; blk < nblk; ++blk, ++tile, ++n) {
+                    const int st = n % kStages;
+                    mbar_wait_converged(&bars->full[st], (n / kStages) & 1);
+                    tc_fence_after();
+#pragma unroll
+                    for (int ks = 0; ks < 2; ++ks) {
+                        const uint64_t a_hi = make_desc(ring_s + st * kTapBytes + ks * 2 * 2048, 2048 >> 4, 8), a_lo = a_hi + (8192 >> 4);
+                        const uint64_t b = make_desc(hb_s + h * kHbHeadBytes + ks * 2 * 256, 256 >> 4, 8);
+                        umma_f16_elect(tmem + kColFc2 + tile * 16, a_hi, b, idesc_fc2, ks != 0);
+                        umma_f16_elect(tmem + kColFc2 + tile * 16, a_lo, b, idesc_fc2, 1);
+                    }
+                    umma_commit_elect(&bars->empty[st]);
+                }
+            }
+            umma_commit_elect(&bars->fc2_done);
+        }
+        }
     } else {
         // ================= epilogue warps: warp w owns TMEM lanes 32*(w%4).. and the 32-column half w/4 =================
         const int q4 = warp & 3, half = warp >> 2, rowid = q4 * 32 + lane;
         const uint32_t lane_base = tmem + ((uint32_t)(q4 * 32) << 16);
-        float *f_rew = reinterpret_cast<float *>(smem + kSmemMain);      // reward features [7][kHfStride]
+        unsigned char *fr = smem + kSmemMain;      // reward features (fp16 hi / lo, FC1's B-operand rows 0-7), parked from their hook
         unsigned long long *dbg = (io.dbg && blockIdx.x == 0 && tid == 0) ? io.dbg : nullptr;
         if (dbg) dbg[0] = clock64();
         pdl_wait();                   // ix / action / the latent pool come from the preceding kernels
         int acc_par = 0;
         // this warp's tree (tree_persist.cuh): its scalars / first path entries live in registers during the tree phase and are
         // parked in shared memory while the warp does network work
-        uint32_t *tree_park = reinterpret_cast<uint32_t *>(smem + kSmemMain + kMaxRoots * kHfStride * 4) + warp * kTreeParkWords;
+        uint32_t *tree_park = reinterpret_cast<uint32_t *>(smem + kSmemMain + kFrBytes) + warp * kTreeParkWords;
         if (fast_tree && warp < nvalid) {
             PTree T;
             ptree_init(tp, T, root0 + warp, lane);
@@ -764,20 +776,28 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_net_tc(TcNet net, TcIO io, Tr
                 mbar_arrive(&bars->act_ready);                      // phase L+1: next layer / this layer's hook may start
                 if (dbg) dbg[3 + 2 * L] = clock64();
                 if ((flags & LF_HOOK_REWARD) && net.has_reward) {
-                    // reward 1x1 accumulators -> BN/ReLU features, parked in their own scratch until the heads' FC pass at the
-                    // end of the simulation (underneath the NEXT layer's MMAs)
+                    // reward 1x1 accumulators -> BN/ReLU features, parked (fp16 hi / lo) until the heads' FC pass at the end of the
+                    // simulation -- or, EfficientZero (efficientzero_model.py:556-562), written out as the input of the LSTM that the
+                    // next kernel evaluates as one batched GEMM over all roots (ez.cu).  Runs underneath the NEXT layer's MMAs.
                     mbar_wait_warp(&bars->rew_ready, sim & 1);
                     tc_fence_after();
-                    head_scatter(net, 1, f_rew, nullptr, tmem, NT, rows_used, nvalid);
                     if (io.ez_feat) {
-                        // EfficientZero (efficientzero_model.py:556-562): the flattened reward features feed an LSTM that is
-                        // evaluated as one batched GEMM over all roots by the next kernel (ez.cu)
-                        asm volatile("bar.sync 1, %0;\n" ::"n"(kEpiThreads) : "memory");
-                        const int nin = net.hc[0] * kP;
-                        for (int i = tid; i < nvalid * nin; i += kEpiThreads) {
-                            const int r = i / nin, j = i - r * nin;
-                            io.ez_feat[(size_t)(root0 + r) * nin + j] = f_rew[r * kHfStride + j];
+                        if (half == 0) {
+                            const int nin = net.hc[0] * kP;
+#pragma unroll
+                            for (int t = 0; t < kMaxTiles; ++t) {
+                                if (t >= NT) continue;
+                                float v[16];
+                                tmem_ld16(lane_base + kColRew + t * 16, v);
+                                if (rowc[t] >= 0)
+                                    for (int c = 0; c < net.hc[0]; ++c)
+                                        io.ez_feat[(size_t)(root0 + (rowc[t] >> 8)) * nin + c * kP + (rowc[t] & 255)] =
+                                            fmaxf(fmaf(v[c], __ldg(net.head_bn + c), __ldg(net.head_bn + 16 + c)), 0.0f);
+                            }
                         }
+                        tc_fence_before();
+                    } else {
+                        head_scatter(net, 1, fr, nullptr, tmem, NT, rows_used, nvalid);
                     }
                     if (dbg) dbg[28] = clock64();
                 }
@@ -792,13 +812,31 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_net_tc(TcNet net, TcIO io, Tr
             // has completed (ordered through act_ready -> MMA issuer -> vp_ready; the explicit barrier keeps racecheck, which
             // does not follow mbarriers, quiet)
             {
-                float *f_vp = reinterpret_cast<float *>(act), *wk = f_vp + ((2 * kMaxRoots * kHfStride + 3) & ~3);   // 16-byte aligned work area
+                unsigned char *fb = act, *hb = act + kFbBytes;
+                float *red = reinterpret_cast<float *>(hb + 3 * kHbHeadBytes);
                 asm volatile("bar.sync 1, %0;\n" ::"n"(kEpiThreads) : "memory");
-                head_scatter(net, 6, nullptr, f_vp, tmem, NT, rows_used, nvalid);
-                asm volatile("bar.sync 1, %0;\n" ::"n"(kEpiThreads) : "memory");
+                if (hmask_fc & 1) {      // the parked reward features become rows 0-7 (hi) / 32-39 (lo) of the B operand
+                    for (int i = tid; i < 2 * 72 * 8; i += kEpiThreads) {
+                        const int part = i / (72 * 8), rem = i - part * (72 * 8), kg = rem >> 3, r = rem & 7;
+                        *reinterpret_cast<uint4 *>(fb + kg * kFbKgBytes + (part * 32 + r) * 16) =
+                            *reinterpret_cast<const uint4 *>(fr + part * (kFrBytes / 2) + (kg * 8 + r) * 16);
+                    }
+                }
+                head_scatter(net, 6, nullptr, fb, tmem, NT, rows_used, nvalid);
+                fence_proxy_async();
+                mbar_arrive(&bars->fcb_ready);                      // FC1 may start
                 if (dbg) dbg[44] = clock64();
-                uint32_t hn = (uint32_t)sim * (9 * nlayers + nfc) + 9 * nlayers;
-                heads_fc(net, io, hmask_fc, ring, bars, hn, f_rew, f_vp, wk, nvalid, root0, dbg);
+                mbar_wait_warp(&bars->fc1_done, sim & 1);
+                tc_fence_after();
+                if (dbg) dbg[45] = clock64();
+                heads_hidden(net, hmask_fc, hb, tmem);
+                fence_proxy_async();
+                mbar_arrive(&bars->fc2b_ready);                     // FC2 may start
+                if (dbg) dbg[46] = clock64();
+                mbar_wait_warp(&bars->fc2_done, sim & 1);
+                tc_fence_after();
+                if (dbg) dbg[47] = clock64();
+                heads_outputs(net, io, hmask_fc, tmem, red, nvalid, root0);
             }
             if (dbg) dbg[27] = clock64();
             __threadfence_block();

@@ -9,9 +9,10 @@ namespace lz {
 constexpr int kMaxResBlocksTc = 4;
 constexpr int kTcMaxLayers = 1 + 4 * kMaxResBlocksTc;
 
-struct TcFc {                      // fully connected part of one head, streamed through the weight ring as 16 KB blocks
-    uint32_t fc1_off, fc2_off;     // byte offsets into TcNet::fcw: FC1 [nin][32] fp32; FC2 [ceil(K/128)][32][128] fp32 (zero padded)
-    int nin, K;                    // FC1 inputs (hc*36), FC2 outputs
+struct TcFc {                      // fully connected part of one head on the tensor cores (net_tc.cu, heads section)
+    uint32_t fc2_off;              // byte offset into TcNet::fcw of this head's FC2 tiles ([ceil(K/128)][hi 8 KB | lo 8 KB], [kg 4][128 outputs][8])
+    int nin, K;                    // FC1 inputs (hc*36), FC2 outputs (0: the head has no FC part here)
+    float fc1_inv, fc2_inv;        // 1 / the power-of-two scale applied to the fp16 weights
 };
 
 struct TcNet {
@@ -20,7 +21,7 @@ struct TcNet {
     const unsigned char *headw;    // [reward hi 2K | lo 2K][value+policy hi 4K | lo 4K]
     const float *head_bn;          // [reward s16 t16 | value s16 t16 | policy s16 t16]
     const float *abias;            // [A][16][36][4] ([c / 4][pixel][c % 4]) action-plane contribution of the dynamics conv, x BN scale
-    const unsigned char *fcw;      // FC weight stream of the three heads (TcFc offsets)
+    const unsigned char *fcw;      // FC weight stream: 18 FC1 stages ([2 k-steps][hi 4 KB | lo 4 KB], [kg 2][128 rows = 32 head + unit][8]) then the FC2 tiles
     TcFc fc[3];                    // reward, value, policy
     Head reward, value, policy;    // folded BN / bias tables of the FC parts (fp32, same tables as the SIMT path)
     int hc[3];

@@ -38,6 +38,8 @@ class MuZeroModelMLP:
         with torch.cuda.device(self.device):
             cabi.check(self._lib.lz_model_create_mlp(cfg, h), "lz_model_create_mlp")
         self._h = h
+        from .muzero_model import _model_serial
+        self._serial = next(_model_serial)      # key of the per-tree lz_search caches (mz_tree)
         self.value_support_size = self.reward_support_size = self._lib.lz_model_support_size(self._h)
         self._loaded = False
 
@@ -102,6 +104,8 @@ class MuZeroModelMLP:
     def __del__(self):
         try:
             if getattr(self, "_h", None):
+                from . import mz_tree
+                mz_tree.drop_model_searches(self._serial)
                 self._lib.lz_model_destroy(self._h)
         except Exception:
             pass

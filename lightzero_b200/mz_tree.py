@@ -147,6 +147,7 @@ class Roots:
             self.device = torch.device("cuda", torch.cuda.current_device())
         self._legal_lists = None
         self._mask = None
+        self._mask_dev = None
         if isinstance(legal_actions_list, (torch.Tensor, np.ndarray)) and np.ndim(legal_actions_list) == 2 and \
                 str(legal_actions_list.dtype).split(".")[-1] in ("uint8", "bool"):
             self._mask = legal_actions_list
@@ -267,8 +268,9 @@ class Roots:
             s = cabi.stream_ptr()
             cabi.check(t.lib.lz_tree_set_ez(t.h, int(self._ez), int(self._lstm_horizon)), "lz_tree_set_ez")
             if self._mask is not None:
-                m = _to_dev(self._mask, torch.uint8, self.device, (self.root_num, A))
-                cabi.check(t.lib.lz_tree_reset_mask(t.h, m.data_ptr(), s), "lz_tree_reset_mask")
+                if self._mask_dev is None:      # uploaded once per Roots, not once per search
+                    self._mask_dev = _to_dev(self._mask, torch.uint8, self.device, (self.root_num, A))
+                cabi.check(t.lib.lz_tree_reset_mask(t.h, self._mask_dev.data_ptr(), s), "lz_tree_reset_mask")
             else:
                 identity = list(range(A))
                 if all(l == identity for l in self._legal_lists):
