@@ -211,7 +211,7 @@ __device__ __forceinline__ void softmax_push(float &m, float &s, float &w, float
 {
     // one exponential per logit, no divergent branch: t = exp(-|x - m|) is the rescale factor of the old sums when x is the new
     // maximum and the new term otherwise (exp(-inf) = 0 for the first logit)
-    const float t = expf(-fabsf(x - m));
+    const float t = __expf(-fabsf(x - m));      // ex2.approx: ~2 ulp; the terms that matter have |x - m| of a few units
     const bool gt = x > m;
     s = gt ? fmaf(s, t, 1.0f) : s + t;
     w = gt ? fmaf(w, t, sup) : fmaf(t, sup, w);

@@ -40,9 +40,6 @@
 
 namespace lz {
 
-#ifndef LZ_FOLD
-#define LZ_FOLD 1      // see the MMA issuer (measured variants; the default is the fastest one on hardware)
-#endif
 
 // ---------------------------------------------------------------------------------------------- geometry
 constexpr int kEpiWarps = 8, kEpiThreads = kEpiWarps * 32;   // two warps per TMEM lane quarter, one 32-column half each
@@ -61,7 +58,11 @@ constexpr int kHeadWBytes = 3 * 2 * 16 * 64 * 2; // three 1x1 heads (hc <= 16), 
 constexpr int kBnSmemBytes = kTcMaxLayers * 128 * 4;   // folded BatchNorm tables of the program's layers
 constexpr int kSmemMain = kActBytes + kStages * kTapBytes + kHeadWBytes + 1024 + kBnSmemBytes;
 constexpr int kHeadScratch = 72 * 8 * 16 * 2 + kEpiWarps * (16 + 3 * 32) * 4;   // kFrBytes (parked reward features) + the parked trees   // + the parked trees (kTreeParkWords per warp)   // reward head features, parked from their hook to the heads' FC pass at the end of the simulation
-constexpr int kSmemBytes = kSmemMain + kHeadScratch;
+// tree <-> network hand-off of the persistent search, per root slot of the CTA: leaf slot, action | value, reward, policy logits
+// (the global copies are still written for the step-wise entry points; reading them back would cost an L2 round trip per use)
+constexpr int kHoWords = 4 + 32;
+constexpr int kHandoffBytes = 8 * kHoWords * 4;
+constexpr int kSmemBytes = kSmemMain + kHeadScratch + kHandoffBytes;
 
 // TMEM columns
 constexpr int kColAcc = 0;        // 3 tiles x 128: [0,64) = A_hi*B_hi + A_lo*B_hi, [64,128) = A_hi*B_lo (one N = 128 MMA)
@@ -72,10 +73,10 @@ constexpr int kTmemCols = 512;
 
 struct TcBars {
     uint64_t full[kStages], empty[kStages];
-    uint64_t acc_ready;     // MMA -> epilogue: this layer's accumulators are complete
-    uint64_t act_ready;     // epilogue -> MMA: activations (and TMEM) are ready for the next layer
-    uint64_t rew_ready;     // MMA -> heads: reward 1x1 accumulators complete (single phase)
-    uint64_t vp_ready;      // MMA -> heads: value/policy 1x1 accumulators complete (single phase)
+    uint64_t acc_ready[2];  // MMA -> epilogue: this layer's accumulators of root group g are complete
+    uint64_t act_ready[2];  // epilogue -> MMA: activations (and TMEM) of root group g are ready for the next layer
+    uint64_t rew_ready;     // MMA -> heads: reward 1x1 accumulators complete (one phase per simulation, one arrival per root group)
+    uint64_t vp_ready;      // MMA -> heads: value/policy 1x1 accumulators complete (likewise)
     uint64_t fcb_ready;     // heads -> MMA: the head features (FC1's B operand) are in shared memory
     uint64_t fc1_done;      // MMA -> heads: FC1 accumulators complete
     uint64_t fc2b_ready;    // heads -> MMA: the hidden activations (FC2's B operand) are in shared memory
@@ -115,51 +116,72 @@ __device__ __forceinline__ void put_half(unsigned char *p, float v, float &rem)
 // 1x1-conv accumulators (TMEM) -> BatchNorm + ReLU -> fp16 hi/lo features in FC1's B-operand layout, for the heads in hmask (bit 0
 // reward -> its parking buffer fr, bit 1 value / bit 2 policy -> rows 8-15 / 16-23 of fb).  Feature k = c * 36 + p of root r sits at
 // k-group k / 8, row (head * 8 + r), element k % 8.  No barrier inside.
+// Row m of the CTA's padded pixel grid -> (root slot r in the CTA, pixel p); false for pad rows / absent roots.  Root group X
+// (roots 0 .. Rx-1) starts at row 0, root group Y (roots Rx .. R-1) at row ybase (a tile boundary); without a split Rx = R.
+struct RowMap { int Rx, R, ybase, nvalid; };
+__device__ __forceinline__ bool row_decode(const RowMap &rm, int m, int &r, int &p)
+{
+    const bool in_y = m >= rm.ybase;
+    const int mm = in_y ? m - rm.ybase : m;
+    const int rr = mm / kRowsPerRoot, q = mm - rr * kRowsPerRoot, y = q / kPitch, x = q - y * kPitch;
+    r = in_y ? rm.Rx + rr : rr;
+    p = y * 6 + x;
+    return (in_y ? (r < rm.R) : (rr < rm.Rx)) && (r < rm.nvalid) && (y < 6) && (x < 6);
+}
+
 __device__ __forceinline__ void head_scatter(const TcNet &net, int hmask, unsigned char *fr, unsigned char *fb, uint32_t tmem, int NT,
-                                             int rows_used, int nvalid)
+                                             const RowMap &rm)
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q4 = warp & 3, half = warp >> 2, rowid = q4 * 32 + lane;
     const uint32_t lane_base = tmem + ((uint32_t)(q4 * 32) << 16);
     for (int t = 0; t < NT; ++t) {
-        const int m = t * 128 + rowid;
-        const int r = m / kRowsPerRoot, q = m - r * kRowsPerRoot, y = q / kPitch, x = q - y * kPitch;
-        const bool valid = (m < rows_used) && (r < nvalid) && (y < 6) && (x < 6);
-        const int p = y * 6 + x;
+        int r, p;
+        const bool valid = row_decode(rm, t * 128 + rowid, r, p);
         float v[16];
-        // warps 0-3 scatter reward + value features, warps 4-7 policy features (any warp may read its lane quarter)
+        // warps 0-3 scatter reward + value features, warps 4-7 policy features (any warp may read its lane quarter).  The channel
+        // loops are unrolled over the 16 accumulator columns (v[] must stay in registers) and predicated on the head's width.
         if (half == 0 && (hmask & 1)) {
             tmem_ld16(lane_base + kColRew + t * 16, v);
-            if (valid)
-                for (int c = 0; c < net.hc[0]; ++c) {
+            if (valid) {
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                    if (c >= net.hc[0]) break;
                     const int k = c * kP + p;
                     unsigned char *d = fr + ((k >> 3) * 8 + r) * 16 + (k & 7) * 2;
                     float rem;
                     put_half(d, fmaxf(fmaf(v[c], __ldg(net.head_bn + c), __ldg(net.head_bn + 16 + c)), 0.0f), rem);
                     *reinterpret_cast<__half *>(d + kFrBytes / 2) = __float2half_rn(rem);
                 }
+            }
         }
         if (half == 0 && (hmask & 2)) {
             tmem_ld16(lane_base + kColVp + t * 32, v);
-            if (valid)
-                for (int c = 0; c < net.hc[1]; ++c) {
+            if (valid) {
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                    if (c >= net.hc[1]) break;
                     const int k = c * kP + p;
                     unsigned char *d = fb + (k >> 3) * kFbKgBytes + (8 + r) * 16 + (k & 7) * 2;
                     float rem;
                     put_half(d, fmaxf(fmaf(v[c], __ldg(net.head_bn + 32 + c), __ldg(net.head_bn + 48 + c)), 0.0f), rem);
                     *reinterpret_cast<__half *>(d + 32 * 16) = __float2half_rn(rem);
                 }
+            }
         }
         if (half == 1 && (hmask & 4)) {
             tmem_ld16(lane_base + kColVp + t * 32 + 16, v);
-            if (valid)
-                for (int c = 0; c < net.hc[2]; ++c) {
+            if (valid) {
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                    if (c >= net.hc[2]) break;
                     const int k = c * kP + p;
                     unsigned char *d = fb + (k >> 3) * kFbKgBytes + (16 + r) * 16 + (k & 7) * 2;
                     float rem;
                     put_half(d, fmaxf(fmaf(v[c], __ldg(net.head_bn + 64 + c), __ldg(net.head_bn + 80 + c)), 0.0f), rem);
                     *reinterpret_cast<__half *>(d + 32 * 16) = __float2half_rn(rem);
                 }
+            }
         }
     }
     tc_fence_before();
@@ -197,25 +219,35 @@ __device__ __forceinline__ void heads_hidden(const TcNet &net, int hmask, unsign
 
 // FC2 read-out: thread (g = root group of 4, wg = TMEM lane quarter, lane) owns output k = tile * 128 + wg * 32 + lane of roots
 // 4 g .. 4 g + 3: logits = D / scale + bias; raw logits to global when asked for; the categorical heads fold them into the
-// canonical one-pass softmax expectation (net6.cuh) and the inverse scalar transform.  red: 2 x 4 x 4 x 3 floats of scratch.
-__device__ __forceinline__ void heads_outputs(const TcNet &net, const TcIO &io, int hmask, uint32_t tmem, float *red, int nvalid, int root0)
+// canonical one-pass softmax expectation (net6.cuh) and the inverse scalar transform.  Same arithmetic per (head, root) as
+// categorical_to_scalar; the two categorical heads are reduced TOGETHER (their 8 max / 16 sum butterflies interleaved, two CTA
+// barriers instead of six: the read-out is a latency chain, not a throughput problem).  red: 2 x 2 x 4 x 4 x 3 floats of scratch.
+__device__ __forceinline__ void heads_outputs(const TcNet &net, const TcIO &io, int hmask, uint32_t tmem, float *red, int nvalid, int root0,
+                                              const float *b2_s, float *ho)
 {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = warp >> 2, wg = warp & 3;
     const uint32_t lane_base = tmem + ((uint32_t)(wg * 32) << 16);
-    int tile = 0;
+    float m[2][4], sm[2][4], ws[2][4];
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { m[h][q] = -INFINITY; sm[h][q] = 0.0f; ws[h][q] = 0.0f; }
+    int tile = 0, boff = 0;
+#pragma unroll
     for (int h = 0; h < 3; ++h) {
         if (!((hmask >> h) & 1)) continue;
         const Head &H = h == 0 ? net.reward : (h == 1 ? net.value : net.policy);
         const int K = H.K, nblk = (K + 127) >> 7;
         const float inv = net.fc[h].fc2_inv;
         float *glog = h == 0 ? io.reward_logits : (h == 1 ? io.value_logits : io.policy_logits);
-        float m[4], sm[4], ws[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) { m[q] = -INFINITY; sm[q] = 0.0f; ws[q] = 0.0f; }
-        for (int blk = 0; blk < nblk; ++blk, ++tile) {
+        // FC2 bias: the copy staged in shared memory at kernel start (the evaluated heads back to back) or global
+        const float *b2 = b2_s ? b2_s + boff : H.b2;
+        boff += K;
+#pragma unroll 1
+        for (int blk = 0; blk < nblk; ++blk, ++tile) {      // rolled: the read-out is a long latency chain, its code must stay small
             const int k = blk * 128 + wg * 32 + lane;
-            const float bias = (k < K) ? __ldg(H.b2 + k) : 0.0f;
+            const float bias = (k < K) ? b2[k] : 0.0f;
             uint32_t a[4], b[4];
             const uint32_t col = lane_base + kColFc2 + tile * 16 + g * 4;
             asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];\n" : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]) : "r"(col));
@@ -230,46 +262,69 @@ __device__ __forceinline__ void heads_outputs(const TcNet &net, const TcIO &io, 
                     if (r >= nvalid) continue;
                     const float o = fmaf(__uint_as_float(a[q]) + __uint_as_float(b[q]), inv, bias);
                     if (glog) glog[(size_t)(root0 + r) * K + k] = o;
-                    if (h < 2) softmax_push(m[q], sm[q], ws[q], o, sup);   // running softmax statistics (net6.cuh: the canonical order)
+                    if (h == 2 && ho && k < 32) ho[r * kHoWords + 4 + k] = o;
+                    if (h < 2) softmax_push(m[h & 1][q], sm[h & 1][q], ws[h & 1][q], o, sup);   // running softmax statistics (net6.cuh: the canonical order)
                 }
             }
         }
-        if (h < 2) {
-            // block-wide combine per root: max, then rescaled sums (4 warps per root group)
-            float mg[4];
+    }
+    // block-wide combine per (head, root): max, then rescaled sums (4 warps per root group); both heads at once
+    float mg[2][4];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) mg[q] = warp_max(m[q]);
-            if (lane == 0) {
+    for (int h = 0; h < 2; ++h)
 #pragma unroll
-                for (int q = 0; q < 4; ++q) red[((g * 4 + wg) * 4 + q) * 3] = mg[q];
-            }
-            asm volatile("bar.sync 1, %0;\n" ::"n"(kEpiThreads) : "memory");
+        for (int q = 0; q < 4; ++q) mg[h][q] = m[h][q];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) mg[h][q] = fmaxf(mg[h][q], __shfl_xor_sync(0xffffffffu, mg[h][q], o));
+    auto red_at = [&](int h, int w4, int q) { return red + (((h * 2 + g) * 4 + w4) * 4 + q) * 3; };
+    if (lane == 0) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) red_at(h, wg, q)[0] = mg[h][q];
+    }
+    asm volatile("bar.sync 1, %0;\n" ::"n"(kEpiThreads) : "memory");
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float M = red_at(h, 0, q)[0];
+#pragma unroll
+            for (int w4 = 1; w4 < 4; ++w4) M = fmaxf(M, red_at(h, w4, q)[0]);
+            const float sc = (m[h][q] == -INFINITY) ? 0.0f : expf(m[h][q] - M);
+            sm[h][q] *= sc;
+            ws[h][q] *= sc;
+        }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                float M = red[((g * 4 + 0) * 4 + q) * 3];
-#pragma unroll
-                for (int w4 = 1; w4 < 4; ++w4) M = fmaxf(M, red[((g * 4 + w4) * 4 + q) * 3]);
-                const float sc = (m[q] == -INFINITY) ? 0.0f : expf(m[q] - M);
-                sm[q] = warp_sum(sm[q] * sc);
-                ws[q] = warp_sum(ws[q] * sc);
+                sm[h][q] += __shfl_xor_sync(0xffffffffu, sm[h][q], o);
+                ws[h][q] += __shfl_xor_sync(0xffffffffu, ws[h][q], o);
             }
-            if (lane == 0) {
+    if (lane == 0) {
 #pragma unroll
-                for (int q = 0; q < 4; ++q) { red[((g * 4 + wg) * 4 + q) * 3 + 1] = sm[q]; red[((g * 4 + wg) * 4 + q) * 3 + 2] = ws[q]; }
-            }
-            asm volatile("bar.sync 1, %0;\n" ::"n"(kEpiThreads) : "memory");
-            if (wg == 0 && lane < 4) {
-                const int q = lane, r = g * 4 + q;
-                if (r < nvalid) {
-                    float S = 0.0f, W = 0.0f;
+        for (int h = 0; h < 2; ++h)
 #pragma unroll
-                    for (int w4 = 0; w4 < 4; ++w4) { S += red[((g * 4 + w4) * 4 + q) * 3 + 1]; W += red[((g * 4 + w4) * 4 + q) * 3 + 2]; }
-                    const float v = inverse_scalar_transform(W / S);
-                    float *dst = h == 0 ? io.reward : io.value;
-                    if (dst) dst[root0 + r] = v;
-                }
-            }
-            asm volatile("bar.sync 1, %0;\n" ::"n"(kEpiThreads) : "memory");   // red is reused by the next head
+            for (int q = 0; q < 4; ++q) { red_at(h, wg, q)[1] = sm[h][q]; red_at(h, wg, q)[2] = ws[h][q]; }
+    }
+    asm volatile("bar.sync 1, %0;\n" ::"n"(kEpiThreads) : "memory");
+    if (wg == 0 && lane < 8) {
+        const int h = lane >> 2, q = lane & 3, r = g * 4 + q;
+        if (r < nvalid && ((hmask >> h) & 1)) {
+            float S = 0.0f, W = 0.0f;
+#pragma unroll
+            for (int w4 = 0; w4 < 4; ++w4) { S += red_at(h, w4, q)[1]; W += red_at(h, w4, q)[2]; }
+            const float v = inverse_scalar_transform(W / S);
+            float *dst = h == 0 ? io.reward : io.value;
+            if (dst) dst[root0 + r] = v;
+            if (ho) ho[r * kHoWords + (h == 0 ? 3 : 2)] = v;
         }
     }
 }
@@ -346,8 +401,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_net_tc(TcNet net, TcIO io, Tr
     const int R = io.roots_per_cta;
     const int root0 = blockIdx.x * R;
     const int nvalid = min(R, io.B - root0);                     // roots of this CTA that exist
-    const int rows_used = R * kRowsPerRoot;
-    const int NT = (rows_used + 127) >> 7;
+    // Root groups (io.split_rx > 0): group X = roots 0 .. Rx-1 in tiles 0 .. NTx-1, group Y = the rest from the next tile boundary on.
+    // Roots never interact, so the groups move through the layers independently: the MMA warp alternates X.L, Y.L, X.(L+1), ... and
+    // the epilogue of one group's layer runs underneath the other group's MMAs (the in-place activation buffer only serialises a
+    // group with itself).  The split is only made when it costs no extra M tile (7 roots -> {5, 2}: 2 + 1 tiles).
+    const int Rx = (io.split_rx > 0 && io.split_rx < R) ? io.split_rx : R;
+    const int NTx = (Rx * kRowsPerRoot + 127) >> 7;
+    const int NT = NTx + (((R - Rx) * kRowsPerRoot + 127) >> 7);
+    const int ngroups = (Rx < R) ? 2 : 1;
+    const RowMap rm = {Rx, R, NTx * 128, nvalid};
     const int npass = io.npass;
     const int nlayers = net.nlayers;
     const int nsims = io.nsims > 0 ? io.nsims : 1;     // > 1 (or persistent): the whole search loop runs inside this launch
@@ -357,10 +419,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_net_tc(TcNet net, TcIO io, Tr
     // ---- one-time setup ----
     if (tid == 0) {
         for (int i = 0; i < kStages; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], 1); }
-        mbar_init(&bars->acc_ready, 1);
-        mbar_init(&bars->act_ready, kEpiThreads);
-        mbar_init(&bars->rew_ready, 1);
-        mbar_init(&bars->vp_ready, 1);
+        for (int g = 0; g < 2; ++g) { mbar_init(&bars->acc_ready[g], 1); mbar_init(&bars->act_ready[g], kEpiThreads); }
+        mbar_init(&bars->rew_ready, ngroups);
+        mbar_init(&bars->vp_ready, ngroups);
         mbar_init(&bars->fcb_ready, kEpiThreads);
         mbar_init(&bars->fc1_done, 1);
         mbar_init(&bars->fc2b_ready, kEpiThreads);
@@ -381,13 +442,33 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_net_tc(TcNet net, TcIO io, Tr
     for (int i = tid; i < nlayers * 128; i += kTcThreads)
         bn_s[i] = __ldg(net.bn + (size_t)net.layer_w[i >> 7] * 128 + (i & 127));
     // persistent search: the exploration-rate table of the PUCT rule next to them when it fits (else it is read from global)
-    const bool fast_tree = persistent && tp.A <= 32 && !io.generic_tree;
+    const bool fast_tree = persistent;      // tree_persist.cuh (A <= 32, checked by tc_launch; larger action spaces use the multi-launch graph)
     const float *pbc_tab = tp.pbc;
     if (fast_tree && (nlayers * 128 + tp.N + 1) * 4 <= kBnSmemBytes) {
         float *pbc_s = bn_s + nlayers * 128;
         for (int i = tid; i <= tp.N; i += kTcThreads) pbc_s[i] = tp.pbc[i];
         pbc_tab = pbc_s;
     }
+    // the FC2 bias vectors of the heads this kernel evaluates, back to back behind them when they fit as well
+    const float *b2_s = nullptr;
+    {
+        int nb2 = 0;
+        for (int h = 0; h < 3; ++h)
+            if ((hmask_fc >> h) & 1) nb2 += net.fc[h].K;
+        const int used = nlayers * 128 + ((pbc_tab != tp.pbc) ? tp.N + 1 : 0);
+        if ((used + nb2) * 4 <= kBnSmemBytes) {
+            float *dst = bn_s + used;
+            int off = 0;
+            for (int h = 0; h < 3; ++h) {
+                if (!((hmask_fc >> h) & 1)) continue;
+                const Head &H = h == 0 ? net.reward : (h == 1 ? net.value : net.policy);
+                for (int i = tid; i < H.K; i += kTcThreads) dst[off + i] = __ldg(H.b2 + i);
+                off += H.K;
+            }
+            b2_s = dst;
+        }
+    }
+    float *ho = reinterpret_cast<float *>(smem + kSmemMain + kHeadScratch);      // tree <-> network hand-off (persistent search)
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -408,7 +489,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_net_tc(TcNet net, TcIO io, Tr
             for (int sim = 0; sim < nsims; ++sim) {     // runs ahead of the consumers: the next simulation's first taps are
                 for (int L = 0; L < nlayers; ++L) {     // already in the ring while the tree work is going on
                     const unsigned char *src = net.convw + (size_t)net.layer_w[L] * (9 * kTapBytes);
-                    for (int tap = 0; tap < 9; ++tap) stage_in(src + (size_t)tap * kTapBytes);
+                    for (int g = 0; g < ngroups; ++g)
+                        for (int tap = 0; tap < 9; ++tap) stage_in(src + (size_t)tap * kTapBytes);
                 }
                 // the heads: FC1 weights of all heads (18 stages), then the FC2 tiles of every head this kernel evaluates
                 for (int i = 0; i < kFc1Stages; ++i) stage_in(net.fcw + (size_t)i * kTapBytes);
@@ -429,105 +511,81 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_net_tc(TcNet net, TcIO io, Tr
         const uint64_t b_desc0 = make_desc(ring_s, kTapKgBytes >> 4, 8);          // stage 0, k-group 0: rows 0-63 hi, 64-127 lo
         unsigned long long *dbg = (io.dbg && blockIdx.x == 0) ? io.dbg : nullptr;
         uint32_t n = 0;
-        for (int sim = 0; sim < nsims; ++sim) {
-        for (int L = 0; L < nlayers; ++L) {
-            const uint32_t ev = (uint32_t)sim * (nlayers + 1) + L;   // act_ready event index: 1 load + nlayers epilogues per simulation
-            mbar_wait_converged(&bars->act_ready, ev & 1);       // inputs written, TMEM accumulators drained
-            tc_fence_after();
-            if (dbg) dbg[32 + 2 * L] = clock64();
-            for (int tap = 0; tap < 9; ++tap, ++n) {
-                const int st = n % kStages;
-                const long long tw0 = dbg ? clock64() : 0;
-                mbar_wait_converged(&bars->full[st], (n / kStages) & 1);
-                if (dbg) dbg[52 + (L == 0 && tap == 0 ? 1 : 0)] += (unsigned long long)(clock64() - tw0);   // [52] ring waits, [53] first tap of a simulation
-                tc_fence_after();
-                const int shift = (tap / 3 - 1) * kPitch + (tap % 3 - 1);
-                // descriptors differ only in the 14-bit start-address field: add 16-byte-unit offsets to a base
-                const uint64_t b0 = b_desc0 + (uint64_t)((st * kTapBytes) >> 4);
-                // fp32-accurate mode, per (tile, tap, k-step): A_hi x B_hi + A_hi x B_lo + A_lo x B_hi.  LZ_FOLD selects how they are
-                // issued (the tap block holds [B_hi | B_lo] as 128 operand rows, so A_hi x [B_hi | B_lo] can be ONE N = 128 MMA):
-                //   0  three N = 64 MMAs into the same 64 columns
-                //   1  N = 128 (A_hi) then N = 64 (A_lo x B_hi into columns 0-63), tile by tile
-                //   2  N = 128 (A_hi) then N = 128 (A_lo x [B_hi | B_lo]; the extra lo x lo term is harmless), tile by tile
-                //   3  as 1, but all tiles' N = 128 MMAs of the tap first, then all tiles' N = 64 MMAs
-                const uint32_t kA = (2 * kPlaneBytes) >> 4, kB = (2 * kTapKgBytes) >> 4, kLo = kPartBytes >> 4, kBlo = (64 * 16) >> 4;
-                if (npass != 3) {
-                    for (int t = 0; t < NT; ++t) {
-                        const uint64_t a0 = a_desc0 + (uint64_t)(t * 128 + shift);
-                        const uint32_t d = tmem + kColAcc + t * kAccCols;
-#pragma unroll
-                        for (int ks = 0; ks < 4; ++ks) umma_f16_elect(d, a0 + ks * kA, b0 + ks * kB, idesc64, (tap | ks) != 0);
-                    }
-                } else {
-#if LZ_FOLD == 0
-                    for (int t = 0; t < NT; ++t) {
-                        const uint64_t a0 = a_desc0 + (uint64_t)(t * 128 + shift);
-                        const uint32_t d = tmem + kColAcc + t * kAccCols;
-#pragma unroll
-                        for (int ks = 0; ks < 4; ++ks) umma_f16_elect(d, a0 + ks * kA, b0 + ks * kB, idesc64, (tap | ks) != 0);
-#pragma unroll
-                        for (int ks = 0; ks < 4; ++ks) umma_f16_elect(d, a0 + ks * kA, b0 + kBlo + ks * kB, idesc64, 1);
-#pragma unroll
-                        for (int ks = 0; ks < 4; ++ks) umma_f16_elect(d, a0 + kLo + ks * kA, b0 + ks * kB, idesc64, 1);
-                    }
-#elif LZ_FOLD == 3
-                    for (int t = 0; t < NT; ++t) {
-                        const uint64_t a0 = a_desc0 + (uint64_t)(t * 128 + shift);
-                        const uint32_t d = tmem + kColAcc + t * kAccCols;
-#pragma unroll
-                        for (int ks = 0; ks < 4; ++ks) umma_f16_elect(d, a0 + ks * kA, b0 + ks * kB, idesc128, (tap | ks) != 0);
-                    }
-                    for (int t = 0; t < NT; ++t) {
-                        const uint64_t a0 = a_desc0 + (uint64_t)(t * 128 + shift);
-                        const uint32_t d = tmem + kColAcc + t * kAccCols;
-#pragma unroll
-                        for (int ks = 0; ks < 4; ++ks) umma_f16_elect(d, a0 + kLo + ks * kA, b0 + ks * kB, idesc64, 1);
-                    }
-#else
-                    for (int t = 0; t < NT; ++t) {
-                        const uint64_t a0 = a_desc0 + (uint64_t)(t * 128 + shift);
-                        const uint32_t d = tmem + kColAcc + t * kAccCols;
-#pragma unroll
-                        for (int ks = 0; ks < 4; ++ks) umma_f16_elect(d, a0 + ks * kA, b0 + ks * kB, idesc128, (tap | ks) != 0);
-#pragma unroll
-                        for (int ks = 0; ks < 4; ++ks) umma_f16_elect(d, a0 + kLo + ks * kA, b0 + ks * kB, LZ_FOLD == 2 ? idesc128 : idesc64, 1);
-                    }
-#endif
-                }
-                umma_commit_elect(&bars->empty[st]);               // frees this ring slot when the MMAs have read it
-            }
-            umma_commit_elect(&bars->acc_ready);
-            if (dbg) dbg[33 + 2 * L] = clock64();
+        // 1x1 head convolutions on layer L's OUTPUT for the tiles [t0, t1) of one root group; the caller has waited for that group's
+        // epilogue.  The value/policy result reuses drained conv accumulator columns (tile 0's), so that hook is only legal on the LAST
+        // layer; the reward result has its own columns.  One arrival per group on the hook's barrier.
+        auto hooks = [&](int L, int t0, int t1) {
             const int flags = net.layer_flags[L];
-            if (flags & (LF_HOOK_REWARD | LF_HOOK_VALPOL)) {
-                // 1x1 head convolutions on this layer's OUTPUT: wait for the epilogue to have written it (the same
-                // phase the next layer waits for; waiting twice on a completed phase is immediate).  The
-                // value/policy result reuses the drained conv accumulator columns, so that hook is only legal on
-                // the LAST layer; the reward result has its own columns.
-                mbar_wait_converged(&bars->act_ready, (ev + 1) & 1);
-                tc_fence_after();
-                for (int hook = 0; hook < 2; ++hook) {
-                    if (!(flags & (hook == 0 ? LF_HOOK_REWARD : LF_HOOK_VALPOL))) continue;
-                    for (int t = 0; t < NT; ++t) {
-                        const uint32_t arow = act_s + (uint32_t)(kMargin + t * 128) * 16u;
-                        for (int ps = 0; ps < npass; ++ps) {
-                            const uint32_t apart = (ps == 2) ? kPartBytes : 0;
+            for (int hook = 0; hook < 2; ++hook) {
+                if (!(flags & (hook == 0 ? LF_HOOK_REWARD : LF_HOOK_VALPOL))) continue;
+                for (int t = t0; t < t1; ++t) {
+                    const uint32_t arow = act_s + (uint32_t)(kMargin + t * 128) * 16u;
+                    for (int ps = 0; ps < npass; ++ps) {
+                        const uint32_t apart = (ps == 2) ? kPartBytes : 0;
 #pragma unroll
-                            for (int ks = 0; ks < 4; ++ks) {
-                                const uint64_t ad = make_desc(arow + apart + ks * 2 * kPlaneBytes, a_lbo, a_sbo);
-                                if (hook == 0) {   // reward head: N = 16, [kg][16 co][8]
-                                    const uint32_t wb = headw_s + ((ps == 1) ? 2048 : 0);
-                                    umma_f16_elect(tmem + kColRew + t * 16, ad, make_desc(wb + ks * 512, 16, 8), idesc16, (ps | ks) != 0);
-                                } else {           // value + policy heads as one N = 32 matrix, [kg][32 co][8]
-                                    const uint32_t wb = headw_s + 4096 + ((ps == 1) ? 4096 : 0);
-                                    umma_f16_elect(tmem + kColVp + t * 32, ad, make_desc(wb + ks * 1024, 32, 8), idesc32, (ps | ks) != 0);
-                                }
+                        for (int ks = 0; ks < 4; ++ks) {
+                            const uint64_t ad = make_desc(arow + apart + ks * 2 * kPlaneBytes, a_lbo, a_sbo);
+                            if (hook == 0) {   // reward head: N = 16, [kg][16 co][8]
+                                const uint32_t wb = headw_s + ((ps == 1) ? 2048 : 0);
+                                umma_f16_elect(tmem + kColRew + t * 16, ad, make_desc(wb + ks * 512, 16, 8), idesc16, (ps | ks) != 0);
+                            } else {           // value + policy heads as one N = 32 matrix, [kg][32 co][8]
+                                const uint32_t wb = headw_s + 4096 + ((ps == 1) ? 4096 : 0);
+                                umma_f16_elect(tmem + kColVp + t * 32, ad, make_desc(wb + ks * 1024, 32, 8), idesc32, (ps | ks) != 0);
                             }
                         }
                     }
-                    umma_commit_elect(hook == 0 ? &bars->rew_ready : &bars->vp_ready);
                 }
+                umma_commit_elect(hook == 0 ? &bars->rew_ready : &bars->vp_ready);
             }
+        };
+        for (int sim = 0; sim < nsims; ++sim) {
+        for (int L = 0; L < nlayers; ++L) {
+            const uint32_t ev = (uint32_t)sim * (nlayers + 1) + L;   // act_ready event index: 1 load + nlayers epilogues per simulation
+            for (int g = 0; g < ngroups; ++g) {
+                const int t0 = g == 0 ? 0 : NTx, t1 = g == 0 ? NTx : NT;
+                mbar_wait_converged(&bars->act_ready[g], ev & 1);    // this group's inputs written, its TMEM accumulators drained
+                tc_fence_after();
+                if (L > 0) hooks(L - 1, t0, t1);                     // head convolutions on the previous layer's output
+                if (dbg && g == 0) dbg[32 + 2 * L] = clock64();
+                for (int ti = 0; ti < 9; ++ti) {
+                    const int tap = ti;
+                    const uint32_t pos = n++;
+                    const int st = pos % kStages;
+                    const long long tw0 = dbg ? clock64() : 0;
+                    mbar_wait_converged(&bars->full[st], (pos / kStages) & 1);
+                    if (dbg) dbg[52 + (L == 0 && tap == 0 && g == 0 ? 1 : 0)] += (unsigned long long)(clock64() - tw0);   // [52] ring waits, [53] first tap of a simulation
+                    tc_fence_after();
+                    const int shift = (tap / 3 - 1) * kPitch + (tap % 3 - 1);
+                    // descriptors differ only in the 14-bit start-address field: add 16-byte-unit offsets to a base
+                    const uint64_t b0 = b_desc0 + (uint64_t)((st * kTapBytes) >> 4);
+                    // fp32-accurate mode, per (tile, tap, k-step): A_hi x [B_hi | B_lo] as ONE N = 128 MMA (the tap block holds the two
+                    // weight parts as 128 operand rows; the two 64-column halves are added at read-out), then A_lo x B_hi (N = 64, into
+                    // columns 0-63).  Measured alternatives (three N = 64 MMAs; N = 128 twice; all tiles' N = 128 first) were slower.
+                    const uint32_t kA = (2 * kPlaneBytes) >> 4, kB = (2 * kTapKgBytes) >> 4, kLo = kPartBytes >> 4;
+                    for (int t = t0; t < t1; ++t) {
+                        const uint64_t a0 = a_desc0 + (uint64_t)(t * 128 + shift);
+                        const uint32_t d = tmem + kColAcc + t * kAccCols;
+                        if (npass != 3) {
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks) umma_f16_elect(d, a0 + ks * kA, b0 + ks * kB, idesc64, (ti | ks) != 0);
+                        } else {
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks) umma_f16_elect(d, a0 + ks * kA, b0 + ks * kB, idesc128, (ti | ks) != 0);
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks) umma_f16_elect(d, a0 + kLo + ks * kA, b0 + ks * kB, idesc64, 1);
+                        }
+                    }
+                    umma_commit_elect(&bars->empty[st]);               // frees this ring slot when the MMAs have read it
+                }
+                umma_commit_elect(&bars->acc_ready[g]);
+                if (dbg && g == ngroups - 1) dbg[33 + 2 * L] = clock64();
+            }
+        }
+        // head convolutions on the last layer's output (waiting twice on a completed phase is immediate)
+        for (int g = 0; g < ngroups; ++g) {
+            mbar_wait_converged(&bars->act_ready[g], ((uint32_t)sim * (nlayers + 1) + nlayers) & 1);
+            tc_fence_after();
+            hooks(nlayers - 1, g == 0 ? 0 : NTx, g == 0 ? NTx : NT);
         }
         // ---- the heads' fully connected layers (weights = M operand from the ring, roots = N columns; see the heads section)
         {
@@ -594,31 +652,31 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_net_tc(TcNet net, TcIO io, Tr
         int rowc[kMaxTiles];
 #pragma unroll
         for (int t = 0; t < kMaxTiles; ++t) {
-            const int m = t * 128 + rowid;
-            const int r = m / kRowsPerRoot, q = m - r * kRowsPerRoot, y = q / kPitch, x = q - y * kPitch;
-            const bool valid = (t < NT) && (m < rows_used) && (r < nvalid) && (y < 6) && (x < 6);
-            rowc[t] = valid ? ((r << 8) | (y * 6 + x)) : -1;
+            int r, p;
+            const bool valid = row_decode(rm, t * 128 + rowid, r, p) && (t < NT);
+            rowc[t] = valid ? ((r << 8) | p) : -1;
         }
-        for (int sim = 0; sim < nsims; ++sim) {
-            if (dbg) dbg[50] = clock64();
+        for (int sim = 0; sim <= nsims; ++sim) {        // iteration nsims: only the back-up of the last simulation (mcts_ctree.py:365-368)
+            if (sim == nsims && !persistent) break;
+            if (dbg && sim < nsims) dbg[50] = clock64();
             if (persistent) {
                 // ---- tree phase: one warp per root of this CTA (roots never interact, so the whole search of these roots
                 // lives in this CTA): back up the previous simulation, then descend to the next leaf.  cnode.cpp:480-500,754-825
                 if (warp < nvalid) {
                     const int b = root0 + warp;
-                    if (fast_tree) {
-                        PTree T;
-                        ptree_unpark(T, tree_park, lane);
-                        if (sim > 0)
-                            ptree_backprop(tp, T, b, lane, io.sim0 + sim, io.reward[b], io.value[b], io.policy_logits + (size_t)b * net.A);
-                        ptree_traverse(tp, T, b, lane, io.deterministic, (unsigned)(io.sim0 + sim), pbc_tab, io.ix_rw, io.action_rw);
+                    PTree T;
+                    ptree_unpark(T, tree_park, lane);
+                    float *my_ho = ho + warp * kHoWords;
+                    if (sim > 0)       // network outputs of the previous simulation: from the hand-off (written by this CTA's read-out)
+                        ptree_backprop(tp, T, b, lane, io.sim0 + sim, my_ho[3], my_ho[2], my_ho + 4);
+                    if (dbg && sim < nsims) dbg[56] = clock64();
+                    if (sim < nsims) {
+                        ptree_traverse(tp, T, b, lane, io.deterministic, (unsigned)(io.sim0 + sim), pbc_tab, io.ix_rw, io.action_rw,
+                                       reinterpret_cast<int *>(my_ho), reinterpret_cast<int *>(my_ho) + 1);
                         ptree_park(T, tree_park, lane);
-                    } else {
-                        if (sim > 0)
-                            tree_backprop(tp, b, lane, io.sim0 + sim, io.reward[b], io.value[b], io.policy_logits + (size_t)b * net.A, nullptr);
-                        tree_traverse(tp, b, lane, io.deterministic, (unsigned)(io.sim0 + sim), io.ix_rw, nullptr, io.action_rw, nullptr, nullptr);
                     }
                 }
+                if (sim == nsims) break;
                 __threadfence_block();
                 asm volatile("bar.sync 1, %0;\n" ::"n"(kEpiThreads) : "memory");
             }
@@ -634,7 +692,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_net_tc(TcNet net, TcIO io, Tr
             // the pool slot holding the input latent of each of this thread's rows (tree -> network hand-off)
             int slot[kMaxTiles];
 #pragma unroll
-            for (int t = 0; t < kMaxTiles; ++t) slot[t] = (rowc[t] >= 0 && io.ix) ? io.ix[root0 + (rowc[t] >> 8)] : 0;
+            for (int t = 0; t < kMaxTiles; ++t)
+                slot[t] = rowc[t] < 0 ? 0 : (persistent ? reinterpret_cast<const int *>(ho)[(rowc[t] >> 8) * kHoWords] : (io.ix ? io.ix[root0 + (rowc[t] >> 8)] : 0));
             auto in_ptr = [&](int t) { return io.latent_base + (size_t)slot[t] * io.slot_stride + (size_t)(root0 + (rowc[t] >> 8)) * (kC * kP); };
             auto in_is_cl = [&](int t) { return io.pool_cl != 0 && slot[t] > 0; };      // slot 0: root latents as the API delivered them (NCHW)
             // ---- load the input activation: gather the latents (two tiles' loads in flight), split to fp16 hi/lo ----
@@ -655,16 +714,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_net_tc(TcNet net, TcIO io, Tr
                         store_split8(p, p + kPartBytes, src + 8 * g);
                     }
                 };
+                // phase 0 of a root group's act_ready: its layer 0 may start (group X while group Y's rows are still being loaded)
+                auto loaded = [&](int t) {
+                    if (t == NTx - 1 || t == NT - 1) {
+                        fence_proxy_async();
+                        tc_fence_before();
+                        mbar_arrive(&bars->act_ready[t == NT - 1 ? ngroups - 1 : 0]);
+                    }
+                };
                 fetch_in(0, va);
                 if (NT > 1) fetch_in(1, vb);
                 put(0, va);
+                loaded(0);
                 if (NT > 2) fetch_in(2, va);
-                if (NT > 1) put(1, vb);
-                if (NT > 2) put(2, va);
+                if (NT > 1) { put(1, vb); loaded(1); }
+                if (NT > 2) { put(2, va); loaded(2); }
             }
-            fence_proxy_async();
-            tc_fence_before();
-            mbar_arrive(&bars->act_ready);                          // phase 0: layer 0 may start
             if (dbg) dbg[1] = clock64();
 
             bool skip_in_scratch = false;      // the residual operand: the input latent until a layer has parked its output
@@ -685,7 +750,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_net_tc(TcNet net, TcIO io, Tr
                 };
                 auto fetch_abias = [&](int t, float (&dst)[32], bool add) {
                     if (rowc[t] < 0) return;
-                    const int action = min(max(io.action[root0 + (rowc[t] >> 8)], 0), net.A - 1);
+                    const int action_raw = persistent ? reinterpret_cast<const int *>(ho)[(rowc[t] >> 8) * kHoWords + 1] : io.action[root0 + (rowc[t] >> 8)];
+                    const int action = min(max(action_raw, 0), net.A - 1);
                     const float4 *ab = reinterpret_cast<const float4 *>(net.abias) + ((size_t)action * 16 + half * 8) * kP + (rowc[t] & 255);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
@@ -702,13 +768,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_net_tc(TcNet net, TcIO io, Tr
                         if (NT > 1) fetch_abias(1, rb, true);
                     }
                 }
-                mbar_wait_warp(&bars->acc_ready, acc_par);
-                acc_par ^= 1;                               // one commit per layer, across simulations
+                mbar_wait_warp(&bars->acc_ready[0], acc_par);
                 tc_fence_after();
                 if (dbg) dbg[2 + 2 * L] = clock64();
 #pragma unroll
                 for (int t = 0; t < kMaxTiles; ++t) {
                     if (t >= NT) continue;
+                    if (t > 0 && t == NTx) {
+                        // root group X is complete: its next layer (or hook) may start while group Y's tiles are processed
+                        fence_proxy_async();
+                        tc_fence_before();
+                        mbar_arrive(&bars->act_ready[0]);
+                        if (dbg) dbg[57] = clock64();
+                        mbar_wait_warp(&bars->acc_ready[1], acc_par);
+                        tc_fence_after();
+                    }
                     const int m = t * 128 + rowid;
                     const bool valid = rowc[t] >= 0;
                     const int p = rowc[t] & 255, b = root0 + (rowc[t] >> 8);
@@ -725,7 +799,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_net_tc(TcNet net, TcIO io, Tr
                         uint32_t ua[16];
                         float v[16];
                         tmem_ld16_issue(lane_base + kColAcc + t * kAccCols + half * 32 + hs * 16, ua);
-                        if (npass == 3 && LZ_FOLD != 0) {
+                        if (npass == 3) {
                             uint32_t ub[16];
                             tmem_ld16_issue(lane_base + kColAcc + t * kAccCols + 64 + half * 32 + hs * 16, ub);
                             tmem_ld_wait();
@@ -771,9 +845,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_net_tc(TcNet net, TcIO io, Tr
                     if (has_res && has_ab && t == 1 && NT > 2) fetch_abias(2, rb, false);
                 }
                 if (park) skip_in_scratch = true;
+                acc_par ^= 1;                                       // one commit per layer and group, across simulations
                 fence_proxy_async();
                 tc_fence_before();
-                mbar_arrive(&bars->act_ready);                      // phase L+1: next layer / this layer's hook may start
+                mbar_arrive(&bars->act_ready[ngroups - 1]);         // phase L+1: next layer / this layer's hook may start
                 if (dbg) dbg[3 + 2 * L] = clock64();
                 if ((flags & LF_HOOK_REWARD) && net.has_reward) {
                     // reward 1x1 accumulators -> BN/ReLU features, parked (fp16 hi / lo) until the heads' FC pass at the end of the
@@ -797,7 +872,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_net_tc(TcNet net, TcIO io, Tr
                         }
                         tc_fence_before();
                     } else {
-                        head_scatter(net, 1, fr, nullptr, tmem, NT, rows_used, nvalid);
+                        head_scatter(net, 1, fr, nullptr, tmem, NT, rm);
                     }
                     if (dbg) dbg[28] = clock64();
                 }
@@ -822,7 +897,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_net_tc(TcNet net, TcIO io, Tr
                             *reinterpret_cast<const uint4 *>(fr + part * (kFrBytes / 2) + (kg * 8 + r) * 16);
                     }
                 }
-                head_scatter(net, 6, nullptr, fb, tmem, NT, rows_used, nvalid);
+                head_scatter(net, 6, nullptr, fb, tmem, NT, rm);
                 fence_proxy_async();
                 mbar_arrive(&bars->fcb_ready);                      // FC1 may start
                 if (dbg) dbg[44] = clock64();
@@ -836,20 +911,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_net_tc(TcNet net, TcIO io, Tr
                 mbar_wait_warp(&bars->fc2_done, sim & 1);
                 tc_fence_after();
                 if (dbg) dbg[47] = clock64();
-                heads_outputs(net, io, hmask_fc, tmem, red, nvalid, root0);
+                heads_outputs(net, io, hmask_fc, tmem, red, nvalid, root0, b2_s, persistent ? ho : nullptr);
             }
             if (dbg) dbg[27] = clock64();
             __threadfence_block();
             asm volatile("bar.sync 1, %0;\n" ::"n"(kEpiThreads) : "memory");
-        }
-        if (persistent && warp < nvalid) {        // back up the last simulation (mcts_ctree.py:365-368)
-            const int b = root0 + warp;
-            if (fast_tree) {
-                PTree T;
-                ptree_unpark(T, tree_park, lane);
-                ptree_backprop(tp, T, b, lane, io.sim0 + nsims, io.reward[b], io.value[b], io.policy_logits + (size_t)b * net.A);
-            }
-            else tree_backprop(tp, b, lane, io.sim0 + nsims, io.reward[b], io.value[b], io.policy_logits + (size_t)b * net.A, nullptr);
         }
     }
 
@@ -935,6 +1001,16 @@ int tc_pick_roots(int B)
     return std::min(std::max(r, 1), kMaxRoots);
 }
 
+// Root-group split of a CTA's R roots (see the kernel): only where {Rx, R - Rx} needs no more 128-row tiles than R roots together.
+static int tc_pick_split(int R)
+{
+    auto tiles = [](int r) { return (r * kRowsPerRoot + 127) / 128; };
+    const int cand[3] = {5, 4, 2};
+    for (int rx : cand)
+        if (rx < R && tiles(rx) + tiles(R - rx) == tiles(R)) return rx;
+    return 0;
+}
+
 int tc_launch(const TcNet &net, const TcIO &io_in, cudaStream_t s, const TreeParams *tp_in)
 {
     TcIO io = io_in;
@@ -946,8 +1022,10 @@ int tc_launch(const TcNet &net, const TcIO &io_in, cudaStream_t s, const TreePar
     LZ_REQUIRE(io.skip_scratch, LZ_EINVAL, "tc_launch: no skip scratch");
     io.dbg = g_dbg;
     io.roots_per_cta = tc_pick_roots(io.B);
-    if (getenv("LZ_TC_GENERIC_TREE")) io.generic_tree = 1;    // A/B switch: tree.cuh's routines inside the persistent kernel
+    LZ_REQUIRE(!io.persistent || tp.A <= 32, LZ_EINVAL, "tc_launch: the persistent search needs A <= 32 (got %d)", tp.A);
     if (const char *e = getenv("LZ_TC_ROOTS")) io.roots_per_cta = std::min(std::max(atoi(e), 1), kMaxRoots);
+    io.split_rx = tc_pick_split(io.roots_per_cta);
+    if (const char *e = getenv("LZ_TC_SPLIT")) io.split_rx = atoi(e);          // A/B switch (0 = one group)
     const int grid = (io.B + io.roots_per_cta - 1) / io.roots_per_cta;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));

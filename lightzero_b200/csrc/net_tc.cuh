@@ -36,9 +36,9 @@ struct TcNet {
 struct TcIO {
     int B;
     int roots_per_cta;             // filled by tc_launch
+    int split_rx;                  // filled by tc_launch: > 0 = the CTA's roots run as two independently pipelined groups {split_rx, rest} (net_tc.cu)
     int npass;                     // 3 = fp32-accurate (hi*hi + hi*lo + lo*hi), 1 = fast (hi*hi)
     int pdl;                       // launch with programmatic stream serialization (inside the search graph)
-    int generic_tree;              // debug (env LZ_TC_GENERIC_TREE): persistent search with tree.cuh's routines instead of tree_persist.cuh
     const float *latent_base;      // input latents: base + ix[b]*slot_stride + b*2304 (NCHW [64][36])
     const int *ix;                 // or nullptr
     size_t slot_stride;

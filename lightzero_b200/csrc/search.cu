@@ -80,7 +80,7 @@ static int enqueue_search(lz_search *q, int deterministic, cudaStream_t s)
         }
         return LZ_OK;
     }
-    if (q->model->kind == 0 && q->model->math != 0 && !getenv("LZ_NO_PERSIST")) {
+    if (q->model->kind == 0 && q->model->math != 0 && t->p.A <= 32 && !getenv("LZ_NO_PERSIST")) {   // tree_persist.cuh: one lane per child
         TcIO io;
         memset(&io, 0, sizeof(io));
         io.B = q->B; io.npass = (q->model->math == 1) ? 3 : 1;

@@ -65,7 +65,8 @@ __device__ __forceinline__ float ptree_ucb(bool active, int vis, float prior, fl
 
 // One PUCT descent (cbatch_traverse body, cnode.cpp:783-824).  pbc_tab: the table in shared memory (or p.pbc).
 __device__ __forceinline__ void ptree_traverse(const TreeParams &p, PTree &T, int b, int lane, int deterministic, unsigned step,
-                                               const float *pbc_tab, int *out_ix, int *out_action)
+                                               const float *pbc_tab, int *out_ix, int *out_action, int *leaf_slot = nullptr,
+                                               int *leaf_action = nullptr)
 {
     const int A = p.A, N = p.N;
     const uint32_t *tree_edges = p.edges + (size_t)b * N * kEdgeFields * A;
@@ -98,14 +99,14 @@ __device__ __forceinline__ void ptree_traverse(const TreeParams &p, PTree &T, in
         // ---- compute_mean_q: sequential fp32 sum over visited children in legal order (cnode.cpp:169-203)
         float q = 0.0f;
         if (vis > 0) q = __fadd_rn(rw, __fmul_rn(discount, __fdiv_rn(vsum, (float)vis)));
+        // every lane runs the same sum; the broadcasts do not depend on the running total, so they pipeline ahead of the add chain
         float total = 0.0f;
-        int tv = 0;
-        unsigned m = __ballot_sync(0xffffffffu, vis > 0);
-        while (m) {
-            const int l = __ffs(m) - 1;
-            m &= m - 1;
-            total = __fadd_rn(total, __shfl_sync(0xffffffffu, q, l));
-            ++tv;
+        const unsigned m = __ballot_sync(0xffffffffu, vis > 0);
+        const int tv = __popc(m);
+#pragma unroll 6
+        for (int l = 0; l < n; ++l) {
+            const float ql = __shfl_sync(0xffffffffu, q, l);
+            if ((m >> l) & 1u) total = __fadd_rn(total, ql);
         }
         float mean_q;
         if (is_root && tv > 0) mean_q = __fdiv_rn(total, (float)tv);
@@ -178,6 +179,8 @@ __device__ __forceinline__ void ptree_traverse(const TreeParams &p, PTree &T, in
         p.search_len[b] = plen;
         if (out_ix) out_ix[b] = slot;     // parent of the leaf: its slot == current_latent_state_index
         if (out_action) out_action[b] = last_action;
+        if (leaf_slot) *leaf_slot = slot;             // e.g. a shared-memory hand-off to the network phase of the same CTA
+        if (leaf_action) *leaf_action = last_action;
     }
     __syncwarp();
 }

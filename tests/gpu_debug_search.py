@@ -44,11 +44,12 @@ def main():
     t0 = s[50]
     rel = lambda i: s[i] - t0
     print("== last simulation of CTA 0, cycles since the start of the simulation (tree phase first)")
-    print(f"   tree done (backprop + traverse)  {rel(51):8d}")
+    print(f"   tree: backprop done {rel(56):8d}  traverse done (warp 0) + CTA barrier {rel(51):8d}")
     print(f"   load done                        {rel(1):8d}")
     for L in range(5):
         print(f"   L{L}: mma issue {rel(32 + 2 * L):8d} -> {rel(33 + 2 * L):8d} | acc ready {rel(2 + 2 * L):8d}  epilogue done {rel(3 + 2 * L):8d}"
               f"   [mma {s[2 + 2 * L] - s[32 + 2 * L]:6d}  epi {s[3 + 2 * L] - s[2 + 2 * L]:6d}]")
+    print(f"   last layer: group X epilogue done (act_ready[0]) {rel(57):8d}")
     print(f"   early reward head done           {rel(28):8d}")
     print(f"   hooks ready                      {rel(24):8d}")
     print(f"   VP heads: scatter done {rel(44):8d}  FC1 {rel(45):8d}  hidden {rel(46):8d}  FC2 {rel(47):8d}  all done {rel(27):8d}")
