@@ -266,6 +266,71 @@ k_conv3x3_generic(ConvG L, const float *__restrict__ in, float *__restrict__ out
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// The stem of the DownSample tower for 4 input channels (DownSample.conv1 + norm1 + ReLU, common.py:334-366; 3x3, stride 2,
+// pad 1, 4 -> 32 channels) on the CUDA cores, written straight into the tensor-core layout (TCL) of the first tcgen05 layer.
+// K = 36 is too thin for the tensor cores; the kernel is FFMA-bound by construction: the 1,152 weights and the folded BatchNorm
+// tables travel BY VALUE in the kernel parameters, so every FFMA takes its weight operand from the constant bank (no weight
+// loads at all) and the only shared-memory traffic is one activation load per 32 FFMAs.  CTA = rows_per_cta full output rows
+// (thread = output pixel, 32 accumulators), input band staged with 16-byte loads (uint8 frames are scaled to [0, 1] here).
+// ------------------------------------------------------------------------------------------------
+struct StemP { float w[4 * 9 * 32]; float scale[32], shift[32]; };
+
+template <bool U8>
+__global__ void __launch_bounds__(256)
+k_stem4_tcl(const __grid_constant__ StemP P, const float *__restrict__ in, const uint8_t *__restrict__ in_u8, int hin, int win,
+            int hout, int wout, int rows_per_cta, Tcl tcl)
+{
+    extern __shared__ __align__(16) float sm[];      // [4][nrows][pitch], column gx at index 4 + gx (index 3: the left padding)
+    const int tid = threadIdx.x, b = blockIdx.y, y0 = blockIdx.x * rows_per_cta;
+    const int nrows = 2 * rows_per_cta + 1, pitch = win + 4, r0 = 2 * y0 - 1, nq = win >> 2;
+    for (int i = tid; i < 4 * nrows * nq; i += 256) {
+        const int q = i % nq, rr = (i / nq) % nrows, c = i / (nq * nrows), gy = r0 + rr;
+        float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        if (gy >= 0 && gy < hin) {
+            const size_t gi = (((size_t)b * 4 + c) * hin + gy) * win + 4 * q;
+            if (U8) {
+                // ScaledFloatFrameWrapper: obs / 255 in float64, cast to float32 == one correctly rounded fp32 division (see
+                // k_conv3x3_generic)
+                const uchar4 u = *reinterpret_cast<const uchar4 *>(in_u8 + gi);
+                v = make_float4(__fdiv_rn((float)u.x, 255.0f), __fdiv_rn((float)u.y, 255.0f), __fdiv_rn((float)u.z, 255.0f),
+                                __fdiv_rn((float)u.w, 255.0f));
+            } else {
+                v = *reinterpret_cast<const float4 *>(in + gi);
+            }
+        }
+        *reinterpret_cast<float4 *>(sm + (size_t)(c * nrows + rr) * pitch + 4 + 4 * q) = v;
+    }
+    for (int i = tid; i < 4 * nrows; i += 256) sm[(size_t)i * pitch + 3] = 0.0f;
+    __syncthreads();
+    const int yl = tid / wout, x = tid - yl * wout, y = y0 + yl;
+    if (yl >= rows_per_cta || y >= hout) return;
+    float acc[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[j] = 0.0f;
+    const float *row0 = sm + (size_t)(2 * yl) * pitch + 2 * x + 3;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const float v = row0[(size_t)(c * nrows + ky) * pitch + kx];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) acc[j] = fmaf(v, P.w[(c * 9 + ky * 3 + kx) * 32 + j], acc[j]);
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[j] = fmaxf(fmaf(acc[j], P.scale[j], P.shift[j]), 0.0f);
+    const int rho = (y + 1) * tcl.pitch + x;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        unsigned char *op = tcl.base + (size_t)b * tcl.img_stride + ((size_t)g * tcl.plane_rows + rho + 1) * 16;
+        store_split8(op, op + tcl.part_stride, acc + 8 * g);
+    }
+}
+
 // nn.AvgPool2d(kernel_size=3, stride=2, padding=1), count_include_pad=True (divisor 9)
 __global__ void k_avgpool3s2(const float *__restrict__ in, float *__restrict__ out, int planes, int hin, int win,
                              int hout, int wout)
@@ -517,7 +582,16 @@ static int tower_tc_run(lz_model *m, int B, const float *d_obs, float *pre_laten
     int rc;
     const int npass = (m->math == 1) ? 3 : 1;
     // stem: conv1 (Cin = 4/12, stride 2) on the CUDA cores, written straight into TCL (uint8 frames are scaled to [0, 1] here)
-    if ((rc = launch_convg(m->tower[0], d_obs, nullptr, nullptr, 1, B, s, &m->T0, d_obs_u8))) return rc;
+    const ConvG &S0 = m->tower[0];
+    if (m->stem_valid && !getenv("LZ_STEM_GENERIC")) {
+        const int rows_per_cta = std::max(1, 256 / S0.wout);
+        const size_t smem = (size_t)4 * (2 * rows_per_cta + 1) * (S0.win + 4) * sizeof(float);
+        dim3 grid(ceil_div(S0.hout, rows_per_cta), B);
+        const StemP &P = *reinterpret_cast<const StemP *>(m->stem_params.data());
+        if (d_obs_u8) k_stem4_tcl<true><<<grid, 256, smem, s>>>(P, nullptr, d_obs_u8, S0.hin, S0.win, S0.hout, S0.wout, rows_per_cta, m->T0);
+        else k_stem4_tcl<false><<<grid, 256, smem, s>>>(P, d_obs, nullptr, S0.hin, S0.win, S0.hout, S0.wout, rows_per_cta, m->T0);
+        LZ_KERNEL_CHECK();
+    } else if ((rc = launch_convg(S0, d_obs, nullptr, nullptr, 1, B, s, &m->T0, d_obs_u8))) return rc;
     auto run = [&](ConvTc p, const Tcl &in, const Tcl &o0, const Tcl *o1, const Tcl *res) {
         p.in = in; p.out[0] = o0;
         if (o1) p.out[1] = *o1;
@@ -1133,6 +1207,16 @@ int lz_model_finalize(lz_model *m)
         L.cin = tower[i].cin; L.cout = tower[i].cout; L.stride = geo[i].stride;
         L.hin = L.win = geo[i].hin; L.hout = L.wout = geo[i].hout;
         m->tower.push_back(L);
+    }
+    // host copy of the stem's weights / folded BatchNorm for k_stem4_tcl (kernel-parameter operands)
+    m->stem_valid = 0;
+    if (tower[0].cin == 4 && tower[0].cout == 32 && h0 % 4 == 0 && (h0 / 2) <= 256) {
+        m->stem_params.assign(sizeof(StemP) / sizeof(float), 0.0f);
+        StemP &SP = *reinterpret_cast<StemP *>(m->stem_params.data());
+        memcpy(SP.w, P.host.data() + tower[0].w, sizeof(SP.w));
+        memcpy(SP.scale, P.host.data() + tower[0].scale, sizeof(SP.scale));
+        memcpy(SP.shift, P.host.data() + tower[0].shift, sizeof(SP.shift));
+        m->stem_valid = 1;
     }
     const int h4 = (h3 - 1) / 2 + 1;
     LZ_REQUIRE(h4 == kHW, LZ_EINVAL, "lz_model_finalize: latent grid %d != %d", h4, kHW);

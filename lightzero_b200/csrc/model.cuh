@@ -92,6 +92,8 @@ struct lz_model {
     size_t n_weight_floats;
     lz::NetDev net;
     std::vector<lz::ConvG> tower;     // DownSample convs in execution order
+    std::vector<float> stem_params;   // host copy of the Cin = 4 stem's weights + folded BN (kernel-parameter operands of k_stem4_tcl, model.cu)
+    int stem_valid;
     int hw, P, K;
     int math;                         // 0 = fp32 FFMA (net6.cuh), 1 = tcgen05 3xFP16 (fp32-accurate), 2 = tcgen05 fp16 single pass
     unsigned char *d_tc;              // packed fp16 hi/lo weights + tables of the tcgen05 path
