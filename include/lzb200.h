@@ -44,6 +44,8 @@ extern "C" {
 typedef struct lz_tree lz_tree;
 typedef struct lz_model lz_model;
 typedef struct lz_search lz_search;
+typedef struct lz_frames lz_frames;       /* device-resident observation frame stacks of B environments */
+typedef struct lz_segments lz_segments;   /* device-resident search statistics of B game segments */
 typedef void *lz_stream;   /* cudaStream_t */
 
 int lz_version(void);
@@ -227,6 +229,12 @@ int lz_search_run_with_reuse(lz_search *q, const float *d_latent_roots, const in
  * EfficientZero mode.  d_hidden{0,1}_roots: f32 [B, lstm_hidden_size] = reward_hidden_state_roots[0] / [1] (NULL = zeros,
  * what initial_inference returns).  The LSTM state of a leaf is zeroed every lstm_horizon_len steps of depth (:856-861). */
 int lz_search_run_ez(lz_search *q, const float *d_latent_roots, const float *d_hidden0_roots, const float *d_hidden1_roots, lz_stream s);
+/* EfficientZeroMCTSCtree.search_with_reuse (mcts_ctree.py:878-1003; ReZero on the value-prefix trees): arguments of lz_search_run_ez
+ * plus d_true_action / d_reuse_value / d_infer_count of lz_search_run_with_reuse.  One CUDA graph (1 + 5 x num_simulations
+ * kernels); is_reset is taken per TREE from the descent (search_len % lstm_horizon_len; the reference indexes a compacted list by
+ * tree at :1040-1046 / cnode.cpp:646). */
+int lz_search_run_ez_with_reuse(lz_search *q, const float *d_latent_roots, const float *d_hidden0_roots, const float *d_hidden1_roots,
+                                const int32_t *d_true_action, const float *d_reuse_value, int32_t *d_infer_count, lz_stream s);
 /* The search-feeding part of _forward_collect (policy/muzero.py:749-779): initial_inference ->
  * reset(mask) -> prepare(noise) -> search.  d_obs f32 [B,obs_c,H,W]; d_mask uint8 [B,A] or NULL;
  * d_noise f32 [B,A] legal-order rows or NULL; d_to_play int32 [B] or NULL (-1).
@@ -258,6 +266,35 @@ int lz_search_num_kernels(const lz_search *q);
 const float *lz_search_latent_pool(const lz_search *q);
 /* EfficientZero: device LSTM-state pool [(S+1)][B][H], which = 0 / 1 for tuple element 0 / 1 (NULL for MuZero). */
 const float *lz_search_hidden_pool(const lz_search *q, int which);
+
+
+/* ---- collector state on the device ----
+ * Observation frame stacks: what the reference collector rebuilds on the host every step with
+ * GameSegment.get_obs() = obs_segment[t : t + frame_stack_num] (lzero/mcts/buffer/game_segment.py:140-156), seeded with
+ * frame_stack_num copies of the first frame (lzero/worker/muzero_collector.py:451-457) and fed one new frame per step
+ * (GameSegment.append, game_segment.py:158-181; muzero_collector.py:520-545).  Here only the NEW uint8 frame of every environment
+ * crosses PCIe (B*H*W bytes instead of B*stack*H*W*4); lz_frames_stacked() is the [B, stack, H, W] uint8 batch (oldest frame
+ * first) that lz_search_collect_u8 consumes.  H*W must be a multiple of 16. */
+int lz_frames_create(int B, int stack, int H, int W, lz_frames **out);
+int lz_frames_destroy(lz_frames *f);
+/* d_new_frames uint8 [B,H,W]; d_reset uint8 [B] or NULL: 1 = the environment was reset, its whole stack becomes the new frame. */
+int lz_frames_push(lz_frames *f, const uint8_t *d_new_frames, const uint8_t *d_reset, lz_stream s);
+/* The same from HOST buffers (pinned memory recommended); they must stay valid until `s` reaches the copies. */
+int lz_frames_push_host(lz_frames *f, const uint8_t *h_new_frames, const uint8_t *h_reset, lz_stream s);
+/* Device pointer of the current stacks; valid until the next push. */
+const uint8_t *lz_frames_stacked(lz_frames *f);
+/* GameSegment.store_search_stats (game_segment.py:241-263, idx=None) for B segments of capacity T: appends
+ * child_visits[b][len[b]][k] = visit_counts[k] / sum(visit_counts) (computed in float64 as Python does, 1e-6 denominator when every
+ * count is 0; k = position in the root's legal-action list, 0 beyond it) and root_values[b][len[b]].  d_visits int32 [B,A] / d_values
+ * f32 [B] as lz_tree_results returns them (-1 beyond the legal list); d_active uint8 [B] or NULL selects the environments that
+ * stepped.  A full segment (len == T) is left unchanged. */
+int lz_segments_create(int B, int T, int A, lz_segments **out);
+int lz_segments_destroy(lz_segments *g);
+int lz_segments_store_search_stats(lz_segments *g, const int32_t *d_visits, const float *d_values, const uint8_t *d_active, lz_stream s);
+/* GameSegment.reset (game_segment.py:340-362) of the statistics: len = 0 where d_done[b] != 0 (NULL: everywhere). */
+int lz_segments_reset(lz_segments *g, const uint8_t *d_done, lz_stream s);
+/* Device pointers: child_visits f32 [B,T,A], root_values f32 [B,T], len int32 [B] (any may be NULL). */
+int lz_segments_data(lz_segments *g, float **d_child_visits, float **d_root_values, int32_t **d_len);
 
 #ifdef __cplusplus
 }

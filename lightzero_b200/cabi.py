@@ -82,6 +82,17 @@ SIGNATURES = {
     "lz_search_latent_pool": (c_void_p, [c_void_p]),
     "lz_search_run_with_reuse": (c_int, [c_void_p] * 6),
     "lz_search_run_ez": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "lz_search_run_ez_with_reuse": (c_int, [c_void_p] * 8),
+    "lz_frames_create": (c_int, [c_int, c_int, c_int, c_int, ctypes.POINTER(c_void_p)]),
+    "lz_frames_destroy": (c_int, [c_void_p]),
+    "lz_frames_push": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "lz_frames_push_host": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "lz_frames_stacked": (c_void_p, [c_void_p]),
+    "lz_segments_create": (c_int, [c_int, c_int, c_int, ctypes.POINTER(c_void_p)]),
+    "lz_segments_destroy": (c_int, [c_void_p]),
+    "lz_segments_store_search_stats": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "lz_segments_reset": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "lz_segments_data": (c_int, [c_void_p, ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p)]),
     "lz_search_hidden_pool": (c_void_p, [c_void_p, c_int]),
 }
 

@@ -128,6 +128,31 @@ static int enqueue_search_reuse(lz_search *q, cudaStream_t s)
     int rc;
     lz_tree *t = q->tree;
     t->step_counter = 0;
+    if (q->hpool) {
+        // EfficientZeroMCTSCtree.search_with_reuse (mcts_ctree.py:878-1003): value-prefix trees, the LSTM step over all roots, is_reset
+        // per tree from the descent; [traverse_with_reuse] + S x [conv trunk + heads, LSTM value-prefix head, backpropagate_with_reuse,
+        // next traverse_with_reuse]
+        if ((rc = tree_launch_traverse_reuse(t, q->d_true_action, q->d_reuse_value, nullptr, q->d_ix, nullptr, q->d_action, nullptr, nullptr, s,
+                                             q->d_is_reset))) return rc;
+        for (int sim = 0; sim < q->S; ++sim) {
+            RecIO io;
+            memset(&io, 0, sizeof(io));
+            io.B = q->B; io.latent_base = q->pool; io.ix = q->d_ix; io.slot_stride = q->slot_stride; io.action = q->d_action;
+            io.next_latent = q->pool + (size_t)(sim + 1) * q->slot_stride;
+            io.reward = q->d_reward; io.value = q->d_value; io.policy_logits = q->d_policy;
+            io.h_base = q->hpool; io.c_base = q->cpool; io.hslot_stride = q->hslot_stride;
+            io.h_out = q->hpool + (size_t)(sim + 1) * q->hslot_stride; io.c_out = q->cpool + (size_t)(sim + 1) * q->hslot_stride;
+            io.is_reset = q->d_is_reset;
+            io.skip_scratch = q->d_skip;
+            if ((rc = model_recurrent(q->model, io, s))) return rc;
+            if ((rc = tree_launch_backprop_reuse(t, sim + 1, q->d_reward, q->d_value, q->d_policy, q->d_reuse_value, nullptr, nullptr, s,
+                                                 q->d_is_reset))) return rc;
+            if (sim + 1 < q->S &&
+                (rc = tree_launch_traverse_reuse(t, q->d_true_action, q->d_reuse_value, nullptr, q->d_ix, nullptr, q->d_action, nullptr, nullptr, s,
+                                                 q->d_is_reset))) return rc;
+        }
+        return LZ_OK;
+    }
     if ((rc = tree_launch_traverse_reuse(t, q->d_true_action, q->d_reuse_value, nullptr, q->d_ix, nullptr, q->d_action, nullptr, nullptr, s))) return rc;
     for (int sim = 0; sim < q->S; ++sim) {
         RecIO io;
@@ -257,13 +282,32 @@ int lz_search_run_ez(lz_search *q, const float *d_latent_roots, const float *d_h
     return run_graph(q, 1, (cudaStream_t)s);
 }
 
+static int run_with_reuse(lz_search *q, const float *d_latent_roots, const int32_t *d_true_action, const float *d_reuse_value,
+                          int32_t *d_infer_count, cudaStream_t s);
+
 int lz_search_run_with_reuse(lz_search *q, const float *d_latent_roots, const int32_t *d_true_action, const float *d_reuse_value,
                              int32_t *d_infer_count, lz_stream s_)
 {
     LZ_REQUIRE(q && d_true_action && d_reuse_value, LZ_EINVAL, "lz_search_run_with_reuse: null argument");
-    LZ_REQUIRE(!q->hpool, LZ_ESTATE, "lz_search_run_with_reuse: MuZero searches only");
+    LZ_REQUIRE(!q->hpool, LZ_ESTATE, "lz_search_run_with_reuse: EfficientZero search, use lz_search_run_ez_with_reuse");
     LZ_REQUIRE(q->tree->prepared, LZ_ESTATE, "lz_search_run_with_reuse: roots not prepared (call lz_tree_prepare first)");
-    cudaStream_t s = (cudaStream_t)s_;
+    return run_with_reuse(q, d_latent_roots, d_true_action, d_reuse_value, d_infer_count, (cudaStream_t)s_);
+}
+
+int lz_search_run_ez_with_reuse(lz_search *q, const float *d_latent_roots, const float *d_hidden0_roots, const float *d_hidden1_roots,
+                                const int32_t *d_true_action, const float *d_reuse_value, int32_t *d_infer_count, lz_stream s_)
+{
+    LZ_REQUIRE(q && d_true_action && d_reuse_value, LZ_EINVAL, "lz_search_run_ez_with_reuse: null argument");
+    LZ_REQUIRE(q->hpool, LZ_ESTATE, "lz_search_run_ez_with_reuse: not an EfficientZero search");
+    LZ_REQUIRE(q->tree->prepared, LZ_ESTATE, "lz_search_run_ez_with_reuse: roots not prepared (call lz_tree_prepare first)");
+    int rc = ez_root_hidden(q, d_hidden0_roots, d_hidden1_roots, (cudaStream_t)s_);
+    if (rc) return rc;
+    return run_with_reuse(q, d_latent_roots, d_true_action, d_reuse_value, d_infer_count, (cudaStream_t)s_);
+}
+
+static int run_with_reuse(lz_search *q, const float *d_latent_roots, const int32_t *d_true_action, const float *d_reuse_value,
+                          int32_t *d_infer_count, cudaStream_t s)
+{
     if (!q->d_true_action) {
         int rc = dev_alloc(&q->d_true_action, (size_t)q->B);
         if (rc == LZ_OK) rc = dev_alloc(&q->d_reuse_value, (size_t)q->B);

@@ -151,11 +151,13 @@ k_tree_backprop_traverse(TreeParams p, int latent_index, const float *reward, co
 template <bool EZ>
 __global__ void __launch_bounds__(kTreeBlock)
 k_tree_traverse_reuse(TreeParams p, unsigned step, const int32_t *true_action, const float *reuse_value, int32_t *ix, int32_t *ix_net,
-                      int32_t *iy, int32_t *act, int32_t *len, int32_t *vtp)
+                      int32_t *iy, int32_t *act, int32_t *len, int32_t *vtp, int32_t *is_reset)
 {
     const int b = blockIdx.x * (kTreeBlock / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (b >= p.B) return;
     tree_traverse<EZ, true>(p, b, lane, 1, step, ix, iy, act, len, vtp, true_action, reuse_value, ix_net);
+    // EfficientZero, fused search: is_reset of the reached node per TREE (mcts_ctree.py:856-861 / 1040-1046: search_len % lstm_horizon_len)
+    if (EZ && is_reset && lane == 0) is_reset[b] = (p.search_len[b] % p.lstm_horizon == 0) ? 1 : 0;
 }
 
 template <bool EZ>
@@ -312,14 +314,14 @@ int tree_launch_backprop_traverse(lz_tree *t, int latent_index, const float *d_r
 }
 
 int tree_launch_traverse_reuse(lz_tree *t, const int32_t *d_true_action, const float *d_reuse_value, int32_t *d_ix, int32_t *d_ix_net,
-                               int32_t *d_iy, int32_t *d_action, int32_t *d_len, int32_t *d_vtp, cudaStream_t s)
+                               int32_t *d_iy, int32_t *d_action, int32_t *d_len, int32_t *d_vtp, cudaStream_t s, int32_t *d_is_reset)
 {
     if (t->p.ez)
         k_tree_traverse_reuse<true><<<tree_grid(t->p.B), kTreeBlock, 0, s>>>(t->p, t->step_counter++, d_true_action, d_reuse_value, d_ix, d_ix_net,
-                                                                            d_iy, d_action, d_len, d_vtp);
+                                                                            d_iy, d_action, d_len, d_vtp, d_is_reset);
     else
         k_tree_traverse_reuse<false><<<tree_grid(t->p.B), kTreeBlock, 0, s>>>(t->p, t->step_counter++, d_true_action, d_reuse_value, d_ix, d_ix_net,
-                                                                             d_iy, d_action, d_len, d_vtp);
+                                                                             d_iy, d_action, d_len, d_vtp, nullptr);
     LZ_KERNEL_CHECK();
     return LZ_OK;
 }

@@ -455,7 +455,7 @@ int tree_launch_backprop_traverse(lz_tree *t, int latent_index, const float *d_r
                                   cudaStream_t s, int32_t *d_is_reset = nullptr);
 // ReZero reuse variants (MuZero trees): d_ix reports -1 for "no inference", d_ix_net is clamped for the network gather
 int tree_launch_traverse_reuse(lz_tree *t, const int32_t *d_true_action, const float *d_reuse_value, int32_t *d_ix, int32_t *d_ix_net,
-                               int32_t *d_iy, int32_t *d_action, int32_t *d_len, int32_t *d_vtp, cudaStream_t s);
+                               int32_t *d_iy, int32_t *d_action, int32_t *d_len, int32_t *d_vtp, cudaStream_t s, int32_t *d_is_reset = nullptr);
 int tree_launch_backprop_reuse(lz_tree *t, int latent_index, const float *d_reward, const float *d_value, const float *d_logits,
                                const float *d_reuse_value, const int32_t *d_batch_rank, const int32_t *d_to_play, cudaStream_t s,
                                const int32_t *d_is_reset = nullptr);

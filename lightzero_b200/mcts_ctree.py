@@ -228,6 +228,38 @@ class EfficientZeroMCTSCtree(MuZeroMCTSCtree):
             return
         self._search_stepwise_ez(roots, model, lat, h0, h1, S, H)
 
+    def search_with_reuse(self, roots: "ez_tree.Roots", model, latent_state_roots, reward_hidden_state_roots,
+                          to_play_batch: Union[int, List[Any]], true_action_list=None, reuse_value_list=None):
+        """mcts_ctree.py:878-1003 (ReZero on the EfficientZero trees) as one CUDA graph (``lz_search_run_ez_with_reuse``); returns
+        ``(length, average_infer)`` like the reference.  Fused only: other model objects drive
+        ``ez_tree.batch_traverse_with_reuse`` / ``batch_backpropagate_with_reuse`` themselves."""
+        S, H = int(self._cfg.num_simulations), int(self._cfg.lstm_horizon_len)
+        assert H > 0
+        if not isinstance(model, EfficientZeroModel):
+            raise NotImplementedError("EfficientZeroMCTSCtree.search_with_reuse is fused only: pass a lightzero_b200 EfficientZeroModel")
+        roots._ez, roots._lstm_horizon = True, H
+        roots._materialize(S, self._params())
+        t = roots._tree
+        dev = roots.device
+
+        def dev_f32(x):
+            if isinstance(x, torch.Tensor):
+                return x.to(dev, torch.float32, non_blocking=True).contiguous()
+            return torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).to(dev, non_blocking=True)
+        lat = dev_f32(latent_state_roots)
+        B = roots.num
+        h0 = dev_f32(reward_hidden_state_roots[0]).reshape(B, -1)
+        h1 = dev_f32(reward_hidden_state_roots[1]).reshape(B, -1)
+        ta = mz_tree._to_dev(true_action_list, torch.int32, dev, (B,))
+        rv = mz_tree._to_dev(reuse_value_list, torch.float32, dev, (B,))
+        counts = torch.empty(S, dtype=torch.int32, device=dev)
+        q = t.search_for(model, S, (1, H))
+        with torch.cuda.device(dev):
+            cabi.check(t.lib.lz_search_run_ez_with_reuse(q, lat.data_ptr(), h0.data_ptr(), h1.data_ptr(), ta.data_ptr(), rv.data_ptr(),
+                                                         counts.data_ptr(), cabi.stream_ptr()), "lz_search_run_ez_with_reuse")
+        c = counts.cpu().numpy()
+        return int(c[-1]), float(c.sum()) / S
+
     def _search_stepwise_ez(self, roots, model, lat, h0, h1, S, H):
         t = roots._tree
         dev = roots.device
@@ -259,3 +291,67 @@ class EfficientZeroMCTSCtree(MuZeroMCTSCtree):
                 cabi.check(t.lib.lz_tree_backpropagate_ez(t.h, sim + 1, vprefix.data_ptr(), value.data_ptr(), pol.data_ptr(),
                                                           reset.data_ptr(), None, cabi.stream_ptr()),
                            "lz_tree_backpropagate_ez")
+
+
+class UniZeroMCTSCtree(MuZeroMCTSCtree):
+    """Mirror of ``lzero.mcts.tree_search.mcts_ctree.UniZeroMCTSCtree`` (mcts_ctree.py:19-208): the MuZero tree unchanged
+    (``mz_tree.Roots``, :64-75), ``deterministic`` taken from the config (default False, :41-42, passed to ``batch_traverse``
+    at :128-137), and a world model that is called with the whole search history:
+    ``model.recurrent_inference(state_action_history, simulation_index, search_depth[, timestep | task_id=...])`` (:160-176),
+    where ``state_action_history`` is the list of ``(latent_states ndarray, last_actions LongTensor)`` of every simulation so far
+    (:147) -- the UniZero transformer re-derives its KV cache from it.  ``search`` returns ``first_action_latent_map`` (:90, :183-189).
+
+    The DRIVER is what this class provides: the trees stay on the GPU (device ``batch_traverse`` / ``batch_backpropagate``), the
+    history hand-off follows the reference's host-array contract (one D2H of the gathered latents / actions / search depths per
+    simulation, exactly what the reference's own loop does at :144-147).  The transformer world model itself (``WorldModel`` with
+    its KV cache, lzero/model/unizero_world_models/) is NOT part of this library: pass the reference's model object, or any
+    object with that ``recurrent_inference`` signature."""
+
+    config = dict(MuZeroMCTSCtree.config, deterministic=False)     # mcts_ctree.py:28-43
+
+    def search(self, roots: "mz_tree.Roots", model, latent_state_roots, to_play_batch: Union[int, List[Any]],
+               timestep: Union[int, List[Any]] = None, task_id: Optional[int] = None) -> dict:
+        S = int(self._cfg.num_simulations)
+        roots._materialize(S, self._params())
+        t = roots._tree
+        dev = roots.device
+        self._make_inverse_transforms(dev)
+        B = roots.num
+        lat0 = latent_state_roots.detach().cpu().numpy() if isinstance(latent_state_roots, torch.Tensor) else np.asarray(latent_state_roots)
+        latent_pool = [np.ascontiguousarray(lat0, dtype=np.float32)]
+        first_action_latent_map = {env_id: {} for env_id in range(B)}
+        state_action_history = []
+        with torch.no_grad(), torch.cuda.device(dev):
+            if hasattr(model, "eval"):
+                model.eval()
+            for simulation_index in range(S):
+                cabi.check(t.lib.lz_tree_traverse(t.h, int(self.deterministic), t.ix.data_ptr(), t.iy.data_ptr(),
+                                                  t.action.data_ptr(), t.search_len.data_ptr(), t.vtp.data_ptr(),
+                                                  cabi.stream_ptr()), "lz_tree_traverse")
+                ix, iy = t.ix.cpu().numpy(), t.iy.cpu().numpy()
+                last_actions = t.action.cpu().long()
+                search_depth = t.search_len.cpu().numpy().tolist()
+                latent_states = np.stack([latent_pool[x][y] for x, y in zip(ix, iy)])          # :141-144
+                state_action_history.append((latent_states, last_actions.to(self._cfg.device)))  # :147
+                if timestep is None:                                                            # :160-176
+                    if task_id is not None:
+                        out = model.recurrent_inference(state_action_history, simulation_index, search_depth, task_id=task_id)
+                    else:
+                        out = model.recurrent_inference(state_action_history, simulation_index, search_depth)
+                else:
+                    if task_id is not None:
+                        out = model.recurrent_inference(state_action_history, simulation_index, search_depth, task_id=task_id)
+                    else:
+                        out = model.recurrent_inference(state_action_history, simulation_index, search_depth, timestep)
+                latent = out.latent_state.detach().cpu().numpy() if isinstance(out.latent_state, torch.Tensor) else np.asarray(out.latent_state)
+                value = self._inv(out.value.to(dev)).reshape(-1).contiguous()                   # :180
+                reward = self._inv_reward(out.reward.to(dev)).reshape(-1).contiguous()          # :181
+                pol = out.policy_logits.to(dev, torch.float32).contiguous()
+                for env_id in range(B):                                                         # :183-189
+                    a = int(last_actions[env_id].item())
+                    if search_depth[env_id] == 1 and a not in first_action_latent_map[env_id]:
+                        first_action_latent_map[env_id][a] = latent[env_id]
+                latent_pool.append(latent)
+                cabi.check(t.lib.lz_tree_backpropagate(t.h, simulation_index + 1, reward.data_ptr(), value.data_ptr(),
+                                                       pol.data_ptr(), None, cabi.stream_ptr()), "lz_tree_backpropagate")
+        return first_action_latent_map

@@ -106,6 +106,52 @@ class SearchRef:
         return latent_pool
 
 
+def unizero_search_ref(search: SearchRef, roots, model, latent_state_roots, to_play_batch, timestep=None, task_id=None):
+    """``UniZeroMCTSCtree.search`` (mcts_ctree.py:77-208) restated on the same tree module: the MuZero tree unchanged, the
+    world model called as ``model.recurrent_inference(state_action_history, simulation_index, search_depth[, timestep])``
+    (:160-176), returns ``first_action_latent_map`` (:90, 183-189).  TEST INFRASTRUCTURE ONLY."""
+    tree = search.tree
+    with torch.no_grad():
+        if hasattr(model, "eval"):
+            model.eval()
+        batch_size = roots.num
+        first_action_latent_map = {env_id: {} for env_id in range(batch_size)}
+        latent_pool = [latent_state_roots]
+        mm = tree.MinMaxStatsList(batch_size)
+        mm.set_delta(search.value_delta_max)
+        state_action_history = []
+        for simulation_index in range(search.num_simulations):
+            results = tree.ResultsWrapper(batch_size)
+            tp_arg = to_play_batch if search.env_type == "not_board_games" else copy.deepcopy(to_play_batch)
+            ix_l, iy_l, last_actions, virtual_to_play = tree.batch_traverse(
+                roots, search.pb_c_base, search.pb_c_init, search.discount_factor, mm, results, list(tp_arg), search.deterministic)
+            latent_states = torch.from_numpy(np.asarray([latent_pool[ix][iy] for ix, iy in zip(ix_l, iy_l)]))
+            actions = torch.from_numpy(np.asarray(last_actions)).long()
+            state_action_history.append((latent_states.detach().cpu().numpy(), actions))
+            search_depth = results.get_search_len()
+            if timestep is None:
+                if task_id is not None:
+                    out = model.recurrent_inference(state_action_history, simulation_index, search_depth, task_id=task_id)
+                else:
+                    out = model.recurrent_inference(state_action_history, simulation_index, search_depth)
+            else:
+                if task_id is not None:
+                    out = model.recurrent_inference(state_action_history, simulation_index, search_depth, task_id=task_id)
+                else:
+                    out = model.recurrent_inference(state_action_history, simulation_index, search_depth, timestep)
+            latent = out.latent_state.detach().cpu().numpy()
+            value = search.value_inv(out.value).detach().cpu().numpy()
+            reward = search.reward_inv(out.reward).detach().cpu().numpy()
+            for env_id in range(batch_size):
+                if search_depth[env_id] == 1 and int(actions[env_id].item()) not in first_action_latent_map[env_id]:
+                    first_action_latent_map[env_id][int(actions[env_id].item())] = latent[env_id]
+            latent_pool.append(latent)
+            tree.batch_backpropagate(simulation_index + 1, search.discount_factor, reward.reshape(-1).tolist(),
+                                     value.reshape(-1).tolist(), out.policy_logits.detach().cpu().numpy().tolist(), mm, results,
+                                     virtual_to_play)
+    return first_action_latent_map
+
+
 def collect_step_ref(search: SearchRef, model, obs, action_mask, to_play, noise_weight=0.25,
                      noises=None, recorder=None):
     """The search-feeding part of MuZeroPolicy._forward_collect (policy/muzero.py:749-779)."""

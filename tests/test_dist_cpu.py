@@ -40,3 +40,29 @@ def test_gloo_world2_gather(tmp_path):
     port = 29500 + os.getpid() % 2000
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert open(tmp_path / "ok0").read() == "True" and open(tmp_path / "ok1").read() == "True"
+
+
+def _seg_worker(rank, world, port, out_dir):
+    import sys
+    sys.path.insert(0, ROOT)
+    from lightzero_b200.collector import gather_segments
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    B, T, A = 3, 4, 5
+    g = torch.Generator().manual_seed(1)
+    cv = torch.rand(world * B, T, A, generator=g)
+    rv = torch.rand(world * B, T, generator=g)
+    ln = torch.randint(0, T + 1, (world * B,), generator=g, dtype=torch.int32)
+    sl = slice(rank * B, (rank + 1) * B)
+    gcv, grv, gln = gather_segments(cv[sl].clone(), rv[sl].clone(), ln[sl].clone())
+    ok = torch.equal(gcv, cv) and torch.equal(grv, rv) and torch.equal(gln, ln)
+    open(os.path.join(out_dir, f"seg{rank}"), "w").write(str(ok))
+    dist.destroy_process_group()
+
+
+def test_gloo_world2_segment_all_gather(tmp_path):
+    """The finished-segment all-gather of the collector: one collective on one packed buffer."""
+    port = 31500 + os.getpid() % 2000
+    mp.spawn(_seg_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert open(tmp_path / "seg0").read() == "True" and open(tmp_path / "seg1").read() == "True"

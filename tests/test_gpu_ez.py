@@ -190,3 +190,56 @@ def test_ez_search_rejects_mismatched_model_and_tree():
     roots.prepare(0.25, noises, [0.] * 8, out.policy_logits, [-1] * 8)
     with pytest.raises(TypeError):
         mz.search(roots, cu, out.latent_state, [-1] * 8)
+
+
+def test_fused_ez_search_with_reuse_equals_piecewise_drive():
+    """EfficientZeroMCTSCtree.search_with_reuse (mcts_ctree.py:878-1003) as one CUDA graph vs the same steps driven one at a time
+    through the public pieces (lz_tree_traverse_with_reuse, EfficientZeroModel.recurrent_inference on every row,
+    lz_tree_backpropagate_with_reuse with the per-tree is_reset): identical visit counts, value bits and inference counts.
+    (The tree entry points themselves are pinned to the shimmed reference ez_tree in test_gpu_tree.py.)"""
+    from lightzero_b200 import cabi
+    B, A, S, H = 64, 6, 25, 3
+    ref, cu, obs, mask, legal, noises, mcts = _setup(B, A, S, masks=True, horizon=H)
+    out = cu.initial_inference(obs.cuda())
+    rng = np.random.default_rng(4)
+    true_action = [int(l[rng.integers(len(l))]) for l in legal]
+    reuse_value = (rng.standard_normal(B) * 0.5).astype(np.float32)
+    roots = mcts.roots(B, legal)
+    roots.prepare(0.25, noises, [0.] * B, out.policy_logits, [-1] * B)
+    length, avg = mcts.search_with_reuse(roots, cu, out.latent_state, out.reward_hidden_state, [-1] * B, true_action, reuse_value.tolist())
+    fused = (roots.get_distributions(), np.asarray(roots.get_values(), np.float32).view(np.uint32).tolist())
+    roots.clear()
+
+    roots = mcts.roots(B, legal)
+    roots.prepare(0.25, noises, [0.] * B, out.policy_logits, [-1] * B)
+    roots._ez, roots._lstm_horizon = True, H
+    roots._materialize(S, mcts._params())
+    t = roots._tree
+    dev = roots.device
+    ta = torch.tensor(true_action, dtype=torch.int32, device=dev)
+    rv = torch.from_numpy(reuse_value).to(dev)
+    lat = out.latent_state
+    pool = torch.empty((S + 1,) + tuple(lat.shape), device=dev)
+    hp0, hp1 = torch.zeros(S + 1, B, 512, device=dev), torch.zeros(S + 1, B, 512, device=dev)
+    pool[0], hp0[0], hp1[0] = lat, out.reward_hidden_state[0].reshape(B, -1), out.reward_hidden_state[1].reshape(B, -1)
+    rows = torch.arange(B, device=dev)
+    counts = []
+    for sim in range(S):
+        cabi.check(t.lib.lz_tree_traverse_with_reuse(t.h, ta.data_ptr(), rv.data_ptr(), t.ix.data_ptr(), t.iy.data_ptr(), t.action.data_ptr(),
+                                                     t.search_len.data_ptr(), t.vtp.data_ptr(), cabi.stream_ptr()), "traverse")
+        counts.append(int((t.ix >= 0).sum().item()))
+        ix = t.ix.clamp(min=0).long()
+        reset = (t.search_len % H == 0).to(torch.int32)
+        o = cu.recurrent_inference(pool[ix, rows], (hp0[ix, rows].unsqueeze(0), hp1[ix, rows].unsqueeze(0)), t.action.clamp(min=0).long(),
+                                   return_scalars=True)
+        pool[sim + 1] = o.latent_state
+        keep = (reset == 0).float().unsqueeze(1)
+        hp0[sim + 1] = o.reward_hidden_state[0].reshape(B, -1) * keep
+        hp1[sim + 1] = o.reward_hidden_state[1].reshape(B, -1) * keep
+        cabi.check(t.lib.lz_tree_backpropagate_with_reuse(t.h, sim + 1, o.value_prefix_scalar.data_ptr(), o.value_scalar.data_ptr(),
+                                                          o.policy_logits.data_ptr(), rv.data_ptr(), None, reset.data_ptr(), None,
+                                                          cabi.stream_ptr()), "backprop")
+    step = (roots.get_distributions(), np.asarray(roots.get_values(), np.float32).view(np.uint32).tolist())
+    assert fused == step
+    assert length == counts[-1] and abs(avg - sum(counts) / S) < 1e-9
+    assert min(counts) < B

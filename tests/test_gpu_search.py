@@ -344,3 +344,67 @@ def test_weight_reload_and_parameter_change_recapture_the_search_graph():
     step = (roots.get_distributions(), np.asarray(roots.get_values(), np.float32).view(np.uint32).tolist())
     roots.clear()
     assert fused == step and fused != reloaded
+
+
+class _ToyWorldModel:
+    """A deterministic stand-in with the UniZero world model's search-time signature (mcts_ctree.py:160-176): CPU fp32 torch, so
+    the reference-side loop and the CUDA-tree driver see identical numbers as long as the trees agree."""
+
+    def __init__(self, A, D=24, K=601, seed=0):
+        g = torch.Generator().manual_seed(seed)
+        self.A, self.D, self.K = A, D, K
+        self.W1 = torch.randn(D, D, generator=g) * 0.4
+        self.W2 = torch.randn(A, D, generator=g)
+        self.Wv = torch.randn(D, K, generator=g) * 0.5
+        self.Wr = torch.randn(D, K, generator=g) * 0.5
+        self.Wp = torch.randn(D, A, generator=g)
+        self.calls = []
+
+    def recurrent_inference(self, state_action_history, simulation_index, search_depth, timestep=None, task_id=None):
+        from lightzero_b200.muzero_model import MZNetworkOutput
+        assert len(state_action_history) == simulation_index + 1 and len(search_depth) == state_action_history[-1][0].shape[0]
+        lat, act = state_action_history[-1]
+        self.calls.append((simulation_index, list(search_depth), timestep))
+        x = torch.from_numpy(np.asarray(lat, np.float32))
+        a = torch.nn.functional.one_hot(act.cpu().long(), self.A).float()
+        nl = torch.tanh(x @ self.W1 + a @ self.W2)
+        # fully peaked categorical outputs: softmax . support is then EXACTLY one support value in any correct fp32 softmax, so the
+        # 1e-7-level differences between softmax implementations cannot flip a PUCT arg-max and the comparison can be bit for bit
+        peak = lambda z: 200.0 * torch.nn.functional.one_hot(z.argmax(1) % 41 + 280, self.K).float()
+        return MZNetworkOutput(peak(nl @ self.Wv), peak(nl @ self.Wr), nl @ self.Wp, nl)
+
+
+@pytest.mark.parametrize("timestep", [None, 7])
+def test_unizero_driver_matches_reference_loop(timestep):
+    """UniZeroMCTSCtree (mcts_ctree.py:19-208) on the CUDA trees vs the restated reference loop on the compiled reference
+    mz_tree, same toy world model: first_action_latent_map, visit counts and root-value bits."""
+    import lightzero_b200 as lzb
+    from oracle.search_ref import SearchRef, load_tree_module, unizero_search_ref
+    B, A, S, D = 40, 9, 30, 24
+    rng = np.random.default_rng(3)
+    mask = (rng.random((B, A)) < 0.7).astype(np.uint8)
+    mask[np.arange(B), rng.integers(0, A, B)] = 1
+    legal = [np.nonzero(mask[b])[0].tolist() for b in range(B)]
+    noises = [rng.dirichlet([0.3] * len(l)).astype(np.float32).tolist() for l in legal]
+    lat0 = rng.standard_normal((B, D)).astype(np.float32)
+    logits0 = rng.standard_normal((B, A)).astype(np.float32)
+    tree, kind = load_tree_module()
+    sref = SearchRef(tree, num_simulations=S, deterministic=True)
+    r_ref = sref.roots(B, legal, action_space_size=A)
+    r_ref.prepare(0.25, noises, [0.] * B, logits0.tolist(), [-1] * B)
+    m_ref = _ToyWorldModel(A, D)
+    map_ref = unizero_search_ref(sref, r_ref, m_ref, lat0, [-1] * B, timestep=timestep)
+
+    mcts = lzb.UniZeroMCTSCtree(dict(num_simulations=S, deterministic=True, discount_factor=0.997, device="cpu"))
+    roots = mcts.roots(B, legal)
+    roots.prepare(0.25, noises, [0.] * B, logits0.tolist(), [-1] * B)
+    m_cu = _ToyWorldModel(A, D)
+    map_cu = mcts.search(roots, m_cu, lat0, [-1] * B, timestep=timestep)
+    assert m_cu.calls == m_ref.calls
+    assert roots.get_distributions() == r_ref.get_distributions()
+    assert np.array_equal(np.asarray(roots.get_values(), np.float32).view(np.uint32),
+                          np.asarray(r_ref.get_values(), np.float32).view(np.uint32))
+    assert [sorted(m.keys()) for m in map_cu.values()] == [sorted(m.keys()) for m in map_ref.values()]
+    for e in range(B):
+        for a, v in map_ref[e].items():
+            assert np.array_equal(np.asarray(map_cu[e][a]), np.asarray(v))
