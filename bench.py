@@ -306,7 +306,15 @@ def ours(args, rank, local_rank, world):
         d_f32 = [(h.to(dev).to(torch.float32) / 255.0) for h in h_u8]
         h_mask = torch.ones(B, A, dtype=torch.uint8).pin_memory()
         h_noise = torch.from_numpy(np.random.default_rng(rank).dirichlet([0.3] * A, size=B).astype(np.float32)).pin_memory()
-        return dict(model=model, policy=policy, h_u8=h_u8, d_f32=d_f32, h_mask=h_mask, h_noise=h_noise,
+        # end-to-end arm with the collector state on the device: the step's host input is ONE new uint8 frame per
+        # environment (what the emulator delivers per step, muzero_collector.py:520-545) + the action mask + the root noise
+        fs = None
+        if not ez and obs_shape[0] == 4:
+            from lightzero_b200.collector import FrameStack
+            fs = FrameStack(B, obs_shape[0], obs_shape[1], obs_shape[2], device=dev)
+            fs.push(h_u8[0][:, 0].contiguous().pin_memory(), reset=torch.ones(B, dtype=torch.uint8).pin_memory())
+        h_new = [h[:, -1].contiguous().pin_memory() for h in h_u8]
+        return dict(model=model, policy=policy, h_u8=h_u8, d_f32=d_f32, h_mask=h_mask, h_noise=h_noise, fs=fs, h_new=h_new,
                     d_mask=h_mask.to(dev), d_noise=h_noise.to(dev), B=B, S=S, A=A, NBUF=NBUF, wl=wl)
 
     def device_step(w, gather=True):
@@ -317,8 +325,16 @@ def ours(args, rank, local_rank, world):
             return r
         return fn
 
-    def e2e_step(w):
-        return lambda i: w["policy"].search_batch(w["h_u8"][i % w["NBUF"]], w["h_mask"], w["h_noise"], None, deterministic=True, read_back=True)
+    def e2e_step(w, full_stack=False):
+        if full_stack or w["fs"] is None:      # the whole uint8 observation stack uploaded every step
+            return lambda i: w["policy"].search_batch(w["h_u8"][i % w["NBUF"]], w["h_mask"], w["h_noise"], None, deterministic=True, read_back=True)
+
+        def fn(i):                             # frame stacks resident on the device: one new frame per environment per step
+            w["fs"].push(w["h_new"][i % w["NBUF"]])
+            d_mask = w["h_mask"].to(dev, non_blocking=True)
+            d_noise = w["h_noise"].to(dev, non_blocking=True)
+            return w["policy"].search_batch(w["fs"].view(), d_mask, d_noise, None, deterministic=True, read_back=True)
+        return fn
 
     def search_only(w):
         """the search() window alone: roots already prepared, latents resident; CUDA events around the graph launch"""
@@ -361,8 +377,11 @@ def ours(args, rank, local_rank, world):
     dev_ms, wall_ms, launches = timed(device_step(W), args.steps, warm)
     clocks = sampler.stop() if rank == 0 else None
     e2e_dev_ms, e2e_wall_ms, _ = timed(e2e_step(W), args.steps, warm)
+    e2e_full_wall_ms = e2e_wall_ms
+    if W["fs"] is not None:
+        _, e2e_full_wall_ms, _ = timed(e2e_step(W, full_stack=True), args.steps, warm)
     graph_avg_ms, graph_min_ms, num_kernels_search = search_only(W)
-    dev_ms, wall_ms, e2e_dev_ms, e2e_wall_ms, graph_avg_ms = maxr(dev_ms, wall_ms, e2e_dev_ms, e2e_wall_ms, graph_avg_ms)
+    dev_ms, wall_ms, e2e_dev_ms, e2e_wall_ms, graph_avg_ms, e2e_full_wall_ms = maxr(dev_ms, wall_ms, e2e_dev_ms, e2e_wall_ms, graph_avg_ms, e2e_full_wall_ms)
 
     # ------------------------------------------------------------------ strong scaling: the north-star split of ONE 1024-root batch
     strong = None
@@ -410,7 +429,8 @@ def ours(args, rank, local_rank, world):
         value = total_roots * S / (ms_per_step * 1e-3)
         e2e_ms = e2e_wall_ms / args.steps          # host-visible time: includes H2D, launch, D2H, final sync
         e2e_value = total_roots * S / (e2e_ms * 1e-3)
-        h2d = W["h_u8"][0].numel() + W["h_mask"].numel() + W["h_noise"].numel() * 4
+        h2d_full = W["h_u8"][0].numel() + W["h_mask"].numel() + W["h_noise"].numel() * 4
+        h2d = (W["h_new"][0].numel() + W["h_mask"].numel() + W["h_noise"].numel() * 4) if W["fs"] is not None else h2d_full
         d2h = B * A * 4 + B * 4 * 3 + B * A * 4
         traffic, traffic_src = _traffic(args.workload if (B, S, A) == (WL["roots"], WL["sims"], WL["actions"]) else "none")
         achieved = B * S * FLOP_RECURRENT / (graph_avg_ms * 1e-3) / 1e12
@@ -433,9 +453,17 @@ def ours(args, rank, local_rank, world):
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms, "device_ms_per_step": e2e_dev_ms / args.steps,
-                    "api": f"lightzero_b200.collect.{type(W['policy']).__name__}.search_batch (pinned host uint8 frames / mask / noise in, pinned host "
-                           f"visits / values out; lz_search_collect_host_u8, {args.h2d_chunks} overlapped H2D chunks; the frames are scaled to [0, 1] "
-                           "inside the first conv kernel exactly like the reference's ScaledFloatFrameWrapper does on the host)"},
+                    "api": (f"lightzero_b200.collector.FrameStack.push (ONE new pinned host uint8 frame per environment per step, the emulator's "
+                            f"per-step output; the {OBS[0]}-frame stacks of GameSegment.get_obs stay on the device) + mask / noise uploads + "
+                            f"lightzero_b200.collect.{type(W['policy']).__name__}.search_batch (lz_search_collect_u8; pinned host visits / values out); "
+                            "the frames are scaled to [0, 1] inside the first conv kernel exactly like the reference's ScaledFloatFrameWrapper")
+                           if W["fs"] is not None else
+                           (f"lightzero_b200.collect.{type(W['policy']).__name__}.search_batch (pinned host uint8 frames / mask / noise in, pinned host "
+                            f"visits / values out; lz_search_collect_host_u8, {args.h2d_chunks} overlapped H2D chunks)"),
+                    "full_stack_upload": {"value": total_roots * S / (e2e_full_wall_ms / args.steps * 1e-3), "ms_per_step": e2e_full_wall_ms / args.steps,
+                                          "h2d_bytes_per_step": h2d_full,
+                                          "note": f"the same step with the whole {OBS[0]}-frame uint8 stack uploaded every step (lz_search_collect_host_u8, "
+                                                  f"{args.h2d_chunks} overlapped H2D chunks): what a collector without device-resident frame stacks pays"}},
             "gpu_launches": int(launches),
             "gpu_launches_note": "counted by the library (lz_debug_launch_count: every kernel it enqueues, graph kernel nodes included) over the timed region",
             "search_graph_kernels": num_kernels_search,

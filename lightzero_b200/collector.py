@@ -50,8 +50,12 @@ class FrameStack:
                 rs = None if reset is None else torch.as_tensor(reset).to(self.device, torch.uint8).contiguous()
                 cabi.check(self._lib.lz_frames_push(self._h, nf.data_ptr(), cabi.ptr(rs), cabi.stream_ptr()), "lz_frames_push")
             else:
-                nf = torch.as_tensor(np.ascontiguousarray(new_frames, dtype=np.uint8)).pin_memory()
-                rs = None if reset is None else torch.as_tensor(np.ascontiguousarray(np.asarray(reset), dtype=np.uint8)).pin_memory()
+                def pinned(x):        # pinned host tensors are used in place; anything else is staged through pinned memory
+                    if isinstance(x, torch.Tensor) and x.dtype == torch.uint8 and x.is_contiguous() and x.is_pinned():
+                        return x
+                    return torch.as_tensor(np.ascontiguousarray(np.asarray(x), dtype=np.uint8)).pin_memory()
+                nf = pinned(new_frames)
+                rs = None if reset is None else pinned(reset)
                 cabi.check(self._lib.lz_frames_push_host(self._h, nf.data_ptr(), cabi.ptr(rs), cabi.stream_ptr()), "lz_frames_push_host")
             assert tuple(nf.shape) == (self.B, self.H, self.W), nf.shape
             self._keep = (nf, rs)
@@ -59,6 +63,11 @@ class FrameStack:
     def stacked_ptr(self) -> int:
         """Device pointer of the [B, stack, H, W] uint8 batch for ``lz_search_collect_u8``; valid until the next push."""
         return int(self._lib.lz_frames_stacked(self._h))
+
+    def view(self) -> torch.Tensor:
+        """Zero-copy uint8 [B, stack, H, W] tensor over the current stacks (valid until the next push): the observation batch for
+        ``MuZeroCollectPolicy.search_batch`` / ``lz_search_collect_u8``."""
+        return _view(self.stacked_ptr(), (self.B, self.stack, self.H, self.W), "|u1", self.device)
 
     def get_obs(self) -> torch.Tensor:
         """A copy of the stacked observations (uint8 [B, stack, H, W], oldest first) -- for tests and for callers that want a tensor."""
