@@ -234,9 +234,42 @@ __device__ __forceinline__ void heads_outputs(const TcNet &net, const TcIO &io, 
 #pragma unroll
         for (int q = 0; q < 4; ++q) { m[h][q] = -INFINITY; sm[h][q] = 0.0f; ws[h][q] = 0.0f; }
     int tile = 0, boff = 0;
+    int hdone = 0;
+#ifndef LZ_NO_JOINT_HEADS
+    if ((hmask & 3) == 3 && net.reward.K == net.value.K && !io.reward_logits && !io.value_logits) {
+        // the two categorical heads of the search (same support size, no raw logits wanted) in ONE loop: 8 independent softmax
+        // recurrences per thread instead of 4 -- the read-out is a chain of dependent latencies, so this nearly halves it
+        const int K = net.reward.K, nblk = (K + 127) >> 7;
+        const float inv0 = net.fc[0].fc2_inv, inv1 = net.fc[1].fc2_inv;
+        const float *b20 = b2_s ? b2_s : net.reward.b2, *b21 = b2_s ? b2_s + K : net.value.b2;
+#pragma unroll 1
+        for (int blk = 0; blk < nblk; ++blk) {
+            const int k = blk * 128 + wg * 32 + lane;
+            const float bias0 = (k < K) ? b20[k] : 0.0f, bias1 = (k < K) ? b21[k] : 0.0f;
+            uint32_t a0[4], c0[4], a1[4], c1[4];
+            const uint32_t col0 = lane_base + kColFc2 + blk * 16 + g * 4, col1 = col0 + nblk * 16;
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];\n" : "=r"(a0[0]), "=r"(a0[1]), "=r"(a0[2]), "=r"(a0[3]) : "r"(col0));
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];\n" : "=r"(c0[0]), "=r"(c0[1]), "=r"(c0[2]), "=r"(c0[3]) : "r"(col0 + 8));
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];\n" : "=r"(a1[0]), "=r"(a1[1]), "=r"(a1[2]), "=r"(a1[3]) : "r"(col1));
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];\n" : "=r"(c1[0]), "=r"(c1[1]), "=r"(c1[2]), "=r"(c1[3]) : "r"(col1 + 8));
+            tmem_ld_wait();
+            tmem_pin(a0); tmem_pin(c0); tmem_pin(a1); tmem_pin(c1);
+            if (k < K) {
+                const float sup = support_at(net.support_min, net.support_step, k);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if (g * 4 + q >= nvalid) continue;
+                    softmax_push(m[0][q], sm[0][q], ws[0][q], fmaf(__uint_as_float(a0[q]) + __uint_as_float(c0[q]), inv0, bias0), sup);
+                    softmax_push(m[1][q], sm[1][q], ws[1][q], fmaf(__uint_as_float(a1[q]) + __uint_as_float(c1[q]), inv1, bias1), sup);
+                }
+            }
+        }
+        tile = 2 * nblk; boff = 2 * K; hdone = 3;
+    }
+#endif
 #pragma unroll
     for (int h = 0; h < 3; ++h) {
-        if (!((hmask >> h) & 1)) continue;
+        if (!((hmask >> h) & 1) || ((hdone >> h) & 1)) continue;
         const Head &H = h == 0 ? net.reward : (h == 1 ? net.value : net.policy);
         const int K = H.K, nblk = (K + 127) >> 7;
         const float inv = net.fc[h].fc2_inv;
@@ -341,7 +374,9 @@ __device__ __forceinline__ void load_row32(const float *root, bool cl, int p, in
         const float4 *src = reinterpret_cast<const float4 *>(root) + (half * 8) * kP + p;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const float4 q = src[j * kP];      // plain loads: the pool / scratch are written by this launch
+            // L2-only (the pool / scratch are written by this launch, and allocating these once-read rows in L1 would compete with the
+            // tensor core's operand fetch for the shared-memory / L1 data array: measured -1.4 % on the search)
+            const float4 q = __ldcg(src + j * kP);
             v[4 * j] = q.x; v[4 * j + 1] = q.y; v[4 * j + 2] = q.z; v[4 * j + 3] = q.w;
         }
     } else {
@@ -357,7 +392,7 @@ __device__ __forceinline__ void store_row16(float *root, bool cl, int p, int c0,
     if (cl) {
         float4 *dst = reinterpret_cast<float4 *>(root) + (c0 >> 2) * kP + p;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) dst[j * kP] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        for (int j = 0; j < 4; ++j) __stcg(dst + j * kP, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
     } else {
         float *dst = root + (size_t)c0 * kP + p;
 #pragma unroll
@@ -755,7 +790,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_net_tc(TcNet net, TcIO io, Tr
                     const float4 *ab = reinterpret_cast<const float4 *>(net.abias) + ((size_t)action * 16 + half * 8) * kP + (rowc[t] & 255);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        const float4 q = __ldg(ab + j * kP);
+                        const float4 q = __ldcg(ab + j * kP);      // 83 KB table, one row per (root, action): L2-only like the skip rows
                         if (add) { dst[4 * j] += q.x; dst[4 * j + 1] += q.y; dst[4 * j + 2] += q.z; dst[4 * j + 3] += q.w; }
                         else { dst[4 * j] = q.x; dst[4 * j + 1] = q.y; dst[4 * j + 2] = q.z; dst[4 * j + 3] = q.w; }
                     }

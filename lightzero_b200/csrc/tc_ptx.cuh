@@ -50,7 +50,10 @@ __device__ __forceinline__ void mbar_wait_warp(uint64_t *bar, uint32_t parity)
         for (uint32_t it = 0; it < (1u << 26) && !ok; ++it) {
             asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
                          : "=r"(ok) : "r"(a), "r"(parity) : "memory");
-            if (!ok) __nanosleep(64);
+#ifndef LZ_POLL_NS
+#define LZ_POLL_NS 64
+#endif
+            if (!ok) __nanosleep(LZ_POLL_NS);
         }
         if (!ok) {
             printf("lz net_tc: mbarrier timeout (block %d warp %d)\n", blockIdx.x, threadIdx.x >> 5);
