@@ -872,7 +872,7 @@ static int pack_tc(lz_model *m, const NetDev &net)
     size_t fc_off2[3];
     size_t off_fc = (off_abias + (size_t)A * kC * kP * 4 + 127) & ~(size_t)127;
     const size_t off_fc0 = off_fc;
-    off_fc += (size_t)18 * 16384;
+    off_fc += (size_t)18 * 12288;
     for (int h = 0; h < 3; ++h) {
         fc_off2[h] = off_fc - off_fc0;
         if (fc_heads[h]->hid > 0) off_fc += (size_t)((fc_heads[h]->K + 127) / 128) * 16384;      // EfficientZero: the reward head's FC part lives in ez.cu
@@ -954,13 +954,14 @@ static int pack_tc(lz_model *m, const NetDev &net)
             *reinterpret_cast<__half *>(hi + off) = a;
             *reinterpret_cast<__half *>(lo + off) = b;
         };
-        // FC1: stage i = inputs [32 i, 32 i + 32): [k-step 2][hi 4 KB | lo 4 KB], each [kg 2][128 rows][8]; row = 32 h + unit
+        // FC1: stage i = inputs [32 i, 32 i + 32): [k-step 2][hi 3 KB | lo 3 KB], each [kg 2][96 rows][8]; row = 32 h + unit.  Only the 96 real
+        // rows are stored and streamed (the M = 128 MMA reads 32 rows of whatever follows into accumulator lanes 96-127, which nobody reads)
         unsigned char *f1 = host.data() + off_fc0;
         for (int i = 0; i < nin; ++i)
             for (int j = 0; j < H.hid; ++j) {
                 const int kstep = i >> 4, kg = (i >> 3) & 1, e = i & 7;
-                unsigned char *base = f1 + (size_t)(kstep >> 1) * 16384 + (size_t)(kstep & 1) * 8192;
-                put(base, base + 4096, ((size_t)kg * 128 + h * 32 + j) * 16 + e * 2, (*W0)[(size_t)j * nin + i] * s1);
+                unsigned char *base = f1 + (size_t)(kstep >> 1) * 12288 + (size_t)(kstep & 1) * 6144;
+                put(base, base + 3072, ((size_t)kg * 96 + h * 32 + j) * 16 + e * 2, (*W0)[(size_t)j * nin + i] * s1);
             }
         // FC2: tile mt = outputs [128 mt, 128 mt + 128): [hi 8 KB | lo 8 KB], each [kg 4][128 rows][8]
         unsigned char *f2 = host.data() + off_fc0 + fc_off2[h];

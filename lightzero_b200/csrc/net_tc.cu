@@ -100,7 +100,8 @@ constexpr int kFbKgBytes = 64 * 16 + 16;                  // FC1 B operand: per 
 constexpr int kFbBytes = 72 * kFbKgBytes;                 // 576 inputs = 72 k-groups: 74,880 B (overlays the activation buffer)
 constexpr int kFrBytes = 72 * 8 * 16 * 2;                 // reward features parked from their hook: [hi | lo][72 k-groups][8 roots][16 B] = 18,432 B
 constexpr int kHbHeadBytes = 4 * 16 * 16;                 // FC2 B operand of one head: [4 k-groups][8 roots hi | 8 roots lo][16 B] = 1 KB
-constexpr int kFc1Stages = 18;                            // 576 inputs / 32 per 16 KB stage (2 k-steps x (A_hi 4 KB + A_lo 4 KB))
+constexpr int kFc1Stages = 18;                            // 576 inputs / 32 per stage (2 k-steps x (A_hi + A_lo))
+constexpr int kFc1StageBytes = 2 * 2 * 2 * 96 * 16;       // 12,288 B: only the 96 real rows (3 heads x 32 units) of the M = 128 operand are streamed
 // TMEM columns of the FC phase (the conv accumulators are drained by then; the value/policy 1x1 results in columns 0-95 are
 // consumed by head_scatter before FC1 starts)
 constexpr int kColFc1 = 0;        // 64: [0,32) hi x hi + lo x hi, [32,64) hi x lo (+ lo x lo)
@@ -514,11 +515,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_net_tc(TcNet net, TcIO io, Tr
         // ================= weight producer =================
         if (lane == 0) {
             uint32_t n = 0;
-            auto stage_in = [&](const unsigned char *src) {      // every stage is released by a tcgen05.commit of its consumer MMAs
+            auto stage_in = [&](const unsigned char *src, uint32_t bytes = kTapBytes) {      // every stage is released by a tcgen05.commit of its consumer MMAs
                 const int st = n % kStages;
                 if (n >= (uint32_t)kStages) mbar_wait(&bars->empty[st], ((n / kStages) - 1) & 1);
-                mbar_expect_tx(&bars->full[st], kTapBytes);
-                bulk_g2s(ring + st * kTapBytes, src, kTapBytes, &bars->full[st]);
+                mbar_expect_tx(&bars->full[st], bytes);
+                bulk_g2s(ring + st * kTapBytes, src, bytes, &bars->full[st]);
                 ++n;
             };
             for (int sim = 0; sim < nsims; ++sim) {     // runs ahead of the consumers: the next simulation's first taps are
@@ -528,7 +529,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_net_tc(TcNet net, TcIO io, Tr
                         for (int tap = 0; tap < 9; ++tap) stage_in(src + (size_t)tap * kTapBytes);
                 }
                 // the heads: FC1 weights of all heads (18 stages), then the FC2 tiles of every head this kernel evaluates
-                for (int i = 0; i < kFc1Stages; ++i) stage_in(net.fcw + (size_t)i * kTapBytes);
+                for (int i = 0; i < kFc1Stages; ++i) stage_in(net.fcw + (size_t)i * kFc1StageBytes, kFc1StageBytes);
                 for (int h = 0; h < 3; ++h) {
                     if (!((hmask_fc >> h) & 1)) continue;
                     const int nblk = (net.fc[h].K + 127) >> 7;
@@ -635,7 +636,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_net_tc(TcNet net, TcIO io, Tr
 #pragma unroll
                 for (int ksi = 0; ksi < 2; ++ksi) {
                     const int kstep = 2 * i + ksi;
-                    const uint64_t a_hi = make_desc(ring_s + st * kTapBytes + ksi * 8192, 2048 >> 4, 8), a_lo = a_hi + (4096 >> 4);
+                    // [k-step][hi 3 KB | lo 3 KB], [kg 2][96 rows][8]: rows 96-127 of the M = 128 operand are whatever follows (unused lanes)
+                    const uint64_t a_hi = make_desc(ring_s + st * kTapBytes + ksi * (kFc1StageBytes / 2), 1536 >> 4, 8), a_lo = a_hi + (3072 >> 4);
                     const uint64_t b = make_desc(fb_s + kstep * 2 * kFbKgBytes, kFbKgBytes >> 4, 8);
                     umma_f16_elect(tmem + kColFc1, a_hi, b, idesc_fc1, kstep != 0);
                     umma_f16_elect(tmem + kColFc1, a_lo, b, idesc_fc1, 1);
@@ -768,6 +770,33 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_net_tc(TcNet net, TcIO io, Tr
             if (dbg) dbg[1] = clock64();
 
             bool skip_in_scratch = false;      // the residual operand: the input latent until a layer has parked its output
+            bool pending_rew = false;
+            auto reward_features = [&]() {
+                    // reward 1x1 accumulators -> BN/ReLU features, parked (fp16 hi / lo) until the heads' FC pass at the end of the
+                    // simulation -- or, EfficientZero (efficientzero_model.py:556-562), written out as the input of the LSTM that the
+                    // next kernel evaluates as one batched GEMM over all roots (ez.cu).  Runs underneath the NEXT layer's MMAs.
+                    mbar_wait_warp(&bars->rew_ready, sim & 1);
+                    tc_fence_after();
+                    if (io.ez_feat) {
+                        if (half == 0) {
+                            const int nin = net.hc[0] * kP;
+#pragma unroll
+                            for (int t = 0; t < kMaxTiles; ++t) {
+                                if (t >= NT) continue;
+                                float v[16];
+                                tmem_ld16(lane_base + kColRew + t * 16, v);
+                                if (rowc[t] >= 0)
+                                    for (int c = 0; c < net.hc[0]; ++c)
+                                        io.ez_feat[(size_t)(root0 + (rowc[t] >> 8)) * nin + c * kP + (rowc[t] & 255)] =
+                                            fmaxf(fmaf(v[c], __ldg(net.head_bn + c), __ldg(net.head_bn + 16 + c)), 0.0f);
+                            }
+                        }
+                        tc_fence_before();
+                    } else {
+                        head_scatter(net, 1, fr, nullptr, tmem, NT, rm);
+                    }
+                    if (dbg) dbg[28] = clock64();
+            };
             for (int L = 0; L < nlayers; ++L) {
                 const int flags = net.layer_flags[L];
                 const float4 *bn4 = reinterpret_cast<const float4 *>(bn_s + L * 128 + half * 32);   // scale; shift 16 float4 further
@@ -885,33 +914,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_net_tc(TcNet net, TcIO io, Tr
                 tc_fence_before();
                 mbar_arrive(&bars->act_ready[ngroups - 1]);         // phase L+1: next layer / this layer's hook may start
                 if (dbg) dbg[3 + 2 * L] = clock64();
-                if ((flags & LF_HOOK_REWARD) && net.has_reward) {
-                    // reward 1x1 accumulators -> BN/ReLU features, parked (fp16 hi / lo) until the heads' FC pass at the end of the
-                    // simulation -- or, EfficientZero (efficientzero_model.py:556-562), written out as the input of the LSTM that the
-                    // next kernel evaluates as one batched GEMM over all roots (ez.cu).  Runs underneath the NEXT layer's MMAs.
-                    mbar_wait_warp(&bars->rew_ready, sim & 1);
-                    tc_fence_after();
-                    if (io.ez_feat) {
-                        if (half == 0) {
-                            const int nin = net.hc[0] * kP;
-#pragma unroll
-                            for (int t = 0; t < kMaxTiles; ++t) {
-                                if (t >= NT) continue;
-                                float v[16];
-                                tmem_ld16(lane_base + kColRew + t * 16, v);
-                                if (rowc[t] >= 0)
-                                    for (int c = 0; c < net.hc[0]; ++c)
-                                        io.ez_feat[(size_t)(root0 + (rowc[t] >> 8)) * nin + c * kP + (rowc[t] & 255)] =
-                                            fmaxf(fmaf(v[c], __ldg(net.head_bn + c), __ldg(net.head_bn + 16 + c)), 0.0f);
-                            }
-                        }
-                        tc_fence_before();
-                    } else {
-                        head_scatter(net, 1, fr, nullptr, tmem, NT, rm);
-                    }
-                    if (dbg) dbg[28] = clock64();
-                }
+                // The reward hook's 1x1 accumulators are consumed one layer LATER: group Y's hook MMAs are only issued at the start of its
+                // next job (after group X's next-layer MMAs), and waiting for them here would hold group X's epilogue back by a whole job
+                if (pending_rew) { reward_features(); pending_rew = false; }
+                if ((flags & LF_HOOK_REWARD) && net.has_reward) pending_rew = true;
             }
+            if (pending_rew) { reward_features(); pending_rew = false; }
 
             // the value / policy 1x1 accumulators must be complete before the head stage reads them / reuses the buffer
             mbar_wait_warp(&bars->vp_ready, sim & 1);

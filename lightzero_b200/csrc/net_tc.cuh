@@ -21,7 +21,7 @@ struct TcNet {
     const unsigned char *headw;    // [reward hi 2K | lo 2K][value+policy hi 4K | lo 4K]
     const float *head_bn;          // [reward s16 t16 | value s16 t16 | policy s16 t16]
     const float *abias;            // [A][16][36][4] ([c / 4][pixel][c % 4]) action-plane contribution of the dynamics conv, x BN scale
-    const unsigned char *fcw;      // FC weight stream: 18 FC1 stages ([2 k-steps][hi 4 KB | lo 4 KB], [kg 2][128 rows = 32 head + unit][8]) then the FC2 tiles
+    const unsigned char *fcw;      // FC weight stream: 18 FC1 stages of 12 KB ([2 k-steps][hi 3 KB | lo 3 KB], [kg 2][96 rows = 32 head + unit][8]) then the FC2 tiles
     TcFc fc[3];                    // reward, value, policy
     Head reward, value, policy;    // folded BN / bias tables of the FC parts (fp32, same tables as the SIMT path)
     int hc[3];

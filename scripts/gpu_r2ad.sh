@@ -1,0 +1,5 @@
+# round 2, call AD: FC1 stream of 96 rows; timing + parity suite
+cd $GRAFT_REPO_ROOT
+mkdir -p gpurun_out
+for rep in 1 2; do ( timeout 200 python tests/gpu_time_search.py 2>&1 | tail -1 ); done | tee gpurun_out/ad_ab.log
+( timeout 1200 python -m pytest tests -q -m gpu 2>&1 | tail -n 4 ) | cut -c1-200
