@@ -62,7 +62,7 @@ __host__ __device__ inline CvGeom cv_geom(const ConvTc &p)
     return g;
 }
 
-template <int N>
+template <int N, bool FOLD>
 __global__ void __launch_bounds__(kCvThreads, 2) k_conv_tc(ConvTc p)
 {
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -78,8 +78,14 @@ __global__ void __launch_bounds__(kCvThreads, 2) k_conv_tc(ConvTc p)
     const int y0 = band * p.band_h;
     const int rin0 = y0 * pitch - 1;
     const int npass = p.npass;
-    uint32_t tmem_cols = 32;                         // power of two >= NT * N: lets two CTAs share the SM's 512 columns
-    while (tmem_cols < (uint32_t)(g.NT * N)) tmem_cols <<= 1;
+    // fp32-accurate mode, N <= 64: A_hi x [B_hi | B_lo] is ONE MMA of 2N columns (the tap block stores, per k-group, the N hi rows followed
+    // by the N lo rows) and A_lo x B_hi a second one of N columns: 2 instead of 3 A-operand-bound instructions per k-step; the accumulator
+    // of a tile is then 2N columns wide ([0, N) and [N, 2N) are added at read-out).  N = 128 keeps three N-column MMAs (2N = 256 columns
+    // would gain nothing: 128.7 + 64.7 vs 3 x 64.7 cycles, profiles/r01e_mma_probe.md).
+    constexpr bool kFold = FOLD;                 // chosen per layer on the host (pick_band)
+    constexpr int NA = kFold ? 2 * N : N;
+    uint32_t tmem_cols = 32;                         // power of two >= NT * NA: lets two CTAs share the SM's 512 columns
+    while (tmem_cols < (uint32_t)(g.NT * NA)) tmem_cols <<= 1;
 
     if (tid == 0) {
         for (int i = 0; i < kCvStages; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], 1); }
@@ -119,11 +125,11 @@ __global__ void __launch_bounds__(kCvThreads, 2) k_conv_tc(ConvTc p)
     } else if (warp == kCvEpiWarps + 1) {
         // ================= MMA issuer =================
         if (LZ_MMA_ISSUER_ON) {
-            const uint32_t idesc = make_idesc_f16(128, N);
+            const uint32_t idesc = make_idesc_f16(128, N), idesc2 = make_idesc_f16(128, NA);
             const uint32_t plane16 = (uint32_t)(g.plane >> 4);
             const uint64_t a_desc0 = make_desc(smem_u32(in_s), plane16, 8);
-            const uint64_t b_desc0 = make_desc(smem_u32(ring), N, 8);            // LBO = N rows x 16 B
-            const uint32_t b_lo16 = (uint32_t)(g.tap_bytes >> 5);                 // lo block offset / 16
+            const uint64_t b_desc0 = make_desc(smem_u32(ring), 2 * N, 8);        // tap block [kg][N hi rows | N lo rows][16 B]: LBO = 2N rows
+            const uint32_t b_lo16 = (uint32_t)N;                                  // the lo rows of a k-group, in 16-byte units
             const uint32_t a_lo16 = (uint32_t)(g.part >> 4);
             const int nks = kg_in / 2;
             mbar_wait(&bars->in_full, 0);
@@ -136,14 +142,22 @@ __global__ void __launch_bounds__(kCvThreads, 2) k_conv_tc(ConvTc p)
                 const uint64_t a_tap = a_desc0 + (uint64_t)((p.tap_phase[tap] * g.phase) >> 4) + (uint64_t)(g.m_lo + p.tap_shift[tap]);
                 for (int t = 0; t < g.NT; ++t) {
                     const uint64_t a0 = a_tap + (uint64_t)(t * 128);
-                    const uint32_t d = tmem + t * N;
-                    for (int ks = 0; ks < nks; ++ks)
-                        LZ_UMMA(d, a0 + ks * 2 * plane16, b0 + ks * 2 * N, idesc, (tap | ks) != 0);
-                    if (npass == 3) {
+                    const uint32_t d = tmem + t * NA;
+                    if (npass != 3) {
                         for (int ks = 0; ks < nks; ++ks)
-                            LZ_UMMA(d, a0 + ks * 2 * plane16, b0 + b_lo16 + ks * 2 * N, idesc, 1);
+                            LZ_UMMA(d, a0 + ks * 2 * plane16, b0 + ks * 4 * N, idesc, (tap | ks) != 0);
+                    } else if (kFold) {
                         for (int ks = 0; ks < nks; ++ks)
-                            LZ_UMMA(d, a0 + a_lo16 + ks * 2 * plane16, b0 + ks * 2 * N, idesc, 1);
+                            LZ_UMMA(d, a0 + ks * 2 * plane16, b0 + ks * 4 * N, idesc2, (tap | ks) != 0);
+                        for (int ks = 0; ks < nks; ++ks)
+                            LZ_UMMA(d, a0 + a_lo16 + ks * 2 * plane16, b0 + ks * 4 * N, idesc, 1);
+                    } else {
+                        for (int ks = 0; ks < nks; ++ks)
+                            LZ_UMMA(d, a0 + ks * 2 * plane16, b0 + ks * 4 * N, idesc, (tap | ks) != 0);
+                        for (int ks = 0; ks < nks; ++ks)
+                            LZ_UMMA(d, a0 + ks * 2 * plane16, b0 + b_lo16 + ks * 4 * N, idesc, 1);
+                        for (int ks = 0; ks < nks; ++ks)
+                            LZ_UMMA(d, a0 + a_lo16 + ks * 2 * plane16, b0 + ks * 4 * N, idesc, 1);
                     }
                 }
                 LZ_UCOMMIT(&bars->empty[st]);
@@ -186,7 +200,13 @@ __global__ void __launch_bounds__(kCvThreads, 2) k_conv_tc(ConvTc p)
                 for (int c0 = 0; c0 < NCG; c0 += 16) {
                     float v[16];
                     const int col = grp * 64 + c0;
-                    tmem_ld16(lane_base + t * N + col, v);
+                    tmem_ld16(lane_base + t * NA + col, v);
+                    if (kFold && npass == 3) {          // the A_hi x B_lo half of the folded accumulator
+                        float v2[16];
+                        tmem_ld16(lane_base + t * NA + N + col, v2);
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v[i] += v2[i];
+                    }
 #pragma unroll
                     for (int i = 0; i < 16; ++i) v[i] = fmaf(v[i], __ldg(p.scale + col + i), __ldg(p.shift + col + i));
                     if (p.res.base && grp == 0 && valid) {
@@ -284,9 +304,11 @@ __global__ void k_pool_tcl(Tcl in, Tcl out, float *out_nchw, int B, int Hout)
 int conv_tc_prepare_launch()
 {
     const int big = 227 * 1024;
-    LZ_CUDA_CHECK(cudaFuncSetAttribute(k_conv_tc<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-    LZ_CUDA_CHECK(cudaFuncSetAttribute(k_conv_tc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-    LZ_CUDA_CHECK(cudaFuncSetAttribute(k_conv_tc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    LZ_CUDA_CHECK(cudaFuncSetAttribute(k_conv_tc<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    LZ_CUDA_CHECK(cudaFuncSetAttribute(k_conv_tc<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    LZ_CUDA_CHECK(cudaFuncSetAttribute(k_conv_tc<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    LZ_CUDA_CHECK(cudaFuncSetAttribute(k_conv_tc<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    LZ_CUDA_CHECK(cudaFuncSetAttribute(k_conv_tc<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     return LZ_OK;
 }
 
@@ -294,14 +316,20 @@ int conv_tc_launch(const ConvTc &p, cudaStream_t s)
 {
     const CvGeom g = cv_geom(p);
     LZ_REQUIRE(g.smem <= 227 * 1024, LZ_EINVAL, "conv_tc: band needs %zu B shared memory", g.smem);
-    LZ_REQUIRE(g.NT * p.N <= 512, LZ_EINVAL, "conv_tc: %d tiles x %d columns exceed TMEM", g.NT, p.N);
+    LZ_REQUIRE(g.NT * conv_tc_acc_cols(p) <= 512, LZ_EINVAL, "conv_tc: %d tiles x %d columns exceed TMEM", g.NT, conv_tc_acc_cols(p));
     LZ_REQUIRE(g.tap_bytes <= 16384 && (p.in.C % 16) == 0, LZ_EINVAL, "conv_tc: unsupported channel counts");
     const int groups = (p.B + p.G - 1) / p.G;
     const int grid = groups * g.nbands;
     switch (p.N) {
-        case 32: k_conv_tc<32><<<grid, kCvThreads, g.smem, s>>>(p); break;
-        case 64: k_conv_tc<64><<<grid, kCvThreads, g.smem, s>>>(p); break;
-        case 128: k_conv_tc<128><<<grid, kCvThreads, g.smem, s>>>(p); break;
+        case 32:
+            if (p.fold) k_conv_tc<32, true><<<grid, kCvThreads, g.smem, s>>>(p);
+            else k_conv_tc<32, false><<<grid, kCvThreads, g.smem, s>>>(p);
+            break;
+        case 64:
+            if (p.fold) k_conv_tc<64, true><<<grid, kCvThreads, g.smem, s>>>(p);
+            else k_conv_tc<64, false><<<grid, kCvThreads, g.smem, s>>>(p);
+            break;
+        case 128: k_conv_tc<128, false><<<grid, kCvThreads, g.smem, s>>>(p); break;
         default: LZ_REQUIRE(false, LZ_EINVAL, "conv_tc: N must be 32, 64 or 128");
     }
     LZ_KERNEL_CHECK();
@@ -317,7 +345,8 @@ float conv_tc_pack(const float *w, int cin, int cout, int ncols, int col0, unsig
     int e = 0;
     if (mx > 0.0f) frexpf(mx, &e);
     const float scale = ldexpf(1.0f, 13 - e);
-    const size_t tap_halves = (size_t)2 * (cin / 8) * ncols * 8, part_halves = tap_halves / 2;
+    // tap block: [k-group ci / 8][ncols hi rows | ncols lo rows][ci % 8]: [B_hi | B_lo] of a k-group is one contiguous 2 x ncols-row operand
+    const size_t tap_halves = (size_t)2 * (cin / 8) * ncols * 8, part_halves = (size_t)ncols * 8;
     __half *h = reinterpret_cast<__half *>(dst);
     for (int t = 0; t < 9; ++t)
         for (int co = 0; co < cout; ++co)
@@ -325,7 +354,7 @@ float conv_tc_pack(const float *w, int cin, int cout, int ncols, int col0, unsig
                 const float sv = w[((size_t)co * cin + ci) * 9 + t] * scale;
                 const __half hi = __float2half_rn(sv);
                 const __half lo = __float2half_rn(sv - __half2float(hi));
-                const size_t off = (size_t)t * tap_halves + ((size_t)(ci / 8) * ncols + col0 + co) * 8 + (ci % 8);
+                const size_t off = (size_t)t * tap_halves + ((size_t)(ci / 8) * 2 * ncols + col0 + co) * 8 + (ci % 8);
                 h[off] = hi;
                 h[off + part_halves] = lo;
             }

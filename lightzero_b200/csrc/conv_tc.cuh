@@ -42,18 +42,21 @@ struct ConvTc {
     Tcl in;                       // input (nphase 1 or 4); its (H, W, pitch) is the output/row-space geometry
     Tcl out[2];                   // column group 0 / 1 (group 1 only for N = 128); nphase 4 = write phase-split
     Tcl res;                      // residual added to group 0 (base == nullptr: none)
-    const unsigned char *w;       // [9 taps][hi | lo][kg_in][N][8] fp16
+    const unsigned char *w;       // [9 taps][kg_in][N hi rows | N lo rows][8] fp16
     const float *scale, *shift;   // [N]
     int tap_phase[9], tap_shift[9];
     int relu[2];
     int N;                        // 32, 64 or 128
     int G, band_h;                // images per CTA (band_h == H when G > 1), image rows per band
     int stages;                   // weight ring depth (2..4)
+    int fold;                     // fp32-accurate mode: A_hi x [B_hi | B_lo] as ONE 2N-column MMA (N <= 64; 2N accumulator columns per tile)
     int B, npass;
 };
 
 int conv_tc_prepare_launch();
 int conv_tc_launch(const ConvTc &p, cudaStream_t s);
+// TMEM accumulator columns per 128-row tile: layers with N <= 64 output columns fold [B_hi | B_lo] into one 2N-column MMA (conv_tc.cu)
+inline int conv_tc_acc_cols(const ConvTc &p) { return (p.fold && p.N <= 64) ? 2 * p.N : p.N; }
 // weights [cout][cin][3][3] -> tap blocks with `ncols` columns, this tensor occupying columns
 // [col0, col0+cout); returns the exact power-of-two scale applied
 float conv_tc_pack(const float *w_torch, int cin, int cout, int ncols, int col0, unsigned char *dst);

@@ -556,25 +556,32 @@ static void pick_band(ConvTc &p)
 {
     const int H = p.in.H, pitch = p.in.pitch, kg = p.in.C / 8;
     double best = -1.0;
-    int best_h = 1, best_g = 1, best_st = 4;
-    for (int G = 1; G <= 4; ++G)
-        for (int bh = (G > 1 ? H : 1); bh <= H; ++bh)
-            for (int st = 2; st <= 4; st += 2) {
-                const int rin = (bh + 2) * pitch + 2, mcount = (G - 1) * rin + bh * pitch, NT = (mcount + 127) / 128;
-                int PR = pitch + 1 + NT * 128 + pitch + 2;
-                if (PR < G * rin) PR = G * rin;
-                const size_t smem = (((size_t)PR * 16 * kg * 2 * p.in.nphase + 127) & ~(size_t)127) + st * (size_t)2 * kg * p.N * 16 + 1024;
-                if (smem > 227 * 1024 || NT * p.N > 512) continue;
-                const int nb = (H + bh - 1) / bh;
-                double score = (double)(G * H * (pitch - 1)) / ((double)nb * NT * 128);       // useful / issued MMA rows
-                const bool two_ctas = smem <= 113 * 1024 && NT * p.N <= 256;                // co-residency overlaps load / MMA / epilogue
-                score *= two_ctas ? 1.35 : 1.0;
-                score *= (st == 4) ? 1.0 : 0.97;
-                if (score > best + 1e-9) { best = score; best_h = bh; best_g = G; best_st = st; }
-            }
+    int best_h = 1, best_g = 1, best_st = 4, best_fold = 0;
+    // fold = A_hi x [B_hi | B_lo] as ONE 2N-column MMA (conv_tc.cu): 2 instead of 3 A-operand-bound MMAs per k-step, but 2N accumulator
+    // columns per tile.  Measured on B200: +8-10 % on the 42x42 / 21x21 layers even with smaller bands, -12 % on the 11x11 layers
+    // (fewer whole images per CTA), so it is not offered below 16 rows.
+    for (int fold = 0; fold <= ((p.N <= 64 && H >= 16) ? 1 : 0); ++fold)
+        for (int G = 1; G <= 4; ++G)
+            for (int bh = (G > 1 ? H : 1); bh <= H; ++bh)
+                for (int st = 2; st <= 4; st += 2) {
+                    const int NA = fold ? 2 * p.N : p.N;
+                    const int rin = (bh + 2) * pitch + 2, mcount = (G - 1) * rin + bh * pitch, NT = (mcount + 127) / 128;
+                    int PR = pitch + 1 + NT * 128 + pitch + 2;
+                    if (PR < G * rin) PR = G * rin;
+                    const size_t smem = (((size_t)PR * 16 * kg * 2 * p.in.nphase + 127) & ~(size_t)127) + st * (size_t)2 * kg * p.N * 16 + 1024;
+                    if (smem > 227 * 1024 || NT * NA > 512) continue;
+                    const int nb = (H + bh - 1) / bh;
+                    double score = (double)(G * H * (pitch - 1)) / ((double)nb * NT * 128);       // useful / issued MMA rows
+                    const bool two_ctas = smem <= 113 * 1024 && NT * NA <= 256;                // co-residency overlaps load / MMA / epilogue
+                    score *= two_ctas ? 1.35 : 1.0;
+                    score *= (st == 4) ? 1.0 : 0.97;
+                    score *= fold ? 1.12 : 1.0;
+                    if (score > best + 1e-9) { best = score; best_h = bh; best_g = G; best_st = st; best_fold = fold; }
+                }
     p.band_h = best_h;
     p.G = best_g;
     p.stages = best_st;
+    p.fold = best_fold;
 }
 
 static int tower_tc_run(lz_model *m, int B, const float *d_obs, float *pre_latent, cudaStream_t s, const uint8_t *d_obs_u8 = nullptr)
