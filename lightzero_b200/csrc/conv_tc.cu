@@ -28,7 +28,10 @@
 
 namespace lz {
 
-constexpr int kCvEpiWarps = 4, kCvEpiThreads = kCvEpiWarps * 32, kCvThreads = kCvEpiThreads + 64;   // 192 threads: 2 CTAs / SM
+// 8 epilogue warps (two per TMEM lane quarter, one half of the output columns each): with the CTA's phases load -> MMA -> epilogue in series and
+// only two CTAs co-resident, the epilogue (and the exposed latency of its residual loads) was the longest phase with 4 warps (clock64 stamps,
+// tests/gpu_debug_tower.py); 320 threads x <= 102 registers still fit two CTAs per SM
+constexpr int kCvEpiWarps = 8, kCvEpiThreads = kCvEpiWarps * 32, kCvThreads = kCvEpiThreads + 64;
 constexpr int kCvStages = 4;          // ring slots reserved in the barrier block; p.stages (2..4) are used
 
 struct CvBars {
@@ -99,6 +102,8 @@ __global__ void __launch_bounds__(kCvThreads, 2) k_conv_tc(ConvTc p)
     tc_fence_after();
     const uint32_t tmem = __shfl_sync(0xffffffffu, bars->tmem_base, 0);
 
+    unsigned long long *dbg = (p.dbg && blockIdx.x == gridDim.x / 2) ? p.dbg : nullptr;
+    if (dbg && tid == 0) dbg[58] = clock64();
     if (warp == kCvEpiWarps) {
         // ================= producer: input band, then the 9 weight taps =================
         if (lane == 0) {
@@ -134,6 +139,7 @@ __global__ void __launch_bounds__(kCvThreads, 2) k_conv_tc(ConvTc p)
             const int nks = kg_in / 2;
             mbar_wait(&bars->in_full, 0);
             tc_fence_after();
+            if (dbg && lane == 0) dbg[59] = clock64();
             for (int tap = 0; tap < 9; ++tap) {
                 const int st = tap % nstages;
                 mbar_wait(&bars->full[st], (tap / nstages) & 1);
@@ -163,14 +169,16 @@ __global__ void __launch_bounds__(kCvThreads, 2) k_conv_tc(ConvTc p)
                 LZ_UCOMMIT(&bars->empty[st]);
             }
             LZ_UCOMMIT(&bars->acc_ready);
+            if (dbg && lane == 0) dbg[60] = clock64();
         }
     } else {
         // ================= epilogue: TMEM -> BN (+residual) (+ReLU) -> fp16 hi/lo -> next layer's TCL =================
-        const int q4 = warp & 3, rowid = q4 * 32 + lane;
+        const int q4 = warp & 3, half = warp >> 2, rowid = q4 * 32 + lane;
         const uint32_t lane_base = tmem + ((uint32_t)(q4 * 32) << 16);
         const int yend = min(y0 + p.band_h, H);
         mbar_wait_warp(&bars->acc_ready, 0);
         tc_fence_after();
+        if (dbg && tid == 0) dbg[61] = clock64();
         for (int t = 0; t < g.NT; ++t) {
             const int m = g.m_lo + t * 128 + rowid;
             const int k = m / g.rin;
@@ -178,8 +186,8 @@ __global__ void __launch_bounds__(kCvThreads, 2) k_conv_tc(ConvTc p)
             const int yy = rho / pitch - 1, xx = rho - (yy + 1) * pitch;
             const bool in_band = (k < nimg) && (rho >= pitch) && (yy >= y0) && (yy < yend);
             const bool valid = in_band && (xx < W);
-#pragma unroll
-            for (int grp = 0; grp < (N == 128 ? 2 : 1); ++grp) {
+            {
+                const int grp = (N == 128) ? half : 0;               // N = 128: one output tensor per warp half; else one half of the columns
                 const Tcl &o = p.out[grp];
                 const bool relu = p.relu[grp] != 0;
                 size_t obase = 0;
@@ -195,11 +203,25 @@ __global__ void __launch_bounds__(kCvThreads, 2) k_conv_tc(ConvTc p)
                         do_write = false;
                     }
                 }
-                constexpr int NCG = (N == 128) ? 64 : N;     // columns of this output tensor
+                constexpr int NCW = (N == 128) ? 64 : N / 2;     // columns this warp handles: [cbase, cbase + NCW) of the output tensor
+                const int cbase = (N == 128) ? 0 : half * NCW;
 #pragma unroll
-                for (int c0 = 0; c0 < NCG; c0 += 16) {
+                for (int cc = 0; cc < NCW; cc += 16) {
                     float v[16];
+                    const int c0 = cbase + cc;
                     const int col = grp * 64 + c0;
+                    // residual operand (TCL hi / lo of the 16 columns): issued BEFORE the TMEM loads so that its L2 / HBM latency overlaps them
+                    const bool has_res = p.res.base && grp == 0 && valid;
+                    uint4 rh[2], rl[2];
+                    if (has_res) {
+#pragma unroll
+                        for (int g2 = 0; g2 < 2; ++g2) {
+                            const unsigned char *rp = p.res.base + (size_t)(img0 + k) * p.res.img_stride +
+                                                      ((size_t)(c0 / 8 + g2) * p.res.plane_rows + rho + 1) * 16;
+                            rh[g2] = __ldg(reinterpret_cast<const uint4 *>(rp));
+                            rl[g2] = __ldg(reinterpret_cast<const uint4 *>(rp + p.res.part_stride));
+                        }
+                    }
                     tmem_ld16(lane_base + t * NA + col, v);
                     if (kFold && npass == 3) {          // the A_hi x B_lo half of the folded accumulator
                         float v2[16];
@@ -209,15 +231,10 @@ __global__ void __launch_bounds__(kCvThreads, 2) k_conv_tc(ConvTc p)
                     }
 #pragma unroll
                     for (int i = 0; i < 16; ++i) v[i] = fmaf(v[i], __ldg(p.scale + col + i), __ldg(p.shift + col + i));
-                    if (p.res.base && grp == 0 && valid) {
+                    if (has_res) {
 #pragma unroll
                         for (int g2 = 0; g2 < 2; ++g2) {
-                            const int kgi = c0 / 8 + g2;
-                            const unsigned char *rp = p.res.base + (size_t)(img0 + k) * p.res.img_stride +
-                                                      ((size_t)kgi * p.res.plane_rows + rho + 1) * 16;
-                            const uint4 rh = __ldg(reinterpret_cast<const uint4 *>(rp));
-                            const uint4 rl = __ldg(reinterpret_cast<const uint4 *>(rp + p.res.part_stride));
-                            const __half2 *hh = reinterpret_cast<const __half2 *>(&rh), *hl = reinterpret_cast<const __half2 *>(&rl);
+                            const __half2 *hh = reinterpret_cast<const __half2 *>(&rh[g2]), *hl = reinterpret_cast<const __half2 *>(&rl[g2]);
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
                                 const float2 a = __half22float2(hh[j]), b = __half22float2(hl[j]);
@@ -240,6 +257,7 @@ __global__ void __launch_bounds__(kCvThreads, 2) k_conv_tc(ConvTc p)
             }
         }
     }
+    if (dbg && tid == 0) { dbg[62] = clock64(); dbg[63] = ((unsigned long long)g.NT << 32) | (unsigned)gridDim.x; }
     tc_fence_before();
     __syncthreads();
     if (warp == kCvEpiWarps + 1) {
@@ -312,8 +330,16 @@ int conv_tc_prepare_launch()
     return LZ_OK;
 }
 
-int conv_tc_launch(const ConvTc &p, cudaStream_t s)
+unsigned long long *tc_debug_buffer();     // net_tc.cu (env LZ_TC_DEBUG at model finalize time)
+
+int conv_tc_launch(const ConvTc &p_in, cudaStream_t s)
 {
+    ConvTc p = p_in;
+    p.dbg = nullptr;
+    if (const char *e = getenv("LZ_CONV_DEBUG")) {          // bring-up only: stamps of the e-th conv_tc launch of every group of 8 (one tower)
+        static int launch_idx = 0;
+        if (tc_debug_buffer() && (launch_idx++ % 8) == atoi(e)) p.dbg = tc_debug_buffer();
+    }
     const CvGeom g = cv_geom(p);
     LZ_REQUIRE(g.smem <= 227 * 1024, LZ_EINVAL, "conv_tc: band needs %zu B shared memory", g.smem);
     LZ_REQUIRE(g.NT * conv_tc_acc_cols(p) <= 512, LZ_EINVAL, "conv_tc: %d tiles x %d columns exceed TMEM", g.NT, conv_tc_acc_cols(p));

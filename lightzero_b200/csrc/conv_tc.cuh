@@ -51,6 +51,7 @@ struct ConvTc {
     int stages;                   // weight ring depth (2..4)
     int fold;                     // fp32-accurate mode: A_hi x [B_hi | B_lo] as ONE 2N-column MMA (N <= 64; 2N accumulator columns per tile)
     int B, npass;
+    unsigned long long *dbg;      // bring-up instrumentation (env LZ_CONV_DEBUG=<layer>): clock64 stamps of the middle CTA, slots 58-63 of the debug buffer
 };
 
 int conv_tc_prepare_launch();
