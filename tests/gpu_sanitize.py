@@ -46,5 +46,31 @@ eroots = emcts.roots(B, [list(range(A))] * B)
 eroots.prepare(0.25, noise, [0.] * B, eo.policy_logits, [1, 2] * (B // 2) + [1])     # two-player branch
 emcts.search(eroots, ecu, eo.latent_state, eo.reward_hidden_state, [1, 2] * (B // 2) + [1])
 print("efficientzero ok", r["values"][:3].tolist(), eroots.get_distributions()[:2])
+# round 2: a batch that takes the {5, 2} root-group split of the persistent kernel (7 roots per CTA), the fused reuse searches, the
+# uint8 entry point fed by the device-resident frame stack, GameSegment statistics
+from lightzero_b200.collector import FrameStack, SegmentStats
+B2 = 148 * 6 + 5
+cu = lzb.MuZeroModel(observation_shape=(4, 84, 84), action_space_size=A).load_state_dict(ref.state_dict())
+pol = MuZeroCollectPolicy(cu, dict(num_simulations=4, deterministic=True, discount_factor=0.997))
+fs = FrameStack(B2, 4, 84, 84)
+rng = np.random.default_rng(5)
+fs.push(rng.integers(0, 256, (B2, 84, 84), dtype=np.uint8), reset=np.ones(B2, np.uint8))
+fs.push(rng.integers(0, 256, (B2, 84, 84), dtype=np.uint8))
+mask2 = torch.ones(B2, A, dtype=torch.uint8).cuda()
+noise2 = torch.from_numpy(rng.dirichlet([0.3] * A, size=B2).astype(np.float32)).cuda()
+r = pol.search_batch(fs.view(), mask2, noise2, None, read_back=False)
+assert int(r["visits"].clamp(min=0).sum()) == B2 * 4
+seg = SegmentStats(B2, 3, A)
+seg.store_search_stats(r["visits"], r["values"])
+seg.reset(np.ones(B2, np.uint8))
+mcts2 = lzb.MuZeroMCTSCtree(dict(num_simulations=4, deterministic=True))
+o2 = cu.initial_inference(torch.rand(20, 4, 84, 84).cuda())
+roots2 = mcts2.roots(20, [list(range(A))] * 20)
+roots2.prepare(0.25, noise[:1].repeat(20, 0), [0.] * 20, o2.policy_logits, [-1] * 20)
+mcts2.search_with_reuse(roots2, cu, o2.latent_state, [-1] * 20, [1] * 20, [0.3] * 20)
+eroots2 = emcts.roots(B, [list(range(A))] * B)
+eroots2.prepare(0.25, noise, [0.] * B, eo.policy_logits, [-1] * B)
+emcts.search_with_reuse(eroots2, ecu, eo.latent_state, eo.reward_hidden_state, [-1] * B, [2] * B, [0.1] * B)
+print("round-2 paths ok", fs.get_obs().shape, eroots2.get_distributions()[:1])
 torch.cuda.synchronize()
 print("sanitize script finished")
