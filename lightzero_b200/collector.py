@@ -47,6 +47,7 @@ class FrameStack:
         with torch.cuda.device(self.device):
             if isinstance(new_frames, torch.Tensor) and new_frames.is_cuda:
                 nf = new_frames.to(torch.uint8).contiguous()
+                assert tuple(nf.shape) == (self.B, self.H, self.W), nf.shape
                 rs = None if reset is None else torch.as_tensor(reset).to(self.device, torch.uint8).contiguous()
                 cabi.check(self._lib.lz_frames_push(self._h, nf.data_ptr(), cabi.ptr(rs), cabi.stream_ptr()), "lz_frames_push")
             else:
@@ -55,9 +56,10 @@ class FrameStack:
                         return x
                     return torch.as_tensor(np.ascontiguousarray(np.asarray(x), dtype=np.uint8)).pin_memory()
                 nf = pinned(new_frames)
+                assert tuple(nf.shape) == (self.B, self.H, self.W), nf.shape
                 rs = None if reset is None else pinned(reset)
+                assert rs is None or rs.numel() == self.B
                 cabi.check(self._lib.lz_frames_push_host(self._h, nf.data_ptr(), cabi.ptr(rs), cabi.stream_ptr()), "lz_frames_push_host")
-            assert tuple(nf.shape) == (self.B, self.H, self.W), nf.shape
             self._keep = (nf, rs)
 
     def stacked_ptr(self) -> int:

@@ -79,8 +79,6 @@ int lz_frames_create(int B, int stack, int H, int W, lz_frames **out)
 {
     LZ_REQUIRE(out && B > 0 && stack > 0 && H > 0 && W > 0, LZ_EINVAL, "lz_frames_create: bad argument");
     LZ_REQUIRE((H * W) % 16 == 0, LZ_EINVAL, "lz_frames_create: H * W = %d is not a multiple of 16", H * W);
-    int dev_count = 0;
-    LZ_CUDA_CHECK(cudaGetDeviceCount(&dev_count));
     lz_frames *f = new lz_frames();
     memset(f, 0, sizeof(*f));
     f->B = B; f->stack = stack; f->frame_bytes = H * W;

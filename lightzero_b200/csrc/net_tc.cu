@@ -57,7 +57,7 @@ constexpr int kStages = 5;                       // 16 KB ring stages: conv taps
 constexpr int kHeadWBytes = 3 * 2 * 16 * 64 * 2; // three 1x1 heads (hc <= 16), hi + lo: 12288 B
 constexpr int kBnSmemBytes = kTcMaxLayers * 128 * 4;   // folded BatchNorm tables of the program's layers
 constexpr int kSmemMain = kActBytes + kStages * kTapBytes + kHeadWBytes + 1024 + kBnSmemBytes;
-constexpr int kHeadScratch = 72 * 8 * 16 * 2 + kEpiWarps * (16 + 3 * 32) * 4;   // kFrBytes (parked reward features) + the parked trees   // + the parked trees (kTreeParkWords per warp)   // reward head features, parked from their hook to the heads' FC pass at the end of the simulation
+constexpr int kHeadScratch = 72 * 8 * 16 * 2 + kEpiWarps * (16 + 3 * 32) * 4;   // kFrBytes (reward features parked from their hook to the heads' FC pass) + the parked trees (kTreeParkWords per warp)
 // tree <-> network hand-off of the persistent search, per root slot of the CTA: leaf slot, action | value, reward, policy logits
 // (the global copies are still written for the step-wise entry points; reading them back would cost an L2 round trip per use)
 constexpr int kHoWords = 4 + 32;
