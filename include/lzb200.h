@@ -98,6 +98,11 @@ int lz_tree_backpropagate(lz_tree *t, int latent_index, const float *d_reward, c
  * The reference tie-break is rand() % len(ties) with no deterministic switch (cnode.cpp:691); these entry points use
  * the first-maximum rule, which is that draw with rand() == 0 (how the parity oracle builds the reference). */
 int lz_tree_set_ez(lz_tree *t, int efficientzero, int lstm_horizon_len);
+/* Tie-breaking of the EfficientZero and *_with_reuse descents, which have no deterministic switch in the reference (they draw
+ * rand() % len(ties) after reseeding from the wall clock, ctree_efficientzero/lib/cnode.cpp:691, ctree_muzero cnode.cpp:610-640):
+ * first_maximum = 1 (default; the reference's draw with rand() == 0, what the parity tests pin) or 0 = a uniform draw from the same tie
+ * list with the counter-based device RNG of lz_tree_traverse(deterministic = 0). */
+int lz_tree_set_tiebreak(lz_tree *t, int first_maximum);
 /* cbatch_traverse (ctree_efficientzero cnode.cpp:876-958); d_is_reset int32 [B] out (may be NULL). */
 int lz_tree_traverse_ez(lz_tree *t, int32_t *d_ix, int32_t *d_iy, int32_t *d_last_action, int32_t *d_search_len,
                         int32_t *d_virtual_to_play, int32_t *d_is_reset, lz_stream s);

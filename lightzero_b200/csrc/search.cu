@@ -60,7 +60,7 @@ static int enqueue_search(lz_search *q, int deterministic, cudaStream_t s)
     if (ez) {
         // EfficientZeroMCTSCtree.search (mcts_ctree.py:671-876): the LSTM step is a GEMM over all roots, so the network
         // is several launches per simulation and the loop stays a multi-kernel graph
-        if ((rc = tree_launch_traverse(t, 1, q->d_ix, nullptr, q->d_action, nullptr, nullptr, s, q->d_is_reset))) return rc;
+        if ((rc = tree_launch_traverse(t, t->p.tie_first, q->d_ix, nullptr, q->d_action, nullptr, nullptr, s, q->d_is_reset))) return rc;
         for (int sim = 0; sim < q->S; ++sim) {
             RecIO io;
             memset(&io, 0, sizeof(io));
@@ -73,7 +73,7 @@ static int enqueue_search(lz_search *q, int deterministic, cudaStream_t s)
             io.skip_scratch = q->d_skip;
             if ((rc = model_recurrent(q->model, io, s))) return rc;
             if (sim + 1 < q->S)
-                rc = tree_launch_backprop_traverse(t, sim + 1, q->d_reward, q->d_value, q->d_policy, 1, q->d_ix, q->d_action, s, q->d_is_reset);
+                rc = tree_launch_backprop_traverse(t, sim + 1, q->d_reward, q->d_value, q->d_policy, t->p.tie_first, q->d_ix, q->d_action, s, q->d_is_reset);
             else
                 rc = tree_launch_backprop(t, sim + 1, q->d_reward, q->d_value, q->d_policy, nullptr, s, q->d_is_reset);
             if (rc) return rc;
@@ -375,7 +375,10 @@ static int collect_device(lz_search *q, const float *d_obs, const uint8_t *d_obs
     if (rc) return rc;
     if ((rc = lz_tree_reset_mask(q->tree, d_mask, s))) return rc;                // :760,769
     if ((rc = lz_tree_prepare(q->tree, io.policy_logits, d_noise, noise_weight, nullptr, d_to_play, s))) return rc;   // :774
-    if (q->hpool && (rc = ez_root_hidden(q, nullptr, nullptr, (cudaStream_t)s))) return rc;
+    if (q->hpool) {      // EfficientZero: zero LSTM state at the roots; the tree has no deterministic argument, the collect call's flag selects its tie-breaking
+        if ((rc = ez_root_hidden(q, nullptr, nullptr, (cudaStream_t)s))) return rc;
+        if ((rc = lz_tree_set_tiebreak(q->tree, deterministic))) return rc;
+    }
     return run_graph(q, deterministic, (cudaStream_t)s);                         // :775
 }
 
@@ -469,7 +472,10 @@ static int collect_host(lz_search *q, const void *h_obs, int obs_u8, const uint8
     if ((rc = lz_tree_reset_mask(q->tree, h_mask ? q->d_mask_stage : nullptr, s))) return rc;
     if ((rc = lz_tree_prepare(q->tree, logits, h_noise ? q->d_noise_stage : nullptr, noise_weight, nullptr,
                               h_to_play ? q->d_tp_stage : nullptr, s))) return rc;
-    if (q->hpool && (rc = ez_root_hidden(q, nullptr, nullptr, s))) return rc;
+    if (q->hpool) {
+        if ((rc = ez_root_hidden(q, nullptr, nullptr, s))) return rc;
+        if ((rc = lz_tree_set_tiebreak(q->tree, deterministic))) return rc;
+    }
     return run_graph(q, deterministic, s);
 }
 

@@ -155,7 +155,7 @@ k_tree_traverse_reuse(TreeParams p, unsigned step, const int32_t *true_action, c
 {
     const int b = blockIdx.x * (kTreeBlock / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (b >= p.B) return;
-    tree_traverse<EZ, true>(p, b, lane, 1, step, ix, iy, act, len, vtp, true_action, reuse_value, ix_net);
+    tree_traverse<EZ, true>(p, b, lane, p.tie_first, step, ix, iy, act, len, vtp, true_action, reuse_value, ix_net);
     // EfficientZero, fused search: is_reset of the reached node per TREE (mcts_ctree.py:856-861 / 1040-1046: search_len % lstm_horizon_len)
     if (EZ && is_reset && lane == 0) is_reset[b] = (p.search_len[b] % p.lstm_horizon == 0) ? 1 : 0;
 }
@@ -178,7 +178,7 @@ k_tree_backprop_traverse_reuse(TreeParams p, int latent_index, const float *rewa
     const int b = blockIdx.x * (kTreeBlock / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (b >= p.B) return;
     tree_backprop<false, true>(p, b, lane, latent_index, reward[b], value[b], logits + (size_t)b * p.A, nullptr, 0, reuse_value[b], -1);
-    tree_traverse<false, true>(p, b, lane, 1, step, nullptr, nullptr, act, nullptr, nullptr, true_action, reuse_value, ix_net);
+    tree_traverse<false, true>(p, b, lane, p.tie_first, step, nullptr, nullptr, act, nullptr, nullptr, true_action, reuse_value, ix_net);
 }
 
 // get_distributions / get_values / get_trajectories (cnode.cpp:237-277,369-417)
@@ -391,7 +391,7 @@ int lz_tree_create(int B, int A, int max_sims, lz_tree **out)
     p.edges = base + o_edges;
     p.n_to_play = (int *)(base + o_ntp); p.n_best = (int *)(base + o_nbest); p.n_reset = (int *)(base + o_nreset);
     p.n_batch = (int *)(base + o_nbatch); p.reuse_state = (int *)(base + o_rstate); p.infer_count = (int *)(base + o_infer);
-    p.ez = 0; p.lstm_horizon = 5;
+    p.ez = 0; p.lstm_horizon = 5; p.tie_first = 1;
     p.legal = (int *)(base + o_legal); p.nlegal = (int *)(base + o_nlegal);
     p.root_visit = (int *)(base + o_rvis); p.root_vsum = (float *)(base + o_rvsum); p.root_reward = (float *)(base + o_rrew);
     p.mm_max = (float *)(base + o_mmax); p.mm_min = (float *)(base + o_mmin);
@@ -500,12 +500,21 @@ int lz_tree_set_ez(lz_tree *t, int efficientzero, int lstm_horizon_len)
     return LZ_OK;
 }
 
+int lz_tree_set_tiebreak(lz_tree *t, int first_maximum)
+{
+    LZ_REQUIRE(t, LZ_EINVAL, "lz_tree_set_tiebreak: null tree");
+    const int v = first_maximum ? 1 : 0;
+    if (t->p.tie_first != v) ++t->generation;       // captured graphs bake TreeParams in
+    t->p.tie_first = v;
+    return LZ_OK;
+}
+
 int lz_tree_traverse_ez(lz_tree *t, int32_t *d_ix, int32_t *d_iy, int32_t *d_last_action, int32_t *d_search_len,
                         int32_t *d_virtual_to_play, int32_t *d_is_reset, lz_stream s)
 {
     LZ_REQUIRE(t && t->p.ez, LZ_ESTATE, "lz_tree_traverse_ez: tree is not in EfficientZero mode (lz_tree_set_ez)");
     LZ_REQUIRE(t->prepared, LZ_ESTATE, "lz_tree_traverse_ez: roots not prepared (call lz_tree_prepare first)");
-    return tree_launch_traverse(t, 1, d_ix, d_iy, d_last_action, d_search_len, d_virtual_to_play, (cudaStream_t)s, d_is_reset);
+    return tree_launch_traverse(t, t->p.tie_first, d_ix, d_iy, d_last_action, d_search_len, d_virtual_to_play, (cudaStream_t)s, d_is_reset);
 }
 
 int lz_tree_backpropagate_ez(lz_tree *t, int latent_index, const float *d_value_prefix, const float *d_value,

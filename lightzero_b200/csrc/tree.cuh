@@ -46,6 +46,7 @@ struct TreeParams {
     // EfficientZero mode (ctree_efficientzero): the edge "reward" word holds the child's VALUE PREFIX, every expanded node
     // carries is_reset, and a step's reward is the prefix difference unless the parent was reset
     int ez, lstm_horizon;
+    int tie_first;             // EfficientZero / *_with_reuse descents (the reference draws rand() % len(ties) there): 1 = first maximum (default), 0 = uniform draw
     int *n_reset;                // [B][N]
     // ReZero search_with_reuse (cnode.cpp:502-549, 597-652, 701-752, 828-932)
     int *n_batch;                // [B][N] batch_index recorded at expansion (the compacted inference row under reuse)

@@ -134,6 +134,7 @@ class MuZeroMCTSCtree(object):
         ta = mz_tree._to_dev(true_action_list, torch.int32, dev, (B,))
         rv = mz_tree._to_dev(reuse_value_list, torch.float32, dev, (B,))
         counts = torch.empty(S, dtype=torch.int32, device=dev)
+        cabi.check(t.lib.lz_tree_set_tiebreak(t.h, int(self.deterministic)), "lz_tree_set_tiebreak")   # the reference draws rand() % len(ties) (cnode.cpp:610-640)
         q = t.search_for(model, S)
         with torch.cuda.device(dev):
             cabi.check(t.lib.lz_search_run_with_reuse(q, lat.data_ptr(), ta.data_ptr(), rv.data_ptr(), counts.data_ptr(),
@@ -196,6 +197,9 @@ class EfficientZeroMCTSCtree(MuZeroMCTSCtree):
     def __init__(self, cfg=None) -> None:
         super().__init__(cfg)
         self._cfg.setdefault("lstm_horizon_len", 5)
+        # the reference tree has no deterministic switch (always rand() % len(ties)); here first maximum is the default (what the
+        # parity tests pin) and ``deterministic=False`` in the config selects the uniform draw (lz_tree_set_tiebreak)
+        self.deterministic = bool(self._cfg.get("deterministic", True))
 
     @classmethod
     def roots(cls, active_collect_env_num: int, legal_actions: List[Any]) -> "ez_tree.Roots":
@@ -210,6 +214,7 @@ class EfficientZeroMCTSCtree(MuZeroMCTSCtree):
         roots._materialize(S, self._params())
         t = roots._tree
         dev = roots.device
+        cabi.check(t.lib.lz_tree_set_tiebreak(t.h, int(self.deterministic)), "lz_tree_set_tiebreak")
 
         def dev_f32(x):
             if isinstance(x, torch.Tensor):
@@ -241,6 +246,7 @@ class EfficientZeroMCTSCtree(MuZeroMCTSCtree):
         roots._materialize(S, self._params())
         t = roots._tree
         dev = roots.device
+        cabi.check(t.lib.lz_tree_set_tiebreak(t.h, int(self.deterministic)), "lz_tree_set_tiebreak")
 
         def dev_f32(x):
             if isinstance(x, torch.Tensor):

@@ -243,3 +243,24 @@ def test_fused_ez_search_with_reuse_equals_piecewise_drive():
     assert fused == step
     assert length == counts[-1] and abs(avg - sum(counts) / S) < 1e-9
     assert min(counts) < B
+
+
+def test_ez_stochastic_tiebreak_is_legal_and_reproducible():
+    """lz_tree_set_tiebreak(0) (config deterministic=False): the EfficientZero descent draws from the reference's tie list
+    (ctree_efficientzero/lib/cnode.cpp:676-691) with the counter-based device RNG: searches stay legal (sum of visits = S, masked actions
+    never visited) and differ from the first-maximum search only where ties exist (all-equal priors and zero values force ties at the root)."""
+    import lightzero_b200 as lzb
+    B, A, S = 32, 6, 12
+    ref, cu, obs, mask, legal, noises, mcts = _setup(B, A, S, masks=True, horizon=3)
+    out = cu.initial_inference(obs.cuda())
+    flat = torch.zeros_like(out.policy_logits)                 # equal priors: every first descent is a tie
+    res = {}
+    for det in (True, False):
+        m = lzb.EfficientZeroMCTSCtree(dict(num_simulations=S, discount_factor=0.997, lstm_horizon_len=3, deterministic=det))
+        roots = m.roots(B, legal)
+        roots.prepare_no_noise([0.] * B, flat, [-1] * B)
+        m.search(roots, cu, out.latent_state, out.reward_hidden_state, [-1] * B)
+        res[det] = roots.get_distributions()
+        assert all(sum(d) == S and len(d) == len(l) for d, l in zip(res[det], legal))
+        roots.clear()
+    assert res[True] != res[False]
