@@ -106,13 +106,13 @@ def test_end_to_end_against_reference_pipeline(B, A, S, masks, math):
     assert all(sum(d) == S for d in got_d)
 
 
-def test_replay_of_reference_pipeline_is_bit_exact():
+@pytest.mark.parametrize("B,A,S", [(48, 18, 50), (128, 18, 200)])
+def test_replay_of_reference_pipeline_is_bit_exact(B, A, S):
     """Replay mode: feed the CUDA trees the network outputs the ORACLE pipeline
     produced (recorded per simulation).  The trees must then reproduce the reference's visit counts
-    and root values bit for bit, on the same seeds."""
+    and root values bit for bit, on the same seeds -- also at BASELINE config 3's 200 simulations on a 128-root shard."""
     from lightzero_b200 import mz_tree
     from oracle.search_ref import SearchRef, collect_step_ref, load_tree_module
-    B, A, S = 48, 18, 50
     ref, cu, obs, mask, legal, noises, mcts = _setup(B, A, S, seed=5, masks=True)
     tree, kind = load_tree_module()
     rec = []
