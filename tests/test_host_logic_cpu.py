@@ -43,3 +43,36 @@ def test_inverse_scalar_transform_has_no_cpu_path():
     from lightzero_b200.scaling_transform import DiscreteSupport, InverseScalarTransform
     with pytest.raises((RuntimeError, LzError, AssertionError)):
         InverseScalarTransform(DiscreteSupport(-300., 301., 1., device="cpu"))(torch.zeros(2, 601))
+
+
+def test_unizero_and_efficientzero_tiebreak_defaults():
+    """UniZeroMCTSCtree: deterministic=False by default (mcts_ctree.py:41-42); EfficientZeroMCTSCtree: first maximum unless the config says
+    otherwise (the reference tree has no switch; lz_tree_set_tiebreak)."""
+    from lightzero_b200.mcts_ctree import EfficientZeroMCTSCtree, UniZeroMCTSCtree
+    assert UniZeroMCTSCtree.default_config().deterministic is False and UniZeroMCTSCtree.default_config().cfg_type == "UniZeroMCTSCtreeDict"
+    assert UniZeroMCTSCtree({}).deterministic is False and UniZeroMCTSCtree(dict(deterministic=True)).deterministic is True
+    assert EfficientZeroMCTSCtree({}).deterministic is True and EfficientZeroMCTSCtree(dict(deterministic=False)).deterministic is False
+
+
+def test_segment_pack_unpack_round_trip():
+    """collector.pack_segments / unpack_segments: the packed buffer of the finished-segment all-gather is lossless."""
+    from lightzero_b200.collector import pack_segments, unpack_segments
+    g = torch.Generator().manual_seed(0)
+    B, T, A = 5, 7, 18
+    cv, rv = torch.rand(B, T, A, generator=g), torch.rand(B, T, generator=g)
+    ln = torch.randint(0, T + 1, (B,), generator=g, dtype=torch.int32)
+    packed = pack_segments(cv, rv, ln)
+    assert packed.shape == (B, T * A + T + 1) and packed.is_contiguous()
+    cv2, rv2, ln2 = unpack_segments(packed, T, A)
+    assert torch.equal(cv2, cv) and torch.equal(rv2, rv) and torch.equal(ln2, ln)
+
+
+def test_collector_state_has_no_cpu_path():
+    import pytest
+    if torch.cuda.is_available():
+        pytest.skip("needs a machine without a GPU")
+    from lightzero_b200.collector import FrameStack, SegmentStats
+    with pytest.raises(Exception):
+        FrameStack(2, 4, 84, 84)
+    with pytest.raises(Exception):
+        SegmentStats(2, 8, 6)
