@@ -128,8 +128,11 @@ class MuZeroCollectPolicy:
                                                               bufs["action"].data_ptr(), bufs["action_pos"].data_ptr(),
                                                               bufs["entropy"].data_ptr(), s), "lz_tree_select_action")
                 if not read_back:
-                    return dict(visits=tree.visits.clone(), values=tree.values.clone(), nlegal=tree.nlegal.clone(),
-                                pred_value=bufs["pred_value"], policy_logits=bufs["logits"])
+                    dev_out = dict(visits=tree.visits.clone(), values=tree.values.clone(), nlegal=tree.nlegal.clone(),
+                                   pred_value=bufs["pred_value"], policy_logits=bufs["logits"])
+                    if select is not None:      # the device-side select_action results stay on the device too
+                        dev_out.update(action=bufs["action"].clone(), entropy=bufs["entropy"].clone())
+                    return dev_out
                 bufs["h_visits"].copy_(tree.visits, non_blocking=True)
                 bufs["h_values"].copy_(tree.values, non_blocking=True)
                 bufs["h_nlegal"].copy_(tree.nlegal, non_blocking=True)

@@ -98,3 +98,29 @@ def test_store_search_stats_matches_game_segment():
         if n:
             assert np.array_equal(cv[b, :n], np.asarray(ref_cv[b], np.float64).astype(np.float32)), b
             assert np.array_equal(rv[b, :n], np.asarray(ref_rv[b], np.float32)), b
+
+
+def test_collect_step_without_read_back_returns_device_actions():
+    """The collector loop of INTEGRATION.md section 5: search_batch(read_back=False, select=...) leaves visits / values / actions on the
+    device (no synchronisation inside the step) and they equal the read-back variant."""
+    import lightzero_b200 as lzb
+    from lightzero_b200.collect import MuZeroCollectPolicy
+    from lightzero_b200.collector import FrameStack, SegmentStats
+    from lightzero_b200.synthetic_weights import synthetic_state_dict
+    B, A, S = 24, 6, 8
+    model = lzb.MuZeroModel(observation_shape=(4, 84, 84), action_space_size=A).load_state_dict(synthetic_state_dict((4, 84, 84), A))
+    pol = MuZeroCollectPolicy(model, dict(num_simulations=S, deterministic=True, discount_factor=0.997))
+    rng = np.random.default_rng(7)
+    fs = FrameStack(B, 4, 84, 84)
+    fs.push(rng.integers(0, 256, (B, 84, 84), dtype=np.uint8), reset=np.ones(B, np.uint8))
+    mask = torch.ones(B, A, dtype=torch.uint8).cuda()
+    noise = torch.from_numpy(rng.dirichlet([0.3] * A, size=B).astype(np.float32)).cuda()
+    dev = pol.search_batch(fs.view(), mask, noise, read_back=False, select=(1.0, True, 3))
+    assert dev["action"].is_cuda and dev["visits"].is_cuda
+    host = pol.search_batch(fs.view(), mask, noise, read_back=True, select=(1.0, True, 3))
+    assert np.array_equal(dev["visits"].cpu().numpy(), np.asarray(host["visits"]))
+    assert np.array_equal(dev["action"].cpu().numpy(), np.asarray(host["action"]))
+    seg = SegmentStats(B, 4, A)
+    seg.store_search_stats(dev["visits"], dev["values"])
+    cv, rv, ln = seg.tensors()
+    assert (ln == 1).all() and torch.allclose(cv[:, 0].sum(1), torch.ones(B, device=cv.device))
