@@ -1,30 +1,29 @@
 // net_tc.cu -- tcgen05 (5th-gen tensor core) path of the MuZero latent-grid networks for sm_100a.
 //
-// One CTA runs the WHOLE recurrent_inference (or the latent-grid tail of initial_inference) for up to 7
-// roots: five 3x3 convolutions + three 1x1 head convolutions as tcgen05.mma with fp32 accumulators in
-// TMEM, BatchNorm/residual/ReLU epilogues out of TMEM, and the small fully connected head layers +
-// softmax-expectation + inverse scalar transform on the CUDA cores.  Activations never leave the SM.
+// One CTA runs the WHOLE recurrent_inference (or the latent-grid tail of initial_inference) for up to 7 roots -- and, in persistent
+// mode, the whole num_simulations loop of their search (tree back-up + descent by one warp per tree, tree_persist.cuh): five 3x3
+// convolutions, three 1x1 head convolutions and the heads' fully connected layers as tcgen05.mma with fp32 accumulators in TMEM;
+// BatchNorm / residual / ReLU epilogues and the softmax expectation + inverse scalar transform straight out of TMEM.  Activations never
+// leave the SM.  DESIGN.md 4.3 / 4.3c describe the design and what bounds it (the L1 / shared-memory data pipe).
 //
-// fp32 accuracy on fp16 tensor cores ("3xFP16"): every fp32 operand v is split v = hi + lo with
-// hi = fp16(v), lo = fp16(v - hi) (22 significant bits); D += A_hi*B_hi + A_hi*B_lo + A_lo*B_hi with fp32
-// accumulation drops only the 2^-22 lo*lo term.  Same bytes per element as fp32 (2+2), three MMAs at
-// the fp16 rate.  Weights are pre-split on the host and pre-scaled by a power of two (exact; folded
-// back into the BatchNorm scale) so their lo parts stay in fp16's normal range.  Mode 2 ("fast")
-// issues only the hi*hi pass.
+// fp32 accuracy on fp16 tensor cores ("3xFP16"): every fp32 operand v is split v = hi + lo with hi = fp16(v), lo = fp16(v - hi) (22
+// significant bits); D += A_hi*B_hi + A_hi*B_lo + A_lo*B_hi with fp32 accumulation drops only the 2^-22 lo*lo term.  The tap block of the
+// weights stores B_hi and B_lo as 128 consecutive operand rows, so A_hi x [B_hi | B_lo] is ONE N = 128 MMA and A_lo x B_hi a second one of
+// N = 64; the two 64-column halves of a tile's accumulator are added at read-out.  Weights are pre-split on the host and pre-scaled by a
+// power of two (exact; folded back into the BatchNorm scale) so their lo parts stay in fp16's normal range.  Mode 2 ("fast") issues only
+// the hi*hi pass.
 //
-// Implicit GEMM without im2col: activations live in shared memory as [k-group of 8 channels][row][8
-// halves] (the UMMA K-major no-swizzle canonical layout with SBO = 128 B, so row r of the operand is at
-// start + 16*r bytes).  Rows are the pixels of a 7-wide padded grid (49 rows per root, column 6 and row
-// 6 zero), so the input of output row m for tap (dy,dx) is row m + 7*dy + dx: each of the 9 taps is the
-// SAME buffer addressed through a descriptor whose start address is shifted by (7*dy+dx)*16 bytes.  The
-// zero pad rows double as the conv padding between rows and between consecutive roots.  M tiles of 128
-// rows cut anywhere (every output row only depends on shifted input rows); all tiles of a layer
-// accumulate in TMEM before the epilogue rewrites the buffer IN PLACE; the ResBlock skip tensor is parked
-// in spare TMEM columns (tcgen05.st) instead of a second shared-memory buffer.
+// Implicit GEMM without im2col: activations live in shared memory as [k-group of 8 channels][row][8 halves] (the UMMA K-major no-swizzle
+// canonical layout with SBO = 128 B, so row r of the operand is at start + 16*r bytes).  Rows are the pixels of a 7-wide padded grid (49
+// rows per root, column 6 and row 6 zero), so the input of output row m for tap (dy,dx) is row m + 7*dy + dx: each of the 9 taps is the
+// SAME buffer addressed through a descriptor whose start address is shifted by (7*dy+dx)*16 bytes.  The zero pad rows double as the conv
+// padding between rows and between consecutive roots.  M tiles of 128 rows cut anywhere; all tiles of a layer (of a root group, see the
+// kernel) accumulate in TMEM before the epilogue rewrites the buffer IN PLACE; the ResBlock skip tensors are parked in an L2-resident
+// scratch (thread-private rows, .cg accesses) -- TMEM is full: 3 tiles x 128 accumulator columns + the reward hook.
 //
-// Warp roles (320 threads): warps 0-7 = epilogue / loads / heads (warp w owns TMEM lanes 32*(w%4).. and the
-// 32-column half w/4 of every accumulator), warp 8 lane 0 = weight producer (cp.async.bulk global->shared
-// ring, mbarrier complete_tx), warp 9 lane 0 = MMA issuer (+ TMEM alloc/dealloc by warp 9).
+// Warp roles (320 threads): warps 0-7 = epilogue / loads / heads / trees (warp w owns TMEM lanes 32*(w%4).. and the 32-column half w/4 of
+// every accumulator), warp 8 lane 0 = weight producer (cp.async.bulk global->shared ring, mbarrier complete_tx), warp 9 = MMA issuer (the
+// whole warp runs the issue loops in uniform control flow, elect.sync picks the lane) + TMEM alloc/dealloc.
 #include <cuda_fp16.h>
 #include <math.h>
 #include <stdlib.h>
